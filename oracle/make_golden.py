@@ -1,0 +1,219 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules (test infrastructure).
+
+Run in the build container only (needs /root/reference):  ``python oracle/make_golden.py``
+
+The reference's ``fourierflow/__init__.py`` imports hydra/xarray/jax/pytorch_lightning (absent
+offline), so the operator sub-package is imported through a stub parent package.
+``fourierflow.routines`` cannot be imported at all; the 10-step Markov rollout fixture is therefore
+produced by driving the reference's own ``FNOFactorized2DBlock`` + ``Normalizer`` + ``LpLoss``
+objects with the loop of routines/grid_2d_markov.py:195-326 written out below.
+
+Each fixture stores: the constructor kwargs (JSON), the full reference ``state_dict``, the input,
+and the reference outputs (final + per-layer taps).  Nothing here is imported by the product.
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+REF = os.environ.get("FFNO_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def import_reference():
+    pkg = types.ModuleType("fourierflow")
+    pkg.__path__ = [os.path.join(REF, "fourierflow")]
+    sys.modules["fourierflow"] = pkg
+    import fourierflow.modules as M  # noqa
+    from fourierflow.modules.loss import LpLoss  # noqa
+    return M, LpLoss
+
+
+def sd_np(module):
+    """state_dict → arrays.  With share_weight=True the reference registers the SAME ParameterList on
+    the block and on every layer (grid_2d.py:125-147), so ``spectral_layers.{l}.fourier_weight.{a}``
+    alias ``fourier_weight.{a}``; the aliases are dropped here and re-created by the loader
+    (tests/golden_util.py) to keep the fixtures small."""
+    sd = module.state_dict()
+    shared = "fourier_weight.0" in sd
+    out = {}
+    for k, v in sd.items():
+        if shared and re.match(r"spectral_layers\.\d+\.fourier_weight\.\d+$", k):
+            continue
+        out["sd::" + k] = v.detach().cpu().numpy()
+    return out
+
+
+def save(name, kwargs, arrays):
+    os.makedirs(OUT, exist_ok=True)
+    arrays = dict(arrays)
+    arrays["kwargs_json"] = np.frombuffer(json.dumps(kwargs).encode(), dtype=np.uint8)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+def perturb_(module, seed, scale=0.5):
+    """Move biases / weight_g / LayerNorm params off their trivial init so parity sees them."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for k, p in module.named_parameters():
+            if k.endswith("bias") or k.endswith("weight_g") or ".3.weight" in k:
+                p.add_(scale * torch.randn(p.shape, generator=g) * p.abs().mean().clamp(min=0.1))
+
+
+def grid2d_case(M, name, kwargs, shape, seed, taps=True, x_scale=1.0):
+    torch.manual_seed(seed)
+    m = M.FNOFactorized2DBlock(**kwargs).eval()
+    perturb_(m, seed + 100)
+    x = x_scale * torch.randn(*shape, generator=torch.Generator().manual_seed(seed + 1))
+    arrays = sd_np(m)
+    arrays["x"] = x.numpy()
+    with torch.no_grad():
+        out = m(x)
+        arrays["forecast"] = out["forecast"].numpy()
+        for i, f in enumerate(out["forecast_list"]):
+            arrays[f"forecast_list{i}"] = f.numpy()
+        if taps:
+            h = m.drop(m.in_proj(x))
+            arrays["tap_lift"] = h.numpy()
+            for l, layer in enumerate(m.spectral_layers):
+                if l == 0 and kwargs.get("mode", "full") != "no-fourier":
+                    arrays["tap_s0"] = layer.forward_fourier(h).numpy()
+                b, _ = layer(h)
+                h = h + b
+                arrays[f"tap_x{l}"] = h.numpy()
+            arrays["tap_b_last"] = b.numpy()
+    save(name, kwargs, arrays)
+
+
+def mesh_case(M, cls, name, kwargs, shape, seed):
+    torch.manual_seed(seed)
+    m = getattr(M, cls)(**kwargs).eval()
+    perturb_(m, seed + 100)
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(seed + 1))
+    arrays = sd_np(m)
+    arrays["x"] = x.numpy()
+    with torch.no_grad():
+        arrays["out"] = m(x).numpy()
+    save(name, kwargs, arrays)
+
+
+def spectral_case(M, name, C, K, shape, seed):
+    """One bare ``SpectralConv2d.forward_fourier`` at the C2 layer shape (N=64, K=16, C=64)."""
+    from fourierflow.modules.factorized_fno.grid_2d import SpectralConv2d
+    torch.manual_seed(seed)
+    layer = SpectralConv2d(in_dim=C, out_dim=C, n_modes=K, forecast_ff=None, backcast_ff=None,
+                           fourier_weight=None, factor=4, ff_weight_norm=True, n_ff_layers=2,
+                           layer_norm=False, use_fork=False, dropout=0.0, mode="full").eval()
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(seed + 1))
+    with torch.no_grad():
+        s = layer.forward_fourier(x)
+    arrays = {"sd::" + k: v.numpy() for k, v in layer.state_dict().items() if "fourier_weight" in k}
+    arrays.update(x=x.numpy(), s=s.numpy())
+    save(name, {"C": C, "K": K}, arrays)
+
+
+def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed):
+    """routines/grid_2d_markov.py:195-326 driven with the reference's own module objects."""
+    torch.manual_seed(seed)
+    conv = M.FNOFactorized2DBlock(**kwargs).eval()
+    perturb_(conv, seed + 100)
+    normalizer = M.Normalizer([conv.input_dim], 1e6)
+    l2 = LpLoss(size_average=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    # smooth-ish trajectories so the rel-L2 denominators are well away from zero
+    base = torch.randn(B, X, X, 1, generator=g)
+    data = base + 0.3 * torch.cumsum(torch.randn(B, X, X, T, generator=g), dim=-1)
+
+    grids = [torch.linspace(0, 1, steps=X) for _ in range(2)]                    # :101-106, low=0 high=1
+    pos = torch.stack(torch.meshgrid(*grids, indexing="ij"), dim=-1)
+    pos = pos.unsqueeze(0).repeat(B, 1, 1, 1)
+
+    # one training-mode pass accumulates the running statistics (:376-378 → _build_features)
+    normalizer.train()
+    feats = torch.cat([data[..., :-1].unsqueeze(-1),
+                       pos.unsqueeze(-2).repeat(1, 1, 1, T - 1, 1)], dim=-1)    # [B,X,Y,T-1,3]
+    feats = feats.permute(0, 3, 1, 2, 4).reshape(B * (T - 1), X, X, 3)
+    normalizer(feats)
+    normalizer.eval()
+
+    yy = data[..., -n_steps:]
+    preds, step_losses, loss = None, [], 0
+    with torch.no_grad():
+        for t in range(n_steps):
+            if t == 0:
+                x = torch.cat([data[..., T - n_steps - 1].unsqueeze(-1), pos], dim=-1)
+            else:
+                x = torch.cat([im, pos], dim=-1)
+            x = normalizer(x)
+            im = conv(x)["forecast"]
+            im = normalizer.inverse(im, channel=0)
+            l = l2(im.reshape(B, -1), yy[..., t].reshape(B, -1))
+            step_losses.append(l)
+            loss = loss + l
+            preds = im if t == 0 else torch.cat((preds, im), dim=-1)
+    arrays = sd_np(conv)
+    arrays.update(data=data.numpy(), preds=preds.numpy(), loss=np.asarray(loss.item()),
+                  step_losses=torch.stack(step_losses).numpy(),
+                  norm_sum=normalizer.sum.numpy(), norm_sum_squared=normalizer.sum_squared.numpy(),
+                  norm_count=normalizer.count.numpy(),
+                  norm_mean=normalizer.mean.numpy(), norm_std=normalizer.std.numpy())
+    save(name, dict(kwargs, n_steps=n_steps), arrays)
+
+
+def main():
+    M, LpLoss = import_reference()
+    c2 = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4,
+              ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0)
+    # (1) the C2 architecture on a reduced grid (32x32 keeps modes=16 legal: 17 rfft bins)
+    grid2d_case(M, "grid2d_c2arch_32", dict(c2, n_layers=4), (1, 32, 32, 3), seed=0)
+    # (2) full-depth C2 model (24 layers), final forecast + last-layer taps only
+    grid2d_case(M, "grid2d_c2_24layers_32", c2, (1, 32, 32, 3), seed=1, taps=False)
+    # (3) stress: gain=1, unshared weights, larger activations, C4-like input_dim=5, non-square
+    grid2d_case(M, "grid2d_gain1_unshared", dict(modes=8, width=64, n_layers=3, input_dim=5,
+                share_weight=False, factor=4, ff_weight_norm=True, gain=1), (2, 16, 24, 5),
+                seed=2, x_scale=3.0)
+    # (4) generic-path options: no weight-norm, LayerNorm, factor 2, width 32, non-pow2 sizes
+    grid2d_case(M, "grid2d_ln_w32", dict(modes=5, width=32, n_layers=2, input_dim=4,
+                share_weight=False, factor=2, ff_weight_norm=False, gain=1, layer_norm=True),
+                (2, 20, 12, 4), seed=3)
+    # (5) fork ablation + shared fork
+    grid2d_case(M, "grid2d_fork", dict(modes=4, width=32, n_layers=2, input_dim=3,
+                share_weight=True, share_fork=True, use_fork=True, factor=4,
+                ff_weight_norm=True, gain=0.5), (1, 16, 16, 3), seed=4)
+    # (6) mode switches
+    for md in ("low-pass", "no-fourier"):
+        grid2d_case(M, "grid2d_" + md.replace("-", ""), dict(modes=4, width=32, n_layers=2,
+                    input_dim=3, share_weight=False, factor=4, ff_weight_norm=True, gain=1,
+                    mode=md), (1, 16, 16, 3), seed=5)
+    # (7) n_modes == L/2+1 on an even length (Nyquist bin kept) and an odd length
+    grid2d_case(M, "grid2d_nyquist", dict(modes=5, width=32, n_layers=1, input_dim=2,
+                share_weight=False, factor=4, ff_weight_norm=True, gain=1), (1, 8, 9, 2), seed=6)
+    # (8) mesh variants: pad +8, linspace grid, per-axis modes, prime lengths after padding
+    mesh_case(M, "FNOFactorizedMesh2D", "mesh2d_small", dict(modes_x=6, modes_y=4, width=32,
+              input_dim=4, n_layers=2, share_weight=False, factor=4, ff_weight_norm=True,
+              n_ff_layers=2, layer_norm=False), (2, 11, 9, 2), seed=7)
+    mesh_case(M, "FNOFactorizedMesh3D", "mesh3d_small", dict(modes_x=4, modes_y=3, modes_z=2,
+              width=32, input_dim=4, output_dim=4, n_layers=2, share_weight=False, factor=4,
+              ff_weight_norm=True, n_ff_layers=2, layer_norm=False), (1, 7, 6, 5, 1), seed=8)
+    mesh_case(M, "FNOFactorizedMesh3D", "mesh3d_w64", dict(modes_x=6, modes_y=6, modes_z=4,
+              width=64, input_dim=4, output_dim=4, n_layers=2, share_weight=True, factor=4,
+              ff_weight_norm=True, n_ff_layers=2, layer_norm=False), (1, 8, 8, 8, 1), seed=9)
+    # (9) one bare spectral layer + FF at the exact C2 layer shape
+    spectral_case(M, "spectral_c2_layer", 64, 16, (1, 32, 64, 64), seed=10)
+    # (10) 10-step Markov rollout with Normalizer / LpLoss
+    rollout_case(M, LpLoss, "rollout_c2arch_16", dict(c2, n_layers=4, modes=8), B=2, X=16, T=12,
+                 n_steps=10, seed=11)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""CPU: pin the oracle restatement (oracle/ffno_oracle.py) to the executed reference's outputs."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load, rel_err
+from oracle import ffno_oracle as O
+
+TOL = 2e-6   # same torch CPU kernels in (almost) the same order; reference fp32 self-noise ~5e-7
+
+
+def _grid2d(name):
+    kw, sd, a = load(name)
+    taps = {}
+    out = O.block_grid2d_forward(sd, a["x"], modes=kw["modes"], n_layers=kw["n_layers"],
+                                 n_ff_layers=kw.get("n_ff_layers", 2),
+                                 layer_norm=kw.get("layer_norm", False),
+                                 use_fork=kw.get("use_fork", False), mode=kw.get("mode", "full"),
+                                 taps=taps)
+    return kw, a, out, taps
+
+
+@pytest.mark.parametrize("name", ["grid2d_c2arch_32", "grid2d_c2_24layers_32", "grid2d_gain1_unshared",
+                                  "grid2d_ln_w32", "grid2d_fork", "grid2d_lowpass",
+                                  "grid2d_nofourier", "grid2d_nyquist"])
+def test_grid2d_block(name):
+    kw, a, out, taps = _grid2d(name)
+    assert rel_err(out["forecast"], a["forecast"]) < TOL
+    for i, f in enumerate(out["forecast_list"]):
+        assert rel_err(f, a[f"forecast_list{i}"]) < TOL
+    if "tap_lift" in a:
+        assert rel_err(taps["lift"], a["tap_lift"]) < TOL
+        for l in range(kw["n_layers"]):
+            assert rel_err(taps[f"x{l}"], a[f"tap_x{l}"]) < TOL
+        assert rel_err(taps[f"b{kw['n_layers'] - 1}"], a["tap_b_last"]) < TOL
+    if "tap_s0" in a:
+        assert rel_err(taps["s0"], a["tap_s0"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["mesh2d_small", "mesh3d_small", "mesh3d_w64"])
+def test_mesh_block(name):
+    kw, sd, a = load(name)
+    modes = [kw["modes_x"], kw["modes_y"]] + ([kw["modes_z"]] if "modes_z" in kw else [])
+    out = O.block_mesh_forward(sd, a["x"], modes=modes, n_layers=kw["n_layers"],
+                               n_ff_layers=kw["n_ff_layers"], layer_norm=kw["layer_norm"])
+    assert out.shape == a["out"].shape
+    assert rel_err(out, a["out"]) < TOL
+
+
+def test_spectral_layer_c2_shape():
+    kw, sd, a = load("spectral_c2_layer")
+    s = O.forward_fourier_grid2d(a["x"], sd["fourier_weight.0"], sd["fourier_weight.1"], kw["K"])
+    assert rel_err(s, a["s"]) < TOL
+
+
+def test_rollout():
+    kw, sd, a = load("rollout_c2arch_16")
+    stats = {"sum": a["norm_sum"], "sum_squared": a["norm_sum_squared"], "count": a["norm_count"]}
+    mean, std = O.normalizer_mean_std(stats)
+    assert torch.allclose(mean, a["norm_mean"]) and torch.allclose(std, a["norm_std"])
+    r = O.markov_rollout(sd, a["data"], stats, modes=kw["modes"], n_layers=kw["n_layers"],
+                         n_steps=kw["n_steps"])
+    assert rel_err(r["preds"], a["preds"]) < 1e-5
+    assert abs(r["loss"].item() - a["loss"].item()) < 1e-5 * abs(a["loss"].item())
+    assert rel_err(r["step_losses"], a["step_losses"]) < 1e-5
+
+
+def test_normalizer_stats_restatement():
+    x = torch.randn(7, 5, 4, 3)
+    st = O.normalizer_stats(x)
+    mean, std = O.normalizer_mean_std(st)
+    flat = x.reshape(-1, 3)
+    assert torch.allclose(mean, flat.mean(0), atol=1e-6)
+    assert torch.allclose(std, flat.std(0, unbiased=False), atol=1e-5)
+    empty = {"sum": torch.zeros(3), "sum_squared": torch.zeros(3), "count": torch.tensor(0.0)}
+    assert torch.equal(O.normalizer_mean_std(empty)[1], torch.full((3,), 1e-8))
+
+
+@pytest.mark.parametrize("L,K", [(64, 16), (40, 12), (109, 32), (8, 5), (9, 5), (256, 64), (39, 12)])
+def test_dft_matrices_match_torch_fft(L, K):
+    """The explicit truncated real-DFT matrices (what the CUDA library builds) reproduce
+    rfft(ortho)[:K] and irfft(zero-padded, n=L, ortho), including the C2R traps."""
+    g = torch.Generator().manual_seed(L * 1000 + K)
+    x = torch.randn(L, 3, dtype=torch.float64, generator=g)
+    D = torch.from_numpy(O.dft_forward_matrix(L, K))
+    F = torch.fft.rfft(x, dim=0, norm="ortho")[:K]
+    got = D @ x
+    assert torch.allclose(got[0::2], F.real, atol=1e-12) and torch.allclose(got[1::2], F.imag, atol=1e-12)
+    R = torch.randn(K, 3, dtype=torch.complex128, generator=g)       # complex DC / Nyquist on purpose
+    pad = torch.zeros(L // 2 + 1, 3, dtype=torch.complex128)
+    pad[:K] = R
+    y = torch.fft.irfft(pad, n=L, dim=0, norm="ortho")
+    E = torch.from_numpy(O.dft_inverse_matrix(L, K))
+    r = torch.empty(2 * K, 3, dtype=torch.float64)
+    r[0::2], r[1::2] = R.real, R.imag
+    assert torch.allclose(E @ r, y, atol=1e-12)
