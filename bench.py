@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native F-FNO forward (contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): Navier–Stokes 64x64 samples/s of the 24-layer F-FNO forward.
+Workload at N=1: configs[1] = torus_li/markov/24_layers, 64x64 grid, batch 32, fp32, random-init weights of that
+architecture, synthetic N(0,1) input features.  One "step" = one forward of the 24-layer stack over one batch of 32
+samples per GPU (weak scaling: 32 samples per rank; N=8 is configs[2], batch 256 sharded over 8 GPUs).
+
+  value : samples/s with the inputs already resident in HBM (CUDA events, L2 flushed between timed steps).
+  e2e   : the same metric through the C-ABI host-buffer entry point (ffno_block_fwd_host): pinned host input
+          copied H2D, forward, forecast copied D2H, all inside the timed region.
+  roofline / cpu_baseline : see DESIGN.md §Measurement.
+
+`--impl reference` times the reference's own CPU path (the torch-CPU oracle port of it — the Python reference tree
+cannot travel to the GPU box) on the host cores, same metric and config, on a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4, ff_weight_norm=True, gain=0.1)
+GRID = 64
+BATCH_PER_GPU = 32
+WORKLOAD = "torus_li/markov/24_layers FNOFactorized2DBlock fwd, 64x64, batch 32/GPU, fp32 (BASELINE configs[1]; N=8 -> configs[2])"
+METRIC = "navier_stokes_64x64_samples_per_sec_24layer_ffno_fwd"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md "clocks line")
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port) on the host cores
+# --------------------------------------------------------------------------------------------------
+def oracle_setup(sample_batch: int):
+    from oracle import ffno_oracle as O          # the one place bench.py touches oracle/: the CPU baseline
+    from fourierflow_b200.modules import FNOFactorized2DBlock
+    torch.manual_seed(0)
+    m = FNOFactorized2DBlock(**C2).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    x = torch.randn(sample_batch, GRID, GRID, 3, generator=torch.Generator().manual_seed(1))
+
+    def step():
+        with torch.no_grad():
+            return O.block_grid2d_forward(sd, x, modes=C2["modes"], n_layers=C2["n_layers"])["forecast"]
+    return step
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = 8
+    step = oracle_setup(sample)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{sample} of the 32 samples per step (CPU)"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample}-sample forward of the 24-layer stack per step, torch CPU oracle port "
+                                   f"of fourierflow.modules (the Python reference tree cannot travel to the GPU box)"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def ev_pair():
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def timed(fn, steps, warmup, flush):
+    """Per-step CUDA-event timing on the current stream; the L2 flush sits outside the events."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(steps):
+        flush()
+        a, b = ev_pair()
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / steps          # ms per step
+
+
+def run_ours(args, rank, world, local):
+    import torch.distributed as dist
+    from fourierflow_b200 import build, distributed as D
+    build.build()
+    from fourierflow_b200.modules import FNOFactorized2DBlock, LpLoss
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.manual_seed(0)
+    model = FNOFactorized2DBlock(**C2).to(dev).eval()
+    B = BATCH_PER_GPU
+    gen = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.randn(B, GRID, GRID, 3, generator=gen).pin_memory()
+    out_host = torch.empty(B, GRID, GRID, 1).pin_memory()
+    x = x_host.to(dev)
+    target = torch.randn(B, GRID, GRID, 1, device=dev)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    plan = model.plan_for(dev, (GRID, GRID))
+    loss_fn = LpLoss()
+
+    def flush():
+        flush_buf.zero_()
+
+    def step():
+        with torch.no_grad():
+            y = model(x)["forecast"]
+            if world > 1:     # the one collective of a sharded run: per-sample losses for the LpLoss mean
+                per = loss_fn.rel_per_sample(y, target).unsqueeze(0)
+                D.gather_sample_losses(per, B * world)
+        return y
+
+    def step_e2e():
+        plan.block_forward_host(x_host, out_host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure():
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms = timed(step, args.steps, args.warmup, flush)
+        launches = plan.last_launch_count
+        ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup), flush)
+        barrier()
+        clocks = sampler.stop()
+        return ms, ms_e2e, launches, clocks
+
+    ms, ms_e2e, launches, clocks = measure()
+    if set(clocks.get("reasons", [])) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}:
+        ms, ms_e2e, launches, clocks = measure()          # re-measure once
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+
+    # ---- roofline of the two per-layer operators, timed alone with CUDA events --------------------
+    peaks, peak_src = measured_peaks()
+    layer = model.spectral_layers[0]
+    xs = torch.randn(B, GRID, GRID, 64, device=dev)
+    with torch.no_grad():
+        lplan = layer._plan(xs)
+        t_spec = timed(lambda: lplan.spectral_forward(0, xs), 20, 5, flush)
+        s = lplan.spectral_forward(0, xs)
+        t_ff = timed(lambda: lplan.ff_forward(0, 0, s, xs), 20, 5, flush)
+    P = B * GRID * GRID
+    Cw, K = 64, C2["modes"]
+    U = P * Cw * 4
+    spec_bytes = 2 * U + 2 * Cw * Cw * K * 8                      # 2U + sum_a C*C*K_a*8
+    ff_flops = 4 * C2["factor"] * Cw * Cw * P                      # 4 f C^2 P
+    spec_gbs = spec_bytes / (t_spec * 1e-3) / 1e9
+    ff_tflops = ff_flops / (t_ff * 1e-3) / 1e12
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    roof_spec = {"kernel": "spectral operator (forward_fourier, both axes)", "bound": "hbm", "achieved": spec_gbs,
+                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": spec_gbs / peaks["hbm_gbs"],
+                 "traffic": traffic.get("spectral"), "ms": t_spec, "algorithmic_bytes": spec_bytes, "peak_source": peak_src}
+    roof_ff = {"kernel": "feed-forward + residual (C->4C->C)", "bound": "tensor", "achieved": ff_tflops,
+               "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ff_tflops / peaks["bf16_tflops"],
+               "traffic": traffic.get("ff"), "ms": t_ff, "algorithmic_flops": ff_flops, "peak_source": peak_src}
+    dominant = roof_ff if t_ff >= t_spec else roof_spec
+
+    if rank != 0:
+        return
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample -------------------------------
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_sample, cpu_reps = 8, 3
+    cstep = oracle_setup(cpu_sample)
+    cstep()
+    t0 = time.perf_counter()
+    for _ in range(cpu_reps):
+        cstep()
+    cpu_v = cpu_sample * cpu_reps / (time.perf_counter() - t0)
+
+    N = world
+    line = {
+        "metric": METRIC, "value": N * B / (ms * 1e-3), "unit": "samples/s", "n_gpus": N, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": N * B, "grid": [GRID, GRID], "n_layers": 24,
+                   "parallelism": f"dp{N} (batch shards, no data-path collective; loss all-gather only)",
+                   "l2": "flushed between timed steps (256 MiB memset outside the timed events)",
+                   "kernel_path": "tcgen05" if plan.uses_umma else "generic-fp32"},
+        "clocks": clocks,
+        "e2e": {"value": N * B / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
+                "api": "ffno_block_fwd_host (pinned host buffers)"},
+        "gpu_launches": int(launches) * args.steps,
+        "roofline": dominant, "roofline_spectral": roof_spec, "roofline_ff": roof_ff,
+        "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{cpu_reps} forwards of {cpu_sample} samples through the 24-layer stack "
+                                   "(torch-CPU oracle port of fourierflow.modules)"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the F-FNO backend has no CPU path (use --impl reference)")
+    if world > 1:
+        from fourierflow_b200 import distributed as D
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        D.init_from_env("nccl")
+    run_ours(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+"""ctypes binding of libffno_b200.so (the C ABI declared in include/ffno_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised.  The library is built in-tree by ``python -m fourierflow_b200.build`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libffno_b200.so")
+
+ABI_VERSION = 1
+MAX_DIMS = 3
+MAX_FF_LAYERS = 4
+
+OK = 0
+MODE = {"full": 0, "low-pass": 1, "no-fourier": 2}
+PATH = {"auto": 0, "generic": 1, "umma": 2}
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("ndim", C.c_int32),
+        ("size", C.c_int32 * MAX_DIMS), ("pad", C.c_int32 * MAX_DIMS), ("modes", C.c_int32 * MAX_DIMS),
+        ("width", C.c_int32), ("in_features", C.c_int32), ("append_grid", C.c_int32),
+        ("out_features", C.c_int32), ("head_hidden", C.c_int32), ("n_layers", C.c_int32),
+        ("ff_factor", C.c_int32), ("n_ff_layers", C.c_int32), ("layer_norm", C.c_int32),
+        ("use_fork", C.c_int32), ("spectral_mode", C.c_int32), ("path", C.c_int32),
+    ]
+
+
+class LinearParams(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("weight_g", C.c_void_p), ("weight_v", C.c_void_p),
+                ("bias", C.c_void_p), ("in_features", C.c_int32), ("out_features", C.c_int32)]
+
+
+class FFParams(C.Structure):
+    _fields_ = [("linear", LinearParams * MAX_FF_LAYERS), ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p)]
+
+
+class LayerParams(C.Structure):
+    _fields_ = [("fourier_weight", C.c_void_p * MAX_DIMS), ("backcast_ff", FFParams), ("forecast_ff", FFParams)]
+
+
+class BlockParams(C.Structure):
+    _fields_ = [("in_proj", LinearParams), ("out0", LinearParams), ("out1", LinearParams),
+                ("layers", C.POINTER(LayerParams)), ("n_layers", C.c_int32)]
+
+
+class Taps(C.Structure):
+    _fields_ = [("lift", C.c_void_p), ("x_after", C.POINTER(C.c_void_p)), ("spectral", C.POINTER(C.c_void_p)),
+                ("b_last", C.c_void_p), ("forecast_list", C.POINTER(C.c_void_p))]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "ffno_last_error": (C.c_char_p, []),
+    "ffno_abi_version": (C.c_int, []),
+    "ffno_device_ok": (C.c_int, []),
+    "ffno_plan_create": (C.c_int, [C.POINTER(Desc), C.POINTER(C.c_void_p)]),
+    "ffno_plan_destroy": (C.c_int, [C.c_void_p]),
+    "ffno_plan_uses_umma": (C.c_int, [C.c_void_p]),
+    "ffno_plan_load_params": (C.c_int, [C.c_void_p, C.POINTER(BlockParams), C.c_void_p]),
+    "ffno_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
+    "ffno_block_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(Taps), C.c_void_p,
+                                 C.c_size_t, C.c_void_p]),
+    "ffno_workspace_bytes_host": (C.c_size_t, [C.c_void_p, C.c_int32]),
+    "ffno_block_fwd_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
+    "ffno_spectral_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_size_t, C.c_void_p]),
+    "ffno_ff_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                              C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ffno_linear_fwd": (C.c_int, [C.POINTER(LinearParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ffno_layernorm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                     C.c_void_p]),
+    "ffno_rel_l2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                              C.c_int64, C.c_void_p, C.c_void_p]),
+    "ffno_rollout_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
+    "ffno_rollout_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p,
+                                   C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ffno_plan_last_launch_count": (C.c_int64, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and set the prototypes of every export."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing — build it with `python -m fourierflow_b200.build` "
+            "(fourierflow_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)          # AttributeError here == ABI mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ffno_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libffno_b200 ABI {lib.ffno_abi_version()} != binding ABI {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != OK:
+        msg = load().ffno_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")

@@ -1,0 +1,293 @@
+"""Host-side glue between the nn.Module mirrors and libffno_b200's C ABI.
+
+PyTorch supplies device memory and the current stream; every arithmetic step of the forward runs in
+the CUDA library.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+# ----------------------------------------------------------------------------------------------
+# checks
+# ----------------------------------------------------------------------------------------------
+
+def require_cuda(x: torch.Tensor, what: str) -> None:
+    if not x.is_cuda:
+        raise RuntimeError(f"{what}: fourierflow_b200 runs on CUDA (sm_100a) only — got a {x.device} tensor; "
+                           "there is no CPU fallback")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"{what}: expected float32, got {x.dtype}")
+
+
+def require_inference(module: nn.Module, x: torch.Tensor) -> None:
+    """The CUDA path is forward-only (the reference's timed path runs under no_grad,
+    fourierflow/routines/base.py:54-56).  Refuse to silently drop a graph."""
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
+        raise RuntimeError(
+            f"{type(module).__name__}: the B200 backend implements the forward pass only; call it under "
+            "torch.no_grad() / torch.inference_mode() (backward is not implemented yet)")
+
+
+def _stream(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dev_param(t: torch.Tensor, keep: list) -> int:
+    """Pointer of a parameter as contiguous fp32 device memory (keeps temporaries alive in `keep`)."""
+    t = t.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    keep.append(t)
+    return t.data_ptr()
+
+
+def linear_params(lin: nn.Linear, keep: list) -> _lib.LinearParams:
+    lp = _lib.LinearParams()
+    if "weight" in lin._parameters and lin._parameters["weight"] is not None:
+        lp.weight = _dev_param(lin._parameters["weight"], keep)
+    else:
+        lp.weight_g = _dev_param(lin.weight_g, keep)
+        lp.weight_v = _dev_param(lin.weight_v, keep)
+    if lin.bias is not None:
+        lp.bias = _dev_param(lin.bias, keep)
+    lp.in_features, lp.out_features = lin.in_features, lin.out_features
+    return lp
+
+
+# ----------------------------------------------------------------------------------------------
+# stateless ops (sub-modules called on their own)
+# ----------------------------------------------------------------------------------------------
+
+def linear_forward(lin: nn.Linear, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    require_cuda(x, "WNLinear.forward")
+    require_inference(lin, x)
+    lib = _lib.load()
+    keep: list = []
+    with torch.cuda.device(x.device):
+        lp = linear_params(lin, keep)
+        x2 = x.contiguous().reshape(-1, lin.in_features)
+        y = torch.empty(x2.shape[0], lin.out_features, device=x.device, dtype=torch.float32)
+        scratch = torch.empty(lin.in_features * lin.out_features, device=x.device, dtype=torch.float32)
+        _lib.check(lib.ffno_linear_fwd(C.byref(lp), x2.data_ptr(), x2.shape[0], y.data_ptr(), int(relu),
+                                       scratch.data_ptr(), scratch.numel() * 4, _stream(x.device)),
+                   "ffno_linear_fwd")
+    return y.reshape(*x.shape[:-1], lin.out_features)
+
+
+def layernorm_forward(ln: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, "LayerNorm")
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        x2 = x.contiguous().reshape(-1, x.shape[-1])
+        y = torch.empty_like(x2)
+        w, b = ln.weight.detach().contiguous(), ln.bias.detach().contiguous()
+        _lib.check(lib.ffno_layernorm_fwd(x2.data_ptr(), w.data_ptr(), b.data_ptr(), x2.shape[0], x2.shape[1],
+                                          y.data_ptr(), _stream(x.device)), "ffno_layernorm_fwd")
+    return y.reshape(x.shape)
+
+
+def rel_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Per-sample ||x_b − y_b||₂ / ||y_b||₂ (modules/loss.py:33-46) for x, y: [B, ...]."""
+    require_cuda(x, "LpLoss.rel")
+    require_cuda(y, "LpLoss.rel")
+    lib = _lib.load()
+    B = x.shape[0]
+    # reshape keeps a (uniformly) strided view such as preds[..., t] without copying
+    x2, y2 = x.reshape(B, -1), y.reshape(B, -1)
+    out = torch.empty(B, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ffno_rel_l2(x2.data_ptr(), x2.stride(0), x2.stride(1), y2.data_ptr(), y2.stride(0),
+                                   y2.stride(1), B, x2.shape[1], out.data_ptr(), _stream(x.device)),
+                   "ffno_rel_l2")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# A plan bound to one module tree (block or single spectral layer)
+# ----------------------------------------------------------------------------------------------
+
+class LayerSpec:
+    """What one spectral layer contributes: fourier weights in TENSOR-AXIS order + its FeedForwards."""
+
+    def __init__(self, fourier_weight: Sequence[Optional[torch.Tensor]], backcast_ff, forecast_ff=None):
+        self.fourier_weight = list(fourier_weight)
+        self.backcast_ff = backcast_ff
+        self.forecast_ff = forecast_ff
+
+
+class StackPlan:
+    """Owns one ``ffno_plan`` (for one device + one spatial shape) and the ctypes parameter structs.
+
+    ``sync_params()`` re-loads (fold weight-norm, re-pack) when any parameter's storage or version
+    counter changed since the last load — the CUDA counterpart of the reference recomputing
+    ``g·v/‖v‖`` in a forward pre-hook on every call (modules/linear.py:49).
+    """
+
+    def __init__(self, device: torch.device, *, size: Sequence[int], pad: Sequence[int], modes: Sequence[int],
+                 width: int, in_features: int, append_grid: bool, out_features: int, head_hidden: int,
+                 n_layers: int, ff_factor: int, n_ff_layers: int, layer_norm: bool, use_fork: bool,
+                 mode: str, path: str = "auto"):
+        self.lib = _lib.load()
+        self.device = device
+        d = _lib.Desc()
+        d.abi_version = _lib.ABI_VERSION
+        d.ndim = len(size)
+        for a in range(len(size)):
+            d.size[a], d.pad[a], d.modes[a] = int(size[a]), int(pad[a]), int(modes[a])
+        d.width, d.in_features, d.append_grid = width, in_features, int(append_grid)
+        d.out_features, d.head_hidden, d.n_layers = out_features, head_hidden, n_layers
+        d.ff_factor, d.n_ff_layers, d.layer_norm = ff_factor, n_ff_layers, int(layer_norm)
+        d.use_fork, d.spectral_mode, d.path = int(use_fork), _lib.MODE[mode], _lib.PATH[path]
+        self.desc = d
+        self.ext = [int(size[a]) + int(pad[a]) for a in range(len(size))]
+        self.size = [int(s) for s in size]
+        self._plan = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.ffno_plan_create(C.byref(d), C.byref(self._plan)), "ffno_plan_create")
+        self._keep: list = []
+        self._version_key = None
+        self._ws: Optional[torch.Tensor] = None
+        self._structs = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None) is not None and self._plan.value:
+                self.lib.ffno_plan_destroy(self._plan)
+                self._plan = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def uses_umma(self) -> bool:
+        return bool(self.lib.ffno_plan_uses_umma(self._plan))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.ffno_plan_last_launch_count(self._plan))
+
+    # ---- parameters ---------------------------------------------------------------------------
+    def sync_params(self, params: List[torch.Tensor], in_proj, out, layers: List[LayerSpec]) -> None:
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key == self._version_key:
+            return
+        keep: list = []
+        bp = _lib.BlockParams()
+        if in_proj is not None:
+            bp.in_proj = linear_params(in_proj, keep)
+            bp.out0 = linear_params(out[0], keep)
+            bp.out1 = linear_params(out[1], keep)
+        arr = (_lib.LayerParams * len(layers))()
+        for l, spec in enumerate(layers):
+            for a, w in enumerate(spec.fourier_weight):
+                if w is not None:
+                    arr[l].fourier_weight[a] = _dev_param(w, keep)
+            self._fill_ff(arr[l].backcast_ff, spec.backcast_ff, keep)
+            if spec.forecast_ff is not None:
+                self._fill_ff(arr[l].forecast_ff, spec.forecast_ff, keep)
+        bp.layers = arr
+        bp.n_layers = len(layers)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ffno_plan_load_params(self._plan, C.byref(bp), _stream(self.device)),
+                       "ffno_plan_load_params")
+        self._keep, self._structs, self._version_key = keep, (bp, arr), key
+
+    @staticmethod
+    def _fill_ff(dst: _lib.FFParams, ff, keep: list) -> None:
+        for i, layer in enumerate(ff.layers):
+            dst.linear[i] = linear_params(layer[0], keep)
+            if isinstance(layer[3], nn.LayerNorm):
+                dst.ln_weight = _dev_param(layer[3].weight, keep)
+                dst.ln_bias = _dev_param(layer[3].bias, keep)
+
+    # ---- workspace ------------------------------------------------------------------------------
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ---- forward entry points ---------------------------------------------------------------------
+    def block_forward(self, x: torch.Tensor, want_taps: bool = False, want_forecast_list: bool = False):
+        B = x.shape[0]
+        d = self.desc
+        with torch.cuda.device(self.device):
+            ws = self._workspace(self.lib.ffno_workspace_bytes(self._plan, B))
+            out = torch.empty(B, *self.size, d.out_features, device=self.device, dtype=torch.float32)
+            taps_struct, taps = None, {}
+            if want_taps or want_forecast_list:
+                t = _lib.Taps()
+                n = d.n_layers
+                if want_taps:
+                    full = (B, *self.ext, d.width)
+                    taps["lift"] = torch.empty(full, device=self.device)
+                    taps["x"] = [torch.empty(full, device=self.device) for _ in range(n)]
+                    taps["b_last"] = torch.empty(full, device=self.device)
+                    t.lift, t.b_last = taps["lift"].data_ptr(), taps["b_last"].data_ptr()
+                    xa = (C.c_void_p * n)(*[v.data_ptr() for v in taps["x"]])
+                    t.x_after = xa
+                    taps["_xa"] = xa
+                    if d.spectral_mode != _lib.MODE["no-fourier"]:
+                        taps["s"] = [torch.empty(full, device=self.device) for _ in range(n)]
+                        sa = (C.c_void_p * n)(*[v.data_ptr() for v in taps["s"]])
+                        t.spectral = sa
+                        taps["_sa"] = sa
+                if want_forecast_list:
+                    taps["forecast_list"] = [torch.empty_like(out) for _ in range(n)]
+                    fa = (C.c_void_p * n)(*[v.data_ptr() for v in taps["forecast_list"]])
+                    t.forecast_list = fa
+                    taps["_fa"] = fa
+                taps_struct = C.byref(t)
+            _lib.check(self.lib.ffno_block_fwd(self._plan, x.data_ptr(), B, out.data_ptr(), taps_struct,
+                                               ws.data_ptr(), ws.numel(), _stream(self.device)), "ffno_block_fwd")
+        return out, taps
+
+    def block_forward_host(self, x_host: torch.Tensor, out_host: torch.Tensor) -> None:
+        """Host-buffer entry point (ffno_block_fwd_host): H2D + forward + D2H + stream sync inside."""
+        B = x_host.shape[0]
+        with torch.cuda.device(self.device):
+            ws = self._workspace(self.lib.ffno_workspace_bytes_host(self._plan, B))
+            _lib.check(self.lib.ffno_block_fwd_host(self._plan, x_host.data_ptr(), B, out_host.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), _stream(self.device)),
+                       "ffno_block_fwd_host")
+
+    def spectral_forward(self, layer: int, x: torch.Tensor) -> torch.Tensor:
+        B = x.shape[0]
+        with torch.cuda.device(self.device):
+            ws = self._workspace(self.lib.ffno_workspace_bytes(self._plan, B))
+            s = torch.empty_like(x)
+            _lib.check(self.lib.ffno_spectral_fwd(self._plan, layer, x.data_ptr(), B, s.data_ptr(), ws.data_ptr(),
+                                                  ws.numel(), _stream(self.device)), "ffno_spectral_fwd")
+        return s
+
+    def ff_forward(self, layer: int, which: int, s: torch.Tensor, residual: Optional[torch.Tensor]) -> torch.Tensor:
+        B = s.shape[0]
+        with torch.cuda.device(self.device):
+            ws = self._workspace(self.lib.ffno_workspace_bytes(self._plan, B))
+            y = torch.empty_like(s)
+            _lib.check(self.lib.ffno_ff_fwd(self._plan, layer, which, s.data_ptr(), _ptr(residual), B, y.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), _stream(self.device)), "ffno_ff_fwd")
+        return y
+
+    def rollout_forward(self, frame0: torch.Tensor, n_steps: int, mean: Sequence[float], std: Sequence[float],
+                        low: float, high: float) -> torch.Tensor:
+        B = frame0.shape[0]
+        X, Y = self.size
+        with torch.cuda.device(self.device):
+            ws = self._workspace(self.lib.ffno_rollout_workspace_bytes(self._plan, B))
+            preds = torch.empty(B, X, Y, n_steps, device=self.device, dtype=torch.float32)
+            m = (C.c_float * 3)(*[float(v) for v in mean])
+            s = (C.c_float * 3)(*[float(v) for v in std])
+            _lib.check(self.lib.ffno_rollout_fwd(self._plan, frame0.data_ptr(), B, n_steps, m, s, float(low),
+                                                 float(high), preds.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                 _stream(self.device)), "ffno_rollout_fwd")
+        return preds

@@ -1,0 +1,557 @@
+// Generic FP32 kernels of the F-FNO forward (see generic_kernels.cuh).  Hand-written CUDA, sm_100a.
+#include "generic_kernels.cuh"
+
+namespace ffno {
+
+thread_local long long g_launch_counter = 0;   // bumped by every launch wrapper (see plan.cu)
+
+// ------------------------------------------------------------------------------------------------
+// Truncated real DFT along a strided axis, as a skinny matrix product with a host-built table.
+// One thread owns one float4 "column" (o, inner4) and all of its n_out outputs, JC at a time.
+// Loads of X are coalesced along `inner`; table reads are warp-uniform (broadcast through L1).
+// ------------------------------------------------------------------------------------------------
+template <int JC>
+__global__ void __launch_bounds__(128)
+axis_transform_kernel(const float4* __restrict__ X, const float* __restrict__ T, float4* __restrict__ Y,
+                      long long ncols, long long inner4, int n_in, int n_out, int ldt, int accumulate) {
+  long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  long long o = col / inner4, i4 = col - o * inner4;
+  const float4* xp = X + o * (long long)n_in * inner4 + i4;
+  float4* yp = Y + o * (long long)n_out * inner4 + i4;
+  for (int j0 = 0; j0 < n_out; j0 += JC) {
+    float4 acc[JC];
+#pragma unroll
+    for (int j = 0; j < JC; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < n_in; ++i) {
+      float4 v = xp[(long long)i * inner4];
+      const float4* t4 = reinterpret_cast<const float4*>(T + (long long)i * ldt + j0);
+#pragma unroll
+      for (int j = 0; j < JC; j += 4) {
+        float4 c = __ldg(t4 + j / 4);
+        acc[j + 0].x = fmaf(c.x, v.x, acc[j + 0].x); acc[j + 0].y = fmaf(c.x, v.y, acc[j + 0].y);
+        acc[j + 0].z = fmaf(c.x, v.z, acc[j + 0].z); acc[j + 0].w = fmaf(c.x, v.w, acc[j + 0].w);
+        acc[j + 1].x = fmaf(c.y, v.x, acc[j + 1].x); acc[j + 1].y = fmaf(c.y, v.y, acc[j + 1].y);
+        acc[j + 1].z = fmaf(c.y, v.z, acc[j + 1].z); acc[j + 1].w = fmaf(c.y, v.w, acc[j + 1].w);
+        acc[j + 2].x = fmaf(c.z, v.x, acc[j + 2].x); acc[j + 2].y = fmaf(c.z, v.y, acc[j + 2].y);
+        acc[j + 2].z = fmaf(c.z, v.z, acc[j + 2].z); acc[j + 2].w = fmaf(c.z, v.w, acc[j + 2].w);
+        acc[j + 3].x = fmaf(c.w, v.x, acc[j + 3].x); acc[j + 3].y = fmaf(c.w, v.y, acc[j + 3].y);
+        acc[j + 3].z = fmaf(c.w, v.z, acc[j + 3].z); acc[j + 3].w = fmaf(c.w, v.w, acc[j + 3].w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < JC; ++j) {
+      if (j0 + j < n_out) {
+        float4* dst = yp + (long long)(j0 + j) * inner4;
+        float4 r = acc[j];
+        if (accumulate) {
+          float4 p = *dst;
+          r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
+        }
+        *dst = r;
+      }
+    }
+  }
+}
+
+int launch_axis_transform(const float* X, const float* T, float* Y, long long outer, int n_in, int n_out,
+                          long long inner, bool accumulate, cudaStream_t st) {
+  FFNO_REQUIRE(inner % 4 == 0, FFNO_ERR_UNSUPPORTED, "axis transform: inner=%lld not a multiple of 4", inner);
+  constexpr int JC = 16;
+  int ldt = (n_out + JC - 1) / JC * JC;   // tables are allocated with this padded leading dimension
+  long long inner4 = inner / 4, ncols = outer * inner4;
+  if (ncols == 0) return FFNO_OK;
+  axis_transform_kernel<JC><<<ceil_div(ncols, 128), 128, 0, st>>>(
+      reinterpret_cast<const float4*>(X), T, reinterpret_cast<float4*>(Y), ncols, inner4, n_in, n_out, ldt,
+      accumulate ? 1 : 0);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("axis_transform_kernel");
+  return FFNO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiled FP32 SGEMM (64x64 block tile, 4x4 per thread, K chunks of 16) with functor A-loader / epilogue.
+// ------------------------------------------------------------------------------------------------
+template <class ALoad, class Epi>
+__global__ void __launch_bounds__(256)
+sgemm64_kernel(ALoad a, const float* __restrict__ Bt, long long b_batch_stride, long long M, int N, int K,
+               Epi epi) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int z = blockIdx.z;
+  const long long m0 = (long long)blockIdx.x * 64;
+  const int n0 = blockIdx.y * 64;
+  const float* B = Bt + (long long)z * b_batch_stride;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    {
+      int r = tid / 4, kk = (tid % 4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M && k0 + kk < K) v = a.load4(z, m0 + r, k0 + kk);
+      As[kk + 0][r] = v.x; As[kk + 1][r] = v.y; As[kk + 2][r] = v.z; As[kk + 3][r] = v.w;
+    }
+    {
+      int k = tid / 16, nn = (tid % 16) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < K && n0 + nn < N)
+        v = __ldg(reinterpret_cast<const float4*>(B + (long long)(k0 + k) * N + n0 + nn));
+      *reinterpret_cast<float4*>(&Bs[k][nn]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int col = n0 + tx * 4;
+  if (col < N) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      long long row = m0 + ty * 4 + i;
+      if (row < M) epi.store4(z, row, col, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
+  }
+}
+
+// ---- mode mix ----------------------------------------------------------------------------------
+struct MixGeom {
+  const float* F;
+  float* R;
+  int K, C;
+  long long p_inner, inner;   // inner = p_inner * C
+};
+struct MixALoad {
+  MixGeom g;
+  __device__ float4 load4(int k, long long row, int kk) const {
+    long long o = row / g.p_inner, p = row - o * g.p_inner;
+    int ri = kk / g.C, ci = kk - ri * g.C;
+    return __ldg(reinterpret_cast<const float4*>(g.F + ((o * g.K + k) * 2 + ri) * g.inner + p * g.C + ci));
+  }
+};
+struct MixEpi {
+  MixGeom g;
+  __device__ void store4(int k, long long row, int col, float4 v) const {
+    long long o = row / g.p_inner, p = row - o * g.p_inner;
+    int ro = col / g.C, co = col - ro * g.C;
+    *reinterpret_cast<float4*>(g.R + ((o * g.K + k) * 2 + ro) * g.inner + p * g.C + co) = v;
+  }
+};
+
+int launch_mode_mix(const float* F, const float* Wblk, float* R, long long outer, int K, long long p_inner,
+                    int C, cudaStream_t st) {
+  FFNO_REQUIRE(C % 4 == 0, FFNO_ERR_UNSUPPORTED, "mode mix: width %d not a multiple of 4", C);
+  MixGeom g{F, R, K, C, p_inner, p_inner * C};
+  long long M = outer * p_inner;
+  if (M == 0 || K == 0) return FFNO_OK;
+  dim3 grid(ceil_div(M, 64), ceil_div(2 * C, 64), K);
+  sgemm64_kernel<<<grid, 256, 0, st>>>(MixALoad{g}, Wblk, (long long)4 * C * C, M, 2 * C, 2 * C, MixEpi{g});
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("sgemm64_kernel<mix>");
+  return FFNO_OK;
+}
+
+// ---- linear ------------------------------------------------------------------------------------
+struct LinALoad {
+  const float* x;
+  int K;
+  __device__ float4 load4(int, long long row, int kk) const {
+    return __ldg(reinterpret_cast<const float4*>(x + row * K + kk));
+  }
+};
+struct LinEpi {
+  const float* bias;
+  const float* residual;
+  float* y;
+  float* y_pre;
+  int N, relu;
+  __device__ void store4(int, long long row, int col, float4 v) const {
+    if (bias) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (y_pre) *reinterpret_cast<float4*>(y_pre + row * N + col) = v;
+    if (residual) {
+      float4 r = __ldg(reinterpret_cast<const float4*>(residual + row * N + col));
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (y) *reinterpret_cast<float4*>(y + row * N + col) = v;
+  }
+};
+
+int launch_linear(const float* x, const float* Wt, const float* bias, const float* residual, float* y,
+                  float* y_pre, long long P, int K, int N, bool relu, cudaStream_t st) {
+  FFNO_REQUIRE(K % 4 == 0 && N % 4 == 0, FFNO_ERR_UNSUPPORTED,
+               "linear: in=%d / out=%d must be multiples of 4", K, N);
+  if (P == 0) return FFNO_OK;
+  dim3 grid(ceil_div(P, 64), ceil_div(N, 64), 1);
+  sgemm64_kernel<<<grid, 256, 0, st>>>(LinALoad{x, K}, Wt, 0, P, N, K,
+                                       LinEpi{bias, residual, y, y_pre, N, relu ? 1 : 0});
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("sgemm64_kernel<linear>");
+  return FFNO_OK;
+}
+
+// ---- LayerNorm + residual: one warp per point -----------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm_residual_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const float* __restrict__ residual,
+                          float* __restrict__ out, float* __restrict__ b_out, long long P, int C) {
+  long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  int lane = threadIdx.x % 32;
+  if (p >= P) return;
+  const float* row = y + p * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += row[c];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { float d = row[c] - mean; v += d * d; }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  float rstd = rsqrtf(v / C + 1e-5f);
+  for (int c = lane; c < C; c += 32) {
+    float b = (row[c] - mean) * rstd * gamma[c] + beta[c];
+    if (b_out) b_out[p * C + c] = b;
+    if (out) out[p * C + c] = residual ? residual[p * C + c] + b : b;
+  }
+}
+
+int launch_layernorm_residual(const float* y, const float* gamma, const float* beta, const float* residual,
+                              float* out, float* b_out, long long P, int C, cudaStream_t st) {
+  if (P == 0) return FFNO_OK;
+  layernorm_residual_kernel<<<ceil_div(P * 32, 256), 256, 0, st>>>(y, gamma, beta, residual, out, b_out, P, C);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("layernorm_residual_kernel");
+  return FFNO_OK;
+}
+
+// ---- lift / head ---------------------------------------------------------------------------------
+struct LiftDev {
+  int ndim, size[3], pad[3], in_features, append_grid, C;
+  const float* grid_vals[3];   // unused here (kept for ABI symmetry)
+};
+
+__device__ __forceinline__ float linspace01(int i, int n) {
+  // float32(np.linspace(0, 1, n)[i]): numpy computes i * (1/(n-1)) in float64 and pins the last sample.
+  if (n <= 1) return 0.f;
+  if (i == n - 1) return 1.f;
+  return (float)((double)i * (1.0 / (double)(n - 1)));
+}
+
+__global__ void __launch_bounds__(256)
+lift_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias,
+            float4* __restrict__ out, long long total4, LiftGeom g) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int C4 = g.C / 4;
+  int c4 = (int)(idx % C4);
+  long long pp = idx / C4;
+  int coord[3] = {0, 0, 0};
+  long long rem = pp;
+  bool in_pad = false;
+  for (int a = g.ndim - 1; a >= 0; --a) {
+    int ext = g.size[a] + g.pad[a];
+    coord[a] = (int)(rem % ext);
+    rem /= ext;
+    in_pad |= coord[a] >= g.size[a];
+  }
+  long long b = rem;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!in_pad) {
+    long long src = b;
+    for (int a = 0; a < g.ndim; ++a) src = src * g.size[a] + coord[a];
+    if (bias) acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    const float* xr = x + src * g.in_features;
+    for (int j = 0; j < g.in_features; ++j) {
+      float v = __ldg(xr + j);
+      float4 w = __ldg(reinterpret_cast<const float4*>(Wt + (long long)j * g.C) + c4);
+      acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y);
+      acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+    }
+    if (g.append_grid) {
+      for (int a = 0; a < g.ndim; ++a) {
+        float v = linspace01(coord[a], g.size[a]);
+        float4 w = __ldg(reinterpret_cast<const float4*>(Wt + (long long)(g.in_features + a) * g.C) + c4);
+        acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y);
+        acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+      }
+    }
+  }
+  out[idx] = acc;
+}
+
+int launch_lift(const float* x, const float* Wt, const float* bias, float* out, int batch, const LiftGeom& g,
+                cudaStream_t st) {
+  FFNO_REQUIRE(g.C % 4 == 0, FFNO_ERR_UNSUPPORTED, "lift: width %d not a multiple of 4", g.C);
+  long long pts = batch;
+  for (int a = 0; a < g.ndim; ++a) pts *= (g.size[a] + g.pad[a]);
+  long long total4 = pts * (g.C / 4);
+  if (total4 == 0) return FFNO_OK;
+  lift_kernel<<<ceil_div(total4, 256), 256, 0, st>>>(x, Wt, bias, reinterpret_cast<float4*>(out), total4, g);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("lift_kernel");
+  return FFNO_OK;
+}
+
+template <int MAXO>
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ b, const float* __restrict__ Weff, const float* __restrict__ beff,
+            float* __restrict__ y, long long n_pts, LiftGeom g, int out_features, int accumulate) {
+  // 16 lanes per (cropped) point
+  long long gp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 16;
+  int sub = threadIdx.x % 16;
+  bool active = gp < n_pts;
+  long long pidx = active ? gp : 0;
+  int coord[3] = {0, 0, 0};
+  long long rem = pidx;
+  for (int a = g.ndim - 1; a >= 0; --a) { coord[a] = (int)(rem % g.size[a]); rem /= g.size[a]; }
+  long long src = rem;
+  for (int a = 0; a < g.ndim; ++a) src = src * (g.size[a] + g.pad[a]) + coord[a];
+  float acc[MAXO];
+#pragma unroll
+  for (int j = 0; j < MAXO; ++j) acc[j] = 0.f;
+  const int C4 = g.C / 4;
+  for (int c4 = sub; c4 < C4; c4 += 16) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(b + src * g.C) + c4);
+#pragma unroll
+    for (int j = 0; j < MAXO; ++j) {
+      if (j < out_features) {
+        float4 w = __ldg(reinterpret_cast<const float4*>(Weff + (long long)j * g.C) + c4);
+        acc[j] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[j]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXO; ++j)
+    for (int o = 8; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o, 16);
+  if (active && sub == 0)
+    for (int j = 0; j < out_features && j < MAXO; ++j) {
+      float v = acc[j] + beff[j];
+      if (accumulate) v += y[pidx * out_features + j];
+      y[pidx * out_features + j] = v;
+    }
+}
+
+int launch_head(const float* b, const float* Weff, const float* beff, float* y, int batch, const LiftGeom& g,
+                int out_features, bool accumulate, cudaStream_t st) {
+  FFNO_REQUIRE(out_features >= 1 && out_features <= 8, FFNO_ERR_UNSUPPORTED,
+               "head: out_features=%d not in [1,8]", out_features);
+  long long pts = batch;
+  for (int a = 0; a < g.ndim; ++a) pts *= g.size[a];
+  if (pts == 0) return FFNO_OK;
+  head_kernel<8><<<ceil_div(pts * 16, 256), 256, 0, st>>>(b, Weff, beff, y, pts, g, out_features,
+                                                          accumulate ? 1 : 0);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("head_kernel");
+  return FFNO_OK;
+}
+
+// ---- parameter preparation -------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+weight_fold_transpose_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                             float* __restrict__ w_t, int out, int in) {
+  int o = blockIdx.x;
+  __shared__ float red[4];
+  float scale = 1.f;
+  if (g) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < in; i += blockDim.x) { float t = v[(long long)o * in + i]; s = fmaf(t, t, s); }
+    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+    __syncthreads();
+    float tot = red[0] + red[1] + red[2] + red[3];
+    scale = g[o] / sqrtf(tot);
+  }
+  for (int i = threadIdx.x; i < in; i += blockDim.x) w_t[(long long)i * out + o] = v[(long long)o * in + i] * scale;
+}
+
+int launch_weight_fold_transpose(const float* v, const float* g, float* w_t, int out, int in, cudaStream_t st) {
+  if (out == 0 || in == 0) return FFNO_OK;
+  weight_fold_transpose_kernel<<<out, 128, 0, st>>>(v, g, w_t, out, in);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("weight_fold_transpose_kernel");
+  return FFNO_OK;
+}
+
+__global__ void __launch_bounds__(256)
+pack_mix_weights_kernel(const float* __restrict__ w, float* __restrict__ Wblk, int C, int K) {
+  // w[i][o][k][2] -> Wblk[k][ri*C+i][ro*C+o] = [[Wr, Wi], [-Wi, Wr]]
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)K * 4 * C * C;
+  if (idx >= total) return;
+  int n2 = 2 * C;
+  int col = (int)(idx % n2);
+  long long t = idx / n2;
+  int row = (int)(t % n2);
+  int k = (int)(t / n2);
+  int ri = row / C, i = row % C, ro = col / C, o = col % C;
+  float wr = w[(((long long)i * C + o) * K + k) * 2 + 0];
+  float wi = w[(((long long)i * C + o) * K + k) * 2 + 1];
+  float val = (ri == ro) ? wr : (ri == 0 ? wi : -wi);
+  Wblk[idx] = val;
+}
+
+int launch_pack_mix_weights(const float* w, float* Wblk, int C, int K, cudaStream_t st) {
+  long long total = (long long)K * 4 * C * C;
+  if (total == 0) return FFNO_OK;
+  pack_mix_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, Wblk, C, K);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("pack_mix_weights_kernel");
+  return FFNO_OK;
+}
+
+__global__ void fold_head_kernel(const float* __restrict__ W0t, const float* __restrict__ b0,
+                                 const float* __restrict__ W1t, const float* __restrict__ b1,
+                                 float* __restrict__ Weff, float* __restrict__ beff, int C, int H, int out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < out * C) {
+    int j = idx / C, c = idx % C;
+    double s = 0.0;
+    for (int h = 0; h < H; ++h) s += (double)W1t[(long long)h * out + j] * (double)W0t[(long long)c * H + h];
+    Weff[idx] = (float)s;
+  }
+  if (idx < out) {
+    double s = b1 ? (double)b1[idx] : 0.0;
+    if (b0)
+      for (int h = 0; h < H; ++h) s += (double)W1t[(long long)h * out + idx] * (double)b0[h];
+    beff[idx] = (float)s;
+  }
+}
+
+int launch_fold_head(const float* W0t, const float* b0, const float* W1t, const float* b1, float* Weff,
+                     float* beff, int C, int H, int out, cudaStream_t st) {
+  fold_head_kernel<<<ceil_div((long long)out * C, 128), 128, 0, st>>>(W0t, b0, W1t, b1, Weff, beff, C, H, out);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("fold_head_kernel");
+  return FFNO_OK;
+}
+
+// ---- rollout glue --------------------------------------------------------------------------------
+__device__ __forceinline__ float torch_linspace(int i, int steps, float low, float high) {
+  // torch.linspace float32 kernel: symmetric evaluation around the midpoint.
+  if (steps <= 1) return low;
+  float step = (high - low) / (float)(steps - 1);
+  int half = steps / 2;
+  return (i < half) ? (low + step * (float)i) : (high - step * (float)(steps - 1 - i));
+}
+
+__global__ void __launch_bounds__(256)
+rollout_features_kernel(const float* __restrict__ frame, long long stride_b, int stride_xy,
+                        float* __restrict__ feat, long long total, int X, int Y, float low, float high,
+                        MeanStd3 ms) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int y = (int)(idx % Y);
+  long long t = idx / Y;
+  int x = (int)(t % X);
+  long long b = t / X;
+  float w = frame[b * stride_b + ((long long)x * Y + y) * stride_xy];
+  float gx = torch_linspace(x, X, low, high), gy = torch_linspace(y, Y, low, high);
+  feat[idx * 3 + 0] = (w - ms.m[0]) / ms.s[0];
+  feat[idx * 3 + 1] = (gx - ms.m[1]) / ms.s[1];
+  feat[idx * 3 + 2] = (gy - ms.m[2]) / ms.s[2];
+}
+
+int launch_rollout_features(const float* frame, long long frame_stride_b, int frame_stride_xy, float* feat,
+                            int batch, int X, int Y, float low, float high, const MeanStd3& mean_std,
+                            cudaStream_t st) {
+  long long total = (long long)batch * X * Y;
+  if (total == 0) return FFNO_OK;
+  rollout_features_kernel<<<ceil_div(total, 256), 256, 0, st>>>(frame, frame_stride_b, frame_stride_xy, feat,
+                                                                total, X, Y, low, high, mean_std);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("rollout_features_kernel");
+  return FFNO_OK;
+}
+
+__global__ void __launch_bounds__(256)
+rollout_denorm_kernel(const float* __restrict__ fc, float* __restrict__ preds, long long total, int n_steps,
+                      int t, MeanStd3 ms) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  preds[idx * n_steps + t] = fc[idx] * ms.s[0] + ms.m[0];
+}
+
+int launch_rollout_denorm(const float* forecast, float* preds, int batch, int XY, int n_steps, int t,
+                          const MeanStd3& mean_std, cudaStream_t st) {
+  long long total = (long long)batch * XY;
+  if (total == 0) return FFNO_OK;
+  rollout_denorm_kernel<<<ceil_div(total, 256), 256, 0, st>>>(forecast, preds, total, n_steps, t, mean_std);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("rollout_denorm_kernel");
+  return FFNO_OK;
+}
+
+}  // namespace ffno
+
+namespace ffno {
+
+__global__ void __launch_bounds__(256)
+linear_any_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias,
+                  float* __restrict__ y, long long total, int K, int N, int relu) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  long long row = idx / N;
+  int col = (int)(idx - row * N);
+  float acc = bias ? bias[col] : 0.f;
+  const float* xr = x + row * K;
+  for (int k = 0; k < K; ++k) acc = fmaf(__ldg(xr + k), __ldg(Wt + (long long)k * N + col), acc);
+  y[idx] = relu ? fmaxf(acc, 0.f) : acc;
+}
+
+int launch_linear_any(const float* x, const float* Wt, const float* bias, float* y, long long P, int K, int N,
+                      bool relu, cudaStream_t st) {
+  if (K % 4 == 0 && N % 4 == 0) return launch_linear(x, Wt, bias, nullptr, y, nullptr, P, K, N, relu, st);
+  long long total = P * N;
+  if (total == 0) return FFNO_OK;
+  linear_any_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, Wt, bias, y, total, K, N, relu ? 1 : 0);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("linear_any_kernel");
+  return FFNO_OK;
+}
+
+__global__ void __launch_bounds__(256)
+rel_l2_kernel(const float* __restrict__ x, long long xsb, long long xsi, const float* __restrict__ y,
+              long long ysb, long long ysi, long long n, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  double d2 = 0.0, y2 = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    float xv = x[b * xsb + i * xsi], yv = y[b * ysb + i * ysi];
+    float d = xv - yv;
+    d2 += (double)d * d;
+    y2 += (double)yv * yv;
+  }
+  __shared__ double sd[8], sy[8];
+  for (int o = 16; o > 0; o >>= 1) { d2 += __shfl_xor_sync(0xffffffffu, d2, o); y2 += __shfl_xor_sync(0xffffffffu, y2, o); }
+  if (threadIdx.x % 32 == 0) { sd[threadIdx.x / 32] = d2; sy[threadIdx.x / 32] = y2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0;
+    for (int w = 0; w < 8; ++w) { a += sd[w]; c += sy[w]; }
+    out[b] = (float)(sqrt(a) / sqrt(c));
+  }
+}
+
+int launch_rel_l2(const float* x, long long xsb, long long xsi, const float* y, long long ysb, long long ysi,
+                  int batch, long long n, float* out, cudaStream_t st) {
+  if (batch == 0) return FFNO_OK;
+  rel_l2_kernel<<<batch, 256, 0, st>>>(x, xsb, xsi, y, ysb, ysi, n, out);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("rel_l2_kernel");
+  return FFNO_OK;
+}
+
+}  // namespace ffno

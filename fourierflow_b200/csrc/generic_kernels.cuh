@@ -1,0 +1,80 @@
+// Generic FP32 (FFMA) kernels of the F-FNO forward: any width (multiple of 4), any axis length, any
+// mode count, 2-D/3-D, LayerNorm/fork options.  They are the always-available CUDA path and the
+// on-device cross-check for the tcgen05 kernels (umma_*.cu), which take over when the shape qualifies.
+#pragma once
+#include "common.cuh"
+
+namespace ffno {
+
+// Y[o][j][inner] (+)= sum_i T[i][j] * X[o][i][inner]      (truncated real DFT along a strided axis)
+//   forward : i = l (axis length L), j = k' (2K rows: Re,Im interleaved), T = D^T
+//   inverse : i = k',                j = l,                               T = E^T
+// Reference: torch.fft.rfft / irfft calls at modules/factorized_fno/grid_2d.py:58,72,76,90.
+int launch_axis_transform(const float* X, const float* T, float* Y, long long outer, int n_in,
+                          int n_out, long long inner, bool accumulate, cudaStream_t st);
+
+// Per-mode complex channel mix as a real block GEMM (grid_2d.py:65-68 "bixy,ioy->boxy"):
+//   R[o][k][ro][p][co] = sum_{ri,ci} F[o][k][ri][p][ci] * W[k][ri*C+ci][ro*C+co]
+// with inner = P_in * C (P_in = points per line after the transformed axis).
+int launch_mode_mix(const float* F, const float* Wblk, float* R, long long outer, int K,
+                    long long p_inner, int C, cudaStream_t st);
+
+// y[P][N] = act(x[P][K] @ Wt[K][N] + bias) (+ residual[P][N]);  optional second store y2 (pre-residual)
+int launch_linear(const float* x, const float* Wt, const float* bias, const float* residual, float* y,
+                  float* y_pre, long long P, int K, int N, bool relu, cudaStream_t st);
+
+// b = LayerNorm(y) * g + beta over the last dim (C); out = residual + b (residual may be NULL);
+// b_out optional.  Reference: modules/feedforward.py:17.
+int launch_layernorm_residual(const float* y, const float* gamma, const float* beta,
+                              const float* residual, float* out, float* b_out, long long P, int C,
+                              cudaStream_t st);
+
+// Lift: optional linspace grid append (mesh_3d.py:178-189), Linear(in->C) (grid_2d.py:157), zero pad on
+// the high side of every spatial axis (mesh_3d.py:164-166).  out: [B, size+pad.., C]
+struct LiftGeom {
+  int ndim;
+  int size[3];
+  int pad[3];
+  int in_features;   // of the given tensor
+  int append_grid;
+  int C;
+};
+int launch_lift(const float* x, const float* Wt /*[in_total][C]*/, const float* bias, float* out,
+                int batch, const LiftGeom& g, cudaStream_t st);
+
+// Head on the cropped last backcast (grid_2d.py:171-172; mesh_3d.py:173-174) with the two activation-free
+// linears pre-multiplied: y[p][j] = sum_c b[p][c] * Weff[j][c] + beff[j].
+int launch_head(const float* b, const float* Weff /*[out][C]*/, const float* beff, float* y, int batch,
+                const LiftGeom& g, int out_features, bool accumulate, cudaStream_t st);
+
+// w_t[in][out] = v[out][in] * g[out] / ||v[out][:]||   (linear.py:49; g == NULL -> plain transpose)
+int launch_weight_fold_transpose(const float* v, const float* g, float* w_t, int out, int in,
+                                 cudaStream_t st);
+
+// fourier_weight [Cin][Cout][K][2] -> real block matrices Wblk[k][2C][2C]
+int launch_pack_mix_weights(const float* w, float* Wblk, int C, int K, cudaStream_t st);
+
+// Weff[j][c] = sum_h W1t[h][j] * W0t[c][h];  beff[j] = sum_h W1t[h][j]*b0[h] + b1[j]   (fp64 accumulate)
+int launch_fold_head(const float* W0t /*[C][H]*/, const float* b0, const float* W1t /*[H][out]*/,
+                     const float* b1, float* Weff, float* beff, int C, int H, int out, cudaStream_t st);
+
+// Rollout glue (routines/grid_2d_markov.py:286-306, modules/normalizer.py:51,62)
+//   feat[b][x][y][0] = (frame - mean0)/std0 ; feat[..][1] = (lin(x) - mean1)/std1 ; [2] likewise
+struct MeanStd3 { float m[3]; float s[3]; };   // passed by value: no device copy, graph-capturable
+int launch_rollout_features(const float* frame, long long frame_stride_b, int frame_stride_xy,
+                            float* feat, int batch, int X, int Y, float low, float high,
+                            const MeanStd3& ms, cudaStream_t st);
+//   preds[b][x][y][t] = fc[b][x][y] * std0 + mean0
+int launch_rollout_denorm(const float* forecast, float* preds, int batch, int XY, int n_steps, int t,
+                          const MeanStd3& ms, cudaStream_t st);
+
+}  // namespace ffno
+
+namespace ffno {
+// y[P][N] = act(x[P][K] @ Wt[K][N] + bias) for any K, N (one thread per output; small/odd shapes)
+int launch_linear_any(const float* x, const float* Wt, const float* bias, float* y, long long P, int K, int N,
+                      bool relu, cudaStream_t st);
+// out[b] = ||x_b - y_b|| / ||y_b||   (modules/loss.py:33-46)
+int launch_rel_l2(const float* x, long long xsb, long long xsi, const float* y, long long ysb, long long ysi,
+                  int batch, long long n, float* out, cudaStream_t st);
+}  // namespace ffno

@@ -1,0 +1,613 @@
+// libffno_b200: plan management and the extern "C" entry points declared in include/ffno_b200.h.
+//
+// A plan owns (a) the truncated real-DFT tables of every axis, built on the host in double precision,
+// (b) the prepared parameters: weight-norm folded + transposed linears, per-mode real block matrices of
+// the spectral weights, the pre-multiplied head, and (UMMA path) their bf16 hi/lo operand tiles.
+// The forward enqueues kernels on the caller's stream and never synchronises.
+#include <cmath>
+#include <map>
+#include <new>
+#include <vector>
+
+#include "generic_kernels.cuh"
+#include "umma_path.cuh"
+
+namespace ffno {
+
+extern thread_local long long g_launch_counter;
+
+char* error_buffer() {
+  static thread_local char buf[512] = "";
+  return buf;
+}
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct Lin {
+  float* wt = nullptr;     // [in][out] folded, transposed
+  float* bias = nullptr;   // [out] (copy) or nullptr
+  int in = 0, out = 0;
+};
+struct FFW {
+  Lin lin[FFNO_MAX_FF_LAYERS];
+  float* ln_w = nullptr;
+  float* ln_b = nullptr;
+};
+struct LayerW {
+  float* wmix[FFNO_MAX_DIMS] = {nullptr, nullptr, nullptr};   // [K][2C][2C]
+  FFW back, fork;
+};
+
+}  // namespace ffno
+
+using namespace ffno;
+
+struct ffno_plan {
+  ffno_desc d;
+  int ext[3] = {1, 1, 1};          // size + pad
+  long long pts = 0;               // padded points per sample
+  long long pts_in = 0;            // input points per sample
+  int in_total = 0;                // in_features + appended grid channels
+  bool use_umma = false;
+  float* d_fwd[3] = {nullptr, nullptr, nullptr};   // [L][ld(2K)]
+  float* d_inv[3] = {nullptr, nullptr, nullptr};   // [2K][ld(L)]
+  bool loaded = false;
+  bool has_io = false;             // lift + head parameters were given (false for a bare spectral layer)
+  std::vector<LayerW> layers;
+  Lin lift;
+  float* head_w = nullptr;         // [out][C]
+  float* head_b = nullptr;         // [out]
+  Lin out0, out1;                  // scratch for the head fold
+  std::vector<void*> owned;        // every cudaMalloc of this plan
+  std::map<const void*, float*> dedup;   // source pointer -> prepared buffer (shared weights)
+  int64_t last_launches = 0;
+  UmmaState* umma = nullptr;
+
+  LiftGeom geom() const {
+    LiftGeom g;
+    g.ndim = d.ndim;
+    for (int a = 0; a < 3; ++a) { g.size[a] = a < d.ndim ? d.size[a] : 1; g.pad[a] = a < d.ndim ? d.pad[a] : 0; }
+    g.in_features = d.in_features;
+    g.append_grid = d.append_grid;
+    g.C = d.width;
+    return g;
+  }
+  int hidden() const { return d.width * d.ff_factor; }
+};
+
+namespace {
+
+int dev_alloc(ffno_plan* p, size_t bytes, float** out) {
+  void* ptr = nullptr;
+  FFNO_CUDA_CHECK(cudaMalloc(&ptr, bytes ? bytes : 4));
+  p->owned.push_back(ptr);
+  *out = static_cast<float*>(ptr);
+  return FFNO_OK;
+}
+
+int pad16(int n) { return (n + 15) / 16 * 16; }
+
+// Truncated ortho real DFT tables (double precision on the host).  See oracle/ffno_oracle.py
+// dft_forward_matrix / dft_inverse_matrix for the independent statement the CPU tests pin to torch.fft:
+//   forward  T[l][2k]   =  cos(2 pi k l / L) / sqrt(L),  T[l][2k+1] = -sin(2 pi k l / L) / sqrt(L)
+//   inverse  T[2k][l]   =  c_k cos(..) / sqrt(L),        T[2k+1][l] = -c_k sin(..) / sqrt(L)
+// c_0 = 1, c_k = 2 (Hermitian half), c_{L/2} = 1 for even L; sin(0) = sin(pi l) = 0 drops Im(DC), Im(Nyquist)
+// exactly as the C2R transform at grid_2d.py:72 does.
+int build_tables(ffno_plan* p) {
+  for (int a = 0; a < p->d.ndim; ++a) {
+    const int L = p->ext[a], K = p->d.modes[a];
+    const int ldf = pad16(2 * K), ldi = pad16(L);
+    std::vector<float> f((size_t)L * ldf, 0.f), inv((size_t)2 * K * ldi, 0.f);
+    const double s = 1.0 / std::sqrt((double)L);
+    for (int l = 0; l < L; ++l)
+      for (int k = 0; k < K; ++k) {
+        // reduce k*l mod L before the multiply: keeps the angle small and exact for large L
+        long long kl = ((long long)k * l) % L;
+        double ang = 2.0 * M_PI * (double)kl / (double)L;
+        double c = std::cos(ang) * s, sn = std::sin(ang) * s;
+        double ck = (k == 0) ? 1.0 : ((L % 2 == 0 && k == L / 2) ? 1.0 : 2.0);
+        f[(size_t)l * ldf + 2 * k] = (float)c;
+        f[(size_t)l * ldf + 2 * k + 1] = (float)(-sn);
+        inv[(size_t)(2 * k) * ldi + l] = (float)(ck * c);
+        inv[(size_t)(2 * k + 1) * ldi + l] = (float)(-ck * sn);
+      }
+    FFNO_TRY(dev_alloc(p, f.size() * 4, &p->d_fwd[a]));
+    FFNO_TRY(dev_alloc(p, inv.size() * 4, &p->d_inv[a]));
+    FFNO_CUDA_CHECK(cudaMemcpy(p->d_fwd[a], f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+    FFNO_CUDA_CHECK(cudaMemcpy(p->d_inv[a], inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return FFNO_OK;
+}
+
+int validate_desc(const ffno_desc* d) {
+  FFNO_REQUIRE(d != nullptr, FFNO_ERR_BAD_ARG, "desc is NULL");
+  FFNO_REQUIRE(d->abi_version == FFNO_ABI_VERSION, FFNO_ERR_BAD_ARG, "ABI version %d != %d", d->abi_version,
+               FFNO_ABI_VERSION);
+  FFNO_REQUIRE(d->ndim == 2 || d->ndim == 3, FFNO_ERR_UNSUPPORTED, "ndim=%d (need 2 or 3)", d->ndim);
+  FFNO_REQUIRE(d->width > 0 && d->width % 4 == 0, FFNO_ERR_UNSUPPORTED, "width=%d must be a positive multiple of 4",
+               d->width);
+  FFNO_REQUIRE(d->n_layers >= 1, FFNO_ERR_BAD_ARG, "n_layers=%d", d->n_layers);
+  FFNO_REQUIRE(d->n_ff_layers >= 1 && d->n_ff_layers <= FFNO_MAX_FF_LAYERS, FFNO_ERR_UNSUPPORTED,
+               "n_ff_layers=%d not in [1,%d]", d->n_ff_layers, FFNO_MAX_FF_LAYERS);
+  FFNO_REQUIRE(d->ff_factor >= 1, FFNO_ERR_BAD_ARG, "ff_factor=%d", d->ff_factor);
+  FFNO_REQUIRE(d->in_features >= 1 && d->out_features >= 1 && d->out_features <= 8, FFNO_ERR_UNSUPPORTED,
+               "in_features=%d out_features=%d", d->in_features, d->out_features);
+  FFNO_REQUIRE(d->head_hidden >= 1, FFNO_ERR_BAD_ARG, "head_hidden=%d", d->head_hidden);
+  FFNO_REQUIRE(d->spectral_mode >= 0 && d->spectral_mode <= 2, FFNO_ERR_BAD_ARG, "spectral_mode=%d", d->spectral_mode);
+  for (int a = 0; a < d->ndim; ++a) {
+    FFNO_REQUIRE(d->size[a] >= 1 && d->pad[a] >= 0, FFNO_ERR_BAD_ARG, "size[%d]=%d pad=%d", a, d->size[a], d->pad[a]);
+    int L = d->size[a] + d->pad[a];
+    // the reference's slice-assign `out_ft[..., :modes] = einsum(x_ft[..., :modes], W)` raises when
+    // modes > L//2+1 — same contract here.
+    FFNO_REQUIRE(d->modes[a] >= 1 && d->modes[a] <= L / 2 + 1, FFNO_ERR_BAD_ARG,
+                 "modes[%d]=%d exceeds the %d rfft bins of a length-%d axis", a, d->modes[a], L / 2 + 1, L);
+  }
+  return FFNO_OK;
+}
+
+// ---- parameter preparation ---------------------------------------------------------------------------
+int prep_linear(ffno_plan* p, const ffno_linear_params& src, int in, int out, Lin* dst, cudaStream_t st) {
+  FFNO_REQUIRE(src.in_features == in && src.out_features == out, FFNO_ERR_BAD_ARG,
+               "linear shape [%d,%d] given, [%d,%d] expected", src.out_features, src.in_features, out, in);
+  const float* v = src.weight ? src.weight : src.weight_v;
+  const float* g = src.weight ? nullptr : src.weight_g;
+  FFNO_REQUIRE(v != nullptr, FFNO_ERR_BAD_ARG, "linear has neither weight nor weight_v");
+  FFNO_REQUIRE(src.weight || src.weight_g, FFNO_ERR_BAD_ARG, "weight_v without weight_g");
+  dst->in = in;
+  dst->out = out;
+  if (!dst->wt) FFNO_TRY(dev_alloc(p, (size_t)in * out * 4, &dst->wt));
+  FFNO_TRY(launch_weight_fold_transpose(v, g, dst->wt, out, in, st));
+  if (src.bias) {
+    if (!dst->bias) FFNO_TRY(dev_alloc(p, (size_t)out * 4, &dst->bias));
+    FFNO_CUDA_CHECK(cudaMemcpyAsync(dst->bias, src.bias, (size_t)out * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    dst->bias = nullptr;
+  }
+  return FFNO_OK;
+}
+
+int prep_ff(ffno_plan* p, const ffno_ff_params& src, FFW* dst, cudaStream_t st) {
+  const int C = p->d.width, H = p->hidden(), n = p->d.n_ff_layers;
+  for (int i = 0; i < n; ++i) {
+    int in = (i == 0) ? C : H, out = (i == n - 1) ? C : H;     // feedforward.py:11-12
+    FFNO_TRY(prep_linear(p, src.linear[i], in, out, &dst->lin[i], st));
+  }
+  if (p->d.layer_norm) {
+    FFNO_REQUIRE(src.ln_weight && src.ln_bias, FFNO_ERR_BAD_ARG, "layer_norm set but LayerNorm params missing");
+    if (!dst->ln_w) FFNO_TRY(dev_alloc(p, (size_t)C * 4, &dst->ln_w));
+    if (!dst->ln_b) FFNO_TRY(dev_alloc(p, (size_t)C * 4, &dst->ln_b));
+    FFNO_CUDA_CHECK(cudaMemcpyAsync(dst->ln_w, src.ln_weight, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+    FFNO_CUDA_CHECK(cudaMemcpyAsync(dst->ln_b, src.ln_bias, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return FFNO_OK;
+}
+
+// ---- workspace carving ---------------------------------------------------------------------------------
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  float* take(size_t n_floats) {
+    float* r = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += (n_floats * 4 + 255) / 256 * 256;
+    return r;
+  }
+};
+
+struct Workspace {
+  float *xa, *xb, *s, *b, *h0, *h1, *F, *R, *tmp, *f, *umma;
+  size_t bytes;
+};
+
+Workspace carve(const ffno_plan* p, int batch, void* base) {
+  Workspace w{};
+  Carver c(base);
+  const long long P = (long long)batch * p->pts;
+  const size_t U = (size_t)P * p->d.width;
+  w.xa = c.take(U);
+  w.xb = c.take(U);
+  w.s = c.take(U);
+  w.b = c.take(U);
+  size_t spec = 0;
+  for (int a = 0; a < p->d.ndim; ++a) {
+    size_t n = U / p->ext[a] * 2 * p->d.modes[a];
+    if (n > spec) spec = n;
+  }
+  w.F = c.take(spec);
+  w.R = c.take(spec);
+  if (!p->use_umma || p->d.n_ff_layers != 2) {
+    w.h0 = c.take(p->d.n_ff_layers > 1 ? (size_t)P * p->hidden() : 0);
+    w.h1 = c.take(p->d.n_ff_layers > 2 ? (size_t)P * p->hidden() : 0);
+  }
+  w.tmp = c.take(p->d.layer_norm ? U : 0);
+  w.f = c.take(p->d.use_fork ? U : 0);
+  w.umma = c.take(p->use_umma ? umma_workspace_floats(p->umma, batch) : 0);
+  w.bytes = c.off;
+  return w;
+}
+
+// ---- generic forward pieces ---------------------------------------------------------------------------
+int spectral_generic(ffno_plan* p, const LayerW& lw, const float* x, int batch, float* s, float* F, float* R,
+                     cudaStream_t st) {
+  const int C = p->d.width;
+  bool first = true;
+  for (int a = p->d.ndim - 1; a >= 0; --a) {     // reference order: last axis first (grid_2d.py:57,75)
+    long long outer = batch, p_inner = 1;
+    for (int i = 0; i < a; ++i) outer *= p->ext[i];
+    for (int i = a + 1; i < p->d.ndim; ++i) p_inner *= p->ext[i];
+    const int L = p->ext[a], K = p->d.modes[a];
+    const long long inner = p_inner * C;
+    FFNO_TRY(launch_axis_transform(x, p->d_fwd[a], F, outer, L, 2 * K, inner, false, st));
+    const float* src = F;
+    if (p->d.spectral_mode == FFNO_MODE_FULL) {
+      FFNO_TRY(launch_mode_mix(F, lw.wmix[a], R, outer, K, p_inner, C, st));
+      src = R;
+    }
+    FFNO_TRY(launch_axis_transform(src, p->d_inv[a], s, outer, 2 * K, L, inner, !first, st));
+    first = false;
+  }
+  return FFNO_OK;
+}
+
+// y = FF(s); if residual: out = residual + y, b_out = y (either may be NULL)
+int ff_generic(ffno_plan* p, const FFW& ff, const float* s, const float* residual, long long P, float* out,
+               float* b_out, const Workspace& w, cudaStream_t st) {
+  const int n = p->d.n_ff_layers, C = p->d.width;
+  const float* cur = s;
+  float* hbuf[2] = {w.h0, w.h1};
+  for (int i = 0; i < n - 1; ++i) {
+    float* dst = hbuf[i & 1];
+    FFNO_TRY(launch_linear(cur, ff.lin[i].wt, ff.lin[i].bias, nullptr, dst, nullptr, P, ff.lin[i].in,
+                           ff.lin[i].out, true, st));
+    cur = dst;
+  }
+  const Lin& last = ff.lin[n - 1];
+  if (!p->d.layer_norm) {
+    FFNO_TRY(launch_linear(cur, last.wt, last.bias, residual, out, b_out, P, last.in, last.out, false, st));
+    if (!residual && !out) return FFNO_OK;
+  } else {
+    FFNO_TRY(launch_linear(cur, last.wt, last.bias, nullptr, w.tmp, nullptr, P, last.in, last.out, false, st));
+    FFNO_TRY(launch_layernorm_residual(w.tmp, ff.ln_w, ff.ln_b, residual, out, b_out, P, C, st));
+  }
+  return FFNO_OK;
+}
+
+int check_ready(const ffno_plan* p, int batch, const void* ws, size_t ws_bytes, size_t need) {
+  FFNO_REQUIRE(p != nullptr, FFNO_ERR_BAD_ARG, "plan is NULL");
+  FFNO_REQUIRE(p->loaded, FFNO_ERR_STATE, "ffno_plan_load_params has not been called");
+  FFNO_REQUIRE(batch >= 0, FFNO_ERR_BAD_ARG, "batch=%d", batch);
+  FFNO_REQUIRE(ws != nullptr || need == 0, FFNO_ERR_WORKSPACE, "workspace is NULL");
+  FFNO_REQUIRE(ws_bytes >= need, FFNO_ERR_WORKSPACE, "workspace %zu B < required %zu B", ws_bytes, need);
+  FFNO_REQUIRE(((uintptr_t)ws & 255) == 0, FFNO_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  return FFNO_OK;
+}
+
+int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, const ffno_taps* taps,
+                   void* workspace, cudaStream_t st) {
+  const Workspace w = carve(p, batch, workspace);
+  const LiftGeom g = p->geom();
+  const long long P = (long long)batch * p->pts;
+  const size_t Ubytes = (size_t)P * p->d.width * 4;
+  const int nl = p->d.n_layers;
+  if (batch == 0) return FFNO_OK;
+
+  FFNO_TRY(launch_lift(x, p->lift.wt, p->lift.bias, w.xa, batch, g, st));
+  if (taps && taps->lift) FFNO_CUDA_CHECK(cudaMemcpyAsync(taps->lift, w.xa, Ubytes, cudaMemcpyDeviceToDevice, st));
+
+  float* cur = w.xa;
+  float* nxt = w.xb;
+  for (int l = 0; l < nl; ++l) {
+    const LayerW& lw = p->layers[l];
+    const bool last = (l == nl - 1);
+    if (p->use_umma) {
+      FFNO_TRY(umma_layer_fwd(p->umma, l, cur, batch, nxt, w.s, w.b, w.F, w.R, w.umma,
+                              (taps && taps->spectral && taps->spectral[l]) || p->d.use_fork, last || p->d.use_fork,
+                              st));
+    } else {
+      const float* s = cur;
+      if (p->d.spectral_mode != FFNO_MODE_NO_FOURIER) {
+        FFNO_TRY(spectral_generic(p, lw, cur, batch, w.s, w.F, w.R, st));
+        s = w.s;
+      }
+      FFNO_TRY(ff_generic(p, lw.back, s, cur, P, nxt, w.b, w, st));
+    }
+    if (p->d.use_fork) {
+      const float* s = (p->d.spectral_mode != FFNO_MODE_NO_FOURIER) ? w.s : cur;
+      FFNO_TRY(ff_generic(p, lw.fork, s, nullptr, P, nullptr, w.f, w, st));
+      if (taps && taps->forecast_list && taps->forecast_list[l])
+        FFNO_TRY(launch_head(w.f, p->head_w, p->head_b, taps->forecast_list[l], batch, g, p->d.out_features, false, st));
+      FFNO_TRY(launch_head(w.f, p->head_w, p->head_b, forecast, batch, g, p->d.out_features, l > 0, st));
+    }
+    if (taps && taps->spectral && taps->spectral[l] && p->d.spectral_mode != FFNO_MODE_NO_FOURIER)
+      FFNO_CUDA_CHECK(cudaMemcpyAsync(taps->spectral[l], w.s, Ubytes, cudaMemcpyDeviceToDevice, st));
+    if (taps && taps->x_after && taps->x_after[l])
+      FFNO_CUDA_CHECK(cudaMemcpyAsync(taps->x_after[l], nxt, Ubytes, cudaMemcpyDeviceToDevice, st));
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  if (taps && taps->b_last) FFNO_CUDA_CHECK(cudaMemcpyAsync(taps->b_last, w.b, Ubytes, cudaMemcpyDeviceToDevice, st));
+  if (!p->d.use_fork)
+    FFNO_TRY(launch_head(w.b, p->head_w, p->head_b, forecast, batch, g, p->d.out_features, false, st));
+  return FFNO_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// extern "C"
+// =====================================================================================================
+extern "C" {
+
+const char* ffno_last_error(void) { return error_buffer(); }
+int ffno_abi_version(void) { return FFNO_ABI_VERSION; }
+
+int ffno_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
+  FFNO_REQUIRE(out_plan != nullptr, FFNO_ERR_BAD_ARG, "out_plan is NULL");
+  *out_plan = nullptr;
+  FFNO_TRY(validate_desc(desc));
+  ffno_plan* p = new (std::nothrow) ffno_plan();
+  FFNO_REQUIRE(p != nullptr, FFNO_ERR_BAD_ARG, "out of host memory");
+  p->d = *desc;
+  p->pts = 1;
+  p->pts_in = 1;
+  for (int a = 0; a < desc->ndim; ++a) {
+    p->ext[a] = desc->size[a] + desc->pad[a];
+    p->pts *= p->ext[a];
+    p->pts_in *= desc->size[a];
+  }
+  p->in_total = desc->in_features + (desc->append_grid ? desc->ndim : 0);
+  p->layers.resize(desc->n_layers);
+  int st = build_tables(p);
+  if (st == FFNO_OK) {
+    const bool ok = umma_supported(desc, p->ext);
+    if (desc->path == FFNO_PATH_UMMA && !ok)
+      st = set_error(FFNO_ERR_UNSUPPORTED, "shape does not qualify for the tcgen05 path: %s", umma_why_not(desc, p->ext));
+    p->use_umma = ok && desc->path != FFNO_PATH_GENERIC;
+    if (st == FFNO_OK && p->use_umma) st = umma_create(&p->umma, desc, p->ext);
+  }
+  if (st != FFNO_OK) {
+    ffno_plan_destroy(p);
+    return st;
+  }
+  *out_plan = p;
+  return FFNO_OK;
+}
+
+int ffno_plan_destroy(ffno_plan* plan) {
+  if (!plan) return FFNO_OK;
+  if (plan->umma) umma_destroy(plan->umma);
+  for (void* ptr : plan->owned) cudaFree(ptr);
+  delete plan;
+  return FFNO_OK;
+}
+
+int ffno_plan_uses_umma(const ffno_plan* plan) { return plan && plan->use_umma ? 1 : 0; }
+
+int ffno_plan_load_params(ffno_plan* p, const ffno_block_params* prm, void* stream) {
+  FFNO_REQUIRE(p && prm, FFNO_ERR_BAD_ARG, "plan/params is NULL");
+  FFNO_REQUIRE(prm->n_layers == p->d.n_layers && prm->layers, FFNO_ERR_BAD_ARG, "params.n_layers=%d, plan has %d",
+               prm->n_layers, p->d.n_layers);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = p->d.width;
+  p->has_io = prm->in_proj.weight || prm->in_proj.weight_v;
+  if (p->has_io) {
+    FFNO_TRY(prep_linear(p, prm->in_proj, p->in_total, C, &p->lift, st));
+    FFNO_TRY(prep_linear(p, prm->out0, C, p->d.head_hidden, &p->out0, st));
+    FFNO_TRY(prep_linear(p, prm->out1, p->d.head_hidden, p->d.out_features, &p->out1, st));
+    if (!p->head_w) FFNO_TRY(dev_alloc(p, (size_t)p->d.out_features * C * 4, &p->head_w));
+    if (!p->head_b) FFNO_TRY(dev_alloc(p, (size_t)p->d.out_features * 4, &p->head_b));
+    FFNO_TRY(launch_fold_head(p->out0.wt, p->out0.bias, p->out1.wt, p->out1.bias, p->head_w, p->head_b, C,
+                              p->d.head_hidden, p->d.out_features, st));
+  }
+
+  // Spectral weights: prepared once per distinct source pointer (share_weight=True aliases one
+  // ParameterList across all layers, grid_2d.py:125-147).  FF weights likewise (share_fork).
+  std::map<const void*, float*> seen_mix;
+  std::map<const void*, int> seen_ff_back, seen_ff_fork;
+  for (int l = 0; l < p->d.n_layers; ++l) {
+    const ffno_layer_params& src = prm->layers[l];
+    LayerW& dst = p->layers[l];
+    if (p->d.spectral_mode == FFNO_MODE_FULL) {
+      for (int a = 0; a < p->d.ndim; ++a) {
+        const float* wsrc = src.fourier_weight[a];
+        FFNO_REQUIRE(wsrc != nullptr, FFNO_ERR_BAD_ARG, "layer %d: fourier_weight[%d] is NULL", l, a);
+        const void* key = (const void*)((uintptr_t)wsrc ^ ((uintptr_t)a << 60));
+        auto it = seen_mix.find(key);
+        if (it != seen_mix.end()) { dst.wmix[a] = it->second; continue; }
+        float*& slot = p->dedup[(const void*)((uintptr_t)(l * 4 + a + 1))];   // stable per (layer, axis) slot
+        if (!slot) FFNO_TRY(dev_alloc(p, (size_t)p->d.modes[a] * 4 * C * C * 4, &slot));
+        FFNO_TRY(launch_pack_mix_weights(wsrc, slot, C, p->d.modes[a], st));
+        dst.wmix[a] = slot;
+        seen_mix[key] = slot;
+      }
+    }
+    {
+      const void* key = src.backcast_ff.linear[0].weight ? (const void*)src.backcast_ff.linear[0].weight
+                                                         : (const void*)src.backcast_ff.linear[0].weight_v;
+      auto it = seen_ff_back.find(key);
+      if (it != seen_ff_back.end()) dst.back = p->layers[it->second].back;
+      else { FFNO_TRY(prep_ff(p, src.backcast_ff, &dst.back, st)); seen_ff_back[key] = l; }
+    }
+    if (p->d.use_fork) {
+      const void* key = src.forecast_ff.linear[0].weight ? (const void*)src.forecast_ff.linear[0].weight
+                                                         : (const void*)src.forecast_ff.linear[0].weight_v;
+      auto it = seen_ff_fork.find(key);
+      if (it != seen_ff_fork.end()) dst.fork = p->layers[it->second].fork;
+      else { FFNO_TRY(prep_ff(p, src.forecast_ff, &dst.fork, st)); seen_ff_fork[key] = l; }
+    }
+  }
+  if (p->use_umma) {
+    std::vector<UmmaLayerSrc> srcs(p->d.n_layers);
+    for (int l = 0; l < p->d.n_layers; ++l) {
+      for (int a = 0; a < 3; ++a) srcs[l].wmix[a] = p->layers[l].wmix[a];
+      srcs[l].w1t = p->layers[l].back.lin[0].wt;
+      srcs[l].b1 = p->layers[l].back.lin[0].bias;
+      srcs[l].w2t = p->layers[l].back.lin[1].wt;
+      srcs[l].b2 = p->layers[l].back.lin[1].bias;
+    }
+    FFNO_TRY(umma_load_params(p->umma, srcs.data(), p->d_fwd, p->d_inv, st));
+  }
+  p->loaded = true;
+  return FFNO_OK;
+}
+
+size_t ffno_workspace_bytes(const ffno_plan* plan, int32_t batch) {
+  if (!plan || batch < 0) return 0;
+  return carve(plan, batch, nullptr).bytes;
+}
+
+int ffno_block_fwd(ffno_plan* p, const float* x, int32_t batch, float* forecast, const ffno_taps* taps,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_workspace_bytes(p, batch)));
+  if (batch == 0) { p->last_launches = 0; return FFNO_OK; }
+  FFNO_REQUIRE(x && forecast, FFNO_ERR_BAD_ARG, "x/forecast is NULL");
+  FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
+  const long long before = g_launch_counter;
+  int st = block_fwd_impl(p, x, batch, forecast, taps, workspace, static_cast<cudaStream_t>(stream));
+  p->last_launches = g_launch_counter - before;
+  return st;
+}
+
+size_t ffno_workspace_bytes_host(const ffno_plan* plan, int32_t batch) {
+  if (!plan || batch < 0) return 0;
+  size_t in = ((size_t)batch * plan->pts_in * plan->d.in_features * 4 + 255) / 256 * 256;
+  size_t out = ((size_t)batch * plan->pts_in * plan->d.out_features * 4 + 255) / 256 * 256;
+  return ffno_workspace_bytes(plan, batch) + in + out;
+}
+
+int ffno_block_fwd_host(ffno_plan* p, const float* x_host, int32_t batch, float* forecast_host, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  const size_t need = ffno_workspace_bytes_host(p, batch);
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, need));
+  FFNO_REQUIRE(x_host && forecast_host, FFNO_ERR_BAD_ARG, "x_host/forecast_host is NULL");
+  FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t in_b = (size_t)batch * p->pts_in * p->d.in_features * 4;
+  const size_t out_b = (size_t)batch * p->pts_in * p->d.out_features * 4;
+  const size_t core = ffno_workspace_bytes(p, batch);
+  char* base = static_cast<char*>(workspace);
+  float* d_in = reinterpret_cast<float*>(base + core);
+  float* d_out = reinterpret_cast<float*>(base + core + (in_b + 255) / 256 * 256);
+  FFNO_CUDA_CHECK(cudaMemcpyAsync(d_in, x_host, in_b, cudaMemcpyHostToDevice, st));
+  const long long before = g_launch_counter;
+  int s = block_fwd_impl(p, d_in, batch, d_out, nullptr, workspace, st);
+  p->last_launches = g_launch_counter - before;
+  if (s != FFNO_OK) return s;
+  FFNO_CUDA_CHECK(cudaMemcpyAsync(forecast_host, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  FFNO_CUDA_CHECK(cudaStreamSynchronize(st));
+  return FFNO_OK;
+}
+
+int ffno_spectral_fwd(ffno_plan* p, int32_t layer, const float* x, int32_t batch, float* s, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_workspace_bytes(p, batch)));
+  FFNO_REQUIRE(layer >= 0 && layer < p->d.n_layers, FFNO_ERR_BAD_ARG, "layer=%d", layer);
+  FFNO_REQUIRE(x && s, FFNO_ERR_BAD_ARG, "x/s is NULL");
+  FFNO_REQUIRE(p->d.spectral_mode != FFNO_MODE_NO_FOURIER, FFNO_ERR_STATE, "plan was built with mode=no-fourier");
+  const Workspace w = carve(p, batch, workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (batch == 0) return FFNO_OK;
+  if (p->use_umma) return umma_spectral_fwd(p->umma, layer, x, batch, s, w.F, w.R, w.umma, st);
+  return spectral_generic(p, p->layers[layer], x, batch, s, w.F, w.R, st);
+}
+
+int ffno_ff_fwd(ffno_plan* p, int32_t layer, int32_t which, const float* s, const float* residual, int32_t batch,
+                float* y, void* workspace, size_t workspace_bytes, void* stream) {
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_workspace_bytes(p, batch)));
+  FFNO_REQUIRE(layer >= 0 && layer < p->d.n_layers, FFNO_ERR_BAD_ARG, "layer=%d", layer);
+  FFNO_REQUIRE(which == 0 || (which == 1 && p->d.use_fork), FFNO_ERR_BAD_ARG, "which=%d", which);
+  FFNO_REQUIRE(s && y, FFNO_ERR_BAD_ARG, "s/y is NULL");
+  const Workspace w = carve(p, batch, workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long P = (long long)batch * p->pts;
+  if (batch == 0) return FFNO_OK;
+  const FFW& ff = which == 0 ? p->layers[layer].back : p->layers[layer].fork;
+  if (p->use_umma && which == 0 && p->d.n_ff_layers == 2 && !p->d.layer_norm)
+    return umma_ff_fwd(p->umma, layer, s, residual, batch, y, w.umma, st);
+  if (residual) return ff_generic(p, ff, s, residual, P, y, nullptr, w, st);
+  return ff_generic(p, ff, s, nullptr, P, nullptr, y, w, st);
+}
+
+int ffno_linear_fwd(const ffno_linear_params* lin, const float* x, int64_t rows, float* y, int32_t relu,
+                    void* scratch, size_t scratch_bytes, void* stream) {
+  FFNO_REQUIRE(lin && x && y, FFNO_ERR_BAD_ARG, "NULL argument");
+  const int in = lin->in_features, out = lin->out_features;
+  FFNO_REQUIRE(in >= 1 && out >= 1 && rows >= 0, FFNO_ERR_BAD_ARG, "linear [%d,%d] rows=%lld", out, in, (long long)rows);
+  FFNO_REQUIRE(scratch && scratch_bytes >= (size_t)in * out * 4, FFNO_ERR_WORKSPACE, "scratch < %zu B", (size_t)in * out * 4);
+  const float* v = lin->weight ? lin->weight : lin->weight_v;
+  FFNO_REQUIRE(v && (lin->weight || lin->weight_g), FFNO_ERR_BAD_ARG, "linear has no usable weight");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* wt = static_cast<float*>(scratch);
+  FFNO_TRY(launch_weight_fold_transpose(v, lin->weight ? nullptr : lin->weight_g, wt, out, in, st));
+  return launch_linear_any(x, wt, lin->bias, y, rows, in, out, relu != 0, st);
+}
+
+int ffno_layernorm_fwd(const float* x, const float* weight, const float* bias, int64_t rows, int32_t C, float* y,
+                       void* stream) {
+  FFNO_REQUIRE(x && weight && bias && y && C >= 1, FFNO_ERR_BAD_ARG, "NULL argument");
+  return launch_layernorm_residual(x, weight, bias, nullptr, y, nullptr, rows, C, static_cast<cudaStream_t>(stream));
+}
+
+int ffno_rel_l2(const float* x, int64_t x_stride_b, int64_t x_stride_i, const float* y, int64_t y_stride_b,
+                int64_t y_stride_i, int32_t batch, int64_t n, float* out, void* stream) {
+  FFNO_REQUIRE(x && y && out && batch >= 0 && n >= 1, FFNO_ERR_BAD_ARG, "bad argument");
+  return launch_rel_l2(x, x_stride_b, x_stride_i, y, y_stride_b, y_stride_i, batch, n, out,
+                       static_cast<cudaStream_t>(stream));
+}
+
+size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch) {
+  if (!plan || batch < 0) return 0;
+  size_t feat = ((size_t)batch * plan->pts_in * 3 * 4 + 255) / 256 * 256;
+  size_t fc = ((size_t)batch * plan->pts_in * 4 + 255) / 256 * 256;
+  return ffno_workspace_bytes(plan, batch) + feat + fc;
+}
+
+int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n_steps, const float* mean_host,
+                     const float* std_host, float low, float high, float* preds, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_rollout_workspace_bytes(p, batch)));
+  FFNO_REQUIRE(frame0 && preds && mean_host && std_host, FFNO_ERR_BAD_ARG, "NULL argument");
+  FFNO_REQUIRE(p->d.ndim == 2 && p->d.in_features == 3 && p->d.out_features == 1 && !p->d.append_grid &&
+                   p->d.pad[0] == 0 && p->d.pad[1] == 0 && !p->d.use_fork,
+               FFNO_ERR_UNSUPPORTED, "rollout needs the torus_li/markov layout (2-D grid, in=3, out=1)");
+  FFNO_REQUIRE(n_steps >= 1, FFNO_ERR_BAD_ARG, "n_steps=%d", n_steps);
+  FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int X = p->d.size[0], Y = p->d.size[1];
+  const size_t core = ffno_workspace_bytes(p, batch);
+  char* base = static_cast<char*>(workspace);
+  float* feat = reinterpret_cast<float*>(base + core);
+  float* fc = reinterpret_cast<float*>(base + core + ((size_t)batch * X * Y * 3 * 4 + 255) / 256 * 256);
+  MeanStd3 ms;
+  for (int i = 0; i < 3; ++i) { ms.m[i] = mean_host[i]; ms.s[i] = std_host[i]; }
+  const long long before = g_launch_counter;
+  for (int t = 0; t < n_steps; ++t) {
+    // step 0 reads the ground-truth frame; later steps read the model's own de-normalised forecast
+    // (routines/grid_2d_markov.py:264-292)
+    if (t == 0) FFNO_TRY(launch_rollout_features(frame0, (long long)X * Y, 1, feat, batch, X, Y, low, high, ms, st));
+    else FFNO_TRY(launch_rollout_features(preds + (t - 1), (long long)X * Y * n_steps, n_steps, feat, batch, X, Y,
+                                          low, high, ms, st));
+    FFNO_TRY(block_fwd_impl(p, feat, batch, fc, nullptr, workspace, st));
+    FFNO_TRY(launch_rollout_denorm(fc, preds, batch, X * Y, n_steps, t, ms, st));
+  }
+  p->last_launches = g_launch_counter - before;
+  return FFNO_OK;
+}
+
+int64_t ffno_plan_last_launch_count(const ffno_plan* plan) { return plan ? plan->last_launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// tcgen05 (UMMA) fast path of the F-FNO layer: interface used by plan.cu.  Implemented in umma_path.cu.
+#pragma once
+#include "common.cuh"
+
+namespace ffno {
+
+struct UmmaState;
+
+// Prepared FP32 parameters of one layer (device pointers owned by the plan) that the UMMA path re-packs
+// into bf16 hi/lo operand tiles.
+struct UmmaLayerSrc {
+  const float* wmix[3];   // per axis [K][2C][2C] real block matrices
+  const float* w1t;       // [C][4C]  folded, transposed FF linear 0
+  const float* b1;        // [4C]
+  const float* w2t;       // [4C][C]
+  const float* b2;        // [C]
+};
+
+bool umma_supported(const ffno_desc* d, const int ext[3]);
+const char* umma_why_not(const ffno_desc* d, const int ext[3]);
+int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]);
+void umma_destroy(UmmaState* s);
+int umma_load_params(UmmaState* s, const UmmaLayerSrc* layers, float* const d_fwd[3], float* const d_inv[3],
+                     cudaStream_t st);
+size_t umma_workspace_floats(const UmmaState* s, int batch);
+
+// One full layer: x_next = x + FF(spectral(x)); optionally also materialises s (spectral output) and
+// b (FF output before the residual; the head input on the last layer).
+int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_next, float* s_out, float* b_out,
+                   float* F, float* R, float* ws, bool want_s, bool want_b, cudaStream_t st);
+int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R,
+                      float* ws, cudaStream_t st);
+int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* y, float* ws,
+                cudaStream_t st);
+
+}  // namespace ffno

@@ -1,0 +1,65 @@
+"""Batch sharding of the rollout over the GPUs of one box.
+
+Samples are independent through the whole forward and rollout, parameters are replicated, and nothing is
+exchanged between layers or steps.  The single collective is the all-gather of the per-sample relative-L2
+values for the ``LpLoss`` mean (modules/loss.py:41-42) — n_steps x B_local floats per rank, once per
+rollout.  One process per GPU; ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is plumbing.
+"""
+from __future__ import annotations
+
+import os
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str = "nccl") -> Tuple[int, int, int]:
+    """(rank, world_size, local_rank) from the torchrun environment; initialises the process group."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice [lo, hi) of ``n`` samples for ``rank`` (first n % world ranks get one more)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    lo, hi = shard_bounds(t.shape[0], rank, world)
+    return t[lo:hi]
+
+
+def gather_sample_losses(local: torch.Tensor, n_global: int) -> torch.Tensor:
+    """all-gather ``local[n_steps, B_local]`` → ``[n_steps, n_global]`` (ragged shards padded, then cut)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    n_steps = local.shape[0]
+    width = -(-n_global // world)
+    padded = local.new_zeros(n_steps, width)
+    padded[:, :local.shape[1]] = local
+    flat = local.new_empty(world * n_steps, width)          # concatenated form: accepted by NCCL and gloo
+    dist.all_gather_into_tensor(flat, padded.contiguous())
+    out = flat.view(world, n_steps, width)
+    pieces = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_global, r, world)
+        pieces.append(out[r, :, :hi - lo])
+    return torch.cat(pieces, dim=1)
+
+
+def rollout_loss(local: torch.Tensor, n_global: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(loss, step_losses) over the GLOBAL batch from per-rank per-sample losses: mean over samples per step,
+    summed over steps (routines/grid_2d_markov.py:313-315)."""
+    allv = gather_sample_losses(local, n_global)
+    step = allv.mean(dim=1)
+    return step.sum(), step

@@ -1,0 +1,98 @@
+"""``Grid2DMarkovExperiment`` — host-side mirror of fourierflow/routines/grid_2d_markov.py (inference path).
+
+The reference class is a pytorch_lightning ``Routine``; this mirror is a plain ``nn.Module`` with the same
+constructor keywords and the same ``forward(batch) -> (loss, step_losses, preds, pred_layer_list)``
+contract for the configuration the BASELINE names (torus_li/markov: position features, normaliser,
+no velocity / force / mu / grid shuffling / difference learning).  The step loop
+(``_valid_step``, grid_2d_markov.py:195-326) runs entirely in libffno_b200 (ffno_rollout_fwd): feature
+build → normalise → layer stack → de-normalise, feeding each forecast back, with no host round trip
+between steps.  The relative-L2 reduction (modules/loss.py:33-46) is ffno_rel_l2 per sample; the mean over
+the batch is the only value a sharded run communicates (see fourierflow_b200/distributed.py).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _ops
+from ..modules.loss import LpLoss
+from ..modules.normalizer import Normalizer
+
+
+class Grid2DMarkovExperiment(nn.Module):
+    def __init__(self, conv: nn.Module, n_steps: Optional[int] = None, num_freq_bands: int = 8, freq_base: int = 2,
+                 low: float = 0, high: float = 1, use_position: bool = True, append_force: bool = False,
+                 append_mu: bool = False, max_accumulations: float = 1e6, should_normalize: bool = True,
+                 use_fourier_position: bool = False, noise_std: float = 0.0, shuffle_grid: bool = False,
+                 use_velocity: bool = False, learn_difference: bool = False, step_size: float = 1.0,
+                 n_test_steps_logged: Optional[int] = None, **kwargs):
+        super().__init__()
+        unsupported = dict(append_force=append_force, append_mu=append_mu, use_fourier_position=use_fourier_position,
+                           shuffle_grid=shuffle_grid, use_velocity=use_velocity, learn_difference=learn_difference)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad or not use_position or not should_normalize:
+            raise RuntimeError("Grid2DMarkovExperiment (B200 backend): only the torus_li/markov feature set is "
+                               f"implemented (use_position + should_normalize); unsupported: {bad}")
+        self.conv = conv
+        self.n_steps = n_steps
+        self.l2_loss = LpLoss(size_average=True)
+        self.low, self.high = low, high
+        self.step_size = step_size
+        self.noise_std = noise_std          # training-only in the reference (:150-151); unused at inference
+        self.normalizer = Normalizer([conv.input_dim], max_accumulations)
+        self.register_buffer('_float', torch.FloatTensor([0.1]))
+        self._ms_cache = None
+
+    # -- statistics (reference: epoch 0 of training only accumulates, grid_2d_markov.py:376-378) -----------
+    @torch.no_grad()
+    def accumulate_statistics(self, data: torch.Tensor) -> None:
+        """Fold every one-step input of ``data[B,X,Y,T]`` (frames 0..T-2 + position grid) into the normaliser."""
+        B, X, Y, T = data.shape
+        pos = self._positions(X, Y, data.device, data.dtype)
+        feats = torch.cat([data[..., :-1].unsqueeze(-1),
+                           pos[None, :, :, None, :].expand(B, X, Y, T - 1, 2)], dim=-1)
+        self.normalizer.accumulate(feats)
+        self._ms_cache = None
+
+    def _positions(self, X, Y, device, dtype):
+        gx = torch.linspace(self.low, self.high, steps=X, device=device, dtype=dtype)
+        gy = torch.linspace(self.low, self.high, steps=Y, device=device, dtype=dtype)
+        return torch.stack(torch.meshgrid(gx, gy, indexing='ij'), dim=-1)
+
+    def _mean_std(self):
+        key = (self.normalizer.sum._version, self.normalizer.count._version, self.normalizer.sum.data_ptr())
+        if self._ms_cache is None or self._ms_cache[0] != key:
+            self._ms_cache = (key, self.normalizer.mean.tolist(), self.normalizer.std.tolist())
+        return self._ms_cache[1], self._ms_cache[2]
+
+    # -- inference -------------------------------------------------------------------------------------
+    def forward(self, data):
+        return self._valid_step(data)
+
+    def predict(self, data: torch.Tensor, n_steps: Optional[int] = None) -> torch.Tensor:
+        """preds[B,X,Y,n_steps] of the Markov rollout started from frame T−n_steps−1 of ``data``."""
+        _ops.require_cuda(data, "Grid2DMarkovExperiment")
+        B, X, Y, T = data.shape
+        n_steps = n_steps or self.n_steps or T - 1
+        plan = self.conv.plan_for(data.device, (X, Y))
+        mean, std = self._mean_std()
+        frame0 = data[..., T - n_steps - 1].contiguous()
+        return plan.rollout_forward(frame0, n_steps, mean, std, self.low, self.high)
+
+    def per_sample_losses(self, preds: torch.Tensor, data: torch.Tensor) -> torch.Tensor:
+        """[n_steps, B] relative L2 of every rollout step against the last n_steps frames of ``data``."""
+        n_steps = preds.shape[-1]
+        yy = data[..., -n_steps:]
+        return torch.stack([self.l2_loss.rel_per_sample(preds[..., t], yy[..., t]) for t in range(n_steps)])
+
+    def _valid_step(self, batch):
+        data = batch['data'] if isinstance(batch, dict) else batch
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.conv.parameters()):
+            _ops.require_inference(self.conv, data)
+        preds = self.predict(data)
+        losses = self.per_sample_losses(preds, data)            # [n_steps, B]
+        step_losses = list(losses.mean(dim=1))                  # LpLoss(size_average) per step (:313)
+        loss = losses.mean(dim=1).sum()                         # loss += l (:315)
+        return loss, step_losses, preds, []

@@ -1,0 +1,28 @@
+"""``StructuredMeshExperiment`` — host-side mirror of fourierflow/routines/structured_mesh.py:8-51
+(validation/test path): ``out = self.model(x)``; relative-L2 against ``y``."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ..modules.loss import LpLoss
+
+
+class StructuredMeshExperiment(nn.Module):
+    def __init__(self, model: nn.Module, loss_scale: float = 1.0, **kwargs):
+        super().__init__()
+        self.model = model
+        self.l2_loss = LpLoss(size_average=True)
+        self.loss_scale = loss_scale
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx=0):
+        x, y = batch['x'], batch['y']
+        B = x.shape[0]
+        out = self.model(x)
+        return self.l2_loss(out.reshape(B, -1), y.reshape(B, -1))
+
+    test_step = validation_step
+
+    def forward(self, batch):
+        return self.model(batch['x'] if isinstance(batch, dict) else batch)

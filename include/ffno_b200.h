@@ -1,0 +1,207 @@
+/*
+ * ffno_b200.h — C ABI of the B200-native Factorized-FNO forward (libffno_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of alasdairtran/fourierflow: the F-FNO layer-stack
+ * forward.  The reference has no FFI (it is eager PyTorch); what binds here is the reference's
+ * nn.Module surface, mirrored by fourierflow_b200/modules (same class names, constructor arguments,
+ * forward signatures and state_dict keys).  Every entry point below names the reference code it
+ * replaces (paths relative to the reference tree, fourierflow/...).
+ *
+ * Conventions
+ *   - All tensors are fp32, contiguous, channels-LAST: activations [B, S1, S2(, S3), C] — the layout
+ *     the reference modules take and return (modules/factorized_fno/grid_2d.py:43, :96).
+ *   - Pointers are DEVICE pointers unless the function name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     except the *_host variants (which copy H2D/D2H on that stream and wait for it).
+ *   - Return value: 0 on success, negative ffno_status otherwise; ffno_last_error() returns a
+ *     thread-local human-readable message.  Nothing throws or aborts across the ABI.
+ *   - Ownership: the caller owns every tensor and the workspace.  The library owns only what lives
+ *     behind an ffno_plan* (DFT tables, folded/packed weights, TMA descriptors), created/destroyed by
+ *     paired calls.  No CPU fallback exists: unsupported shapes return FFNO_ERR_UNSUPPORTED.
+ *   - Threading: entry points are re-entrant; one plan must not be used from two threads at once.
+ */
+#ifndef FFNO_B200_H
+#define FFNO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FFNO_API __attribute__((visibility("default")))
+#else
+#define FFNO_API
+#endif
+
+#define FFNO_ABI_VERSION 1
+#define FFNO_MAX_DIMS 3
+#define FFNO_MAX_FF_LAYERS 4
+
+typedef enum {
+  FFNO_OK = 0,
+  FFNO_ERR_BAD_ARG = -1,      /* null pointer, inconsistent sizes */
+  FFNO_ERR_UNSUPPORTED = -2,  /* shape/option the CUDA path does not implement */
+  FFNO_ERR_CUDA = -3,         /* a CUDA runtime/driver call failed (message has the cudaError) */
+  FFNO_ERR_WORKSPACE = -4,    /* workspace too small */
+  FFNO_ERR_STATE = -5         /* e.g. forward before ffno_plan_load_params */
+} ffno_status;
+
+typedef enum {                /* SpectralConv2d `mode`, grid_2d.py:44,64,69 */
+  FFNO_MODE_FULL = 0,
+  FFNO_MODE_LOW_PASS = 1,
+  FFNO_MODE_NO_FOURIER = 2
+} ffno_spectral_mode;
+
+typedef enum {                /* which implementation a plan may use */
+  FFNO_PATH_AUTO = 0,         /* tcgen05 kernels when the shape qualifies, else the generic FP32 kernels */
+  FFNO_PATH_GENERIC = 1,      /* FP32 FFMA kernels only (any width / length / mode count) */
+  FFNO_PATH_UMMA = 2          /* tcgen05 kernels only; plan creation fails if the shape does not qualify */
+} ffno_path;
+
+/* Static description of one operator stack (everything except the batch size).
+ * Mirrors the constructor arguments of FNOFactorized2DBlock (grid_2d.py:103-107),
+ * FNOFactorizedMesh2D (mesh_2d.py:108-109) and FNOFactorizedMesh3D (mesh_3d.py:116-118). */
+typedef struct {
+  int32_t abi_version;            /* = FFNO_ABI_VERSION */
+  int32_t ndim;                   /* spatial axes: 2 or 3 */
+  int32_t size[FFNO_MAX_DIMS];    /* spatial extent of the INPUT, tensor-axis order (X, Y, Z) */
+  int32_t pad[FFNO_MAX_DIMS];     /* zeros appended on the high side of each axis after the lift
+                                     (mesh variants: 8, mesh_3d.py:120,165; periodic grid: 0) */
+  int32_t modes[FFNO_MAX_DIMS];   /* retained rfft bins per tensor axis */
+  int32_t width;                  /* C */
+  int32_t in_features;            /* width of the tensor given to forward (before grid append) */
+  int32_t append_grid;            /* 1: concatenate linspace(0,1,size_a) per axis (mesh_3d.py:178-189) */
+  int32_t out_features;           /* head output width (1, or output_dim) */
+  int32_t head_hidden;            /* 128 (grid_2d.py:150-152) */
+  int32_t n_layers;
+  int32_t ff_factor;              /* hidden = ff_factor * width (feedforward.py:11-12) */
+  int32_t n_ff_layers;            /* feedforward.py:10 (shipped configs: 2) */
+  int32_t layer_norm;             /* LayerNorm(width) on the FF output (feedforward.py:17) */
+  int32_t use_fork;               /* forecast fork (grid_2d.py:48,164-167) */
+  int32_t spectral_mode;          /* ffno_spectral_mode */
+  int32_t path;                   /* ffno_path */
+} ffno_desc;
+
+/* One WNLinear (modules/linear.py:41-51).  Either `weight` (plain nn.Linear) or weight_g+weight_v
+ * (torch weight_norm: w = g * v / ||v||_row, recomputed by the reference on every call). */
+typedef struct {
+  const float* weight;            /* [out, in] or NULL */
+  const float* weight_g;          /* [out] (stored [out,1]) or NULL */
+  const float* weight_v;          /* [out, in] or NULL */
+  const float* bias;              /* [out] or NULL */
+  int32_t in_features;
+  int32_t out_features;
+} ffno_linear_params;
+
+/* FeedForward (modules/feedforward.py:6-24): n_ff_layers linears (+ optional LayerNorm on the last) */
+typedef struct {
+  ffno_linear_params linear[FFNO_MAX_FF_LAYERS];
+  const float* ln_weight;         /* [width] or NULL */
+  const float* ln_bias;
+} ffno_ff_params;
+
+/* One spectral layer (SpectralConv2d, grid_2d.py:10-49).  fourier_weight is indexed by TENSOR AXIS
+ * (0 = X = first spatial axis), each [C, C, K_a, 2] fp32 with (re, im) innermost.  The host mirror
+ * resolves the reference's inconsistent ParameterList order (grid_2d: [0]->Y,[1]->X; mesh: [0]->X ...). */
+typedef struct {
+  const float* fourier_weight[FFNO_MAX_DIMS];
+  ffno_ff_params backcast_ff;
+  ffno_ff_params forecast_ff;     /* only read when use_fork */
+} ffno_layer_params;
+
+typedef struct {
+  ffno_linear_params in_proj;     /* lift, grid_2d.py:112,157 */
+  ffno_linear_params out0;        /* head, grid_2d.py:150-152: Linear(C,128) -> Linear(128,out), no activation */
+  ffno_linear_params out1;
+  const ffno_layer_params* layers;
+  int32_t n_layers;
+} ffno_block_params;
+
+/* Optional per-layer taps for per-layer parity (device pointers, any may be NULL). */
+typedef struct {
+  float* lift;                    /* [B, S.., C]   x after in_proj (+pad) */
+  float* const* x_after;          /* n_layers pointers: x after the residual of layer l */
+  float* const* spectral;         /* n_layers pointers: forward_fourier output of layer l */
+  float* b_last;                  /* backcast of the last layer (head input) */
+  float* const* forecast_list;    /* use_fork: n_layers pointers [B, S.., out_features] */
+} ffno_taps;
+
+typedef struct ffno_plan ffno_plan;
+
+FFNO_API const char* ffno_last_error(void);
+FFNO_API int ffno_abi_version(void);
+/* 1 if a CUDA device of compute capability 10.x is present and usable. */
+FFNO_API int ffno_device_ok(void);
+
+/* Plan lifetime.  Builds DFT tables (host double -> device) and reserves folded/packed weights. */
+FFNO_API int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan);
+FFNO_API int ffno_plan_destroy(ffno_plan* plan);
+/* 1 if the plan runs the tcgen05 (UMMA) kernels, 0 if it runs the generic FP32 kernels. */
+FFNO_API int ffno_plan_uses_umma(const ffno_plan* plan);
+
+/* Fold weight-norm (linear.py:49), re-layout spectral weights to per-mode real block matrices and
+ * (UMMA path) split to bf16 hi/lo operand tiles.  Call again whenever a parameter changes. */
+FFNO_API int ffno_plan_load_params(ffno_plan* plan, const ffno_block_params* params, void* stream);
+
+/* Bytes of scratch the forward needs for `batch` samples. */
+FFNO_API size_t ffno_workspace_bytes(const ffno_plan* plan, int32_t batch);
+
+/* Whole-stack forward: replaces FNOFactorized2DBlock.forward (grid_2d.py:154-177) and
+ * FNOFactorizedMesh2D/3D.forward (mesh_2d.py:149-165, mesh_3d.py:160-176).
+ *   x        [B, size.., in_features]
+ *   forecast [B, size.., out_features]
+ * taps may be NULL. */
+FFNO_API int ffno_block_fwd(ffno_plan* plan, const float* x, int32_t batch, float* forecast,
+                   const ffno_taps* taps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same through HOST buffers: copies x H2D, runs, copies forecast D2H, waits.  Device scratch is the
+ * caller's `workspace` (device) plus two staging areas carved from it; see ffno_workspace_bytes_host. */
+FFNO_API size_t ffno_workspace_bytes_host(const ffno_plan* plan, int32_t batch);
+FFNO_API int ffno_block_fwd_host(ffno_plan* plan, const float* x_host, int32_t batch, float* forecast_host,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Layer-level entry points (module-level drop-ins).  `layer` indexes the loaded parameters.
+ *   ffno_spectral_fwd   = SpectralConv2d.forward_fourier (grid_2d.py:51-99; mesh_3d.py:55-112)
+ *   ffno_ff_fwd         = FeedForward.forward (feedforward.py:21-24); which: 0 backcast, 1 forecast;
+ *                         if residual != NULL, y = residual + FF(s)  (grid_2d.py:169)
+ * x, s, y: [B, S.. (padded extent), C]. */
+FFNO_API int ffno_spectral_fwd(ffno_plan* plan, int32_t layer, const float* x, int32_t batch, float* s,
+                      void* workspace, size_t workspace_bytes, void* stream);
+FFNO_API int ffno_ff_fwd(ffno_plan* plan, int32_t layer, int32_t which, const float* s, const float* residual,
+                int32_t batch, float* y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stateless WNLinear.forward (modules/linear.py:41-51): y[rows, out] = act(x[rows, in] @ W^T + b).
+ * `scratch` (device, >= in*out*4 bytes) receives the folded, transposed weight. */
+FFNO_API int ffno_linear_fwd(const ffno_linear_params* lin, const float* x, int64_t rows, float* y, int32_t relu,
+                    void* scratch, size_t scratch_bytes, void* stream);
+/* nn.LayerNorm(C) over the last dim, eps 1e-5 (modules/feedforward.py:17). */
+FFNO_API int ffno_layernorm_fwd(const float* x, const float* weight, const float* bias, int64_t rows, int32_t C,
+                       float* y, void* stream);
+/* LpLoss.rel per sample (modules/loss.py:33-46): out[b] = ||x_b - y_b||_2 / ||y_b||_2 over n elements;
+ * element (b, i) of x lives at x[b*x_stride_b + i*x_stride_i] (same for y).  The mean over the (sharded)
+ * batch is the caller's one collective. */
+FFNO_API int ffno_rel_l2(const float* x, int64_t x_stride_b, int64_t x_stride_i, const float* y, int64_t y_stride_b,
+                int64_t y_stride_i, int32_t batch, int64_t n, float* out, void* stream);
+
+/* 10-step Markov rollout of Grid2DMarkovExperiment._valid_step (routines/grid_2d_markov.py:195-326)
+ * for the torus_li/markov configuration (use_position, should_normalize; 2-D periodic grid only):
+ *   frame0 [B, X, Y]        ground-truth vorticity fed to step 0
+ *   mean/std [in_features]  Normalizer statistics (modules/normalizer.py:68-77), host pointers
+ *   preds  [B, X, Y, n_steps]
+ * Each step: concat(frame, position grid linspace(low, high)) -> normalise -> stack forward ->
+ * de-normalise with channel 0.  The loss reduction is left to the caller (needs the targets). */
+FFNO_API int ffno_rollout_fwd(ffno_plan* plan, const float* frame0, int32_t batch, int32_t n_steps,
+                     const float* mean_host, const float* std_host, float low, float high,
+                     float* preds, void* workspace, size_t workspace_bytes, void* stream);
+FFNO_API size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch);
+
+/* Number of kernel launches the last ffno_block_fwd / ffno_rollout_fwd on this plan enqueued. */
+FFNO_API int64_t ffno_plan_last_launch_count(const ffno_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFNO_B200_H */

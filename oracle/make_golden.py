@@ -170,8 +170,39 @@ def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed):
     save(name, dict(kwargs, n_steps=n_steps), arrays)
 
 
+def init_case(M):
+    """Seeded-construction checksums: the mirrors must draw the same random numbers in the same order."""
+    cases = {
+        "FNOFactorized2DBlock": [
+            dict(modes=16, width=64, n_layers=3, input_dim=3, share_weight=True, factor=4,
+                 ff_weight_norm=True, gain=0.1),
+            dict(modes=4, width=32, n_layers=2, input_dim=5, share_weight=False, share_fork=True,
+                 use_fork=True, factor=2, ff_weight_norm=False, gain=1, layer_norm=True),
+        ],
+        "FNOFactorizedMesh2D": [dict(modes_x=6, modes_y=4, width=32, input_dim=4, n_layers=2,
+                                     share_weight=False, factor=4, ff_weight_norm=True, n_ff_layers=2,
+                                     layer_norm=False)],
+        "FNOFactorizedMesh3D": [dict(modes_x=4, modes_y=3, modes_z=2, width=32, input_dim=4, output_dim=4,
+                                     n_layers=2, share_weight=True, factor=4, ff_weight_norm=True,
+                                     n_ff_layers=2, layer_norm=False)],
+    }
+    out = []
+    for cls, kws in cases.items():
+        for i, kw in enumerate(kws):
+            torch.manual_seed(1234 + i)
+            m = getattr(M, cls)(**kw)
+            sd = m.state_dict()
+            out.append({"cls": cls, "kwargs": kw, "seed": 1234 + i,
+                        "keys": {k: [list(v.shape), float(v.double().sum()), float(v.double().abs().sum())]
+                                 for k, v in sd.items()}})
+    with open(os.path.join(OUT, "init_parity.json"), "w") as f:
+        json.dump(out, f)
+    print("init_parity.json written")
+
+
 def main():
     M, LpLoss = import_reference()
+    init_case(M)
     c2 = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4,
               ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0)
     # (1) the C2 architecture on a reduced grid (32x32 keeps modes=16 legal: 17 rfft bins)

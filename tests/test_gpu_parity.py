@@ -1,0 +1,251 @@
+"""GPU (B200): parity of the CUDA path, called through the C ABI via the nn.Module mirrors, against
+(a) the committed golden fixtures produced by the executed reference and (b) the CPU oracle on seeded
+inputs, plus size-independent properties at the full BASELINE sizes.
+
+Tolerances: the north star allows rtol 1e-4 (fp32) per layer and per 10-step rollout, measured as
+max|y-ref| / max|ref|.  The generic FP32 kernels are held to 1e-5; the tcgen05 path
+(3xBF16 split, fp32 accumulate) to 1e-4.
+"""
+import os
+
+import pytest
+import torch
+
+from golden_util import load, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_GENERIC = 1e-5
+TOL_UMMA = 1e-4
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fourierflow_b200 import _lib
+    assert _lib.load().ffno_device_ok() == 1, "libffno_b200 does not see an sm_100 device"
+
+
+def M():
+    import fourierflow_b200.modules as m
+    return m
+
+
+def build(cls, kw, sd):
+    m = getattr(M(), cls)(**kw)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval()
+
+
+def tol_for(plan):
+    return TOL_UMMA if plan.uses_umma else TOL_GENERIC
+
+
+PATHS = ["generic", "auto"]
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name", ["grid2d_c2arch_32", "grid2d_gain1_unshared", "grid2d_ln_w32", "grid2d_fork",
+                                  "grid2d_lowpass", "grid2d_nofourier", "grid2d_nyquist"])
+def test_grid2d_block_golden_per_layer(name, path, monkeypatch):
+    monkeypatch.setenv("FFNO_B200_PATH", path)
+    kw, sd, a = load(name)
+    m = build("FNOFactorized2DBlock", kw, sd)
+    x = a["x"].cuda()
+    with torch.no_grad():
+        out = m(x)
+        fc, taps = m.forward_with_taps(x)
+    plan = m.plan_for(x.device, x.shape[1:3])
+    tol = tol_for(plan)
+    errs = {"forecast": rel_err(out["forecast"], a["forecast"])}
+    assert torch.equal(out["forecast"], fc)
+    for i, f in enumerate(out["forecast_list"]):
+        errs[f"forecast_list{i}"] = rel_err(f, a[f"forecast_list{i}"])
+    errs["lift"] = rel_err(taps["lift"], a["tap_lift"])
+    for l in range(kw["n_layers"]):
+        errs[f"x{l}"] = rel_err(taps["x"][l], a[f"tap_x{l}"])
+    errs["b_last"] = rel_err(taps["b_last"], a["tap_b_last"])
+    if "tap_s0" in a:
+        errs["s0"] = rel_err(taps["s"][0], a["tap_s0"])
+    print(name, path, "umma" if plan.uses_umma else "generic", {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_c2_24_layer_stack_golden(path, monkeypatch):
+    monkeypatch.setenv("FFNO_B200_PATH", path)
+    kw, sd, a = load("grid2d_c2_24layers_32")
+    m = build("FNOFactorized2DBlock", kw, sd)
+    with torch.no_grad():
+        out = m(a["x"].cuda())["forecast"]
+    plan = m.plan_for(out.device, a["x"].shape[1:3])
+    e = rel_err(out, a["forecast"])
+    print("24 layers", path, f"{e:.2e}")
+    assert e < tol_for(plan)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name,cls", [("mesh2d_small", "FNOFactorizedMesh2D"), ("mesh3d_small", "FNOFactorizedMesh3D"),
+                                      ("mesh3d_w64", "FNOFactorizedMesh3D")])
+def test_mesh_blocks_golden(name, cls, path, monkeypatch):
+    monkeypatch.setenv("FFNO_B200_PATH", path)
+    kw, sd, a = load(name)
+    m = build(cls, kw, sd)
+    with torch.no_grad():
+        out = m(a["x"].cuda())
+    assert out.shape == a["out"].shape
+    e = rel_err(out, a["out"])
+    print(name, path, f"{e:.2e}")
+    assert e < TOL_UMMA if path == "auto" else e < TOL_GENERIC
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_spectral_layer_c2_shape_golden(path, monkeypatch):
+    """SpectralConv2d.forward_fourier at N=64, K=16, C=64 through ffno_spectral_fwd."""
+    monkeypatch.setenv("FFNO_B200_PATH", path)
+    from fourierflow_b200.modules.factorized_fno.grid_2d import SpectralConv2d
+    kw, sd, a = load("spectral_c2_layer")
+    layer = SpectralConv2d(in_dim=64, out_dim=64, n_modes=16, forecast_ff=None, backcast_ff=None,
+                           fourier_weight=None, factor=4, ff_weight_norm=True, n_ff_layers=2, layer_norm=False,
+                           use_fork=False, dropout=0.0, mode="full")
+    layer.load_state_dict(sd, strict=False)
+    layer = layer.cuda().eval()
+    with torch.no_grad():
+        s = layer.forward_fourier(a["x"].cuda())
+    e = rel_err(s, a["s"])
+    print("spectral", path, f"{e:.2e}")
+    assert e < TOL_UMMA if path == "auto" else e < TOL_GENERIC
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_rollout_golden(path, monkeypatch):
+    """10-step Markov rollout (normalise → stack → de-normalise, feeding back) vs the reference-driven fixture."""
+    monkeypatch.setenv("FFNO_B200_PATH", path)
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    kw, sd, a = load("rollout_c2arch_16")
+    n_steps = kw.pop("n_steps")
+    conv = build("FNOFactorized2DBlock", kw, sd)
+    exp = Grid2DMarkovExperiment(conv, n_steps=n_steps).cuda().eval()
+    exp.normalizer.sum.copy_(a["norm_sum"])
+    exp.normalizer.sum_squared.copy_(a["norm_sum_squared"])
+    exp.normalizer.count.copy_(a["norm_count"])
+    with torch.no_grad():
+        loss, step_losses, preds, _ = exp({"data": a["data"].cuda()})
+    e = rel_err(preds, a["preds"])
+    print("rollout", path, f"preds {e:.2e} loss {loss.item():.6f} vs {a['loss'].item():.6f}")
+    assert e < TOL_UMMA
+    assert abs(loss.item() - a["loss"].item()) < 1e-4 * abs(a["loss"].item())
+    assert rel_err(torch.stack(step_losses), a["step_losses"]) < 1e-4
+
+
+def _c2_model(n_layers=24, seed=0):
+    torch.manual_seed(seed)
+    return M().FNOFactorized2DBlock(modes=16, width=64, n_layers=n_layers, input_dim=3, share_weight=True, factor=4,
+                                    ff_weight_norm=True, gain=0.1).eval()
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_c2_against_oracle_on_seeded_inputs(path, monkeypatch):
+    """C2 architecture, 64x64 grid, B=2, 4 layers: CUDA vs the CPU oracle run here on the same inputs."""
+    monkeypatch.setenv("FFNO_B200_PATH", path)
+    from oracle import ffno_oracle as O
+    m = _c2_model(n_layers=4, seed=3)
+    x = torch.randn(2, 64, 64, 3, generator=torch.Generator().manual_seed(4))
+    taps = {}
+    ref = O.block_grid2d_forward({k: v.detach() for k, v in m.state_dict().items()}, x, modes=16, n_layers=4, taps=taps)
+    mc = m.cuda()
+    with torch.no_grad():
+        fc, t = mc.forward_with_taps(x.cuda())
+    tol = tol_for(mc.plan_for(fc.device, (64, 64)))
+    assert rel_err(fc, ref["forecast"]) < tol
+    for l in range(4):
+        assert rel_err(t["x"][l], taps[f"x{l}"]) < tol
+        assert rel_err(t["s"][l], taps[f"s{l}"]) < tol
+
+
+def test_full_size_c2_properties():
+    """BASELINE size (B=32, 64x64, 24 layers): properties that need no oracle run —
+    batch independence/permutation equivariance, determinism, generic-vs-fast-path agreement,
+    and linearity of the spectral operator."""
+    m = _c2_model().cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(32, 64, 64, 3, device="cuda", generator=g)
+    with torch.no_grad():
+        y = m(x)["forecast"]
+        assert torch.equal(y, m(x)["forecast"])                              # deterministic
+        perm = torch.randperm(32, device="cuda", generator=g)
+        assert rel_err(m(x[perm])["forecast"], y[perm]) < 1e-6               # samples are independent units
+        assert rel_err(m(x[:5])["forecast"], y[:5]) < 1e-6                   # ragged batch
+        os.environ["FFNO_B200_PATH"] = "generic"
+        try:
+            yg = m(x)["forecast"]
+        finally:
+            os.environ.pop("FFNO_B200_PATH")
+        e = rel_err(y, yg)
+        print("full-size auto vs generic", f"{e:.2e}")
+        assert e < TOL_UMMA
+        layer = m.spectral_layers[0]
+        a = torch.randn(4, 64, 64, 64, device="cuda", generator=g)
+        b = torch.randn(4, 64, 64, 64, device="cuda", generator=g)
+        lin = layer.forward_fourier(2.0 * a - 3.0 * b)
+        assert rel_err(lin, 2.0 * layer.forward_fourier(a) - 3.0 * layer.forward_fourier(b)) < TOL_UMMA
+        # a constant field only excites the DC bin of each axis: output is constant over the grid
+        c = torch.ones(1, 64, 64, 64, device="cuda") * torch.randn(64, device="cuda", generator=g)
+        sc = layer.forward_fourier(c)
+        assert (sc - sc[:, :1, :1, :]).abs().max() < 1e-4 * sc.abs().max()
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    m = _c2_model(n_layers=2).cuda()
+    x = torch.randn(3, 64, 64, 3).pin_memory()
+    out = torch.empty(3, 64, 64, 1).pin_memory()
+    with torch.no_grad():
+        plan = m.plan_for(torch.device("cuda", torch.cuda.current_device()), (64, 64))
+        plan.block_forward_host(x, out)
+        y = m(x.cuda())["forecast"]
+    assert torch.equal(out.cuda(), y)
+
+
+def test_edge_cases():
+    m = _c2_model(n_layers=1).cuda()
+    with torch.no_grad():
+        assert m(torch.empty(0, 64, 64, 3, device="cuda"))["forecast"].shape == (0, 64, 64, 1)     # empty batch
+        x = torch.randn(2, 3, 64, 64, device="cuda").permute(0, 2, 3, 1)                              # non-contiguous
+        assert rel_err(m(x)["forecast"], m(x.contiguous())["forecast"]) == 0.0
+        with pytest.raises(RuntimeError):
+            m(torch.randn(1, 64, 64, 4, device="cuda"))                                              # wrong feature count
+        with pytest.raises(RuntimeError, match="rfft bins"):
+            m(torch.randn(1, 8, 8, 3, device="cuda"))                                                # modes 16 > 8//2+1
+    with pytest.raises(RuntimeError, match="forward pass only"):
+        m(torch.randn(1, 64, 64, 3, device="cuda"))                                                  # grad mode on
+
+
+def test_params_resync_after_inplace_update():
+    """The reference re-folds weight-norm on every call; the plan must notice in-place parameter edits."""
+    m = _c2_model(n_layers=1).cuda()
+    x = torch.randn(1, 64, 64, 3, device="cuda")
+    with torch.no_grad():
+        y0 = m(x)["forecast"].clone()
+        m.spectral_layers[0].backcast_ff.layers[0][0].weight_g.mul_(1.5)
+        y1 = m(x)["forecast"]
+    assert rel_err(y1, y0) > 1e-3
+
+
+def test_submodules_standalone_vs_oracle():
+    from oracle import ffno_oracle as O
+    mods = M()
+    torch.manual_seed(9)
+    ff = mods.FeedForward(64, 4, True, 2, True, 0.0).eval()
+    lin = mods.WNLinear(5, 12, wnorm=True).eval()
+    x = torch.randn(3, 7, 64)
+    ref = O.feed_forward({k: v.detach() for k, v in ff.state_dict().items()}, "", x, 2, True)
+    refl = torch.nn.functional.linear(torch.randn(4, 5, generator=torch.Generator().manual_seed(1)), lin.weight, lin.bias)
+    with torch.no_grad():
+        assert rel_err(ff.cuda()(x.cuda()), ref) < TOL_GENERIC
+        xl = torch.randn(4, 5, generator=torch.Generator().manual_seed(1))
+        assert rel_err(lin.cuda()(xl.cuda()), refl.detach()) < TOL_GENERIC
+    a, b = torch.randn(6, 50, 3), torch.randn(6, 50, 3)
+    got = mods.LpLoss().rel(a.cuda()[..., 1], b.cuda()[..., 1])
+    assert abs(got.item() - O.lp_loss_rel(a[..., 1], b[..., 1]).item()) < 1e-6

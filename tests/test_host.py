@@ -1,0 +1,169 @@
+"""CPU: host-side logic and the C-ABI boundary (no GPU compute): symbols, struct layout, state_dict
+schema / seeded init parity against the executed reference, loud failure without a device."""
+import copy
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+import torch
+
+from golden_util import GOLDEN, load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ffno_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fourierflow_b200 import build, _lib
+    build.build()                      # no-op when up to date
+    return _lib.load()
+
+
+def _header_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"FFNO_API\s+[\w\s\*]+?\b(ffno_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from fourierflow_b200 import _lib
+    declared = _header_symbols()
+    assert len(declared) >= 19
+    assert sorted(_lib.EXPORTS) == declared            # binding covers the header exactly
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (ffno_\w+)", nm))
+    assert set(declared) <= exported
+    assert lib.ffno_abi_version() == _lib.ABI_VERSION
+
+
+def test_ctypes_structs_match_the_c_header():
+    """sizeof/offsetof of every ABI struct as gcc sees the header == the ctypes mirror."""
+    from fourierflow_b200 import _lib
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "ffno_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ffno_desc), sizeof(ffno_linear_params), sizeof(ffno_ff_params),
+         sizeof(ffno_layer_params), sizeof(ffno_block_params), sizeof(ffno_taps));
+  printf("%zu %zu %zu %zu\n", offsetof(ffno_desc, width), offsetof(ffno_desc, path),
+         offsetof(ffno_layer_params, forecast_ff), offsetof(ffno_block_params, layers));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
+        open(src, "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    sizes = [C.sizeof(t) for t in (_lib.Desc, _lib.LinearParams, _lib.FFParams, _lib.LayerParams,
+                                   _lib.BlockParams, _lib.Taps)]
+    offs = [_lib.Desc.width.offset, _lib.Desc.path.offset, _lib.LayerParams.forecast_ff.offset,
+            _lib.BlockParams.layers.offset]
+    assert [int(v) for v in out] == sizes + offs
+
+
+def test_plan_create_fails_loudly_without_a_device(lib):
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from fourierflow_b200 import _lib
+    d = _lib.Desc()
+    d.abi_version, d.ndim = _lib.ABI_VERSION, 2
+    d.size[0] = d.size[1] = 16
+    d.modes[0] = d.modes[1] = 4
+    d.width, d.in_features, d.out_features, d.head_hidden = 32, 3, 1, 128
+    d.n_layers, d.ff_factor, d.n_ff_layers = 1, 4, 2
+    plan = C.c_void_p()
+    st = lib.ffno_plan_create(C.byref(d), C.byref(plan))
+    assert st == -3 and not plan.value                         # FFNO_ERR_CUDA, never a CPU fallback
+    assert b"cuda" in lib.ffno_last_error().lower()
+    assert lib.ffno_device_ok() == 0
+
+
+def test_plan_create_rejects_bad_descriptors(lib):
+    from fourierflow_b200 import _lib
+    d = _lib.Desc()
+    plan = C.c_void_p()
+    assert lib.ffno_plan_create(C.byref(d), C.byref(plan)) == -1          # wrong ABI version
+    d.abi_version, d.ndim = _lib.ABI_VERSION, 2
+    d.size[0], d.size[1], d.modes[0], d.modes[1] = 40, 40, 32, 4
+    d.width, d.in_features, d.out_features, d.head_hidden = 64, 3, 1, 128
+    d.n_layers, d.ff_factor, d.n_ff_layers = 1, 4, 2
+    # modes 32 on a 40-long axis has only 21 rfft bins: the reference raises too
+    assert lib.ffno_plan_create(C.byref(d), C.byref(plan)) == -1
+    assert b"rfft bins" in lib.ffno_last_error()
+
+
+def _cls(name):
+    import fourierflow_b200.modules as M
+    return getattr(M, name)
+
+
+def test_seeded_init_matches_reference():
+    cases = json.load(open(os.path.join(GOLDEN, "init_parity.json")))
+    for c in cases:
+        torch.manual_seed(c["seed"])
+        m = _cls(c["cls"])(**c["kwargs"])
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(c["keys"].keys()), c["cls"]
+        for k, (shape, s, a) in c["keys"].items():
+            v = sd[k].double()
+            assert list(v.shape) == shape, k
+            assert abs(v.sum().item() - s) <= 1e-6 * max(1.0, a), k
+            assert abs(v.abs().sum().item() - a) <= 1e-6 * max(1.0, a), k
+
+
+@pytest.mark.parametrize("name,cls", [("grid2d_c2arch_32", "FNOFactorized2DBlock"),
+                                      ("grid2d_fork", "FNOFactorized2DBlock"),
+                                      ("grid2d_ln_w32", "FNOFactorized2DBlock"),
+                                      ("mesh2d_small", "FNOFactorizedMesh2D"),
+                                      ("mesh3d_w64", "FNOFactorizedMesh3D")])
+def test_reference_checkpoints_load_strict(name, cls):
+    kw, sd, _ = load(name)
+    m = _cls(cls)(**kw)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    m2 = copy.deepcopy(m)                                      # SWA deep-copies the routine (linear.py:53-79)
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2) and v1.data_ptr() != v2.data_ptr()
+    if "fourier_weight.0" in sd:                               # shared ParameterList stays shared
+        assert m.spectral_layers[0].fourier_weight[0] is m.fourier_weight[0]
+        assert m2.spectral_layers[1].fourier_weight[0] is m2.fourier_weight[0]
+
+
+def test_weight_property_folds_weight_norm():
+    from fourierflow_b200.modules import WNLinear
+    from oracle.ffno_oracle import weight_norm_fold
+    lin = WNLinear(8, 5, wnorm=True)
+    with torch.no_grad():
+        lin.weight_g.mul_(1.7)
+    assert torch.allclose(lin.weight, weight_norm_fold(lin.weight_g, lin.weight_v))
+    assert list(lin.state_dict().keys()) == ["bias", "weight_g", "weight_v"]
+    assert list(WNLinear(8, 5).state_dict().keys()) == ["weight", "bias"]
+
+
+def test_forward_refuses_cpu_tensors_and_autograd():
+    m = _cls("FNOFactorized2DBlock")(modes=4, width=32, n_layers=1, input_dim=3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        with torch.no_grad():
+            m(torch.randn(1, 8, 8, 3))
+    with pytest.raises(RuntimeError, match="dropout"):
+        _cls("FNOFactorized2DBlock")(modes=4, width=32, dropout=0.1)
+
+
+def test_normalizer_mirror_matches_oracle():
+    from fourierflow_b200.modules import Normalizer
+    from oracle import ffno_oracle as O
+    n = Normalizer([3], 1e6)
+    x = torch.randn(5, 4, 4, 3)
+    n.train()
+    y = n(x)
+    mean, std = O.normalizer_mean_std(O.normalizer_stats(x))
+    assert torch.allclose(n.mean, mean) and torch.allclose(n.std, std)
+    assert torch.allclose(y, (x - mean) / std)
+    n.eval()
+    assert torch.allclose(n.inverse(y[..., :1], channel=0), x[..., :1], atol=1e-5)
+    assert set(n.state_dict()) == {"count", "n_accumulations", "sum", "sum_squared", "one", "std_epsilon"}
