@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "generic_kernels.cuh"
+#include "umma_kernels.cuh"
 #include "umma_path.cuh"
 
 namespace ffno {
@@ -606,6 +607,12 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
   }
   p->last_launches = g_launch_counter - before;
   return FFNO_OK;
+}
+
+int ffno_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int32_t N, int32_t K, int32_t a_mn,
+                       int32_t b_mn, int32_t variant, void* stream) {
+  FFNO_REQUIRE(A && B && D, FFNO_ERR_BAD_ARG, "NULL argument");
+  return launch_umma_selftest(A, B, D, N, K, a_mn, b_mn, variant, static_cast<cudaStream_t>(stream));
 }
 
 int64_t ffno_plan_last_launch_count(const ffno_plan* plan) { return plan ? plan->last_launches : 0; }

@@ -1,0 +1,36 @@
+// tcgen05 kernels of the F-FNO layer for width C = 64, FF factor 4 (hidden 256): declarations.
+#pragma once
+#include "common.cuh"
+
+namespace ffno {
+
+constexpr int kUmmaC = 64;
+constexpr int kUmmaH = 256;
+constexpr int kFFImageBytes = 131072;        // W1 hi|lo (32 KB each) + W2 hi|lo (32 KB each), smem image
+constexpr int kMixImageBytes = 65536;        // per (axis, mode): B hi (32 KB) | B lo (32 KB), smem image
+
+// w1t [64][256], w2t [256][64] (folded, transposed FP32) -> bf16 hi/lo operand image (K-major, SWIZZLE_128B)
+int launch_pack_ff_image(const float* w1t, const float* w2t, uint8_t* image, cudaStream_t st);
+// Wblk [K][128][128] (real block form of the complex mode weights) -> K images of kMixImageBytes
+int launch_pack_mix_image(const float* wblk, uint8_t* image, int K, cudaStream_t st);
+
+// x_out[p] = residual[p] + W2 relu(W1 s[p] + b1) + b2,  b_out[p] = the FF output (either may be NULL)
+int launch_ff_umma(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,
+                   const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st);
+
+// Per-mode complex channel mix of one or more axes in one launch.
+struct MixAxis {
+  const float* F;
+  float* R;
+  const uint8_t* image;   // K images
+  long long outer, p_inner;
+  int K;
+};
+int launch_mix_umma(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st);
+
+// Diagnostics: D[128][N] = A[128][K] * B[N][K]^T with bf16 inputs (raw ushort), one CTA, every layout variant
+// the kernels rely on (a_mn / b_mn: operand stored MN-major; variant: LBO/SBO interpretation under test).
+int launch_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int N, int K, int a_mn, int b_mn,
+                         int variant, cudaStream_t st);
+
+}  // namespace ffno

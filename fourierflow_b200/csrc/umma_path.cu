@@ -1,19 +1,155 @@
-// tcgen05 (UMMA) fast path — placeholder until the kernels land; every shape reports "unsupported"
-// so plans fall back to the generic FP32 CUDA kernels (still CUDA, never CPU).
+// tcgen05 (UMMA) fast path of the F-FNO layer for width 64 / FF factor 4: state, parameter images, dispatch.
+//
+// v1 pipeline per layer (2-D: 7 launches):
+//   per axis:  truncated forward DFT (FP32 table kernel)  ->  per-mode complex mix on tcgen05 (3xBF16)
+//              ->  truncated inverse DFT accumulated into s (FP32 table kernel)
+//   then:      FeedForward + residual on tcgen05 (3xBF16, hidden activations never leave the SM)
+#include <map>
+#include <vector>
+
+#include "generic_kernels.cuh"
+#include "umma_kernels.cuh"
 #include "umma_path.cuh"
 
 namespace ffno {
-struct UmmaState {};
-bool umma_supported(const ffno_desc*, const int*) { return false; }
-const char* umma_why_not(const ffno_desc*, const int*) { return "tcgen05 path not built yet"; }
-int umma_create(UmmaState**, const ffno_desc*, const int*) { return set_error(FFNO_ERR_UNSUPPORTED, "no umma"); }
-void umma_destroy(UmmaState*) {}
-int umma_load_params(UmmaState*, const UmmaLayerSrc*, float* const*, float* const*, cudaStream_t) { return FFNO_OK; }
+
+struct UmmaLayer {
+  uint8_t* mix_image[3] = {nullptr, nullptr, nullptr};
+  uint8_t* ff_image = nullptr;
+  const float* b1 = nullptr;
+  const float* b2 = nullptr;
+};
+
+struct UmmaState {
+  ffno_desc d;
+  int ext[3];
+  int sm_count = 148;
+  std::vector<UmmaLayer> layers;
+  std::vector<void*> owned;
+  std::map<std::pair<const void*, int>, uint8_t*> mix_cache;   // (source, axis) -> image
+  std::map<const void*, uint8_t*> ff_cache;
+  float* d_fwd[3] = {nullptr, nullptr, nullptr};
+  float* d_inv[3] = {nullptr, nullptr, nullptr};
+};
+
+const char* umma_why_not(const ffno_desc* d, const int*) {
+  if (d->width != kUmmaC) return "width != 64";
+  if (d->ff_factor != 4) return "ff_factor != 4";
+  if (d->n_ff_layers != 2) return "n_ff_layers != 2";
+  if (d->layer_norm) return "layer_norm";
+  if (d->use_fork) return "use_fork";
+  if (d->spectral_mode == FFNO_MODE_NO_FOURIER) return "mode no-fourier";
+  return nullptr;
+}
+bool umma_supported(const ffno_desc* d, const int* ext) { return umma_why_not(d, ext) == nullptr; }
+
+int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]) {
+  UmmaState* s = new UmmaState();
+  s->d = *d;
+  for (int a = 0; a < 3; ++a) s->ext[a] = ext[a];
+  int dev = 0;
+  FFNO_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  FFNO_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    delete s;
+    return set_error(FFNO_ERR_UNSUPPORTED, "tcgen05 path needs compute capability 10.x, device is %d.%d", prop.major,
+                     prop.minor);
+  }
+  s->sm_count = prop.multiProcessorCount;
+  s->layers.resize(d->n_layers);
+  *out = s;
+  return FFNO_OK;
+}
+
+void umma_destroy(UmmaState* s) {
+  if (!s) return;
+  for (void* p : s->owned) cudaFree(p);
+  delete s;
+}
+
+static int alloc_bytes(UmmaState* s, size_t bytes, uint8_t** out) {
+  void* p = nullptr;
+  FFNO_CUDA_CHECK(cudaMalloc(&p, bytes));
+  s->owned.push_back(p);
+  *out = static_cast<uint8_t*>(p);
+  return FFNO_OK;
+}
+
+int umma_load_params(UmmaState* s, const UmmaLayerSrc* layers, float* const d_fwd[3], float* const d_inv[3],
+                     cudaStream_t st) {
+  for (int a = 0; a < 3; ++a) { s->d_fwd[a] = d_fwd[a]; s->d_inv[a] = d_inv[a]; }
+  std::map<std::pair<const void*, int>, bool> mix_done;
+  std::map<const void*, bool> ff_done;
+  for (int l = 0; l < s->d.n_layers; ++l) {
+    UmmaLayer& L = s->layers[l];
+    const UmmaLayerSrc& src = layers[l];
+    if (s->d.spectral_mode == FFNO_MODE_FULL) {
+      for (int a = 0; a < s->d.ndim; ++a) {
+        auto key = std::make_pair((const void*)src.wmix[a], a);
+        uint8_t*& img = s->mix_cache[key];
+        if (!img) FFNO_TRY(alloc_bytes(s, (size_t)s->d.modes[a] * kMixImageBytes, &img));
+        if (!mix_done[key]) {
+          FFNO_TRY(launch_pack_mix_image(src.wmix[a], img, s->d.modes[a], st));
+          mix_done[key] = true;
+        }
+        L.mix_image[a] = img;
+      }
+    }
+    uint8_t*& img = s->ff_cache[(const void*)src.w1t];
+    if (!img) FFNO_TRY(alloc_bytes(s, kFFImageBytes, &img));
+    if (!ff_done[(const void*)src.w1t]) {
+      FFNO_TRY(launch_pack_ff_image(src.w1t, src.w2t, img, st));
+      ff_done[(const void*)src.w1t] = true;
+    }
+    L.ff_image = img;
+    L.b1 = src.b1;
+    L.b2 = src.b2;
+  }
+  return FFNO_OK;
+}
+
 size_t umma_workspace_floats(const UmmaState*, int) { return 0; }
-int umma_layer_fwd(UmmaState*, int, const float*, int, float*, float*, float*, float*, float*, float*, bool, bool,
-                   cudaStream_t) { return set_error(FFNO_ERR_UNSUPPORTED, "no umma"); }
-int umma_spectral_fwd(UmmaState*, int, const float*, int, float*, float*, float*, float*, cudaStream_t) {
-  return set_error(FFNO_ERR_UNSUPPORTED, "no umma"); }
-int umma_ff_fwd(UmmaState*, int, const float*, const float*, int, float*, float*, cudaStream_t) {
-  return set_error(FFNO_ERR_UNSUPPORTED, "no umma"); }
+
+int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R, float*,
+                      cudaStream_t st) {
+  const UmmaLayer& L = s->layers[layer];
+  bool first = true;
+  for (int a = s->d.ndim - 1; a >= 0; --a) {
+    long long outer = batch, p_inner = 1;
+    for (int i = 0; i < a; ++i) outer *= s->ext[i];
+    for (int i = a + 1; i < s->d.ndim; ++i) p_inner *= s->ext[i];
+    const int Ln = s->ext[a], K = s->d.modes[a];
+    const long long inner = p_inner * kUmmaC;
+    FFNO_TRY(launch_axis_transform(x, s->d_fwd[a], F, outer, Ln, 2 * K, inner, false, st));
+    const float* src = F;
+    if (s->d.spectral_mode == FFNO_MODE_FULL) {
+      MixAxis ax{F, R, L.mix_image[a], outer, p_inner, K};
+      FFNO_TRY(launch_mix_umma(&ax, 1, s->sm_count, st));
+      src = R;
+    }
+    FFNO_TRY(launch_axis_transform(src, s->d_inv[a], s_out, outer, 2 * K, Ln, inner, !first, st));
+    first = false;
+  }
+  return FFNO_OK;
+}
+
+int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* y, float*,
+                cudaStream_t st) {
+  const UmmaLayer& L = s->layers[layer];
+  long long P = batch;
+  for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
+  if (residual) return launch_ff_umma(s_in, residual, y, nullptr, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  return launch_ff_umma(s_in, nullptr, nullptr, y, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+}
+
+int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_next, float* s_out, float* b_out,
+                   float* F, float* R, float* ws, bool /*want_s*/, bool want_b, cudaStream_t st) {
+  const UmmaLayer& L = s->layers[layer];
+  FFNO_TRY(umma_spectral_fwd(s, layer, x, batch, s_out, F, R, ws, st));
+  long long P = batch;
+  for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
+  return launch_ff_umma(s_out, x, x_next, want_b ? b_out : nullptr, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+}
+
 }  // namespace ffno

@@ -198,6 +198,12 @@ FFNO_API int ffno_rollout_fwd(ffno_plan* plan, const float* frame0, int32_t batc
                      float* preds, void* workspace, size_t workspace_bytes, void* stream);
 FFNO_API size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch);
 
+/* Diagnostics: one tcgen05 product D[128][N] = A[128][K] * B[N][K]^T (bf16 bit patterns in, FP32 out) through
+ * the operand layouts / descriptors the kernels use (a_mn / b_mn: operand stored MN-major; variant selects the
+ * LBO/SBO convention under test).  Used by tests/test_gpu_umma.py to pin the layout conventions on hardware. */
+FFNO_API int ffno_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int32_t N, int32_t K, int32_t a_mn,
+                       int32_t b_mn, int32_t variant, void* stream);
+
 /* Number of kernel launches the last ffno_block_fwd / ffno_rollout_fwd on this plan enqueued. */
 FFNO_API int64_t ffno_plan_last_launch_count(const ffno_plan* plan);
 
