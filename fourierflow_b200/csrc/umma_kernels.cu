@@ -463,6 +463,207 @@ int launch_mix_umma(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t 
 }
 
 // =======================================================================================================
+// Truncated real DFT along a strided axis (forward: torch.fft.rfft(...)[:K] at grid_2d.py:58,76; inverse:
+// torch.fft.irfft of the zero-padded bins at :72,:90) as a tcgen05 product against a host-built table.
+//   tile = 2 groups of 64 consecutive `inner` elements (M = 128), K = the transformed axis in chunks of 64,
+//   N = npad output rows.  The X tile is already "MN-major" in memory (for a fixed axis index the 64 inner
+//   elements are contiguous), so it is split to bf16 and stored without any transpose.
+// =======================================================================================================
+constexpr int AX_SMEM_A = 0;                       // hi 16 KB | lo 16 KB : [mb 2][kg 8][8 x 128 B]
+constexpr int AX_SMEM_BAR = 32768;
+constexpr int AX_SMEM_B = 32768 + 1024;            // table image (1024-aligned)
+
+size_t table_image_bytes(int n_in, int n_out) {
+  const int npad = (n_out + 15) / 16 * 16, kchunks = (n_in + 63) / 64;
+  return (size_t)2 * kchunks * npad * 128;
+}
+
+__global__ void __launch_bounds__(256)
+pack_table_image_kernel(const float* __restrict__ T, int ldt, int n_in, int n_out, int npad, int kchunks,
+                        uint8_t* __restrict__ image) {
+  const int total = kchunks * 64 * npad;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = idx % npad, i = idx / npad;
+  const float v = (i < n_in && j < n_out) ? T[(long long)i * ldt + j] : 0.f;
+  const uint32_t half = (uint32_t)kchunks * npad * 128u;
+  const uint32_t off = (uint32_t)(i / 64) * ((uint32_t)npad * 128u) + kmajor_sw128_offset(j, i % 64);
+  __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  *reinterpret_cast<__nv_bfloat16*>(image + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(image + half + off) = lo;
+}
+
+int launch_pack_table_image(const float* T, int ldt, int n_in, int n_out, uint8_t* image, cudaStream_t st) {
+  const int npad = (n_out + 15) / 16 * 16, kchunks = (n_in + 63) / 64;
+  const int total = kchunks * 64 * npad;
+  pack_table_image_kernel<<<ceil_div(total, 256), 256, 0, st>>>(T, ldt, n_in, n_out, npad, kchunks, image);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("pack_table_image_kernel");
+  return FFNO_OK;
+}
+
+__global__ void __launch_bounds__(128, 2) axis_umma_kernel(AxisXform p, int n_tiles, int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sAh = smem + AX_SMEM_A;
+  uint8_t* sAl = sAh + 16384;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + AX_SMEM_BAR);
+  uint64_t* bar_mma = bar_w + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+  uint8_t* sB = smem + AX_SMEM_B;
+  const uint32_t b_half = (uint32_t)p.kchunks * p.npad * 128u;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  if (tid == 0) {
+    const uint32_t total = 2u * b_half;
+    mbar_expect_tx(bar_w, total);
+    for (uint32_t off = 0; off < total; off += 32768u) {
+      const uint32_t n = (total - off) < 32768u ? (total - off) : 32768u;
+      bulk_g2s(sB + off, p.table + off, n, bar_w);
+    }
+  }
+  const uint32_t idesc = make_idesc_bf16(128, p.npad, /*a_mn=*/1, /*b_mn=*/0);
+  const long long gpi = p.inner >> 6;                 // 64-element groups per outer index
+  const long long n_groups = p.outer * gpi;
+  uint32_t phase = 0;
+  bool w_ready = false;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long G0 = (long long)tile * 2;
+#pragma unroll 1
+    for (int kc = 0; kc < p.kchunks; ++kc) {
+      // ---- X chunk (64 axis indices x 128 inner elements) -> bf16 hi/lo, MN-major SW128 ----------------
+      {
+        float4 v[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int idx = it * 128 + tid, il = idx >> 5, gsel = (idx >> 4) & 1, c4 = idx & 15;
+          const long long G = G0 + gsel;
+          const int i = kc * 64 + il;
+          if (G < n_groups && i < p.n_in) {
+            const long long o = G / gpi, g = G - o * gpi;
+            v[it] = ldg_stream(p.X + ((o * p.n_in + i) * p.inner + g * 64 + c4 * 4));
+          } else {
+            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int idx = it * 128 + tid, il = idx >> 5, gsel = (idx >> 4) & 1, c4 = idx & 15;
+          uint32_t h0, l0, h1, l1;
+          split2(v[it].x, v[it].y, h0, l0);
+          split2(v[it].z, v[it].w, h1, l1);
+          const uint32_t off = (uint32_t)gsel * 8192u + (uint32_t)(il >> 3) * 1024u + (uint32_t)(il & 7) * 128u +
+                               (uint32_t)(((c4 >> 1) ^ (il & 7)) << 4) + (uint32_t)(c4 & 1) * 8u;
+          *reinterpret_cast<uint2*>(sAh + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(sAl + off) = make_uint2(l0, l1);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (!w_ready) {
+        mbar_wait(bar_w, 0);
+        w_ready = true;
+      }
+      if (tid == 0) {
+        tc_fence_after();
+        const int rem = p.n_in - kc * 64;
+        const int ksteps = rem >= 64 ? 4 : (rem + 15) / 16;
+        const uint32_t b_blk = smem_u32(sB) + (uint32_t)kc * ((uint32_t)p.npad * 128u);
+        uint32_t acc = kc > 0 ? 1u : 0u;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = smem_u32(pass == 2 ? sAl : sAh);
+          const uint32_t b = b_blk + (pass == 1 ? b_half : 0u);
+#pragma unroll 1
+          for (int ks = 0; ks < ksteps; ++ks) {
+            // MN-major A: 64-wide mn blocks 8 KB apart (LBO), 8-row k groups 1 KB apart (SBO); one K step = 2 groups
+            const uint64_t ad = make_smem_desc_sw128(a + (uint32_t)ks * 2048u, 8192u, 1024u);
+            umma_bf16_ss(tmem, ad, desc_kmajor(b, ks * 16), idesc, acc);
+            acc = 1u;
+          }
+        }
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, phase);
+      phase ^= 1;
+      tc_fence_after();
+    }
+    // ---- epilogue: D[128 inner elements x n_out] -> Y[o][j][inner] (coalesced along inner) ---------------
+    {
+      const long long G = G0 + (tid >> 6);
+      const bool live = G < n_groups;
+      long long o = 0, g = 0;
+      if (live) { o = G / gpi; g = G - o * gpi; }
+      float* ybase = p.Y + (o * p.n_out) * p.inner + g * 64 + (tid & 63);
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.npad; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + c0, v);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < p.n_out) {
+              float* dst = ybase + (long long)(c0 + j) * p.inner;
+              float r = __uint_as_float(v[j]);
+              if (p.accumulate) r += *dst;
+              *dst = r;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+int launch_axis_umma(const AxisXform& p, int sm_count, cudaStream_t st) {
+  FFNO_REQUIRE(p.inner % 64 == 0, FFNO_ERR_UNSUPPORTED, "axis_umma: inner=%lld not a multiple of 64", p.inner);
+  FFNO_REQUIRE(p.npad >= 16 && p.npad <= 256 && p.npad % 16 == 0, FFNO_ERR_UNSUPPORTED, "axis_umma: npad=%d", p.npad);
+  const size_t img = table_image_bytes(p.n_in, p.n_out);
+  const size_t smem = AX_SMEM_B + img;
+  FFNO_REQUIRE(smem <= 227 * 1024, FFNO_ERR_UNSUPPORTED, "axis_umma: table image %zu B does not fit in shared memory", img);
+  const long long n_groups = p.outer * (p.inner / 64);
+  if (n_groups == 0) return FFNO_OK;
+  static size_t configured = 0;
+  if (smem > configured) {
+    FFNO_CUDA_CHECK(cudaFuncSetAttribute(axis_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int tmem_cols = 32;
+  while (tmem_cols < p.npad) tmem_cols *= 2;
+  const int n_tiles = (int)((n_groups + 1) / 2);
+  int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (ctas_per_sm > 2) ctas_per_sm = 2;
+  if (ctas_per_sm * tmem_cols > 512) ctas_per_sm = 512 / tmem_cols;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int max_grid = sm_count * ctas_per_sm;
+  const int grid = n_tiles < max_grid ? n_tiles : max_grid;
+  axis_umma_kernel<<<grid, 128, smem, st>>>(p, n_tiles, tmem_cols);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("axis_umma_kernel");
+  return FFNO_OK;
+}
+
+// =======================================================================================================
 // Self-test of the descriptor / layout conventions (one CTA).
 // =======================================================================================================
 __device__ __forceinline__ uint32_t mnmajor_sw128_offset(int mn, int k, int k_total) {

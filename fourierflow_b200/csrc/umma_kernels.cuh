@@ -28,6 +28,22 @@ struct MixAxis {
 };
 int launch_mix_umma(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st);
 
+// Truncated real DFT along a strided axis on tcgen05 (forward and inverse are the same product with a
+// different table):   Y[o][j][inner] (+)= sum_i T[i][j] * X[o][i][inner],   inner % 64 == 0, n_out <= 256
+//   A = X tile (128 inner elements x n_in), stored MN-major straight from its natural layout;
+//   B = table image [npad rows j][n_in] K-major (bf16 hi | lo), built once per plan by launch_pack_table_image.
+struct AxisXform {
+  const float* X;
+  float* Y;
+  const uint8_t* table;    // image: hi half then lo half, each kchunks * npad * 128 bytes
+  long long outer, inner;
+  int n_in, n_out, npad, kchunks, accumulate;
+};
+size_t table_image_bytes(int n_in, int n_out);
+int launch_pack_table_image(const float* T /*[n_in][ldt]*/, int ldt, int n_in, int n_out, uint8_t* image,
+                            cudaStream_t st);
+int launch_axis_umma(const AxisXform& p, int sm_count, cudaStream_t st);
+
 // Diagnostics: D[128][N] = A[128][K] * B[N][K]^T with bf16 inputs (raw ushort), one CTA, every layout variant
 // the kernels rely on (a_mn / b_mn: operand stored MN-major; variant: LBO/SBO interpretation under test).
 int launch_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int N, int K, int a_mn, int b_mn,

@@ -30,7 +30,14 @@ struct UmmaState {
   std::map<const void*, uint8_t*> ff_cache;
   float* d_fwd[3] = {nullptr, nullptr, nullptr};
   float* d_inv[3] = {nullptr, nullptr, nullptr};
+  uint8_t* fwd_image[3] = {nullptr, nullptr, nullptr};   // tcgen05 table images (NULL -> FP32 table kernel)
+  uint8_t* inv_image[3] = {nullptr, nullptr, nullptr};
 };
+
+static int pad16i(int n) { return (n + 15) / 16 * 16; }
+static bool axis_fits_umma(int n_in, int n_out) {
+  return n_out <= 256 && 32768 + 1024 + table_image_bytes(n_in, n_out) <= (size_t)227 * 1024;
+}
 
 const char* umma_why_not(const ffno_desc* d, const int*) {
   if (d->width != kUmmaC) return "width != 64";
@@ -79,6 +86,17 @@ static int alloc_bytes(UmmaState* s, size_t bytes, uint8_t** out) {
 int umma_load_params(UmmaState* s, const UmmaLayerSrc* layers, float* const d_fwd[3], float* const d_inv[3],
                      cudaStream_t st) {
   for (int a = 0; a < 3; ++a) { s->d_fwd[a] = d_fwd[a]; s->d_inv[a] = d_inv[a]; }
+  for (int a = 0; a < s->d.ndim; ++a) {
+    const int Ln = s->ext[a], K2 = 2 * s->d.modes[a];
+    if (!s->fwd_image[a] && axis_fits_umma(Ln, K2)) {
+      FFNO_TRY(alloc_bytes(s, table_image_bytes(Ln, K2), &s->fwd_image[a]));
+      FFNO_TRY(launch_pack_table_image(d_fwd[a], pad16i(K2), Ln, K2, s->fwd_image[a], st));
+    }
+    if (!s->inv_image[a] && axis_fits_umma(K2, Ln)) {
+      FFNO_TRY(alloc_bytes(s, table_image_bytes(K2, Ln), &s->inv_image[a]));
+      FFNO_TRY(launch_pack_table_image(d_inv[a], pad16i(Ln), K2, Ln, s->inv_image[a], st));
+    }
+  }
   std::map<std::pair<const void*, int>, bool> mix_done;
   std::map<const void*, bool> ff_done;
   for (int l = 0; l < s->d.n_layers; ++l) {
@@ -121,14 +139,24 @@ int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float*
     for (int i = a + 1; i < s->d.ndim; ++i) p_inner *= s->ext[i];
     const int Ln = s->ext[a], K = s->d.modes[a];
     const long long inner = p_inner * kUmmaC;
-    FFNO_TRY(launch_axis_transform(x, s->d_fwd[a], F, outer, Ln, 2 * K, inner, false, st));
+    if (s->fwd_image[a]) {
+      AxisXform t{x, F, s->fwd_image[a], outer, inner, Ln, 2 * K, pad16i(2 * K), (Ln + 63) / 64, 0};
+      FFNO_TRY(launch_axis_umma(t, s->sm_count, st));
+    } else {
+      FFNO_TRY(launch_axis_transform(x, s->d_fwd[a], F, outer, Ln, 2 * K, inner, false, st));
+    }
     const float* src = F;
     if (s->d.spectral_mode == FFNO_MODE_FULL) {
       MixAxis ax{F, R, L.mix_image[a], outer, p_inner, K};
       FFNO_TRY(launch_mix_umma(&ax, 1, s->sm_count, st));
       src = R;
     }
-    FFNO_TRY(launch_axis_transform(src, s->d_inv[a], s_out, outer, 2 * K, Ln, inner, !first, st));
+    if (s->inv_image[a]) {
+      AxisXform t{src, s_out, s->inv_image[a], outer, inner, 2 * K, Ln, pad16i(Ln), (2 * K + 63) / 64, first ? 0 : 1};
+      FFNO_TRY(launch_axis_umma(t, s->sm_count, st));
+    } else {
+      FFNO_TRY(launch_axis_transform(src, s->d_inv[a], s_out, outer, 2 * K, Ln, inner, !first, st));
+    }
     first = false;
   }
   return FFNO_OK;
