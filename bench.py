@@ -281,12 +281,15 @@ def run_ours(args, rank, world, local):
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample -------------------------------
     cpu_sample, cpu_reps = 8, 3
-    cstep = oracle_setup(cpu_sample)
-    cores = pick_cpu_threads(cstep)
-    t0 = time.perf_counter()
-    for _ in range(cpu_reps):
-        cstep()
-    cpu_v = cpu_sample * cpu_reps / (time.perf_counter() - t0)
+    if args.no_cpu_baseline:
+        cores, cpu_v = 0, None
+    else:
+        cstep = oracle_setup(cpu_sample)
+        cores = pick_cpu_threads(cstep)
+        t0 = time.perf_counter()
+        for _ in range(cpu_reps):
+            cstep()
+        cpu_v = cpu_sample * cpu_reps / (time.perf_counter() - t0)
 
     N = world
     line = {
@@ -316,6 +319,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -216,8 +216,7 @@ Workspace carve(const ffno_plan* p, int batch, void* base) {
   w.b = c.take(U);
   size_t spec = 0;
   for (int a = 0; a < p->d.ndim; ++a) {
-    size_t n = U / p->ext[a] * 2 * p->d.modes[a];
-    if (n > spec) spec = n;
+    spec += U / p->ext[a] * 2 * p->d.modes[a];     // every axis' spectra live side by side
   }
   w.F = c.take(spec);
   w.R = c.take(spec);

@@ -44,6 +44,12 @@ int launch_pack_table_image(const float* T /*[n_in][ldt]*/, int ldt, int n_in, i
                             cudaStream_t st);
 int launch_axis_umma(const AxisXform& p, int sm_count, cudaStream_t st);
 
+// Warp-specialised, double-buffered versions (umma_pipelined.cu): same arithmetic, loads / MMAs / epilogues overlap.
+int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st);   // axes run concurrently
+int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st);
+int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,
+                   const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st);
+
 // Diagnostics: D[128][N] = A[128][K] * B[N][K]^T with bf16 inputs (raw ushort), one CTA, every layout variant
 // the kernels rely on (a_mn / b_mn: operand stored MN-major; variant: LBO/SBO interpretation under test).
 int launch_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int N, int K, int a_mn, int b_mn,

@@ -4,6 +4,7 @@
 //   per axis:  truncated forward DFT (FP32 table kernel)  ->  per-mode complex mix on tcgen05 (3xBF16)
 //              ->  truncated inverse DFT accumulated into s (FP32 table kernel)
 //   then:      FeedForward + residual on tcgen05 (3xBF16, hidden activations never leave the SM)
+#include <cstdlib>
 #include <map>
 #include <vector>
 
@@ -30,6 +31,7 @@ struct UmmaState {
   std::map<const void*, uint8_t*> ff_cache;
   float* d_fwd[3] = {nullptr, nullptr, nullptr};
   float* d_inv[3] = {nullptr, nullptr, nullptr};
+  bool v1 = false;                                       // FFNO_UMMA_V1=1: non-pipelined kernels (cross-check)
   uint8_t* fwd_image[3] = {nullptr, nullptr, nullptr};   // tcgen05 table images (NULL -> FP32 table kernel)
   uint8_t* inv_image[3] = {nullptr, nullptr, nullptr};
 };
@@ -64,6 +66,8 @@ int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]) {
                      prop.minor);
   }
   s->sm_count = prop.multiProcessorCount;
+  const char* v1 = getenv("FFNO_UMMA_V1");
+  s->v1 = v1 && v1[0] == '1';
   s->layers.resize(d->n_layers);
   *out = s;
   return FFNO_OK;
@@ -129,14 +133,28 @@ int umma_load_params(UmmaState* s, const UmmaLayerSrc* layers, float* const d_fw
 
 size_t umma_workspace_floats(const UmmaState*, int) { return 0; }
 
-int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R, float*,
-                      cudaStream_t st) {
-  const UmmaLayer& L = s->layers[layer];
+// F / R hold every axis back to back: axis a starts at spec_offset(a) floats.
+static size_t spec_offset(const UmmaState* s, int batch, int axis) {
+  size_t P = (size_t)batch;
+  for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
+  size_t off = 0;
+  for (int a = 0; a < axis; ++a) off += P / s->ext[a] * 2 * s->d.modes[a] * kUmmaC;
+  return off;
+}
+
+static void axis_geom(const UmmaState* s, int batch, int a, long long* outer, long long* p_inner) {
+  *outer = batch;
+  *p_inner = 1;
+  for (int i = 0; i < a; ++i) *outer *= s->ext[i];
+  for (int i = a + 1; i < s->d.ndim; ++i) *p_inner *= s->ext[i];
+}
+
+static int spectral_v1(UmmaState* s, const UmmaLayer& L, const float* x, int batch, float* s_out, float* F, float* R,
+                       cudaStream_t st) {
   bool first = true;
   for (int a = s->d.ndim - 1; a >= 0; --a) {
-    long long outer = batch, p_inner = 1;
-    for (int i = 0; i < a; ++i) outer *= s->ext[i];
-    for (int i = a + 1; i < s->d.ndim; ++i) p_inner *= s->ext[i];
+    long long outer, p_inner;
+    axis_geom(s, batch, a, &outer, &p_inner);
     const int Ln = s->ext[a], K = s->d.modes[a];
     const long long inner = p_inner * kUmmaC;
     if (s->fwd_image[a]) {
@@ -162,13 +180,50 @@ int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float*
   return FFNO_OK;
 }
 
+// Pipelined path: all forward transforms in one launch, all mode mixes in one launch, then one inverse launch per
+// axis (the second and third accumulate into s).
+int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R, float*,
+                      cudaStream_t st) {
+  const UmmaLayer& L = s->layers[layer];
+  bool all_umma = true;
+  for (int a = 0; a < s->d.ndim; ++a) all_umma &= (s->fwd_image[a] != nullptr) && (s->inv_image[a] != nullptr);
+  if (s->v1 || !all_umma) return spectral_v1(s, L, x, batch, s_out, F, R, st);
+
+  AxisXform fwd[3];
+  MixAxis mix[3];
+  for (int a = 0; a < s->d.ndim; ++a) {
+    long long outer, p_inner;
+    axis_geom(s, batch, a, &outer, &p_inner);
+    const int Ln = s->ext[a], K = s->d.modes[a];
+    float* Fa = F + spec_offset(s, batch, a);
+    float* Ra = R + spec_offset(s, batch, a);
+    fwd[a] = AxisXform{x, Fa, s->fwd_image[a], outer, p_inner * kUmmaC, Ln, 2 * K, pad16i(2 * K), (Ln + 63) / 64, 0};
+    mix[a] = MixAxis{Fa, Ra, L.mix_image[a], outer, p_inner, K};
+  }
+  FFNO_TRY(launch_axis_pipe(fwd, s->d.ndim, s->sm_count, st));
+  const bool full = s->d.spectral_mode == FFNO_MODE_FULL;
+  if (full) FFNO_TRY(launch_mix_pipe(mix, s->d.ndim, s->sm_count, st));
+  bool first = true;
+  for (int a = s->d.ndim - 1; a >= 0; --a) {
+    long long outer, p_inner;
+    axis_geom(s, batch, a, &outer, &p_inner);
+    const int Ln = s->ext[a], K = s->d.modes[a];
+    const float* src = (full ? R : F) + spec_offset(s, batch, a);
+    AxisXform inv{src, s_out, s->inv_image[a], outer, p_inner * kUmmaC, 2 * K, Ln, pad16i(Ln), (2 * K + 63) / 64, first ? 0 : 1};
+    FFNO_TRY(launch_axis_pipe(&inv, 1, s->sm_count, st));
+    first = false;
+  }
+  return FFNO_OK;
+}
+
 int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* y, float*,
                 cudaStream_t st) {
   const UmmaLayer& L = s->layers[layer];
   long long P = batch;
   for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
-  if (residual) return launch_ff_umma(s_in, residual, y, nullptr, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
-  return launch_ff_umma(s_in, nullptr, nullptr, y, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  auto ff = s->v1 ? launch_ff_umma : launch_ff_pipe;
+  if (residual) return ff(s_in, residual, y, nullptr, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  return ff(s_in, nullptr, nullptr, y, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
 }
 
 int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_next, float* s_out, float* b_out,
@@ -177,7 +232,8 @@ int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_
   FFNO_TRY(umma_spectral_fwd(s, layer, x, batch, s_out, F, R, ws, st));
   long long P = batch;
   for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
-  return launch_ff_umma(s_out, x, x_next, want_b ? b_out : nullptr, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  auto ff = s->v1 ? launch_ff_umma : launch_ff_pipe;
+  return ff(s_out, x, x_next, want_b ? b_out : nullptr, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
 }
 
 }  // namespace ffno

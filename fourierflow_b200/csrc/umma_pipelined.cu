@@ -1,0 +1,685 @@
+// Warp-specialised, mbarrier-pipelined tcgen05 kernels of the F-FNO layer (width 64 / hidden 256), sm_100a.
+//
+// One CTA per SM, 9 warps:
+//   warps 0-3  epilogue   (TMEM lanes 0..127 -> registers -> bias/activation/split or global stores)
+//   warp  4    MMA issuer (lane 0 issues tcgen05.mma + tcgen05.commit)
+//   warps 5-8  loaders    (coalesced FP32 global loads -> BF16 hi/lo split -> swizzled operand tiles in smem)
+// Operand tiles in shared memory and accumulators in tensor memory are double-buffered and handed over with
+// full/empty mbarriers, so the global loads of tile t+1, the MMAs of tile t and the epilogue of tile t-1 overlap.
+// (The v1 kernels in umma_kernels.cu do the same arithmetic with one warpgroup and no overlap; they stay as the
+// cross-check, selectable with FFNO_UMMA_V1=1.)
+#include "umma.cuh"
+#include "umma_kernels.cuh"
+
+namespace ffno {
+
+extern thread_local long long g_launch_counter;
+using namespace umma;
+
+namespace {
+
+constexpr int kThreads = 288;
+constexpr int kEpiWarps = 4;
+constexpr int kMmaWarp = 4;
+constexpr int kLoaderThread0 = 160;
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void store_split4_at(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t off, float4 v) {
+  uint32_t h0, l0, h1, l1;
+  split2(v.x, v.y, h0, l0);
+  split2(v.z, v.w, h1, l1);
+  *reinterpret_cast<uint2*>(tile_hi + off) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(tile_lo + off) = make_uint2(l0, l1);
+}
+
+}  // namespace
+
+// =======================================================================================================
+// Axis transform (forward / inverse truncated DFT), up to 3 axes per launch (blockIdx.y = axis)
+// =======================================================================================================
+constexpr int AXP_A_STAGE = 32768;                 // hi 16 KB | lo 16 KB
+constexpr int AXP_BAR = 2 * AXP_A_STAGE;           // 65536
+constexpr int AXP_TABLE = AXP_BAR + 1024;
+
+struct AxisSet {
+  AxisXform ax[3];
+  int n_tiles[3];
+  int tmem_cols[3];
+};
+
+__global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
+  const AxisXform& p = set.ax[blockIdx.y];
+  const int n_tiles = set.n_tiles[blockIdx.y];
+  if ((int)blockIdx.x >= n_tiles) return;
+  const int tmem_cols = set.tmem_cols[blockIdx.y];
+  const int stage_cols = tmem_cols >> 1;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AXP_BAR);
+  uint64_t* a_full = bars;          // [2]
+  uint64_t* a_empty = bars + 2;     // [2]
+  uint64_t* d_full = bars + 4;      // [2]
+  uint64_t* d_empty = bars + 6;     // [2]
+  uint64_t* bar_w = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sB = smem + AXP_TABLE;
+  const uint32_t b_half = (uint32_t)p.kchunks * p.npad * 128u;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 128);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&d_full[i], 1);
+      mbar_init(&d_empty[i], 128);
+    }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const long long gpi = p.inner >> 6;
+  const long long n_groups = p.outer * gpi;
+
+  if (warp < kEpiWarps) {
+    // ---------------------------------------------------------------- epilogue
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      const int ds = n & 1;
+      mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
+      tc_fence_after();
+      const long long G = (long long)tile * 2 + (tid >> 6);
+      const bool live = G < n_groups;
+      long long o = 0, g = 0;
+      if (live) { o = G / gpi; g = G - o * gpi; }
+      float* ybase = p.Y + (o * p.n_out) * p.inner + g * 64 + (tid & 63);
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.npad; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + (uint32_t)(ds * stage_cols + c0), v);
+        tmem_ld_wait();
+        if (c0 + 32 >= p.npad) {       // last read of this accumulator stage: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&d_empty[ds]);
+        }
+        if (live) {
+          if (p.accumulate) {
+            float old[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = (c0 + j < p.n_out) ? ybase[(long long)(c0 + j) * p.inner] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.n_out) ybase[(long long)(c0 + j) * p.inner] = __uint_as_float(v[j]) + old[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < p.n_out) ybase[(long long)(c0 + j) * p.inner] = __uint_as_float(v[j]);
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t total = 2u * b_half;
+      mbar_expect_tx(bar_w, total);
+      for (uint32_t off = 0; off < total; off += 32768u) {
+        const uint32_t nb = (total - off) < 32768u ? (total - off) : 32768u;
+        bulk_g2s(sB + off, p.table + off, nb, bar_w);
+      }
+      mbar_wait(bar_w, 0);
+      const uint32_t idesc = make_idesc_bf16(128, p.npad, 1, 0);
+      int item = 0, n = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+        const int ds = n & 1;
+        mbar_wait(&d_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
+        const uint32_t d_addr = tmem + (uint32_t)(ds * stage_cols);
+        for (int kc = 0; kc < p.kchunks; ++kc, ++item) {
+          const int as = item & 1;
+          mbar_wait(&a_full[as], (uint32_t)(item >> 1) & 1u);
+          tc_fence_after();
+          const int rem = p.n_in - kc * 64;
+          const int ksteps = rem >= 64 ? 4 : (rem + 15) / 16;
+          const uint32_t a_hi = smem_u32(smem + as * AXP_A_STAGE), a_lo = a_hi + 16384u;
+          const uint32_t b_blk = smem_u32(sB) + (uint32_t)kc * ((uint32_t)p.npad * 128u);
+          uint32_t acc = kc > 0 ? 1u : 0u;
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? a_lo : a_hi;
+            const uint32_t b = b_blk + (pass == 1 ? b_half : 0u);
+#pragma unroll 1
+            for (int ks = 0; ks < ksteps; ++ks) {
+              umma_bf16_ss(d_addr, make_smem_desc_sw128(a + (uint32_t)ks * 2048u, 8192u, 1024u), desc_kmajor(b, ks * 16),
+                           idesc, acc);
+              acc = 1u;
+            }
+          }
+          umma_commit(&a_empty[as]);
+        }
+        umma_commit(&d_full[ds]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- loaders
+    const int lt = tid - kLoaderThread0;
+    int item = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long G0 = (long long)tile * 2;
+      for (int kc = 0; kc < p.kchunks; ++kc, ++item) {
+        const int as = item & 1;
+        float4 v[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int idx = it * 128 + lt, il = idx >> 5, gsel = (idx >> 4) & 1, c4 = idx & 15;
+          const long long G = G0 + gsel;
+          const int i = kc * 64 + il;
+          if (G < n_groups && i < p.n_in) {
+            const long long o = G / gpi, g = G - o * gpi;
+            v[it] = ldg_stream(p.X + ((o * p.n_in + i) * p.inner + g * 64 + c4 * 4));
+          } else {
+            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
+        uint8_t* sAh = smem + as * AXP_A_STAGE;
+        uint8_t* sAl = sAh + 16384;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int idx = it * 128 + lt, il = idx >> 5, gsel = (idx >> 4) & 1, c4 = idx & 15;
+          const uint32_t off = (uint32_t)gsel * 8192u + (uint32_t)(il >> 3) * 1024u + (uint32_t)(il & 7) * 128u +
+                               (uint32_t)(((c4 >> 1) ^ (il & 7)) << 4) + (uint32_t)(c4 & 1) * 8u;
+          store_split4_at(sAh, sAl, off, v[it]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a_full[as]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st) {
+  FFNO_REQUIRE(n_axes >= 1 && n_axes <= 3, FFNO_ERR_BAD_ARG, "axis_pipe: n_axes=%d", n_axes);
+  AxisSet set;
+  size_t smem = 0;
+  int max_tiles = 0;
+  for (int a = 0; a < n_axes; ++a) {
+    const AxisXform& p = axes[a];
+    FFNO_REQUIRE(p.inner % 64 == 0, FFNO_ERR_UNSUPPORTED, "axis_pipe: inner=%lld not a multiple of 64", p.inner);
+    FFNO_REQUIRE(p.npad >= 16 && p.npad <= 256 && p.npad % 16 == 0, FFNO_ERR_UNSUPPORTED, "axis_pipe: npad=%d", p.npad);
+    const size_t need = AXP_TABLE + table_image_bytes(p.n_in, p.n_out);
+    FFNO_REQUIRE(need <= 227 * 1024, FFNO_ERR_UNSUPPORTED, "axis_pipe: table does not fit in shared memory");
+    smem = need > smem ? need : smem;
+    set.ax[a] = p;
+    const long long n_groups = p.outer * (p.inner / 64);
+    set.n_tiles[a] = (int)((n_groups + 1) / 2);
+    int cols = 32;
+    while (cols < 2 * p.npad) cols *= 2;
+    set.tmem_cols[a] = cols;
+    max_tiles = set.n_tiles[a] > max_tiles ? set.n_tiles[a] : max_tiles;
+  }
+  if (max_tiles == 0) return FFNO_OK;
+  static size_t configured = 0;
+  if (smem > configured) {
+    FFNO_CUDA_CHECK(cudaFuncSetAttribute(axis_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int per_axis = sm_count / n_axes;
+  if (per_axis < 1) per_axis = 1;
+  const int gx = max_tiles < per_axis ? max_tiles : per_axis;
+  axis_pipe_kernel<<<dim3(gx, n_axes), kThreads, smem, st>>>(set);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("axis_pipe_kernel");
+  return FFNO_OK;
+}
+
+// =======================================================================================================
+// Per-mode complex channel mix, all axes in one launch (blockIdx.z = axis, blockIdx.y = mode)
+//   work item = (row tile, K block): K block 0 = real parts, 1 = imaginary parts of the 128-wide mix row
+// =======================================================================================================
+constexpr int MXP_A_STAGE = 32768;
+constexpr int MXP_B = 2 * MXP_A_STAGE;             // 65536: B image 64 KB
+constexpr int MXP_BAR = MXP_B + 65536;             // 131072
+constexpr int MXP_TOTAL = MXP_BAR + 128;
+
+struct MixSet {
+  MixAxis ax[3];
+  int tiles_per_cta[3];
+};
+
+__global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
+  const MixAxis& ax = set.ax[blockIdx.z];
+  const int k = blockIdx.y;
+  if (k >= ax.K) return;
+  const long long M = ax.outer * ax.p_inner;
+  const int n_tiles = (int)((M + 127) / 128);
+  const int tpc = set.tiles_per_cta[blockIdx.z];
+  const int tile_begin = blockIdx.x * tpc;
+  if (tile_begin >= n_tiles) return;
+  const int tile_end = min(n_tiles, tile_begin + tpc);
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sB = smem + MXP_B;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MXP_BAR);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + 2;
+  uint64_t* d_full = bars + 4;
+  uint64_t* d_empty = bars + 6;
+  uint64_t* bar_w = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 128);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&d_full[i], 1);
+      mbar_init(&d_empty[i], 128);
+    }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const long long inner = ax.p_inner * 64;
+
+  if (warp < kEpiWarps) {
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int n = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
+      const int ds = n & 1;
+      mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
+      tc_fence_after();
+      const long long row = (long long)tile * 128 + tid;
+      long long o = 0, pp = 0;
+      if (row < M) { o = row / ax.p_inner; pp = row - o * ax.p_inner; }
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + (uint32_t)(ds * 128 + q * 32), v);
+        tmem_ld_wait();
+        if (q == 3) {
+          tc_fence_before();
+          mbar_arrive(&d_empty[ds]);
+        }
+        if (row < M) {
+          float* dst = ax.R + ((o * ax.K + k) * 2 + (q >> 1)) * inner + pp * 64 + (q & 1) * 32;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            *reinterpret_cast<float4*>(dst + c4 * 4) =
+                make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]),
+                            __uint_as_float(v[c4 * 4 + 3]));
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, kMixImageBytes);
+      const uint8_t* img = ax.image + (long long)k * kMixImageBytes;
+      bulk_g2s(sB, img, 32768, bar_w);
+      bulk_g2s(sB + 32768, img + 32768, 32768, bar_w);
+      mbar_wait(bar_w, 0);
+      constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t b_hi = smem_u32(sB), b_lo = b_hi + 32768u;
+      int item = 0, n = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
+        const int ds = n & 1;
+        mbar_wait(&d_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
+        const uint32_t d_addr = tmem + (uint32_t)(ds * 128);
+        for (int kb = 0; kb < 2; ++kb, ++item) {
+          const int as = item & 1;
+          mbar_wait(&a_full[as], (uint32_t)(item >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + as * MXP_A_STAGE), a_lo = a_hi + 16384u;
+          uint32_t acc = kb > 0 ? 1u : 0u;
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? a_lo : a_hi;
+            const uint32_t b = ((pass == 1) ? b_lo : b_hi) + (uint32_t)kb * 16384u;
+#pragma unroll 1
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_bf16_ss(d_addr, desc_kmajor(a, ks * 16), desc_kmajor(b, ks * 16), IDESC, acc);
+              acc = 1u;
+            }
+          }
+          umma_commit(&a_empty[as]);
+        }
+        umma_commit(&d_full[ds]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int lt = tid - kLoaderThread0;
+    int item = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const long long row0 = (long long)tile * 128;
+      for (int half = 0; half < 2; ++half, ++item) {
+        const int as = item & 1;
+        float4 v[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
+          const long long row = row0 + r;
+          if (row < M) {
+            const long long o = row / ax.p_inner, pp = row - o * ax.p_inner;
+            v[it] = ldg_stream(ax.F + ((o * ax.K + k) * 2 + half) * inner + pp * 64 + c4 * 4);
+          } else {
+            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
+        uint8_t* sAh = smem + as * MXP_A_STAGE;
+        uint8_t* sAl = sAh + 16384;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
+          store_split4_at(sAh, sAl, kmajor_sw128_offset(r, c4 * 4), v[it]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a_full[as]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st) {
+  FFNO_REQUIRE(n_axes >= 1 && n_axes <= 3, FFNO_ERR_BAD_ARG, "mix_pipe: n_axes=%d", n_axes);
+  static bool configured = false;
+  if (!configured) {
+    FFNO_CUDA_CHECK(cudaFuncSetAttribute(mix_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MXP_TOTAL));
+    configured = true;
+  }
+  MixSet set;
+  int maxK = 0, total_modes = 0;
+  long long total_tiles = 0;
+  for (int a = 0; a < n_axes; ++a) {
+    set.ax[a] = axes[a];
+    maxK = axes[a].K > maxK ? axes[a].K : maxK;
+    total_modes += axes[a].K;
+    total_tiles += (long long)axes[a].K * ((axes[a].outer * axes[a].p_inner + 127) / 128);
+  }
+  if (total_tiles == 0) return FFNO_OK;
+  int grid_x = 1;
+  for (int a = 0; a < n_axes; ++a) {
+    const long long tiles = (axes[a].outer * axes[a].p_inner + 127) / 128;
+    long long ctas_per_mode = (long long)sm_count / (total_modes > 0 ? total_modes : 1);
+    if (ctas_per_mode < 1) ctas_per_mode = 1;
+    long long tpc = (tiles + ctas_per_mode - 1) / ctas_per_mode;
+    if (tpc < 1) tpc = 1;
+    set.tiles_per_cta[a] = (int)tpc;
+    const int gx = (int)((tiles + tpc - 1) / tpc);
+    grid_x = gx > grid_x ? gx : grid_x;
+  }
+  mix_pipe_kernel<<<dim3(grid_x, maxK, n_axes), kThreads, MXP_TOTAL, st>>>(set);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("mix_pipe_kernel");
+  return FFNO_OK;
+}
+
+// =======================================================================================================
+// FeedForward + residual, pipelined:
+//   G1 (two halves of 128 hidden units, N=128)  ->  epilogue-1 per 64-column chunk (+b1, ReLU, split -> A2[2 stages])
+//   G2 per chunk (N=64, accumulating into D2[2 stages])  ->  final epilogue (+b2, +residual, store)
+// =======================================================================================================
+constexpr int FFP_W = 0;                           // 128 KB image
+constexpr int FFP_A1 = 131072;                     // hi 16 | lo 16
+constexpr int FFP_A2 = FFP_A1 + 32768;             // 2 stages x (hi 16 | lo 16)
+constexpr int FFP_BIAS = FFP_A2 + 65536;           // 229376
+constexpr int FFP_BAR = FFP_BIAS + 320 * 4;        // 230656
+constexpr int FFP_TOTAL = FFP_BAR + 160;           // 230816 <= 232448
+
+__global__ void __launch_bounds__(kThreads, 1)
+ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, float* __restrict__ x_out,
+               float* __restrict__ b_out, const uint8_t* __restrict__ image, const float* __restrict__ b1,
+               const float* __restrict__ b2, long long P, int n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* sb1 = reinterpret_cast<float*>(smem + FFP_BIAS);
+  float* sb2 = sb1 + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FFP_BAR);
+  uint64_t* a1_full = bars;        // count 128 (loaders)
+  uint64_t* a1_empty = bars + 1;   // commit
+  uint64_t* d1_full = bars + 2;    // [2] commit
+  uint64_t* d1_empty = bars + 4;   // [2] 128 (epilogue)
+  uint64_t* a2_full = bars + 6;    // [2] 128 (epilogue)
+  uint64_t* a2_empty = bars + 8;   // [2] commit
+  uint64_t* d2_full = bars + 10;   // [2] commit
+  uint64_t* d2_empty = bars + 12;  // [2] 128 (epilogue)
+  uint64_t* bar_w = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(a1_full, 128);
+    mbar_init(a1_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d1_full[i], 1);
+      mbar_init(&d1_empty[i], 128);
+      mbar_init(&a2_full[i], 128);
+      mbar_init(&a2_empty[i], 1);
+      mbar_init(&d2_full[i], 1);
+      mbar_init(&d2_empty[i], 128);
+    }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  for (int i = tid; i < 256; i += kThreads) sb1[i] = b1 ? b1[i] : 0.f;
+  if (tid < 64) sb2[tid] = b2 ? b2[tid] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: D1 half h at h*128 (128 cols each), D2 stage t at 256 + t*64
+  const uint32_t sW1h = smem_u32(smem + FFP_W), sW1l = sW1h + 32768u, sW2h = sW1h + 65536u, sW2l = sW1h + 98304u;
+
+  if (warp < kEpiWarps) {
+    // ---------------------------------------------------------------- epilogue warps (thread = row)
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int h = j >> 1;
+        if ((j & 1) == 0) {
+          mbar_wait(&d1_full[h], (uint32_t)n & 1u);
+          tc_fence_after();
+        }
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + (j & 1) * 64), v0);
+        tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + (j & 1) * 64 + 32), v1);
+        tmem_ld_wait();
+        if (j & 1) {                       // both chunks of this D1 half are in registers: release it
+          tc_fence_before();
+          mbar_arrive(&d1_empty[h]);
+        }
+        const int c = n * 4 + j, stg = c & 1;
+        mbar_wait(&a2_empty[stg], ((uint32_t)(c >> 1) & 1u) ^ 1u);
+        uint8_t* sA2h = smem + FFP_A2 + stg * 32768;
+        uint8_t* sA2l = sA2h + 16384;
+        const float* bj = sb1 + j * 64;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = cc * 8 + q * 2;
+            float a = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]) + bj[col];
+            float b = __uint_as_float(col + 1 < 32 ? v0[col + 1] : v1[col + 1 - 32]) + bj[col + 1];
+            split2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[q], lo[q]);
+          }
+          const uint32_t off = (uint32_t)tid * 128u + (uint32_t)((cc ^ (tid & 7)) << 4);
+          *reinterpret_cast<uint4*>(sA2h + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sA2l + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a2_full[stg]);
+      }
+      // ---- final epilogue of this tile
+      const int ds = n & 1;
+      mbar_wait(&d2_full[ds], (uint32_t)(n >> 1) & 1u);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tmem + lane_base + (uint32_t)(256 + ds * 64), v0);
+      tmem_ld32(tmem + lane_base + (uint32_t)(256 + ds * 64 + 32), v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&d2_empty[ds]);
+      const long long row = (long long)tile * 128 + tid;
+      if (row < P) {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          float4 b;
+          b.x = __uint_as_float(c4 < 8 ? v0[c4 * 4 + 0] : v1[c4 * 4 - 32 + 0]) + sb2[c4 * 4 + 0];
+          b.y = __uint_as_float(c4 < 8 ? v0[c4 * 4 + 1] : v1[c4 * 4 - 32 + 1]) + sb2[c4 * 4 + 1];
+          b.z = __uint_as_float(c4 < 8 ? v0[c4 * 4 + 2] : v1[c4 * 4 - 32 + 2]) + sb2[c4 * 4 + 2];
+          b.w = __uint_as_float(c4 < 8 ? v0[c4 * 4 + 3] : v1[c4 * 4 - 32 + 3]) + sb2[c4 * 4 + 3];
+          if (b_out) *reinterpret_cast<float4*>(b_out + row * 64 + c4 * 4) = b;
+          if (x_out) {
+            float4 o = b;
+            if (residual) {
+              float4 r = *reinterpret_cast<const float4*>(residual + row * 64 + c4 * 4);
+              o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            *reinterpret_cast<float4*>(x_out + row * 64 + c4 * 4) = o;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, 131072);
+      for (int i = 0; i < 4; ++i) bulk_g2s(smem + FFP_W + i * 32768, image + i * 32768, 32768, bar_w);
+      mbar_wait(bar_w, 0);
+      constexpr uint32_t IDESC_G1 = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t a1_hi = smem_u32(smem + FFP_A1), a1_lo = a1_hi + 16384u;
+      int n = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+        mbar_wait(a1_full, (uint32_t)n & 1u);
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&d1_empty[h], ((uint32_t)n & 1u) ^ 1u);
+          tc_fence_after();
+          uint32_t acc = 0u;
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? a1_lo : a1_hi;
+            const uint32_t b = ((pass == 1) ? sW1l : sW1h) + (uint32_t)h * 16384u;
+#pragma unroll 1
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_bf16_ss(tmem + (uint32_t)(h * 128), desc_kmajor(a, ks * 16), desc_kmajor(b, ks * 16), IDESC_G1, acc);
+              acc = 1u;
+            }
+          }
+          umma_commit(&d1_full[h]);
+        }
+        umma_commit(a1_empty);
+        const int ds = n & 1;
+        for (int j = 0; j < 4; ++j) {
+          const int c = n * 4 + j, stg = c & 1;
+          mbar_wait(&a2_full[stg], (uint32_t)(c >> 1) & 1u);
+          if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t a2_hi = smem_u32(smem + FFP_A2 + stg * 32768), a2_lo = a2_hi + 16384u;
+          uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? a2_lo : a2_hi;
+            const uint32_t b = ((pass == 1) ? sW2l : sW2h) + (uint32_t)j * 8192u;
+#pragma unroll 1
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_bf16_ss(tmem + (uint32_t)(256 + ds * 64), desc_kmajor(a, ks * 16), desc_kmajor(b, ks * 16), IDESC_G2, acc);
+              acc = 1u;
+            }
+          }
+          umma_commit(&a2_empty[stg]);
+        }
+        umma_commit(&d2_full[ds]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- loaders: s tile -> A1
+    const int lt = tid - kLoaderThread0;
+    uint8_t* sA1h = smem + FFP_A1;
+    uint8_t* sA1l = sA1h + 16384;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      const long long row0 = (long long)tile * 128;
+      float4 v[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
+        v[it] = (row0 + r < P) ? ldg_stream(s + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(a1_empty, ((uint32_t)n & 1u) ^ 1u);
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
+        store_split4_at(sA1h, sA1l, kmajor_sw128_offset(r, c4 * 4), v[it]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(a1_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,
+                   const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st) {
+  if (P == 0) return FFNO_OK;
+  static bool configured = false;
+  if (!configured) {
+    FFNO_CUDA_CHECK(cudaFuncSetAttribute(ff_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFP_TOTAL));
+    configured = true;
+  }
+  const int n_tiles = ceil_div(P, 128);
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  ff_pipe_kernel<<<grid, kThreads, FFP_TOTAL, st>>>(s, residual, x_out, b_out, image, b1, b2, P, n_tiles);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("ff_pipe_kernel");
+  return FFNO_OK;
+}
+
+}  // namespace ffno

@@ -120,20 +120,24 @@ for v in (0, 1):
 CASES["ff_4096"] = (ff_case, (4096,))
 CASES["ff_131072"] = (ff_case, (131072,))
 CASES["block24"] = (block_case, ())
+CASES["block24_v1"] = (block_case, ())     # run with FFNO_UMMA_V1=1 (set by the driver loop below)
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] in CASES:
+    if len(sys.argv) == 2 and sys.argv[1] in CASES and os.environ.get("FFNO_DIAG_CHILD") == "1":
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         fn, args = CASES[sys.argv[1]]
         print("RESULT " + json.dumps(fn(*args)))
         return
     names = sys.argv[1:] or list(CASES)
     out = {}
-    for name in CASES:
+    for name in names:
         try:
+            env = dict(os.environ, FFNO_DIAG_CHILD="1")
+            if name.endswith("_v1"):
+                env["FFNO_UMMA_V1"] = "1"
             r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True,
-                               timeout=180)
+                               timeout=180, env=env)
             line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
             out[name] = json.loads(line[-1][7:]) if line else {"rc": r.returncode, "stderr": r.stderr[-600:]}
         except subprocess.TimeoutExpired:
