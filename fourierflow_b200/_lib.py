@@ -81,7 +81,7 @@ EXPORTS = {
                                      C.c_void_p]),
     "ffno_rel_l2": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                               C.c_int64, C.c_void_p, C.c_void_p]),
-    "ffno_rollout_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
+    "ffno_rollout_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
     "ffno_rollout_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p,
                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ffno_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

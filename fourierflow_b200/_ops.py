@@ -283,7 +283,7 @@ class StackPlan:
         B = frame0.shape[0]
         X, Y = self.size
         with torch.cuda.device(self.device):
-            ws = self._workspace(self.lib.ffno_rollout_workspace_bytes(self._plan, B))
+            ws = self._workspace(self.lib.ffno_rollout_workspace_bytes(self._plan, B, n_steps))
             preds = torch.empty(B, X, Y, n_steps, device=self.device, dtype=torch.float32)
             m = (C.c_float * 3)(*[float(v) for v in mean])
             s = (C.c_float * 3)(*[float(v) for v in std])

@@ -5,6 +5,7 @@
 // the spectral weights, the pre-multiplied head, and (UMMA path) their bf16 hi/lo operand tiles.
 // The forward enqueues kernels on the caller's stream and never synchronises.
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <new>
 #include <vector>
@@ -68,6 +69,25 @@ struct ffno_plan {
   std::map<const void*, float*> dedup;   // source pointer -> prepared buffer (shared weights)
   int64_t last_launches = 0;
   UmmaState* umma = nullptr;
+
+  // CUDA-graph replay of the launch sequence (kills ~120 launch gaps per forward).  A slot is keyed by everything
+  // baked into the captured kernel arguments; the first call with a new key runs eagerly, the second captures.
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    int batch = -1, n_steps = 0, seen = 0;
+    void* ws = nullptr;
+    MeanStd3 ms{};
+    float low = 0.f, high = 0.f;
+    int64_t launches = 0;
+    void reset() {
+      if (exec) cudaGraphExecDestroy(exec);
+      exec = nullptr;
+      batch = -1;
+      seen = 0;
+    }
+  };
+  GraphSlot g_block, g_rollout;
+  bool graphs = true;
 
   LiftGeom geom() const {
     LiftGeom g;
@@ -202,6 +222,7 @@ struct Carver {
 
 struct Workspace {
   float *xa, *xb, *s, *b, *h0, *h1, *F, *R, *tmp, *f, *umma;
+  float *io_in, *io_out;      // fixed-address staging of the stack input / forecast (CUDA-graph replay, host entry)
   size_t bytes;
 };
 
@@ -227,6 +248,8 @@ Workspace carve(const ffno_plan* p, int batch, void* base) {
   w.tmp = c.take(p->d.layer_norm ? U : 0);
   w.f = c.take(p->d.use_fork ? U : 0);
   w.umma = c.take(p->use_umma ? umma_workspace_floats(p->umma, batch) : 0);
+  w.io_in = c.take((size_t)batch * p->pts_in * p->d.in_features);
+  w.io_out = c.take((size_t)batch * p->pts_in * p->d.out_features);
   w.bytes = c.off;
   return w;
 }
@@ -335,6 +358,65 @@ int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, con
   return FFNO_OK;
 }
 
+
+// Capture `body` (which only enqueues kernels on `st`) into an executable graph.  Returns false (and leaves the
+// stream usable) if capture is not possible; the caller then launches eagerly.
+template <class Body>
+bool capture_graph(cudaStream_t st, cudaGraphExec_t* exec, int64_t* launches, Body body) {
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const long long before = g_launch_counter;
+  const int status = body();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &graph);
+  *launches = g_launch_counter - before;
+  if (status != FFNO_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return false;
+  }
+  const cudaError_t ei = cudaGraphInstantiate(exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) {
+    cudaGetLastError();
+    *exec = nullptr;
+    return false;
+  }
+  return true;
+}
+
+// Stack forward on the fixed staging buffers w.io_in -> w.io_out, replayed from a graph when possible.
+int block_fwd_staged(ffno_plan* p, int batch, void* workspace, cudaStream_t st) {
+  const Workspace w = carve(p, batch, workspace);
+  ffno_plan::GraphSlot& g = p->g_block;
+  if (p->graphs) {
+    if (g.exec && g.batch == batch && g.ws == workspace) {
+      FFNO_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+      p->last_launches = g.launches;
+      return FFNO_OK;
+    }
+    if (g.batch == batch && g.ws == workspace && g.seen >= 1 && !g.exec) {
+      if (capture_graph(st, &g.exec, &g.launches, [&] { return block_fwd_impl(p, w.io_in, batch, w.io_out, nullptr, workspace, st); })) {
+        FFNO_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+        p->last_launches = g.launches;
+        return FFNO_OK;
+      }
+      p->graphs = false;       // capture refused: stay eager for the life of this plan
+    } else if (g.batch != batch || g.ws != workspace) {
+      g.reset();
+      g.batch = batch;
+      g.ws = workspace;
+    }
+    g.seen++;
+  }
+  const long long before = g_launch_counter;
+  const int status = block_fwd_impl(p, w.io_in, batch, w.io_out, nullptr, workspace, st);
+  p->last_launches = g_launch_counter - before;
+  return status;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -370,6 +452,10 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
     p->pts_in *= desc->size[a];
   }
   p->in_total = desc->in_features + (desc->append_grid ? desc->ndim : 0);
+  {
+    const char* g = getenv("FFNO_B200_GRAPH");
+    p->graphs = !(g && g[0] == '0');
+  }
   p->layers.resize(desc->n_layers);
   int st = build_tables(p);
   if (st == FFNO_OK) {
@@ -389,6 +475,8 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
 
 int ffno_plan_destroy(ffno_plan* plan) {
   if (!plan) return FFNO_OK;
+  plan->g_block.reset();
+  plan->g_rollout.reset();
   if (plan->umma) umma_destroy(plan->umma);
   for (void* ptr : plan->owned) cudaFree(ptr);
   delete plan;
@@ -403,6 +491,8 @@ int ffno_plan_load_params(ffno_plan* p, const ffno_block_params* prm, void* stre
                prm->n_layers, p->d.n_layers);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int C = p->d.width;
+  p->g_block.reset();          // captured graphs point at the previous parameter buffers' contents: rebuild
+  p->g_rollout.reset();
   p->has_io = prm->in_proj.weight || prm->in_proj.weight_v;
   if (p->has_io) {
     FFNO_TRY(prep_linear(p, prm->in_proj, p->in_total, C, &p->lift, st));
@@ -476,38 +566,37 @@ int ffno_block_fwd(ffno_plan* p, const float* x, int32_t batch, float* forecast,
   if (batch == 0) { p->last_launches = 0; return FFNO_OK; }
   FFNO_REQUIRE(x && forecast, FFNO_ERR_BAD_ARG, "x/forecast is NULL");
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
+  cudaStream_t cst = static_cast<cudaStream_t>(stream);
+  if (!taps && p->graphs) {
+    const Workspace w = carve(p, batch, workspace);
+    const size_t in_b = (size_t)batch * p->pts_in * p->d.in_features * 4;
+    const size_t out_b = (size_t)batch * p->pts_in * p->d.out_features * 4;
+    FFNO_CUDA_CHECK(cudaMemcpyAsync(w.io_in, x, in_b, cudaMemcpyDeviceToDevice, cst));
+    FFNO_TRY(block_fwd_staged(p, batch, workspace, cst));
+    FFNO_CUDA_CHECK(cudaMemcpyAsync(forecast, w.io_out, out_b, cudaMemcpyDeviceToDevice, cst));
+    return FFNO_OK;
+  }
   const long long before = g_launch_counter;
-  int st = block_fwd_impl(p, x, batch, forecast, taps, workspace, static_cast<cudaStream_t>(stream));
+  int st = block_fwd_impl(p, x, batch, forecast, taps, workspace, cst);
   p->last_launches = g_launch_counter - before;
   return st;
 }
 
-size_t ffno_workspace_bytes_host(const ffno_plan* plan, int32_t batch) {
-  if (!plan || batch < 0) return 0;
-  size_t in = ((size_t)batch * plan->pts_in * plan->d.in_features * 4 + 255) / 256 * 256;
-  size_t out = ((size_t)batch * plan->pts_in * plan->d.out_features * 4 + 255) / 256 * 256;
-  return ffno_workspace_bytes(plan, batch) + in + out;
-}
+size_t ffno_workspace_bytes_host(const ffno_plan* plan, int32_t batch) { return ffno_workspace_bytes(plan, batch); }
 
 int ffno_block_fwd_host(ffno_plan* p, const float* x_host, int32_t batch, float* forecast_host, void* workspace,
                         size_t workspace_bytes, void* stream) {
-  const size_t need = ffno_workspace_bytes_host(p, batch);
-  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, need));
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_workspace_bytes(p, batch)));
+  if (batch == 0) { p->last_launches = 0; return FFNO_OK; }
   FFNO_REQUIRE(x_host && forecast_host, FFNO_ERR_BAD_ARG, "x_host/forecast_host is NULL");
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Workspace w = carve(p, batch, workspace);
   const size_t in_b = (size_t)batch * p->pts_in * p->d.in_features * 4;
   const size_t out_b = (size_t)batch * p->pts_in * p->d.out_features * 4;
-  const size_t core = ffno_workspace_bytes(p, batch);
-  char* base = static_cast<char*>(workspace);
-  float* d_in = reinterpret_cast<float*>(base + core);
-  float* d_out = reinterpret_cast<float*>(base + core + (in_b + 255) / 256 * 256);
-  FFNO_CUDA_CHECK(cudaMemcpyAsync(d_in, x_host, in_b, cudaMemcpyHostToDevice, st));
-  const long long before = g_launch_counter;
-  int s = block_fwd_impl(p, d_in, batch, d_out, nullptr, workspace, st);
-  p->last_launches = g_launch_counter - before;
-  if (s != FFNO_OK) return s;
-  FFNO_CUDA_CHECK(cudaMemcpyAsync(forecast_host, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  FFNO_CUDA_CHECK(cudaMemcpyAsync(w.io_in, x_host, in_b, cudaMemcpyHostToDevice, st));
+  FFNO_TRY(block_fwd_staged(p, batch, workspace, st));
+  FFNO_CUDA_CHECK(cudaMemcpyAsync(forecast_host, w.io_out, out_b, cudaMemcpyDeviceToHost, st));
   FFNO_CUDA_CHECK(cudaStreamSynchronize(st));
   return FFNO_OK;
 }
@@ -569,17 +658,18 @@ int ffno_rel_l2(const float* x, int64_t x_stride_b, int64_t x_stride_i, const fl
                        static_cast<cudaStream_t>(stream));
 }
 
-size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch) {
-  if (!plan || batch < 0) return 0;
-  size_t feat = ((size_t)batch * plan->pts_in * 3 * 4 + 255) / 256 * 256;
-  size_t fc = ((size_t)batch * plan->pts_in * 4 + 255) / 256 * 256;
-  return ffno_workspace_bytes(plan, batch) + feat + fc;
+size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch, int32_t n_steps) {
+  if (!plan || batch < 0 || n_steps < 0) return 0;
+  size_t frame = ((size_t)batch * plan->pts_in * 4 + 255) / 256 * 256;
+  size_t preds = ((size_t)batch * plan->pts_in * n_steps * 4 + 255) / 256 * 256;
+  return ffno_workspace_bytes(plan, batch) + frame + preds;
 }
 
 int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n_steps, const float* mean_host,
                      const float* std_host, float low, float high, float* preds, void* workspace,
                      size_t workspace_bytes, void* stream) {
-  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_rollout_workspace_bytes(p, batch)));
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_rollout_workspace_bytes(p, batch, n_steps)));
+  if (batch == 0) { p->last_launches = 0; return FFNO_OK; }
   FFNO_REQUIRE(frame0 && preds && mean_host && std_host, FFNO_ERR_BAD_ARG, "NULL argument");
   FFNO_REQUIRE(p->d.ndim == 2 && p->d.in_features == 3 && p->d.out_features == 1 && !p->d.append_grid &&
                    p->d.pad[0] == 0 && p->d.pad[1] == 0 && !p->d.use_fork,
@@ -588,23 +678,57 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int X = p->d.size[0], Y = p->d.size[1];
-  const size_t core = ffno_workspace_bytes(p, batch);
+  const Workspace w = carve(p, batch, workspace);
   char* base = static_cast<char*>(workspace);
-  float* feat = reinterpret_cast<float*>(base + core);
-  float* fc = reinterpret_cast<float*>(base + core + ((size_t)batch * X * Y * 3 * 4 + 255) / 256 * 256);
+  const size_t frame_b = (size_t)batch * X * Y * 4;
+  float* frame_st = reinterpret_cast<float*>(base + w.bytes);
+  float* preds_st = reinterpret_cast<float*>(base + w.bytes + (frame_b + 255) / 256 * 256);
   MeanStd3 ms;
   for (int i = 0; i < 3; ++i) { ms.m[i] = mean_host[i]; ms.s[i] = std_host[i]; }
-  const long long before = g_launch_counter;
-  for (int t = 0; t < n_steps; ++t) {
-    // step 0 reads the ground-truth frame; later steps read the model's own de-normalised forecast
-    // (routines/grid_2d_markov.py:264-292)
-    if (t == 0) FFNO_TRY(launch_rollout_features(frame0, (long long)X * Y, 1, feat, batch, X, Y, low, high, ms, st));
-    else FFNO_TRY(launch_rollout_features(preds + (t - 1), (long long)X * Y * n_steps, n_steps, feat, batch, X, Y,
-                                          low, high, ms, st));
-    FFNO_TRY(block_fwd_impl(p, feat, batch, fc, nullptr, workspace, st));
-    FFNO_TRY(launch_rollout_denorm(fc, preds, batch, X * Y, n_steps, t, ms, st));
+
+  // the whole step loop: features -> layer stack -> de-normalise, each forecast feeding the next step
+  // (routines/grid_2d_markov.py:263-321); every pointer it touches lives in the caller's workspace
+  auto body = [&]() -> int {
+    for (int t = 0; t < n_steps; ++t) {
+      if (t == 0) FFNO_TRY(launch_rollout_features(frame_st, (long long)X * Y, 1, w.io_in, batch, X, Y, low, high, ms, st));
+      else FFNO_TRY(launch_rollout_features(preds_st + (t - 1), (long long)X * Y * n_steps, n_steps, w.io_in, batch, X,
+                                            Y, low, high, ms, st));
+      FFNO_TRY(block_fwd_impl(p, w.io_in, batch, w.io_out, nullptr, workspace, st));
+      FFNO_TRY(launch_rollout_denorm(w.io_out, preds_st, batch, X * Y, n_steps, t, ms, st));
+    }
+    return FFNO_OK;
+  };
+
+  FFNO_CUDA_CHECK(cudaMemcpyAsync(frame_st, frame0, frame_b, cudaMemcpyDeviceToDevice, st));
+  ffno_plan::GraphSlot& g = p->g_rollout;
+  bool done = false;
+  if (p->graphs) {
+    const bool same = g.batch == batch && g.ws == workspace && g.n_steps == n_steps && g.low == low && g.high == high &&
+                      memcmp(&g.ms, &ms, sizeof(ms)) == 0;
+    if (same && g.exec) {
+      FFNO_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+      p->last_launches = g.launches;
+      done = true;
+    } else if (same && g.seen >= 1) {
+      if (capture_graph(st, &g.exec, &g.launches, body)) {
+        FFNO_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+        p->last_launches = g.launches;
+        done = true;
+      } else {
+        p->graphs = false;
+      }
+    } else if (!same) {
+      g.reset();
+      g.batch = batch; g.ws = workspace; g.n_steps = n_steps; g.low = low; g.high = high; g.ms = ms;
+    }
+    if (!done) g.seen++;
   }
-  p->last_launches = g_launch_counter - before;
+  if (!done) {
+    const long long before = g_launch_counter;
+    FFNO_TRY(body());
+    p->last_launches = g_launch_counter - before;
+  }
+  FFNO_CUDA_CHECK(cudaMemcpyAsync(preds, preds_st, frame_b * n_steps, cudaMemcpyDeviceToDevice, st));
   return FFNO_OK;
 }
 

@@ -45,6 +45,7 @@ int launch_pack_table_image(const float* T /*[n_in][ldt]*/, int ldt, int n_in, i
 int launch_axis_umma(const AxisXform& p, int sm_count, cudaStream_t st);
 
 // Warp-specialised, double-buffered versions (umma_pipelined.cu): same arithmetic, loads / MMAs / epilogues overlap.
+bool axis_pipe_fits(int n_in, int n_out);
 int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st);   // axes run concurrently
 int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st);
 int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,

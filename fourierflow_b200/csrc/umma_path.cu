@@ -186,7 +186,9 @@ int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float*
                       cudaStream_t st) {
   const UmmaLayer& L = s->layers[layer];
   bool all_umma = true;
-  for (int a = 0; a < s->d.ndim; ++a) all_umma &= (s->fwd_image[a] != nullptr) && (s->inv_image[a] != nullptr);
+  for (int a = 0; a < s->d.ndim; ++a)
+    all_umma &= (s->fwd_image[a] != nullptr) && (s->inv_image[a] != nullptr) &&
+                axis_pipe_fits(s->ext[a], 2 * s->d.modes[a]) && axis_pipe_fits(2 * s->d.modes[a], s->ext[a]);
   if (s->v1 || !all_umma) return spectral_v1(s, L, x, batch, s_out, F, R, st);
 
   AxisXform fwd[3];

@@ -41,6 +41,15 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
                : "l"(p));
   return v;
 }
+// Ampere-style async copy (SASS: LDGSTS): 16 bytes global -> shared, L2-only; src_bytes = 0 zero-fills.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void store_split4_at(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t off, float4 v) {
   uint32_t h0, l0, h1, l1;
   split2(v.x, v.y, h0, l0);
@@ -54,9 +63,11 @@ __device__ __forceinline__ void store_split4_at(uint8_t* tile_hi, uint8_t* tile_
 // =======================================================================================================
 // Axis transform (forward / inverse truncated DFT), up to 3 axes per launch (blockIdx.y = axis)
 // =======================================================================================================
-constexpr int AXP_A_STAGE = 32768;                 // hi 16 KB | lo 16 KB
+constexpr int AXP_A_STAGE = 32768;                 // operand stage: hi 16 KB | lo 16 KB
 constexpr int AXP_BAR = 2 * AXP_A_STAGE;           // 65536
-constexpr int AXP_TABLE = AXP_BAR + 1024;
+constexpr int AXP_STAGING = AXP_BAR + 1024;        // kAxStages x 32 KB of raw FP32 (cp.async landing zone)
+constexpr int kAxStages = 3;
+constexpr int AXP_TABLE = AXP_STAGING + kAxStages * 32768;
 
 struct AxisSet {
   AxisXform ax[3];
@@ -115,7 +126,11 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       const long long G = (long long)tile * 2 + (tid >> 6);
       const bool live = G < n_groups;
       long long o = 0, g = 0;
-      if (live) { o = G / gpi; g = G - o * gpi; }
+      if (live) {
+        const unsigned uo = (unsigned)G / (unsigned)gpi;
+        o = uo;
+        g = (unsigned)G - uo * (unsigned)gpi;
+      }
       float* ybase = p.Y + (o * p.n_out) * p.inner + g * 64 + (tid & 63);
 #pragma unroll 1
       for (int c0 = 0; c0 < p.npad; c0 += 32) {
@@ -186,43 +201,65 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- loaders
+    // Each thread streams its own 16 x 16 B of every work item through a private slice of the staging ring with
+    // cp.async (kAxStages items = 96 KB in flight per CTA, no registers held), then converts the item that has
+    // landed: FP32 -> BF16 hi/lo, MN-major SWIZZLE_128B operand stage.  A thread only ever reads what it copied,
+    // so the ring needs no cross-thread synchronisation (per-thread cp.async groups).
     const int lt = tid - kLoaderThread0;
-    int item = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long G0 = (long long)tile * 2;
-      for (int kc = 0; kc < p.kchunks; ++kc, ++item) {
-        const int as = item & 1;
-        float4 v[16];
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_items = my_tiles * p.kchunks;
+    const int gsel = (lt >> 4) & 1, c4 = lt & 15;
+    uint8_t* stg_base = smem + AXP_STAGING + lt * 16;
+    auto issue = [&](int item) {
+      if (item < n_items) {
+        const int tile = (int)blockIdx.x + (item / p.kchunks) * (int)gridDim.x;
+        const int kc = item - (item / p.kchunks) * p.kchunks;
+        const long long G = (long long)tile * 2 + gsel;
+        const bool live = G < n_groups;
+        const int o = live ? (int)((unsigned)G / (unsigned)gpi) : 0;
+        const int g = live ? (int)((unsigned)G - (unsigned)o * (unsigned)gpi) : 0;
+        const float* src0 = p.X + ((long long)o * p.n_in) * p.inner + (long long)g * 64 + c4 * 4;
+        uint8_t* dst = stg_base + (item % kAxStages) * 32768;
 #pragma unroll
         for (int it = 0; it < 16; ++it) {
-          const int idx = it * 128 + lt, il = idx >> 5, gsel = (idx >> 4) & 1, c4 = idx & 15;
-          const long long G = G0 + gsel;
-          const int i = kc * 64 + il;
-          if (G < n_groups && i < p.n_in) {
-            const long long o = G / gpi, g = G - o * gpi;
-            v[it] = ldg_stream(p.X + ((o * p.n_in + i) * p.inner + g * 64 + c4 * 4));
-          } else {
-            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          const int i = kc * 64 + it * 4 + (lt >> 5);
+          const bool ok = live && i < p.n_in;
+          cp_async16(dst + it * 2048, ok ? (const void*)(src0 + (long long)i * p.inner) : (const void*)p.X, ok ? 16u : 0u);
         }
-        mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
-        uint8_t* sAh = smem + as * AXP_A_STAGE;
-        uint8_t* sAl = sAh + 16384;
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int idx = it * 128 + lt, il = idx >> 5, gsel = (idx >> 4) & 1, c4 = idx & 15;
-          const uint32_t off = (uint32_t)gsel * 8192u + (uint32_t)(il >> 3) * 1024u + (uint32_t)(il & 7) * 128u +
-                               (uint32_t)(((c4 >> 1) ^ (il & 7)) << 4) + (uint32_t)(c4 & 1) * 8u;
-          store_split4_at(sAh, sAl, off, v[it]);
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&a_full[as]);
       }
+      cp_async_commit();
+    };
+    for (int q = 0; q < kAxStages; ++q) issue(q);
+    for (int item = 0; item < n_items; ++item) {
+      cp_async_wait<kAxStages - 1>();
+      const uint8_t* src = stg_base + (item % kAxStages) * 32768;
+      float4 v[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * 2048);
+      const int as = item & 1;
+      mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
+      uint8_t* sAh = smem + as * AXP_A_STAGE;
+      uint8_t* sAl = sAh + 16384;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int il = it * 4 + (lt >> 5);
+        const uint32_t off = (uint32_t)gsel * 8192u + (uint32_t)(il >> 3) * 1024u + (uint32_t)(il & 7) * 128u +
+                             (uint32_t)(((c4 >> 1) ^ (il & 7)) << 4) + (uint32_t)(c4 & 1) * 8u;
+        store_split4_at(sAh, sAl, off, v[it]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[as]);
+      issue(item + kAxStages);
     }
+    cp_async_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+bool axis_pipe_fits(int n_in, int n_out) {
+  return n_out <= 256 && AXP_TABLE + table_image_bytes(n_in, n_out) <= (size_t)227 * 1024;
 }
 
 int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st) {
@@ -236,6 +273,7 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
     FFNO_REQUIRE(p.npad >= 16 && p.npad <= 256 && p.npad % 16 == 0, FFNO_ERR_UNSUPPORTED, "axis_pipe: npad=%d", p.npad);
     const size_t need = AXP_TABLE + table_image_bytes(p.n_in, p.n_out);
     FFNO_REQUIRE(need <= 227 * 1024, FFNO_ERR_UNSUPPORTED, "axis_pipe: table does not fit in shared memory");
+    FFNO_REQUIRE(p.outer * (p.inner / 64) < (1ll << 31), FFNO_ERR_UNSUPPORTED, "axis_pipe: too many groups");
     smem = need > smem ? need : smem;
     set.ax[a] = p;
     const long long n_groups = p.outer * (p.inner / 64);
@@ -267,7 +305,9 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
 constexpr int MXP_A_STAGE = 32768;
 constexpr int MXP_B = 2 * MXP_A_STAGE;             // 65536: B image 64 KB
 constexpr int MXP_BAR = MXP_B + 65536;             // 131072
-constexpr int MXP_TOTAL = MXP_BAR + 128;
+constexpr int MXP_STAGING = MXP_BAR + 1024;        // kMxStages x 32 KB raw FP32 (cp.async landing zone)
+constexpr int kMxStages = 3;
+constexpr int MXP_TOTAL = MXP_STAGING + kMxStages * 32768;     // 230400 <= 232448
 
 struct MixSet {
   MixAxis ax[3];
@@ -325,7 +365,11 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
       tc_fence_after();
       const long long row = (long long)tile * 128 + tid;
       long long o = 0, pp = 0;
-      if (row < M) { o = row / ax.p_inner; pp = row - o * ax.p_inner; }
+      if (row < M) {
+        const unsigned uo = (unsigned)row / (unsigned)ax.p_inner;
+        o = uo;
+        pp = (unsigned)row - uo * (unsigned)ax.p_inner;
+      }
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         uint32_t v[32];
@@ -382,36 +426,46 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
     }
     __syncwarp();
   } else {
+    // cp.async staging ring, one private slice per thread (see axis_pipe_kernel)
     const int lt = tid - kLoaderThread0;
-    int item = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const long long row0 = (long long)tile * 128;
-      for (int half = 0; half < 2; ++half, ++item) {
-        const int as = item & 1;
-        float4 v[16];
+    const int n_items = (tile_end - tile_begin) * 2;
+    const int c4 = lt & 15, rsub = lt >> 4;
+    const unsigned p_in = (unsigned)ax.p_inner;
+    uint8_t* stg_base = smem + MXP_STAGING + lt * 16;
+    auto issue = [&](int item) {
+      if (item < n_items) {
+        const int tile = tile_begin + (item >> 1), half = item & 1;
+        uint8_t* dst = stg_base + (item % kMxStages) * 32768;
 #pragma unroll
         for (int it = 0; it < 16; ++it) {
-          const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
-          const long long row = row0 + r;
-          if (row < M) {
-            const long long o = row / ax.p_inner, pp = row - o * ax.p_inner;
-            v[it] = ldg_stream(ax.F + ((o * ax.K + k) * 2 + half) * inner + pp * 64 + c4 * 4);
-          } else {
-            v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          const long long row = (long long)tile * 128 + it * 8 + rsub;
+          const bool ok = row < M;
+          const unsigned urow = ok ? (unsigned)row : 0u;
+          const unsigned o = urow / p_in, pp = urow - o * p_in;
+          const float* src = ax.F + (((long long)o * ax.K + k) * 2 + half) * inner + (long long)pp * 64 + c4 * 4;
+          cp_async16(dst + it * 2048, ok ? (const void*)src : (const void*)ax.F, ok ? 16u : 0u);
         }
-        mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
-        uint8_t* sAh = smem + as * MXP_A_STAGE;
-        uint8_t* sAl = sAh + 16384;
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
-          store_split4_at(sAh, sAl, kmajor_sw128_offset(r, c4 * 4), v[it]);
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&a_full[as]);
       }
+      cp_async_commit();
+    };
+    for (int q = 0; q < kMxStages; ++q) issue(q);
+    for (int item = 0; item < n_items; ++item) {
+      cp_async_wait<kMxStages - 1>();
+      const uint8_t* src = stg_base + (item % kMxStages) * 32768;
+      float4 v[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * 2048);
+      const int as = item & 1;
+      mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
+      uint8_t* sAh = smem + as * MXP_A_STAGE;
+      uint8_t* sAl = sAh + 16384;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) store_split4_at(sAh, sAl, kmajor_sw128_offset(it * 8 + rsub, c4 * 4), v[it]);
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[as]);
+      issue(item + kMxStages);
     }
+    cp_async_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -464,7 +518,14 @@ constexpr int FFP_BIAS = FFP_A2 + 65536;           // 229376
 constexpr int FFP_BAR = FFP_BIAS + 320 * 4;        // 230656
 constexpr int FFP_TOTAL = FFP_BAR + 160;           // 230816 <= 232448
 
-__global__ void __launch_bounds__(kThreads, 1)
+// Roles (17 warps): 0-3 chunk epilogue (D1 -> +b1, ReLU, split -> A2), 4-7 store warps (prefetch the residual
+// rows, then D2 + b2 + residual -> global), 8 MMA issuer, 9-12 / 13-16 two loader teams on alternating tiles (each
+// keeps one 32 KB tile of s in flight in registers while the other converts).
+constexpr int kFFThreads = 544;
+constexpr int kFFMmaWarp = 8;
+constexpr int kFFLoaderThread0 = 288;
+
+__global__ void __launch_bounds__(kFFThreads, 1)
 ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, float* __restrict__ x_out,
                float* __restrict__ b_out, const uint8_t* __restrict__ image, const float* __restrict__ b1,
                const float* __restrict__ b2, long long P, int n_tiles) {
@@ -472,14 +533,14 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
   float* sb1 = reinterpret_cast<float*>(smem + FFP_BIAS);
   float* sb2 = sb1 + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FFP_BAR);
-  uint64_t* a1_full = bars;        // count 128 (loaders)
+  uint64_t* a1_full = bars;        // count 128 (one loader team)
   uint64_t* a1_empty = bars + 1;   // commit
   uint64_t* d1_full = bars + 2;    // [2] commit
-  uint64_t* d1_empty = bars + 4;   // [2] 128 (epilogue)
-  uint64_t* a2_full = bars + 6;    // [2] 128 (epilogue)
+  uint64_t* d1_empty = bars + 4;   // [2] 128 (chunk epilogue)
+  uint64_t* a2_full = bars + 6;    // [2] 128 (chunk epilogue)
   uint64_t* a2_empty = bars + 8;   // [2] commit
   uint64_t* d2_full = bars + 10;   // [2] commit
-  uint64_t* d2_empty = bars + 12;  // [2] 128 (epilogue)
+  uint64_t* d2_empty = bars + 12;  // [2] 128 (store warps)
   uint64_t* bar_w = bars + 14;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
@@ -502,7 +563,7 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  for (int i = tid; i < 256; i += kThreads) sb1[i] = b1 ? b1[i] : 0.f;
+  for (int i = tid; i < 256; i += kFFThreads) sb1[i] = b1 ? b1[i] : 0.f;
   if (tid < 64) sb2[tid] = b2 ? b2[tid] : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -511,8 +572,8 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
   // TMEM columns: D1 half h at h*128 (128 cols each), D2 stage t at 256 + t*64
   const uint32_t sW1h = smem_u32(smem + FFP_W), sW1l = sW1h + 32768u, sW2h = sW1h + 65536u, sW2l = sW1h + 98304u;
 
-  if (warp < kEpiWarps) {
-    // ---------------------------------------------------------------- epilogue warps (thread = row)
+  if (warp < 4) {
+    // ---------------------------------------------------------------- chunk epilogue (thread = row)
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
@@ -553,38 +614,54 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
         fence_proxy_async_smem();
         mbar_arrive(&a2_full[stg]);
       }
-      // ---- final epilogue of this tile
+    }
+  } else if (warp < 8) {
+    // ---------------------------------------------------------------- store warps (thread = row)
+    const int rt = tid - 128;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      const long long row = (long long)tile * 128 + rt;
+      const bool live = row < P;
+      float4 r[16];
+      if (residual && live) {              // issued before the accumulator is ready: latency hides behind the MMAs
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) r[c4] = ldg_stream(residual + row * 64 + c4 * 4);
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) r[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       const int ds = n & 1;
       mbar_wait(&d2_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
-      uint32_t v0[32], v1[32];
-      tmem_ld32(tmem + lane_base + (uint32_t)(256 + ds * 64), v0);
-      tmem_ld32(tmem + lane_base + (uint32_t)(256 + ds * 64 + 32), v1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&d2_empty[ds]);
-      const long long row = (long long)tile * 128 + tid;
-      if (row < P) {
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          float4 b;
-          b.x = __uint_as_float(c4 < 8 ? v0[c4 * 4 + 0] : v1[c4 * 4 - 32 + 0]) + sb2[c4 * 4 + 0];
-          b.y = __uint_as_float(c4 < 8 ? v0[c4 * 4 + 1] : v1[c4 * 4 - 32 + 1]) + sb2[c4 * 4 + 1];
-          b.z = __uint_as_float(c4 < 8 ? v0[c4 * 4 + 2] : v1[c4 * 4 - 32 + 2]) + sb2[c4 * 4 + 2];
-          b.w = __uint_as_float(c4 < 8 ? v0[c4 * 4 + 3] : v1[c4 * 4 - 32 + 3]) + sb2[c4 * 4 + 3];
-          if (b_out) *reinterpret_cast<float4*>(b_out + row * 64 + c4 * 4) = b;
-          if (x_out) {
-            float4 o = b;
-            if (residual) {
-              float4 r = *reinterpret_cast<const float4*>(residual + row * 64 + c4 * 4);
-              o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + (uint32_t)(256 + ds * 64 + half * 32), v);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          mbar_arrive(&d2_empty[ds]);
+        }
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c4 = half * 8 + q;
+            float4 b;
+            b.x = __uint_as_float(v[q * 4 + 0]) + sb2[c4 * 4 + 0];
+            b.y = __uint_as_float(v[q * 4 + 1]) + sb2[c4 * 4 + 1];
+            b.z = __uint_as_float(v[q * 4 + 2]) + sb2[c4 * 4 + 2];
+            b.w = __uint_as_float(v[q * 4 + 3]) + sb2[c4 * 4 + 3];
+            if (b_out) *reinterpret_cast<float4*>(b_out + row * 64 + c4 * 4) = b;
+            if (x_out) {
+              float4 o = make_float4(b.x + r[c4].x, b.y + r[c4].y, b.z + r[c4].z, b.w + r[c4].w);
+              *reinterpret_cast<float4*>(x_out + row * 64 + c4 * 4) = o;
             }
-            *reinterpret_cast<float4*>(x_out + row * 64 + c4 * 4) = o;
           }
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kFFMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       mbar_expect_tx(bar_w, 131072);
@@ -638,12 +715,14 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
     }
     __syncwarp();
   } else {
-    // ---------------------------------------------------------------- loaders: s tile -> A1
-    const int lt = tid - kLoaderThread0;
+    // ---------------------------------------------------------------- loader teams: s tile -> A1
+    const int team = (tid - kFFLoaderThread0) >> 7;
+    const int lt = (tid - kFFLoaderThread0) & 127;
     uint8_t* sA1h = smem + FFP_A1;
     uint8_t* sA1l = sA1h + 16384;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      if ((n & 1) != team) continue;
       const long long row0 = (long long)tile * 128;
       float4 v[16];
 #pragma unroll
@@ -676,7 +755,7 @@ int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b
   }
   const int n_tiles = ceil_div(P, 128);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  ff_pipe_kernel<<<grid, kThreads, FFP_TOTAL, st>>>(s, residual, x_out, b_out, image, b1, b2, P, n_tiles);
+  ff_pipe_kernel<<<grid, kFFThreads, FFP_TOTAL, st>>>(s, residual, x_out, b_out, image, b1, b2, P, n_tiles);
   ++g_launch_counter;
   FFNO_LAUNCH_CHECK("ff_pipe_kernel");
   return FFNO_OK;

@@ -158,7 +158,9 @@ FFNO_API int ffno_block_fwd(ffno_plan* plan, const float* x, int32_t batch, floa
                    const ffno_taps* taps, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same through HOST buffers: copies x H2D, runs, copies forecast D2H, waits.  Device scratch is the
- * caller's `workspace` (device) plus two staging areas carved from it; see ffno_workspace_bytes_host. */
+ * caller's `workspace` (device), which already contains the two staging areas.
+ * Calls without taps replay a CUDA graph of the launch sequence from their second use on (same batch and
+ * workspace); set FFNO_B200_GRAPH=0 to force eager launches. */
 FFNO_API size_t ffno_workspace_bytes_host(const ffno_plan* plan, int32_t batch);
 FFNO_API int ffno_block_fwd_host(ffno_plan* plan, const float* x_host, int32_t batch, float* forecast_host,
                         void* workspace, size_t workspace_bytes, void* stream);
@@ -196,7 +198,7 @@ FFNO_API int ffno_rel_l2(const float* x, int64_t x_stride_b, int64_t x_stride_i,
 FFNO_API int ffno_rollout_fwd(ffno_plan* plan, const float* frame0, int32_t batch, int32_t n_steps,
                      const float* mean_host, const float* std_host, float low, float high,
                      float* preds, void* workspace, size_t workspace_bytes, void* stream);
-FFNO_API size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch);
+FFNO_API size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch, int32_t n_steps);
 
 /* Diagnostics: one tcgen05 product D[128][N] = A[128][K] * B[N][K]^T (bf16 bit patterns in, FP32 out) through
  * the operand layouts / descriptors the kernels use (a_mn / b_mn: operand stored MN-major; variant selects the
