@@ -86,6 +86,7 @@ EXPORTS = {
                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ffno_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_void_p]),
+    "ffno_debug_timeline": (C.c_int, [C.c_int32, C.c_void_p]),
     "ffno_plan_last_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

@@ -738,6 +738,10 @@ int ffno_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int32_t N
   return launch_umma_selftest(A, B, D, N, K, a_mn, b_mn, variant, static_cast<cudaStream_t>(stream));
 }
 
+int ffno_debug_timeline(int32_t enable, int64_t* host_out) {
+  return debug_timeline(enable, reinterpret_cast<long long*>(host_out));
+}
+
 int64_t ffno_plan_last_launch_count(const ffno_plan* plan) { return plan ? plan->last_launches : 0; }
 
 }  // extern "C"

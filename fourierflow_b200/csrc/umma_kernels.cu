@@ -700,6 +700,18 @@ umma_selftest_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const bool a_tmem = (variant & 2) != 0;          // A operand from tensor memory (K = 64): columns [256-N.. hmm
+  if (a_tmem) {
+    // row = this thread; pack (k, k+1) into one 32-bit column, low half = even k; A lives at columns 256.. of a
+    // 512-column allocation is not available here (256 allocated): use columns N..N+31 (N <= 192 in this mode)
+    uint32_t v[32];
+    for (int c = 0; c < 32; ++c) v[c] = (uint32_t)A[tid * K + 2 * c] | ((uint32_t)A[tid * K + 2 * c + 1] << 16);
+    tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)N, v);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   if (tid == 0) {
     const uint32_t idesc = make_idesc_bf16(128, N, a_mn, b_mn);
     const uint32_t mn_lbo = (uint32_t)(K / 8) * 1024u, mn_sbo = 1024u;
@@ -711,7 +723,8 @@ umma_selftest_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict_
       if (b_mn) bd = (variant & 1) ? make_smem_desc_sw128(smem_u32(sB) + ks * 2048, mn_sbo, mn_lbo)
                                    : make_smem_desc_sw128(smem_u32(sB) + ks * 2048, mn_lbo, mn_sbo);
       else bd = desc_kmajor(smem_u32(sB) + (ks >> 2) * (N * 128), (ks & 3) * 16);
-      umma_bf16_ss(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      if (a_tmem) umma_bf16_ts(tmem, tmem + (uint32_t)N + (uint32_t)ks * 8u, bd, idesc, ks > 0 ? 1u : 0u);
+      else umma_bf16_ss(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
     }
     umma_commit(bar);
   }
@@ -734,6 +747,7 @@ int launch_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int N, 
                "selftest: N=%d K=%d", N, K);
   FFNO_REQUIRE((!a_mn && !b_mn) || K % 8 == 0, FFNO_ERR_BAD_ARG, "selftest: K");
   FFNO_REQUIRE(!b_mn || N % 64 == 0, FFNO_ERR_BAD_ARG, "selftest: MN-major B needs N %% 64 == 0");
+  FFNO_REQUIRE(!(variant & 2) || (K == 64 && N <= 192 && !a_mn), FFNO_ERR_BAD_ARG, "selftest: TMEM-A mode needs K=64, N<=192");
   const int smem = 196608 + 64;
   FFNO_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_selftest_kernel<<<1, 128, smem, st>>>(A, B, D, N, K, a_mn, b_mn, variant);

@@ -51,6 +51,9 @@ int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t 
 int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,
                    const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st);
 
+// Diagnostics: in-kernel clock64 timeline of block 0 of ff_pipe_kernel ([role 8][tile 16][event 8]).
+int debug_timeline(int enable, long long* host_out);
+
 // Diagnostics: D[128][N] = A[128][K] * B[N][K]^T with bf16 inputs (raw ushort), one CTA, every layout variant
 // the kernels rely on (a_mn / b_mn: operand stored MN-major; variant: LBO/SBO interpretation under test).
 int launch_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int N, int K, int a_mn, int b_mn,

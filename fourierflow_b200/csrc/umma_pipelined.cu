@@ -16,12 +16,26 @@ namespace ffno {
 extern thread_local long long g_launch_counter;
 using namespace umma;
 
+// Optional in-kernel timeline (diagnostics): block 0 records clock64() at pipeline events into g_timeline
+// [role 8][tile 16][event 8]; enabled by ffno_debug_timeline(1).  Costs one predicated store per event.
+__device__ long long g_timeline[8 * 16 * 8];
+__device__ int g_timeline_on = 0;
+#define TL(role, tile_n, ev)                                                                      \
+  do {                                                                                            \
+    if (g_timeline_on && blockIdx.x == 0 && (tile_n) < 16 && (threadIdx.x & 31) == 0)             \
+      g_timeline[((role) * 16 + (tile_n)) * 8 + (ev)] = clock64();                                \
+  } while (0)
+
 namespace {
 
-constexpr int kThreads = 288;
+// axis / mix kernels: 4 epilogue warps, 1 MMA warp, 16 loader-converter warps.  The FP32 -> BF16 hi/lo conversion is
+// ~25 instructions per float4 and is what bounds these kernels, so it is spread over as many warps as fit.
+constexpr int kLoaders = 512;
+constexpr int kThreads = 160 + kLoaders;       // 672
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kLoaderThread0 = 160;
+constexpr int kLdPerThread = 2048 / kLoaders;  // float4 per thread per 32 KB work item
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
@@ -96,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 128);
+      mbar_init(&a_full[i], kLoaders);
       mbar_init(&a_empty[i], 1);
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 128);
@@ -143,12 +157,17 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
         }
         if (live) {
           if (p.accumulate) {
-            float old[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) old[j] = (c0 + j < p.n_out) ? ybase[(long long)(c0 + j) * p.inner] : 0.f;
+            for (int j0 = 0; j0 < 32; j0 += 8) {        // 8 independent read-modify-writes in flight per thread
+              float old[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.n_out) ybase[(long long)(c0 + j) * p.inner] = __uint_as_float(v[j]) + old[j];
+              for (int j = 0; j < 8; ++j)
+                old[j] = (c0 + j0 + j < p.n_out) ? ybase[(long long)(c0 + j0 + j) * p.inner] : 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (c0 + j0 + j < p.n_out)
+                  ybase[(long long)(c0 + j0 + j) * p.inner] = __uint_as_float(v[j0 + j]) + old[j];
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -208,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     const int lt = tid - kLoaderThread0;
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_items = my_tiles * p.kchunks;
-    const int gsel = (lt >> 4) & 1, c4 = lt & 15;
+    const int gsel = (lt >> 4) & 1, c4 = lt & 15, rsub = lt >> 5;            // rsub: 0..15
     uint8_t* stg_base = smem + AXP_STAGING + lt * 16;
     auto issue = [&](int item) {
       if (item < n_items) {
@@ -221,10 +240,11 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
         const float* src0 = p.X + ((long long)o * p.n_in) * p.inner + (long long)g * 64 + c4 * 4;
         uint8_t* dst = stg_base + (item % kAxStages) * 32768;
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int i = kc * 64 + it * 4 + (lt >> 5);
+        for (int it = 0; it < kLdPerThread; ++it) {
+          const int i = kc * 64 + it * 16 + rsub;
           const bool ok = live && i < p.n_in;
-          cp_async16(dst + it * 2048, ok ? (const void*)(src0 + (long long)i * p.inner) : (const void*)p.X, ok ? 16u : 0u);
+          cp_async16(dst + it * (kLoaders * 16), ok ? (const void*)(src0 + (long long)i * p.inner) : (const void*)p.X,
+                     ok ? 16u : 0u);
         }
       }
       cp_async_commit();
@@ -233,16 +253,16 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     for (int item = 0; item < n_items; ++item) {
       cp_async_wait<kAxStages - 1>();
       const uint8_t* src = stg_base + (item % kAxStages) * 32768;
-      float4 v[16];
+      float4 v[kLdPerThread];
 #pragma unroll
-      for (int it = 0; it < 16; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * 2048);
+      for (int it = 0; it < kLdPerThread; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * (kLoaders * 16));
       const int as = item & 1;
       mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
       uint8_t* sAh = smem + as * AXP_A_STAGE;
       uint8_t* sAl = sAh + 16384;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int il = it * 4 + (lt >> 5);
+      for (int it = 0; it < kLdPerThread; ++it) {
+        const int il = it * 16 + rsub;
         const uint32_t off = (uint32_t)gsel * 8192u + (uint32_t)(il >> 3) * 1024u + (uint32_t)(il & 7) * 128u +
                              (uint32_t)(((c4 >> 1) ^ (il & 7)) << 4) + (uint32_t)(c4 & 1) * 8u;
         store_split4_at(sAh, sAl, off, v[it]);
@@ -338,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 128);
+      mbar_init(&a_full[i], kLoaders);
       mbar_init(&a_empty[i], 1);
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 128);
@@ -429,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
     // cp.async staging ring, one private slice per thread (see axis_pipe_kernel)
     const int lt = tid - kLoaderThread0;
     const int n_items = (tile_end - tile_begin) * 2;
-    const int c4 = lt & 15, rsub = lt >> 4;
+    const int c4 = lt & 15, rsub = lt >> 4;                                   // rsub: 0..31
     const unsigned p_in = (unsigned)ax.p_inner;
     uint8_t* stg_base = smem + MXP_STAGING + lt * 16;
     auto issue = [&](int item) {
@@ -437,13 +457,13 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
         const int tile = tile_begin + (item >> 1), half = item & 1;
         uint8_t* dst = stg_base + (item % kMxStages) * 32768;
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const long long row = (long long)tile * 128 + it * 8 + rsub;
+        for (int it = 0; it < kLdPerThread; ++it) {
+          const long long row = (long long)tile * 128 + it * 32 + rsub;
           const bool ok = row < M;
           const unsigned urow = ok ? (unsigned)row : 0u;
           const unsigned o = urow / p_in, pp = urow - o * p_in;
           const float* src = ax.F + (((long long)o * ax.K + k) * 2 + half) * inner + (long long)pp * 64 + c4 * 4;
-          cp_async16(dst + it * 2048, ok ? (const void*)src : (const void*)ax.F, ok ? 16u : 0u);
+          cp_async16(dst + it * (kLoaders * 16), ok ? (const void*)src : (const void*)ax.F, ok ? 16u : 0u);
         }
       }
       cp_async_commit();
@@ -452,15 +472,16 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
     for (int item = 0; item < n_items; ++item) {
       cp_async_wait<kMxStages - 1>();
       const uint8_t* src = stg_base + (item % kMxStages) * 32768;
-      float4 v[16];
+      float4 v[kLdPerThread];
 #pragma unroll
-      for (int it = 0; it < 16; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * 2048);
+      for (int it = 0; it < kLdPerThread; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * (kLoaders * 16));
       const int as = item & 1;
       mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
       uint8_t* sAh = smem + as * MXP_A_STAGE;
       uint8_t* sAl = sAh + 16384;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) store_split4_at(sAh, sAl, kmajor_sw128_offset(it * 8 + rsub, c4 * 4), v[it]);
+      for (int it = 0; it < kLdPerThread; ++it)
+        store_split4_at(sAh, sAl, kmajor_sw128_offset(it * 32 + rsub, c4 * 4), v[it]);
       fence_proxy_async_smem();
       mbar_arrive(&a_full[as]);
       issue(item + kMxStages);
@@ -518,12 +539,13 @@ constexpr int FFP_BIAS = FFP_A2 + 65536;           // 229376
 constexpr int FFP_BAR = FFP_BIAS + 320 * 4;        // 230656
 constexpr int FFP_TOTAL = FFP_BAR + 160;           // 230816 <= 232448
 
-// Roles (17 warps): 0-3 chunk epilogue (D1 -> +b1, ReLU, split -> A2), 4-7 store warps (prefetch the residual
-// rows, then D2 + b2 + residual -> global), 8 MMA issuer, 9-12 / 13-16 two loader teams on alternating tiles (each
-// keeps one 32 KB tile of s in flight in registers while the other converts).
+// Roles (17 warps): 0-3 / 4-7 two chunk-epilogue teams (team t turns the odd/even 64-column chunks of D1 into the
+// A2 stage t: +b1, ReLU, BF16 hi/lo split), 8-11 store warps (prefetch the residual rows, then D2 + b2 + residual ->
+// global), 12 MMA issuer, 13-16 loaders (s tile -> A1, next tile's loads in flight in registers).
+// The per-element epilogue arithmetic (~7 instructions) is what bounds this kernel, hence 12 of 17 warps do it.
 constexpr int kFFThreads = 544;
-constexpr int kFFMmaWarp = 8;
-constexpr int kFFLoaderThread0 = 288;
+constexpr int kFFMmaWarp = 12;
+constexpr int kFFLoaderThread0 = 416;
 
 __global__ void __launch_bounds__(kFFThreads, 1)
 ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, float* __restrict__ x_out,
@@ -533,11 +555,11 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
   float* sb1 = reinterpret_cast<float*>(smem + FFP_BIAS);
   float* sb2 = sb1 + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FFP_BAR);
-  uint64_t* a1_full = bars;        // count 128 (one loader team)
+  uint64_t* a1_full = bars;        // count 128 (loaders)
   uint64_t* a1_empty = bars + 1;   // commit
   uint64_t* d1_full = bars + 2;    // [2] commit
-  uint64_t* d1_empty = bars + 4;   // [2] 128 (chunk epilogue)
-  uint64_t* a2_full = bars + 6;    // [2] 128 (chunk epilogue)
+  uint64_t* d1_empty = bars + 4;   // [2] 256 (both chunk-epilogue teams)
+  uint64_t* a2_full = bars + 6;    // [2] 128 (team t)
   uint64_t* a2_empty = bars + 8;   // [2] commit
   uint64_t* d2_full = bars + 10;   // [2] commit
   uint64_t* d2_empty = bars + 12;  // [2] 128 (store warps)
@@ -550,7 +572,7 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
     mbar_init(a1_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d1_full[i], 1);
-      mbar_init(&d1_empty[i], 128);
+      mbar_init(&d1_empty[i], 256);
       mbar_init(&a2_full[i], 128);
       mbar_init(&a2_empty[i], 1);
       mbar_init(&d2_full[i], 1);
@@ -572,57 +594,59 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
   // TMEM columns: D1 half h at h*128 (128 cols each), D2 stage t at 256 + t*64
   const uint32_t sW1h = smem_u32(smem + FFP_W), sW1l = sW1h + 32768u, sW2h = sW1h + 65536u, sW2l = sW1h + 98304u;
 
-  if (warp < 4) {
-    // ---------------------------------------------------------------- chunk epilogue (thread = row)
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  if (warp < 8) {
+    // ---------------------------------------------------------------- chunk epilogue teams (thread = row)
+    const int team = warp >> 2, rt = tid & 127;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint8_t* sA2h = smem + FFP_A2 + team * 32768;
+    uint8_t* sA2l = sA2h + 16384;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int h = j >> 1;
-        if ((j & 1) == 0) {
-          mbar_wait(&d1_full[h], (uint32_t)n & 1u);
-          tc_fence_after();
-        }
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * h + team;              // this team's chunk of D1 half h: columns team*64 .. +63
+        const int q = 2 * n + h;                 // running index of this team's chunks (A2 stage = team)
+        mbar_wait(&d1_full[h], (uint32_t)n & 1u);
+        tc_fence_after();
+        if (warp == 0) TL(0, n, h == 0 ? 0 : 4);
         uint32_t v0[32], v1[32];
-        tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + (j & 1) * 64), v0);
-        tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + (j & 1) * 64 + 32), v1);
+        tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + team * 64), v0);
+        tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + team * 64 + 32), v1);
         tmem_ld_wait();
-        if (j & 1) {                       // both chunks of this D1 half are in registers: release it
-          tc_fence_before();
-          mbar_arrive(&d1_empty[h]);
-        }
-        const int c = n * 4 + j, stg = c & 1;
-        mbar_wait(&a2_empty[stg], ((uint32_t)(c >> 1) & 1u) ^ 1u);
-        uint8_t* sA2h = smem + FFP_A2 + stg * 32768;
-        uint8_t* sA2l = sA2h + 16384;
+        tc_fence_before();
+        mbar_arrive(&d1_empty[h]);
+        if (warp == 0) TL(0, n, h == 0 ? 1 : 5);
+        mbar_wait(&a2_empty[team], ((uint32_t)q & 1u) ^ 1u);
+        if (warp == 0) TL(0, n, h == 0 ? 2 : 6);
         const float* bj = sb1 + j * 64;
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int col = cc * 8 + q * 2;
+          for (int e = 0; e < 4; ++e) {
+            const int col = cc * 8 + e * 2;
             float a = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]) + bj[col];
             float b = __uint_as_float(col + 1 < 32 ? v0[col + 1] : v1[col + 1 - 32]) + bj[col + 1];
-            split2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[q], lo[q]);
+            split2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[e], lo[e]);
           }
-          const uint32_t off = (uint32_t)tid * 128u + (uint32_t)((cc ^ (tid & 7)) << 4);
+          const uint32_t off = (uint32_t)rt * 128u + (uint32_t)((cc ^ (rt & 7)) << 4);
           *reinterpret_cast<uint4*>(sA2h + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(sA2l + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         fence_proxy_async_smem();
-        mbar_arrive(&a2_full[stg]);
+        mbar_arrive(&a2_full[team]);
+        if (warp == 0) TL(0, n, h == 0 ? 3 : 7);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // ---------------------------------------------------------------- store warps (thread = row)
-    const int rt = tid - 128;
+    const int rt = tid - 256;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       const long long row = (long long)tile * 128 + rt;
       const bool live = row < P;
+      if (warp == 8) TL(1, n, 0);
       float4 r[16];
       if (residual && live) {              // issued before the accumulator is ready: latency hides behind the MMAs
 #pragma unroll
@@ -634,24 +658,26 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
       const int ds = n & 1;
       mbar_wait(&d2_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
+      if (warp == 8) TL(1, n, 1);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_base + (uint32_t)(256 + ds * 64 + half * 32), v);
         tmem_ld_wait();
+        if (warp == 8 && half == 0) TL(1, n, 2);
         if (half == 1) {
           tc_fence_before();
           mbar_arrive(&d2_empty[ds]);
         }
         if (live) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int c4 = half * 8 + q;
+          for (int e = 0; e < 8; ++e) {
+            const int c4 = half * 8 + e;
             float4 b;
-            b.x = __uint_as_float(v[q * 4 + 0]) + sb2[c4 * 4 + 0];
-            b.y = __uint_as_float(v[q * 4 + 1]) + sb2[c4 * 4 + 1];
-            b.z = __uint_as_float(v[q * 4 + 2]) + sb2[c4 * 4 + 2];
-            b.w = __uint_as_float(v[q * 4 + 3]) + sb2[c4 * 4 + 3];
+            b.x = __uint_as_float(v[e * 4 + 0]) + sb2[c4 * 4 + 0];
+            b.y = __uint_as_float(v[e * 4 + 1]) + sb2[c4 * 4 + 1];
+            b.z = __uint_as_float(v[e * 4 + 2]) + sb2[c4 * 4 + 2];
+            b.w = __uint_as_float(v[e * 4 + 3]) + sb2[c4 * 4 + 3];
             if (b_out) *reinterpret_cast<float4*>(b_out + row * 64 + c4 * 4) = b;
             if (x_out) {
               float4 o = make_float4(b.x + r[c4].x, b.y + r[c4].y, b.z + r[c4].z, b.w + r[c4].w);
@@ -660,6 +686,7 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
           }
         }
       }
+      if (warp == 8) TL(1, n, 3);
     }
   } else if (warp == kFFMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
@@ -673,6 +700,7 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
       int n = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
         mbar_wait(a1_full, (uint32_t)n & 1u);
+        TL(2, n, 0);
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&d1_empty[h], ((uint32_t)n & 1u) ^ 1u);
           tc_fence_after();
@@ -690,13 +718,15 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
           umma_commit(&d1_full[h]);
         }
         umma_commit(a1_empty);
+        TL(2, n, 1);
         const int ds = n & 1;
         for (int j = 0; j < 4; ++j) {
-          const int c = n * 4 + j, stg = c & 1;
-          mbar_wait(&a2_full[stg], (uint32_t)(c >> 1) & 1u);
+          const int team = j & 1, q = 2 * n + (j >> 1);
+          mbar_wait(&a2_full[team], (uint32_t)q & 1u);
           if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t a2_hi = smem_u32(smem + FFP_A2 + stg * 32768), a2_lo = a2_hi + 16384u;
+          TL(2, n, 2 + j);
+          const uint32_t a2_hi = smem_u32(smem + FFP_A2 + team * 32768), a2_lo = a2_hi + 16384u;
           uint32_t acc = j > 0 ? 1u : 0u;
 #pragma unroll 1
           for (int pass = 0; pass < 3; ++pass) {
@@ -708,22 +738,22 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
               acc = 1u;
             }
           }
-          umma_commit(&a2_empty[stg]);
+          umma_commit(&a2_empty[team]);
         }
         umma_commit(&d2_full[ds]);
+        TL(2, n, 6);
       }
     }
     __syncwarp();
   } else {
-    // ---------------------------------------------------------------- loader teams: s tile -> A1
-    const int team = (tid - kFFLoaderThread0) >> 7;
-    const int lt = (tid - kFFLoaderThread0) & 127;
+    // ---------------------------------------------------------------- loaders: s tile -> A1
+    const int lt = tid - kFFLoaderThread0;
     uint8_t* sA1h = smem + FFP_A1;
     uint8_t* sA1l = sA1h + 16384;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      if ((n & 1) != team) continue;
       const long long row0 = (long long)tile * 128;
+      if (lt < 32) TL(3, n, 0);
       float4 v[16];
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
@@ -731,18 +761,31 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
         v[it] = (row0 + r < P) ? ldg_stream(s + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       mbar_wait(a1_empty, ((uint32_t)n & 1u) ^ 1u);
+      if (lt < 32) TL(3, n, 1);
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
         const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
         store_split4_at(sA1h, sA1l, kmajor_sw128_offset(r, c4 * 4), v[it]);
       }
+      if (lt < 32) TL(3, n, 2);
       fence_proxy_async_smem();
       mbar_arrive(a1_full);
+      if (lt < 32) TL(3, n, 3);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int debug_timeline(int enable, long long* host_out /*[1024] or NULL*/) {
+  if (host_out) FFNO_CUDA_CHECK(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 1024));
+  if (enable >= 0) {
+    long long zero[1024] = {0};
+    FFNO_CUDA_CHECK(cudaMemcpyToSymbol(g_timeline, zero, sizeof(zero)));
+    FFNO_CUDA_CHECK(cudaMemcpyToSymbol(g_timeline_on, &enable, sizeof(int)));
+  }
+  return FFNO_OK;
 }
 
 int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,

@@ -206,6 +206,10 @@ FFNO_API size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batc
 FFNO_API int ffno_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int32_t N, int32_t K, int32_t a_mn,
                        int32_t b_mn, int32_t variant, void* stream);
 
+/* Diagnostics: arm (enable = 1) / disarm (0) / only read (-1) the in-kernel clock64 timeline of block 0 of the
+ * pipelined FF kernel; host_out (may be NULL) receives [role 8][tile 16][event 8] cycle stamps. */
+FFNO_API int ffno_debug_timeline(int32_t enable, int64_t* host_out);
+
 /* Number of kernel launches the last ffno_block_fwd / ffno_rollout_fwd on this plan enqueued. */
 FFNO_API int64_t ffno_plan_last_launch_count(const ffno_plan* plan);
 

@@ -249,3 +249,42 @@ def test_submodules_standalone_vs_oracle():
     a, b = torch.randn(6, 50, 3), torch.randn(6, 50, 3)
     got = mods.LpLoss().rel(a.cuda()[..., 1], b.cuda()[..., 1])
     assert abs(got.item() - O.lp_loss_rel(a[..., 1], b[..., 1]).item()) < 1e-6
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("shape,modes", [((1, 256, 256), 64),      # C4 geometry: Kochkov 256^2, modes 64
+                                          ((3, 48, 80), 16),        # non-power-of-two, non-square, ragged batch
+                                          ((2, 64, 40), 12)])       # axis length not a multiple of 16
+def test_grid2d_other_geometries_vs_oracle(shape, modes, path, monkeypatch):
+    """BASELINE configs[3] geometry and awkward sizes: CUDA vs the CPU oracle on seeded inputs."""
+    monkeypatch.setenv("FFNO_B200_PATH", path)
+    from oracle import ffno_oracle as O
+    torch.manual_seed(11)
+    m = M().FNOFactorized2DBlock(modes=modes, width=64, n_layers=2, input_dim=5, share_weight=True, factor=4,
+                                 ff_weight_norm=True, gain=0.1).eval()
+    x = torch.randn(*shape, 5, generator=torch.Generator().manual_seed(12))
+    ref = O.block_grid2d_forward({k: v.detach() for k, v in m.state_dict().items()}, x, modes=modes, n_layers=2)
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())["forecast"]
+    e = rel_err(y, ref["forecast"])
+    print(shape, modes, path, f"{e:.2e}")
+    assert e < tol_for(mc.plan_for(y.device, shape[1:]))
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_mesh3d_c5_geometry_vs_oracle(path, monkeypatch):
+    """BASELINE configs[4] geometry: 32^3 cube padded to 40^3, modes (12,12,8), width 64, unshared weights."""
+    monkeypatch.setenv("FFNO_B200_PATH", path)
+    from oracle import ffno_oracle as O
+    torch.manual_seed(13)
+    m = M().FNOFactorizedMesh3D(modes_x=12, modes_y=12, modes_z=8, width=64, input_dim=4, output_dim=4, n_layers=2,
+                                share_weight=False, factor=4, ff_weight_norm=True, n_ff_layers=2, layer_norm=False).eval()
+    x = torch.randn(2, 32, 32, 32, 1, generator=torch.Generator().manual_seed(14))
+    ref = O.block_mesh_forward({k: v.detach() for k, v in m.state_dict().items()}, x, modes=(12, 12, 8), n_layers=2)
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())
+    e = rel_err(y, ref)
+    print("mesh3d c5", path, f"{e:.2e}")
+    assert e < tol_for(mc.plan_for(y.device, (32, 32, 32)))

@@ -43,7 +43,7 @@ def selftest(N, K, a_mn, b_mn, variant):
     return out
 
 
-def ff_case(P):
+def ff_case(P, what="both"):
     import torch
     import fourierflow_b200.modules as M
     from golden_like import rel
@@ -69,14 +69,16 @@ def ff_case(P):
         os.environ["FFNO_B200_PATH"] = "umma"
         pu = layer._plan(s)
         assert pu.uses_umma
-        yu = pu.ff_forward(0, 0, s, x)
-        bu = pu.ff_forward(0, 0, s, None)
-        torch.cuda.synchronize()
-        res["ff_residual_rel"] = rel(yu, yg)
-        res["ff_rel"] = rel(bu, bg)
-        su = pu.spectral_forward(0, x)
-        torch.cuda.synchronize()
-        res["spectral_rel"] = rel(su, sg)
+        if what in ("both", "ff"):
+            yu = pu.ff_forward(0, 0, s, x)
+            bu = pu.ff_forward(0, 0, s, None)
+            torch.cuda.synchronize()
+            res["ff_residual_rel"] = rel(yu, yg)
+            res["ff_rel"] = rel(bu, bg)
+        if what in ("both", "spectral"):
+            su = pu.spectral_forward(0, x)
+            torch.cuda.synchronize()
+            res["spectral_rel"] = rel(su, sg)
     return res
 
 
@@ -117,8 +119,12 @@ for v in (0, 1):
     CASES[f"st_amn_v{v}"] = (selftest, (64, 64, 1, 0, v))
     CASES[f"st_bmn_v{v}"] = (selftest, (64, 64, 0, 1, v))
     CASES[f"st_amn_bmn_N128_K128_v{v}"] = (selftest, (128, 128, 1, 1, v))
+CASES["st_atmem_N64"] = (selftest, (64, 64, 0, 0, 2))
+CASES["st_atmem_N128"] = (selftest, (128, 64, 0, 0, 2))
 CASES["ff_4096"] = (ff_case, (4096,))
 CASES["ff_131072"] = (ff_case, (131072,))
+CASES["ffonly_131072"] = (ff_case, (131072, "ff"))
+CASES["speconly_131072"] = (ff_case, (131072, "spectral"))
 CASES["block24"] = (block_case, ())
 CASES["block24_v1"] = (block_case, ())     # run with FFNO_UMMA_V1=1 (set by the driver loop below)
 
