@@ -51,6 +51,11 @@ int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t 
 int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,
                    const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st);
 
+// v3 FF: hidden activations staged in tensor memory (TS-mode GEMM2), coalesced output through a smem staging tile,
+// loader sums up to three spectral partial outputs (s1 / s2 may be NULL).
+int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float* residual, float* x_out, float* b_out,
+                 const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st);
+
 // Diagnostics: in-kernel clock64 timeline of block 0 of ff_pipe_kernel ([role 8][tile 16][event 8]).
 int debug_timeline(int enable, long long* host_out);
 

@@ -32,6 +32,7 @@ struct UmmaState {
   float* d_fwd[3] = {nullptr, nullptr, nullptr};
   float* d_inv[3] = {nullptr, nullptr, nullptr};
   bool v1 = false;                                       // FFNO_UMMA_V1=1: non-pipelined kernels (cross-check)
+  bool ff_v2 = false;                                    // FFNO_FF_V2=1: FF with hidden activations in smem (A/B)
   uint8_t* fwd_image[3] = {nullptr, nullptr, nullptr};   // tcgen05 table images (NULL -> FP32 table kernel)
   uint8_t* inv_image[3] = {nullptr, nullptr, nullptr};
 };
@@ -68,6 +69,8 @@ int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]) {
   s->sm_count = prop.multiProcessorCount;
   const char* v1 = getenv("FFNO_UMMA_V1");
   s->v1 = v1 && v1[0] == '1';
+  const char* v2 = getenv("FFNO_FF_V2");
+  s->ff_v2 = v2 && v2[0] == '1';
   s->layers.resize(d->n_layers);
   *out = s;
   return FFNO_OK;
@@ -131,7 +134,11 @@ int umma_load_params(UmmaState* s, const UmmaLayerSrc* layers, float* const d_fw
   return FFNO_OK;
 }
 
-size_t umma_workspace_floats(const UmmaState*, int) { return 0; }
+size_t umma_workspace_floats(const UmmaState* s, int batch) {
+  size_t U = (size_t)batch * kUmmaC;
+  for (int a = 0; a < s->d.ndim; ++a) U *= s->ext[a];
+  return (size_t)(s->d.ndim - 1) * U;      // per-axis spectral outputs of axes 1.. (axis 0 uses the plan's `s`)
+}
 
 // F / R hold every axis back to back: axis a starts at spec_offset(a) floats.
 static size_t spec_offset(const UmmaState* s, int batch, int axis) {
@@ -218,24 +225,67 @@ int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float*
   return FFNO_OK;
 }
 
+// Per-axis spectral outputs (no accumulation): s_axis[a] receives the inverse transform of axis a; the FF loader sums
+// them.  3 launches per layer: all forward transforms, all mode mixes, all inverse transforms.
+static bool all_axes_pipe(const UmmaState* s) {
+  bool ok = !s->v1;
+  for (int a = 0; a < s->d.ndim; ++a)
+    ok &= (s->fwd_image[a] != nullptr) && (s->inv_image[a] != nullptr) && axis_pipe_fits(s->ext[a], 2 * s->d.modes[a]) &&
+          axis_pipe_fits(2 * s->d.modes[a], s->ext[a]);
+  return ok;
+}
+
+static int spectral_split(UmmaState* s, const UmmaLayer& L, const float* x, int batch, float* const s_axis[3], float* F,
+                          float* R, cudaStream_t st) {
+  AxisXform fwd[3], inv[3];
+  MixAxis mix[3];
+  const bool full = s->d.spectral_mode == FFNO_MODE_FULL;
+  for (int a = 0; a < s->d.ndim; ++a) {
+    long long outer, p_inner;
+    axis_geom(s, batch, a, &outer, &p_inner);
+    const int Ln = s->ext[a], K = s->d.modes[a];
+    float* Fa = F + spec_offset(s, batch, a);
+    float* Ra = R + spec_offset(s, batch, a);
+    fwd[a] = AxisXform{x, Fa, s->fwd_image[a], outer, p_inner * kUmmaC, Ln, 2 * K, pad16i(2 * K), (Ln + 63) / 64, 0};
+    mix[a] = MixAxis{Fa, Ra, L.mix_image[a], outer, p_inner, K};
+    inv[a] = AxisXform{full ? Ra : Fa, s_axis[a], s->inv_image[a], outer, p_inner * kUmmaC, 2 * K, Ln, pad16i(Ln),
+                       (2 * K + 63) / 64, 0};
+  }
+  FFNO_TRY(launch_axis_pipe(fwd, s->d.ndim, s->sm_count, st));
+  if (full) FFNO_TRY(launch_mix_pipe(mix, s->d.ndim, s->sm_count, st));
+  return launch_axis_pipe(inv, s->d.ndim, s->sm_count, st);
+}
+
 int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* y, float*,
                 cudaStream_t st) {
   const UmmaLayer& L = s->layers[layer];
   long long P = batch;
   for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
-  auto ff = s->v1 ? launch_ff_umma : launch_ff_pipe;
-  if (residual) return ff(s_in, residual, y, nullptr, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
-  return ff(s_in, nullptr, nullptr, y, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  float* xo = residual ? y : nullptr;
+  float* bo = residual ? nullptr : y;
+  if (s->v1) return launch_ff_umma(s_in, residual, xo, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  if (s->ff_v2) return launch_ff_pipe(s_in, residual, xo, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  return launch_ff_ts(s_in, nullptr, nullptr, residual, xo, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
 }
 
 int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_next, float* s_out, float* b_out,
-                   float* F, float* R, float* ws, bool /*want_s*/, bool want_b, cudaStream_t st) {
+                   float* F, float* R, float* ws, bool want_s, bool want_b, cudaStream_t st) {
   const UmmaLayer& L = s->layers[layer];
-  FFNO_TRY(umma_spectral_fwd(s, layer, x, batch, s_out, F, R, ws, st));
   long long P = batch;
   for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
-  auto ff = s->v1 ? launch_ff_umma : launch_ff_pipe;
-  return ff(s_out, x, x_next, want_b ? b_out : nullptr, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  float* bo = want_b ? b_out : nullptr;
+  if (!want_s && !s->ff_v2 && all_axes_pipe(s)) {
+    // fast path: per-axis inverse outputs s_out (axis 0) and ws + (a-1) * U (axes 1, 2), summed by the FF loader
+    const size_t U = (size_t)P * kUmmaC;
+    float* s_axis[3] = {s_out, ws, ws + U};
+    FFNO_TRY(spectral_split(s, L, x, batch, s_axis, F, R, st));
+    return launch_ff_ts(s_axis[0], s->d.ndim > 1 ? s_axis[1] : nullptr, s->d.ndim > 2 ? s_axis[2] : nullptr, x, x_next, bo,
+                        L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  }
+  FFNO_TRY(umma_spectral_fwd(s, layer, x, batch, s_out, F, R, ws, st));
+  if (s->v1) return launch_ff_umma(s_out, x, x_next, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  if (s->ff_v2) return launch_ff_pipe(s_out, x, x_next, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+  return launch_ff_ts(s_out, nullptr, nullptr, x, x_next, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
 }
 
 }  // namespace ffno

@@ -64,6 +64,22 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// 3-pass BF16 product over KSTEPS K steps of 16 (K-major SW128 operands within one 64-wide K block): descriptors are
+// formed by adding the K offset (32 B >> 4 = 2 per step) to precomputed bases, fully unrolled — the single issuing
+// thread must spend a handful of instructions per tcgen05.mma, not a descriptor rebuild, or it becomes the bottleneck.
+template <int KSTEPS>
+__device__ __forceinline__ void issue3_kmajor(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                              uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint64_t a = (pass == 2) ? a_lo : a_hi;
+    const uint64_t b = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      umma_bf16_ss(tmem_d, a + (uint64_t)(ks * 2), b + (uint64_t)(ks * 2), idesc, (pass == 0 && ks == 0) ? acc_first : 1u);
+  }
+}
+
 __device__ __forceinline__ void store_split4_at(uint8_t* tile_hi, uint8_t* tile_lo, uint32_t off, float4 v) {
   uint32_t h0, l0, h1, l1;
   split2(v.x, v.y, h0, l0);
@@ -137,6 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       const int ds = n & 1;
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
+      if (warp == 0 && blockIdx.y == 0) TL(5, n, 0);
       const long long G = (long long)tile * 2 + (tid >> 6);
       const bool live = G < n_groups;
       long long o = 0, g = 0;
@@ -154,6 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
         if (c0 + 32 >= p.npad) {       // last read of this accumulator stage: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&d_empty[ds]);
+          if (warp == 0 && blockIdx.y == 0) TL(5, n, 1);
         }
         if (live) {
           if (p.accumulate) {
@@ -175,6 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
           }
         }
       }
+      if (warp == 0 && blockIdx.y == 0) TL(5, n, 2);
     }
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
@@ -196,25 +215,40 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
           const int as = item & 1;
           mbar_wait(&a_full[as], (uint32_t)(item >> 1) & 1u);
           tc_fence_after();
+          if (blockIdx.y == 0) TL(6, n, 0);
           const int rem = p.n_in - kc * 64;
           const int ksteps = rem >= 64 ? 4 : (rem + 15) / 16;
-          const uint32_t a_hi = smem_u32(smem + as * AXP_A_STAGE), a_lo = a_hi + 16384u;
-          const uint32_t b_blk = smem_u32(sB) + (uint32_t)kc * ((uint32_t)p.npad * 128u);
-          uint32_t acc = kc > 0 ? 1u : 0u;
+          // MN-major A: 64-wide mn blocks 8 KB apart (LBO), 8-row k groups 1 KB apart (SBO); one K step = 2 groups
+          const uint64_t dAh = make_smem_desc_sw128(smem_u32(smem + as * AXP_A_STAGE), 8192u, 1024u);
+          const uint64_t dAl = dAh + (uint64_t)(16384 >> 4);
+          const uint64_t dBh = desc_kmajor(smem_u32(sB) + (uint32_t)kc * ((uint32_t)p.npad * 128u), 0);
+          const uint64_t dBl = dBh + (uint64_t)(b_half >> 4);
+          const uint32_t acc0 = kc > 0 ? 1u : 0u;
+          if (ksteps == 4) {
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint64_t a = (pass == 2) ? dAl : dAh, b = (pass == 1) ? dBl : dBh;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16_ss(d_addr, a + (uint64_t)(ks * (2048 >> 4)), b + (uint64_t)(ks * 2), idesc,
+                             (pass == 0 && ks == 0) ? acc0 : 1u);
+            }
+          } else {
+            uint32_t acc = acc0;
 #pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = (pass == 2) ? a_lo : a_hi;
-            const uint32_t b = b_blk + (pass == 1 ? b_half : 0u);
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint64_t a = (pass == 2) ? dAl : dAh, b = (pass == 1) ? dBl : dBh;
 #pragma unroll 1
-            for (int ks = 0; ks < ksteps; ++ks) {
-              umma_bf16_ss(d_addr, make_smem_desc_sw128(a + (uint32_t)ks * 2048u, 8192u, 1024u), desc_kmajor(b, ks * 16),
-                           idesc, acc);
-              acc = 1u;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                umma_bf16_ss(d_addr, a + (uint64_t)(ks * (2048 >> 4)), b + (uint64_t)(ks * 2), idesc, acc);
+                acc = 1u;
+              }
             }
           }
           umma_commit(&a_empty[as]);
         }
         umma_commit(&d_full[ds]);
+        if (blockIdx.y == 0) TL(6, n, 1);
       }
     }
     __syncwarp();
@@ -252,12 +286,14 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     for (int q = 0; q < kAxStages; ++q) issue(q);
     for (int item = 0; item < n_items; ++item) {
       cp_async_wait<kAxStages - 1>();
+      if (lt < 32 && blockIdx.y == 0) TL(7, item, 0);
       const uint8_t* src = stg_base + (item % kAxStages) * 32768;
       float4 v[kLdPerThread];
 #pragma unroll
       for (int it = 0; it < kLdPerThread; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * (kLoaders * 16));
       const int as = item & 1;
       mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
+      if (lt < 32 && blockIdx.y == 0) TL(7, item, 1);
       uint8_t* sAh = smem + as * AXP_A_STAGE;
       uint8_t* sAl = sAh + 16384;
 #pragma unroll
@@ -269,7 +305,9 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_full[as]);
+      if (lt < 32 && blockIdx.y == 0) TL(7, item, 2);
       issue(item + kAxStages);
+      if (lt < 32 && blockIdx.y == 0) TL(7, item, 3);
     }
     cp_async_wait<0>();
   }
@@ -417,7 +455,8 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
       bulk_g2s(sB + 32768, img + 32768, 32768, bar_w);
       mbar_wait(bar_w, 0);
       constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
-      const uint32_t b_hi = smem_u32(sB), b_lo = b_hi + 32768u;
+      const uint64_t dBh = desc_kmajor(smem_u32(sB), 0), dBl = desc_kmajor(smem_u32(sB) + 32768u, 0);
+      const uint64_t dAh = desc_kmajor(smem_u32(smem), 0), dAl = desc_kmajor(smem_u32(smem) + 16384u, 0);
       int item = 0, n = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
         const int ds = n & 1;
@@ -427,18 +466,8 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
           const int as = item & 1;
           mbar_wait(&a_full[as], (uint32_t)(item >> 1) & 1u);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(smem + as * MXP_A_STAGE), a_lo = a_hi + 16384u;
-          uint32_t acc = kb > 0 ? 1u : 0u;
-#pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = (pass == 2) ? a_lo : a_hi;
-            const uint32_t b = ((pass == 1) ? b_lo : b_hi) + (uint32_t)kb * 16384u;
-#pragma unroll 1
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16_ss(d_addr, desc_kmajor(a, ks * 16), desc_kmajor(b, ks * 16), IDESC, acc);
-              acc = 1u;
-            }
-          }
+          const uint64_t a_off = (uint64_t)(as * (MXP_A_STAGE >> 4)), b_off = (uint64_t)(kb * (16384 >> 4));
+          issue3_kmajor<4>(d_addr, dAh + a_off, dAl + a_off, dBh + b_off, dBl + b_off, IDESC, kb > 0 ? 1u : 0u);
           umma_commit(&a_empty[as]);
         }
         umma_commit(&d_full[ds]);
@@ -696,48 +725,35 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
       mbar_wait(bar_w, 0);
       constexpr uint32_t IDESC_G1 = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
-      const uint32_t a1_hi = smem_u32(smem + FFP_A1), a1_lo = a1_hi + 16384u;
+      // every operand descriptor of the tile loop, built once
+      const uint64_t dA1h = desc_kmajor(smem_u32(smem + FFP_A1), 0), dA1l = desc_kmajor(smem_u32(smem + FFP_A1) + 16384u, 0);
+      const uint64_t dW1h = desc_kmajor(sW1h, 0), dW1l = desc_kmajor(sW1l, 0);
+      const uint64_t dW2h = desc_kmajor(sW2h, 0), dW2l = desc_kmajor(sW2l, 0);
+      const uint64_t dA2h0 = desc_kmajor(smem_u32(smem + FFP_A2), 0), dA2l0 = desc_kmajor(smem_u32(smem + FFP_A2) + 16384u, 0);
+      constexpr uint64_t kStage = 32768 >> 4, kHalf = 16384 >> 4, kBlk = 8192 >> 4;   // descriptor address units (16 B)
       int n = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
         mbar_wait(a1_full, (uint32_t)n & 1u);
         TL(2, n, 0);
+#pragma unroll
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&d1_empty[h], ((uint32_t)n & 1u) ^ 1u);
           tc_fence_after();
-          uint32_t acc = 0u;
-#pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = (pass == 2) ? a1_lo : a1_hi;
-            const uint32_t b = ((pass == 1) ? sW1l : sW1h) + (uint32_t)h * 16384u;
-#pragma unroll 1
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16_ss(tmem + (uint32_t)(h * 128), desc_kmajor(a, ks * 16), desc_kmajor(b, ks * 16), IDESC_G1, acc);
-              acc = 1u;
-            }
-          }
+          issue3_kmajor<4>(tmem + (uint32_t)(h * 128), dA1h, dA1l, dW1h + h * kHalf, dW1l + h * kHalf, IDESC_G1, 0u);
           umma_commit(&d1_full[h]);
         }
         umma_commit(a1_empty);
         TL(2, n, 1);
         const int ds = n & 1;
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int team = j & 1, q = 2 * n + (j >> 1);
           mbar_wait(&a2_full[team], (uint32_t)q & 1u);
           if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
           tc_fence_after();
           TL(2, n, 2 + j);
-          const uint32_t a2_hi = smem_u32(smem + FFP_A2 + team * 32768), a2_lo = a2_hi + 16384u;
-          uint32_t acc = j > 0 ? 1u : 0u;
-#pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = (pass == 2) ? a2_lo : a2_hi;
-            const uint32_t b = ((pass == 1) ? sW2l : sW2h) + (uint32_t)j * 8192u;
-#pragma unroll 1
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16_ss(tmem + (uint32_t)(256 + ds * 64), desc_kmajor(a, ks * 16), desc_kmajor(b, ks * 16), IDESC_G2, acc);
-              acc = 1u;
-            }
-          }
+          issue3_kmajor<4>(tmem + (uint32_t)(256 + ds * 64), dA2h0 + team * kStage, dA2l0 + team * kStage, dW2h + j * kBlk,
+                           dW2l + j * kBlk, IDESC_G2, j > 0 ? 1u : 0u);
           umma_commit(&a2_empty[team]);
         }
         umma_commit(&d2_full[ds]);
@@ -776,6 +792,285 @@ ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, 
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =======================================================================================================
+// FeedForward + residual, v3: the hidden activations never touch shared memory.
+//   G1   : D1[128 x 256] = A1 (smem, 2 stages) x W1 (smem)                       (SS, N = 128 halves)
+//   epi  : D1 chunk -> +b1, ReLU, BF16 hi/lo -> tcgen05.st into TMEM operand stage A2[team]
+//   G2   : D2[128 x 64] += A2 (TMEM) x W2 (smem)                                  (TS: A operand from tensor memory)
+//   store: D2 -> +b2 -> swizzled FP32 staging tile in smem -> coalesced (+ residual) global stores
+// The loader sums up to three per-axis spectral outputs (s = s_x + s_y (+ s_z), grid_2d.py:94) while it splits, so
+// the inverse transforms never read-modify-write a shared buffer.
+// TMEM columns: D1 0..255 | D2 stage 256 + 64 t | A2 stage 384 + 64 t (hi 0..31, lo 32..63).
+// =======================================================================================================
+constexpr int FF3_W = 0;
+constexpr int FF3_A1 = 131072;                     // 2 stages x (hi 16 KB | lo 16 KB)
+constexpr int FF3_OUT = FF3_A1 + 65536;            // 196608: 128 rows x 256 B staging
+constexpr int FF3_BIAS = FF3_OUT + 32768;          // 229376
+constexpr int FF3_BAR = FF3_BIAS + 320 * 4;        // 230656
+constexpr int FF3_TOTAL = FF3_BAR + 192;           // 230848 <= 232448
+
+__global__ void __launch_bounds__(kFFThreads, 1)
+ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
+             const float* __restrict__ residual, float* __restrict__ x_out, float* __restrict__ b_out,
+             const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2, long long P,
+             int n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* sb1 = reinterpret_cast<float*>(smem + FF3_BIAS);
+  float* sb2 = sb1 + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FF3_BAR);
+  uint64_t* a1_full = bars;         // [2] 128 (loaders)
+  uint64_t* a1_empty = bars + 2;    // [2] commit
+  uint64_t* d1_full = bars + 4;     // [2] commit
+  uint64_t* d1_empty = bars + 6;    // [2] 256 (both epilogue teams)
+  uint64_t* a2_full = bars + 8;     // [2] 128 (team t)
+  uint64_t* a2_empty = bars + 10;   // [2] commit
+  uint64_t* d2_full = bars + 12;    // [2] commit
+  uint64_t* d2_empty = bars + 14;   // [2] 128 (store warps)
+  uint64_t* bar_w = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a1_full[i], 128);
+      mbar_init(&a1_empty[i], 1);
+      mbar_init(&d1_full[i], 1);
+      mbar_init(&d1_empty[i], 256);
+      mbar_init(&a2_full[i], 128);
+      mbar_init(&a2_empty[i], 1);
+      mbar_init(&d2_full[i], 1);
+      mbar_init(&d2_empty[i], 128);
+    }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  for (int i = tid; i < 256; i += kFFThreads) sb1[i] = b1 ? b1[i] : 0.f;
+  if (tid < 64) sb2[tid] = b2 ? b2[tid] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 8) {
+    // ---------------------------------------------------------------- chunk epilogue teams (thread = row)
+    const int team = warp >> 2;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t a2_addr = tmem + lane_base + (uint32_t)(384 + team * 64);
+    int n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * h + team;              // chunk of hidden units j*64 .. j*64+63
+        const int q = 2 * n + h;                 // running chunk index of this team (its A2 stage is `team`)
+        mbar_wait(&d1_full[h], (uint32_t)n & 1u);
+        tc_fence_after();
+        const float* bj = sb1 + j * 64;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {      // 32 columns at a time keeps the live registers at ~64
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + team * 64 + part * 32), v);
+          tmem_ld_wait();
+          if (part == 1) {                          // D1 chunk fully read: release this half to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&d1_empty[h]);
+          }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int col = part * 32 + 2 * e;
+            float a = __uint_as_float(v[2 * e]) + bj[col];
+            float b = __uint_as_float(v[2 * e + 1]) + bj[col + 1];
+            split2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[e], lo[e]);
+          }
+          if (part == 0) {
+            mbar_wait(&a2_empty[team], ((uint32_t)q & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          tmem_st16(a2_addr + (uint32_t)(part * 16), hi);
+          tmem_st16(a2_addr + 32u + (uint32_t)(part * 16), lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&a2_full[team]);
+      }
+    }
+  } else if (warp < 12) {
+    // ---------------------------------------------------------------- store warps
+    const int rt = tid - 256;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint8_t* sOut = smem + FF3_OUT;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      const long long row0 = (long long)tile * 128;
+      float4 r[16];
+      if (residual) {                      // coalesced prefetch, issued long before the accumulator is ready
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+          const int idx = it * 128 + rt, rr = idx >> 4, c4 = idx & 15;
+          r[it] = (row0 + rr < P) ? ldg_stream(residual + (row0 + rr) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 16; ++it) r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const int ds = n & 1;
+      mbar_wait(&d2_full[ds], (uint32_t)(n >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_base + (uint32_t)(256 + ds * 64 + half * 32), v);
+        tmem_ld_wait();
+        if (half == 1) {
+          tc_fence_before();
+          mbar_arrive(&d2_empty[ds]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c4 = half * 8 + e;
+          float4 b;
+          b.x = __uint_as_float(v[e * 4 + 0]) + sb2[c4 * 4 + 0];
+          b.y = __uint_as_float(v[e * 4 + 1]) + sb2[c4 * 4 + 1];
+          b.z = __uint_as_float(v[e * 4 + 2]) + sb2[c4 * 4 + 2];
+          b.w = __uint_as_float(v[e * 4 + 3]) + sb2[c4 * 4 + 3];
+          *reinterpret_cast<float4*>(sOut + rt * 256 + ((c4 ^ (rt & 15)) << 4)) = b;      // XOR swizzle: conflict-free
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int idx = it * 128 + rt, rr = idx >> 4, c4 = idx & 15;
+        const long long row = row0 + rr;
+        const float4 b = *reinterpret_cast<const float4*>(sOut + rr * 256 + ((c4 ^ (rr & 15)) << 4));
+        if (row < P) {
+          if (b_out) *reinterpret_cast<float4*>(b_out + row * 64 + c4 * 4) = b;
+          if (x_out)
+            *reinterpret_cast<float4*>(x_out + row * 64 + c4 * 4) =
+                make_float4(b.x + r[it].x, b.y + r[it].y, b.z + r[it].z, b.w + r[it].w);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  } else if (warp == kFFMmaWarp) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, 131072);
+      for (int i = 0; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
+      mbar_wait(bar_w, 0);
+      constexpr uint32_t IDESC_G1 = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
+      const uint32_t sW = smem_u32(smem + FF3_W);
+      const uint64_t dA1h = desc_kmajor(smem_u32(smem + FF3_A1), 0), dA1l = desc_kmajor(smem_u32(smem + FF3_A1) + 16384u, 0);
+      const uint64_t dW1h = desc_kmajor(sW, 0), dW1l = desc_kmajor(sW + 32768u, 0);
+      const uint64_t dW2h = desc_kmajor(sW + 65536u, 0), dW2l = desc_kmajor(sW + 98304u, 0);
+      constexpr uint64_t kStage = 32768 >> 4, kHalf = 16384 >> 4, kBlk = 8192 >> 4;
+      int n = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+        const int st = n & 1;
+        mbar_wait(&a1_full[st], (uint32_t)(n >> 1) & 1u);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&d1_empty[h], ((uint32_t)n & 1u) ^ 1u);
+          tc_fence_after();
+          issue3_kmajor<4>(tmem + (uint32_t)(h * 128), dA1h + st * kStage, dA1l + st * kStage, dW1h + h * kHalf,
+                           dW1l + h * kHalf, IDESC_G1, 0u);
+          umma_commit(&d1_full[h]);
+        }
+        umma_commit(&a1_empty[st]);
+        const int ds = n & 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int team = j & 1, q = 2 * n + (j >> 1);
+          mbar_wait(&a2_full[team], (uint32_t)q & 1u);
+          if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d2 = tmem + (uint32_t)(256 + ds * 64);
+          const uint32_t a_hi = tmem + (uint32_t)(384 + team * 64), a_lo = a_hi + 32u;
+          const uint64_t bh = dW2h + j * kBlk, bl = dW2l + j * kBlk;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? a_lo : a_hi;
+            const uint64_t b = (pass == 1) ? bl : bh;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16_ts(d2, a + (uint32_t)(ks * 8), b + (uint64_t)(ks * 2), IDESC_G2,
+                           (pass == 0 && ks == 0) ? (j > 0 ? 1u : 0u) : 1u);
+          }
+          umma_commit(&a2_empty[team]);
+        }
+        umma_commit(&d2_full[ds]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- loaders: (s0 + s1 + s2) tile -> A1[stage]
+    const int lt = tid - kFFLoaderThread0;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      const long long row0 = (long long)tile * 128;
+      const int st = n & 1;
+      float4 v[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
+        v[it] = (row0 + r < P) ? ldg_stream(s0 + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll 1
+      for (int src = 1; src < 3; ++src) {
+        const float* sp = src == 1 ? s1 : s2;
+        if (!sp) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4 t[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int idx = (half * 8 + it) * 128 + lt, r = idx >> 4, c4 = idx & 15;
+            t[it] = (row0 + r < P) ? ldg_stream(sp + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float4& a = v[half * 8 + it];
+            a.x += t[it].x; a.y += t[it].y; a.z += t[it].z; a.w += t[it].w;
+          }
+        }
+      }
+      mbar_wait(&a1_empty[st], ((uint32_t)(n >> 1) & 1u) ^ 1u);
+      uint8_t* sA1h = smem + FF3_A1 + st * 32768;
+      uint8_t* sA1l = sA1h + 16384;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
+        store_split4_at(sA1h, sA1l, kmajor_sw128_offset(r, c4 * 4), v[it]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a1_full[st]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float* residual, float* x_out, float* b_out,
+                 const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st) {
+  if (P == 0) return FFNO_OK;
+  static bool configured = false;
+  if (!configured) {
+    FFNO_CUDA_CHECK(cudaFuncSetAttribute(ff_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF3_TOTAL));
+    configured = true;
+  }
+  const int n_tiles = ceil_div(P, 128);
+  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
+  ff_ts_kernel<<<grid, kFFThreads, FF3_TOTAL, st>>>(s0, s1, s2, residual, x_out, b_out, image, b1, b2, P, n_tiles);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("ff_ts_kernel");
+  return FFNO_OK;
 }
 
 int debug_timeline(int enable, long long* host_out /*[1024] or NULL*/) {
