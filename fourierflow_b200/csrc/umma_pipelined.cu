@@ -31,10 +31,10 @@ namespace {
 // axis / mix kernels: 4 epilogue warps, 1 MMA warp, 16 loader-converter warps.  The FP32 -> BF16 hi/lo conversion is
 // ~25 instructions per float4 and is what bounds these kernels, so it is spread over as many warps as fit.
 constexpr int kLoaders = 512;
-constexpr int kThreads = 160 + kLoaders;       // 672
-constexpr int kEpiWarps = 4;
-constexpr int kMmaWarp = 4;
-constexpr int kLoaderThread0 = 160;
+constexpr int kEpiWarps = 8;                   // two teams of 4 (one per TMEM lane quadrant), splitting the columns
+constexpr int kMmaWarp = kEpiWarps;
+constexpr int kLoaderThread0 = (kEpiWarps + 1) * 32;
+constexpr int kThreads = kLoaderThread0 + kLoaders;       // 800
 constexpr int kLdPerThread = 2048 / kLoaders;  // float4 per thread per 32 KB work item
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       mbar_init(&a_full[i], kLoaders);
       mbar_init(&a_empty[i], 1);
       mbar_init(&d_full[i], 1);
-      mbar_init(&d_empty[i], 128);
+      mbar_init(&d_empty[i], kEpiWarps * 32);
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -146,15 +146,16 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   const long long n_groups = p.outer * gpi;
 
   if (warp < kEpiWarps) {
-    // ---------------------------------------------------------------- epilogue
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ---------------------------------------------------------------- epilogue: two teams, alternate 32-column chunks
+    const int team = warp >> 2, rt = tid & 127;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       const int ds = n & 1;
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 0);
-      const long long G = (long long)tile * 2 + (tid >> 6);
+      const long long G = (long long)tile * 2 + (rt >> 6);
       const bool live = G < n_groups;
       long long o = 0, g = 0;
       if (live) {
@@ -162,36 +163,47 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
         o = uo;
         g = (unsigned)G - uo * (unsigned)gpi;
       }
-      float* ybase = p.Y + (o * p.n_out) * p.inner + g * 64 + (tid & 63);
+      float* ybase = p.Y + (o * p.n_out) * p.inner + g * 64 + (rt & 63);
+      const int n_chunks = p.npad >> 5;            // 32-column chunks (npad is a multiple of 16: last chunk may be half)
+      const int total_chunks = (p.npad + 31) >> 5;
+      (void)n_chunks;
+      bool released = false;
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.npad; c0 += 32) {
+      for (int ch = team; ch < total_chunks; ch += 2) {
+        const int c0 = ch * 32;
         uint32_t v[32];
         tmem_ld32(tmem + lane_base + (uint32_t)(ds * stage_cols + c0), v);
         tmem_ld_wait();
-        if (c0 + 32 >= p.npad) {       // last read of this accumulator stage: hand it back to the MMA warp
+        if (ch + 2 >= total_chunks) {   // this team's last read of the stage
           tc_fence_before();
           mbar_arrive(&d_empty[ds]);
+          released = true;
           if (warp == 0 && blockIdx.y == 0) TL(5, n, 1);
         }
         if (live) {
+          float* dst = ybase + (long long)c0 * p.inner;
           if (p.accumulate) {
 #pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 8) {        // 8 independent read-modify-writes in flight per thread
-              float old[8];
+            for (int j0 = 0; j0 < 32; j0 += 16) {
+              float old[16];
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                old[j] = (c0 + j0 + j < p.n_out) ? ybase[(long long)(c0 + j0 + j) * p.inner] : 0.f;
+              for (int j = 0; j < 16; ++j) old[j] = (c0 + j0 + j < p.n_out) ? dst[(long long)(j0 + j) * p.inner] : 0.f;
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (c0 + j0 + j < p.n_out)
-                  ybase[(long long)(c0 + j0 + j) * p.inner] = __uint_as_float(v[j0 + j]) + old[j];
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j0 + j < p.n_out) dst[(long long)(j0 + j) * p.inner] = __uint_as_float(v[j0 + j]) + old[j];
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.n_out) ybase[(long long)(c0 + j) * p.inner] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < p.n_out) *dst = __uint_as_float(v[j]);
+              dst += p.inner;
+            }
           }
         }
+      }
+      if (!released) {                  // a team with no chunk in this tile still owes its arrivals
+        tc_fence_before();
+        mbar_arrive(&d_empty[ds]);
       }
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 2);
     }
@@ -364,8 +376,9 @@ constexpr int MXP_A_STAGE = 32768;
 constexpr int MXP_B = 2 * MXP_A_STAGE;             // 65536: B image 64 KB
 constexpr int MXP_BAR = MXP_B + 65536;             // 131072
 constexpr int MXP_STAGING = MXP_BAR + 1024;        // kMxStages x 32 KB raw FP32 (cp.async landing zone)
-constexpr int kMxStages = 3;
-constexpr int MXP_TOTAL = MXP_STAGING + kMxStages * 32768;     // 230400 <= 232448
+constexpr int kMxStages = 2;
+constexpr int MXP_OUT = MXP_STAGING + kMxStages * 32768;       // 32 KB FP32 output staging (one re / im segment)
+constexpr int MXP_TOTAL = MXP_OUT + 32768;                     // 230400 <= 232448
 
 struct MixSet {
   MixAxis ax[3];
@@ -399,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
       mbar_init(&a_full[i], kLoaders);
       mbar_init(&a_empty[i], 1);
       mbar_init(&d_full[i], 1);
-      mbar_init(&d_empty[i], 128);
+      mbar_init(&d_empty[i], kEpiWarps * 32);
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -415,36 +428,45 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
   const long long inner = ax.p_inner * 64;
 
   if (warp < kEpiWarps) {
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // two epilogue teams: team 0 drains the real segment (columns 0..63), team 1 the imaginary one, each 32 columns
+    // at a time through its own swizzled 16 KB staging tile so the global stores are full 128-byte lines
+    const int team = warp >> 2, rt = tid & 127, seg = team;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint8_t* sOut = smem + MXP_OUT + team * 16384;
     int n = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
       const int ds = n & 1;
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
-      const long long row = (long long)tile * 128 + tid;
-      long long o = 0, pp = 0;
-      if (row < M) {
-        const unsigned uo = (unsigned)row / (unsigned)ax.p_inner;
-        o = uo;
-        pp = (unsigned)row - uo * (unsigned)ax.p_inner;
-      }
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
+      for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
-        tmem_ld32(tmem + lane_base + (uint32_t)(ds * 128 + q * 32), v);
+        tmem_ld32(tmem + lane_base + (uint32_t)(ds * 128 + seg * 64 + half * 32), v);
         tmem_ld_wait();
-        if (q == 3) {
+        if (half == 1) {
           tc_fence_before();
           mbar_arrive(&d_empty[ds]);
         }
-        if (row < M) {
-          float* dst = ax.R + ((o * ax.K + k) * 2 + (q >> 1)) * inner + pp * 64 + (q & 1) * 32;
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4)
-            *reinterpret_cast<float4*>(dst + c4 * 4) =
-                make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]),
-                            __uint_as_float(v[c4 * 4 + 3]));
+        for (int e = 0; e < 8; ++e)
+          *reinterpret_cast<float4*>(sOut + rt * 128 + ((e ^ (rt & 7)) << 4)) =
+              make_float4(__uint_as_float(v[e * 4]), __uint_as_float(v[e * 4 + 1]), __uint_as_float(v[e * 4 + 2]),
+                          __uint_as_float(v[e * 4 + 3]));
+        if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int idx = it * 128 + rt, rr = idx >> 3, c4 = idx & 7;
+          const long long row = (long long)tile * 128 + rr;
+          if (row < M) {
+            const unsigned uo = (unsigned)row / (unsigned)ax.p_inner;
+            const unsigned pp = (unsigned)row - uo * (unsigned)ax.p_inner;
+            float* dst = ax.R + (((long long)uo * ax.K + k) * 2 + seg) * inner + (long long)pp * 64 + half * 32 + c4 * 4;
+            *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(sOut + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+          }
         }
+        if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
     }
   } else if (warp == kMmaWarp) {
@@ -870,6 +892,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         const int q = 2 * n + h;                 // running chunk index of this team (its A2 stage is `team`)
         mbar_wait(&d1_full[h], (uint32_t)n & 1u);
         tc_fence_after();
+        if (warp == 0) TL(0, n, h * 4 + 0);
         const float* bj = sb1 + j * 64;
 #pragma unroll
         for (int part = 0; part < 2; ++part) {      // 32 columns at a time keeps the live registers at ~64
@@ -879,6 +902,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           if (part == 1) {                          // D1 chunk fully read: release this half to the MMA warp
             tc_fence_before();
             mbar_arrive(&d1_empty[h]);
+            if (warp == 0) TL(0, n, h * 4 + 1);
           }
           uint32_t hi[16], lo[16];
 #pragma unroll
@@ -891,6 +915,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           if (part == 0) {
             mbar_wait(&a2_empty[team], ((uint32_t)q & 1u) ^ 1u);
             tc_fence_after();
+            if (warp == 0) TL(0, n, h * 4 + 2);
           }
           tmem_st16(a2_addr + (uint32_t)(part * 16), hi);
           tmem_st16(a2_addr + 32u + (uint32_t)(part * 16), lo);
@@ -898,6 +923,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a2_full[team]);
+        if (warp == 0) TL(0, n, h * 4 + 3);
       }
     }
   } else if (warp < 12) {
@@ -908,6 +934,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       const long long row0 = (long long)tile * 128;
+      if (warp == 8) TL(1, n, 0);
       float4 r[16];
       if (residual) {                      // coalesced prefetch, issued long before the accumulator is ready
 #pragma unroll
@@ -922,6 +949,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       const int ds = n & 1;
       mbar_wait(&d2_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
+      if (warp == 8) TL(1, n, 1);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -943,6 +971,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 8) TL(1, n, 2);
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
         const int idx = it * 128 + rt, rr = idx >> 4, c4 = idx & 15;
@@ -956,6 +985,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 8) TL(1, n, 3);
     }
   } else if (warp == kFFMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
@@ -974,6 +1004,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
         const int st = n & 1;
         mbar_wait(&a1_full[st], (uint32_t)(n >> 1) & 1u);
+        TL(2, n, 0);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&d1_empty[h], ((uint32_t)n & 1u) ^ 1u);
@@ -983,6 +1014,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           umma_commit(&d1_full[h]);
         }
         umma_commit(&a1_empty[st]);
+        TL(2, n, 1);
         const int ds = n & 1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -990,6 +1022,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           mbar_wait(&a2_full[team], (uint32_t)q & 1u);
           if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
           tc_fence_after();
+          TL(2, n, 2 + j);
           const uint32_t d2 = tmem + (uint32_t)(256 + ds * 64);
           const uint32_t a_hi = tmem + (uint32_t)(384 + team * 64), a_lo = a_hi + 32u;
           const uint64_t bh = dW2h + j * kBlk, bl = dW2l + j * kBlk;
@@ -1005,6 +1038,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           umma_commit(&a2_empty[team]);
         }
         umma_commit(&d2_full[ds]);
+        TL(2, n, 6);
       }
     }
     __syncwarp();
@@ -1015,6 +1049,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       const long long row0 = (long long)tile * 128;
       const int st = n & 1;
+      if (lt < 32) TL(3, n, 0);
       float4 v[16];
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
@@ -1040,7 +1075,9 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           }
         }
       }
+      if (lt < 32) TL(3, n, 1);
       mbar_wait(&a1_empty[st], ((uint32_t)(n >> 1) & 1u) ^ 1u);
+      if (lt < 32) TL(3, n, 2);
       uint8_t* sA1h = smem + FF3_A1 + st * 32768;
       uint8_t* sA1l = sA1h + 16384;
 #pragma unroll
@@ -1050,6 +1087,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       }
       fence_proxy_async_smem();
       mbar_arrive(&a1_full[st]);
+      if (lt < 32) TL(3, n, 3);
     }
   }
   tc_fence_before();

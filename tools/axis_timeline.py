@@ -23,7 +23,14 @@ with torch.no_grad():
         plan.spectral_forward(0, x)
     torch.cuda.synchronize()
     lib.ffno_debug_timeline(1, None)
-    plan.spectral_forward(0, x)          # the LAST axis launch (inverse X, accumulate) overwrites earlier stamps
+    m2 = FNOFactorized2DBlock(modes=16, width=64, n_layers=1, input_dim=3, share_weight=True, factor=4, ff_weight_norm=True,
+                              gain=0.1).cuda().eval()
+    xin = torch.randn(32, 64, 64, 3, device="cuda")
+    os.environ["FFNO_B200_GRAPH"] = "0"
+    m2(xin)
+    torch.cuda.synchronize()
+    lib.ffno_debug_timeline(1, None)
+    m2(xin)                              # layer path: fwd (both axes), mix, inv (both axes): the inverse launch stamps last
     torch.cuda.synchronize()
     buf = np.zeros(1024, dtype=np.int64)
     lib.ffno_debug_timeline(0, buf.ctypes.data_as(C.c_void_p))
