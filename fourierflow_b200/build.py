@@ -62,6 +62,8 @@ def _build_locked(verbose: bool) -> str:
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc(), *ARCH, *FLAGS, "-c", src, "-o", obj]
+        if os.environ.get("FFNO_TIMELINE") == "1":      # diagnostics build: in-kernel clock64 stamps (tools/*_timeline.py)
+            cmd.insert(1, "-DFFNO_TIMELINE")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -20,11 +20,15 @@ using namespace umma;
 // [role 8][tile 16][event 8]; enabled by ffno_debug_timeline(1).  Costs one predicated store per event.
 __device__ long long g_timeline[8 * 16 * 8];
 __device__ int g_timeline_on = 0;
+#ifdef FFNO_TIMELINE
 #define TL(role, tile_n, ev)                                                                      \
   do {                                                                                            \
     if (g_timeline_on && blockIdx.x == 0 && (tile_n) < 16 && (threadIdx.x & 31) == 0)             \
       g_timeline[((role) * 16 + (tile_n)) * 8 + (ev)] = clock64();                                \
   } while (0)
+#else
+#define TL(role, tile_n, ev) do {} while (0)
+#endif
 
 namespace {
 
@@ -77,6 +81,20 @@ __device__ __forceinline__ void issue3_kmajor(uint32_t tmem_d, uint64_t a_hi, ui
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks)
       umma_bf16_ss(tmem_d, a + (uint64_t)(ks * 2), b + (uint64_t)(ks * 2), idesc, (pass == 0 && ks == 0) ? acc_first : 1u);
+  }
+}
+
+template <int KSTEPS>
+__device__ __forceinline__ void issue3_kmajor_elect(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
+                                                    uint64_t b_lo, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint64_t a = (pass == 2) ? a_lo : a_hi;
+    const uint64_t b = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      umma_bf16_ss_elect(tmem_d, a + (uint64_t)(ks * 2), b + (uint64_t)(ks * 2), idesc,
+                         (pass == 0 && ks == 0) ? acc_first : 1u);
   }
 }
 
@@ -209,13 +227,16 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     }
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t total = 2u * b_half;
-      mbar_expect_tx(bar_w, total);
-      for (uint32_t off = 0; off < total; off += 32768u) {
-        const uint32_t nb = (total - off) < 32768u ? (total - off) : 32768u;
-        bulk_g2s(sB + off, p.table + off, nb, bar_w);
+    {   // the whole warp walks the schedule (warp-uniform); elect.sync picks the issuing lane per instruction
+      if (lane == 0) {
+        const uint32_t total = 2u * b_half;
+        mbar_expect_tx(bar_w, total);
+        for (uint32_t off = 0; off < total; off += 32768u) {
+          const uint32_t nb = (total - off) < 32768u ? (total - off) : 32768u;
+          bulk_g2s(sB + off, p.table + off, nb, bar_w);
+        }
       }
+      __syncwarp();
       mbar_wait(bar_w, 0);
       const uint32_t idesc = make_idesc_bf16(128, p.npad, 1, 0);
       int item = 0, n = 0;
@@ -227,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
           const int as = item & 1;
           mbar_wait(&a_full[as], (uint32_t)(item >> 1) & 1u);
           tc_fence_after();
-          if (blockIdx.y == 0) TL(6, n, 0);
+          if (lane == 0 && blockIdx.y == 0) TL(6, n, 0);
           const int rem = p.n_in - kc * 64;
           const int ksteps = rem >= 64 ? 4 : (rem + 15) / 16;
           // MN-major A: 64-wide mn blocks 8 KB apart (LBO), 8-row k groups 1 KB apart (SBO); one K step = 2 groups
@@ -242,8 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
               const uint64_t a = (pass == 2) ? dAl : dAh, b = (pass == 1) ? dBl : dBh;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16_ss(d_addr, a + (uint64_t)(ks * (2048 >> 4)), b + (uint64_t)(ks * 2), idesc,
-                             (pass == 0 && ks == 0) ? acc0 : 1u);
+                umma_bf16_ss_elect(d_addr, a + (uint64_t)(ks * (2048 >> 4)), b + (uint64_t)(ks * 2), idesc,
+                                   (pass == 0 && ks == 0) ? acc0 : 1u);
             }
           } else {
             uint32_t acc = acc0;
@@ -252,15 +273,15 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
               const uint64_t a = (pass == 2) ? dAl : dAh, b = (pass == 1) ? dBl : dBh;
 #pragma unroll 1
               for (int ks = 0; ks < ksteps; ++ks) {
-                umma_bf16_ss(d_addr, a + (uint64_t)(ks * (2048 >> 4)), b + (uint64_t)(ks * 2), idesc, acc);
+                umma_bf16_ss_elect(d_addr, a + (uint64_t)(ks * (2048 >> 4)), b + (uint64_t)(ks * 2), idesc, acc);
                 acc = 1u;
               }
             }
           }
-          umma_commit(&a_empty[as]);
+          umma_commit_elect(&a_empty[as]);
         }
-        umma_commit(&d_full[ds]);
-        if (blockIdx.y == 0) TL(6, n, 1);
+        umma_commit_elect(&d_full[ds]);
+        if (lane == 0 && blockIdx.y == 0) TL(6, n, 1);
       }
     }
     __syncwarp();
@@ -470,11 +491,14 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
-      mbar_expect_tx(bar_w, kMixImageBytes);
-      const uint8_t* img = ax.image + (long long)k * kMixImageBytes;
-      bulk_g2s(sB, img, 32768, bar_w);
-      bulk_g2s(sB + 32768, img + 32768, 32768, bar_w);
+    {
+      if (lane == 0) {
+        mbar_expect_tx(bar_w, kMixImageBytes);
+        const uint8_t* img = ax.image + (long long)k * kMixImageBytes;
+        bulk_g2s(sB, img, 32768, bar_w);
+        bulk_g2s(sB + 32768, img + 32768, 32768, bar_w);
+      }
+      __syncwarp();
       mbar_wait(bar_w, 0);
       constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
       const uint64_t dBh = desc_kmajor(smem_u32(sB), 0), dBl = desc_kmajor(smem_u32(sB) + 32768u, 0);
@@ -489,10 +513,10 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
           mbar_wait(&a_full[as], (uint32_t)(item >> 1) & 1u);
           tc_fence_after();
           const uint64_t a_off = (uint64_t)(as * (MXP_A_STAGE >> 4)), b_off = (uint64_t)(kb * (16384 >> 4));
-          issue3_kmajor<4>(d_addr, dAh + a_off, dAl + a_off, dBh + b_off, dBl + b_off, IDESC, kb > 0 ? 1u : 0u);
-          umma_commit(&a_empty[as]);
+          issue3_kmajor_elect<4>(d_addr, dAh + a_off, dAl + a_off, dBh + b_off, dBl + b_off, IDESC, kb > 0 ? 1u : 0u);
+          umma_commit_elect(&a_empty[as]);
         }
-        umma_commit(&d_full[ds]);
+        umma_commit_elect(&d_full[ds]);
       }
     }
     __syncwarp();
@@ -989,9 +1013,12 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     }
   } else if (warp == kFFMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      mbar_expect_tx(bar_w, 131072);
-      for (int i = 0; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
+    {
+      if (lane == 0) {
+        mbar_expect_tx(bar_w, 131072);
+        for (int i = 0; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
+      }
+      __syncwarp();
       mbar_wait(bar_w, 0);
       constexpr uint32_t IDESC_G1 = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
@@ -1004,17 +1031,17 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
         const int st = n & 1;
         mbar_wait(&a1_full[st], (uint32_t)(n >> 1) & 1u);
-        TL(2, n, 0);
+        if (lane == 0) TL(2, n, 0);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&d1_empty[h], ((uint32_t)n & 1u) ^ 1u);
           tc_fence_after();
-          issue3_kmajor<4>(tmem + (uint32_t)(h * 128), dA1h + st * kStage, dA1l + st * kStage, dW1h + h * kHalf,
-                           dW1l + h * kHalf, IDESC_G1, 0u);
-          umma_commit(&d1_full[h]);
+          issue3_kmajor_elect<4>(tmem + (uint32_t)(h * 128), dA1h + st * kStage, dA1l + st * kStage, dW1h + h * kHalf,
+                                 dW1l + h * kHalf, IDESC_G1, 0u);
+          umma_commit_elect(&d1_full[h]);
         }
-        umma_commit(&a1_empty[st]);
-        TL(2, n, 1);
+        umma_commit_elect(&a1_empty[st]);
+        if (lane == 0) TL(2, n, 1);
         const int ds = n & 1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1022,7 +1049,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           mbar_wait(&a2_full[team], (uint32_t)q & 1u);
           if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          TL(2, n, 2 + j);
+          if (lane == 0) TL(2, n, 2 + j);
           const uint32_t d2 = tmem + (uint32_t)(256 + ds * 64);
           const uint32_t a_hi = tmem + (uint32_t)(384 + team * 64), a_lo = a_hi + 32u;
           const uint64_t bh = dW2h + j * kBlk, bl = dW2l + j * kBlk;
@@ -1032,13 +1059,13 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
             const uint64_t b = (pass == 1) ? bl : bh;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_bf16_ts(d2, a + (uint32_t)(ks * 8), b + (uint64_t)(ks * 2), IDESC_G2,
-                           (pass == 0 && ks == 0) ? (j > 0 ? 1u : 0u) : 1u);
+              umma_bf16_ts_elect(d2, a + (uint32_t)(ks * 8), b + (uint64_t)(ks * 2), IDESC_G2,
+                                 (pass == 0 && ks == 0) ? (j > 0 ? 1u : 0u) : 1u);
           }
-          umma_commit(&a2_empty[team]);
+          umma_commit_elect(&a2_empty[team]);
         }
-        umma_commit(&d2_full[ds]);
-        TL(2, n, 6);
+        umma_commit_elect(&d2_full[ds]);
+        if (lane == 0) TL(2, n, 6);
       }
     }
     __syncwarp();
