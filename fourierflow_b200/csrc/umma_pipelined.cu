@@ -8,6 +8,8 @@
 // full/empty mbarriers, so the global loads of tile t+1, the MMAs of tile t and the epilogue of tile t-1 overlap.
 // (The v1 kernels in umma_kernels.cu do the same arithmetic with one warpgroup and no overlap; they stay as the
 // cross-check, selectable with FFNO_UMMA_V1=1.)
+#include <type_traits>
+
 #include "umma.cuh"
 #include "umma_kernels.cuh"
 
@@ -257,26 +259,22 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
           const uint64_t dBh = desc_kmajor(smem_u32(sB) + (uint32_t)kc * ((uint32_t)p.npad * 128u), 0);
           const uint64_t dBl = dBh + (uint64_t)(b_half >> 4);
           const uint32_t acc0 = kc > 0 ? 1u : 0u;
-          if (ksteps == 4) {
+          auto issue = [&](auto KS) {
+            constexpr int kSteps = decltype(KS)::value;
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
               const uint64_t a = (pass == 2) ? dAl : dAh, b = (pass == 1) ? dBl : dBh;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
+              for (int ks = 0; ks < kSteps; ++ks)
                 umma_bf16_ss_elect(d_addr, a + (uint64_t)(ks * (2048 >> 4)), b + (uint64_t)(ks * 2), idesc,
                                    (pass == 0 && ks == 0) ? acc0 : 1u);
             }
-          } else {
-            uint32_t acc = acc0;
-#pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint64_t a = (pass == 2) ? dAl : dAh, b = (pass == 1) ? dBl : dBh;
-#pragma unroll 1
-              for (int ks = 0; ks < ksteps; ++ks) {
-                umma_bf16_ss_elect(d_addr, a + (uint64_t)(ks * (2048 >> 4)), b + (uint64_t)(ks * 2), idesc, acc);
-                acc = 1u;
-              }
-            }
+          };
+          switch (ksteps) {       // warp-uniform
+            case 4: issue(std::integral_constant<int, 4>{}); break;
+            case 3: issue(std::integral_constant<int, 3>{}); break;
+            case 2: issue(std::integral_constant<int, 2>{}); break;
+            default: issue(std::integral_constant<int, 1>{}); break;
           }
           umma_commit_elect(&a_empty[as]);
         }
@@ -296,22 +294,24 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     const int n_items = my_tiles * p.kchunks;
     const int gsel = (lt >> 4) & 1, c4 = lt & 15, rsub = lt >> 5;            // rsub: 0..15
     uint8_t* stg_base = smem + AXP_STAGING + lt * 16;
+    const long long row_step = 16 * p.inner;                 // floats between the rows this thread copies
     auto issue = [&](int item) {
       if (item < n_items) {
-        const int tile = (int)blockIdx.x + (item / p.kchunks) * (int)gridDim.x;
-        const int kc = item - (item / p.kchunks) * p.kchunks;
+        int tq = item, kc = 0;
+        if (p.kchunks > 1) { tq = item / p.kchunks; kc = item - tq * p.kchunks; }
+        const int tile = (int)blockIdx.x + tq * (int)gridDim.x;
         const long long G = (long long)tile * 2 + gsel;
         const bool live = G < n_groups;
         const int o = live ? (int)((unsigned)G / (unsigned)gpi) : 0;
         const int g = live ? (int)((unsigned)G - (unsigned)o * (unsigned)gpi) : 0;
-        const float* src0 = p.X + ((long long)o * p.n_in) * p.inner + (long long)g * 64 + c4 * 4;
+        const int i0 = kc * 64 + rsub;
+        const float* src = p.X + ((long long)o * p.n_in + i0) * p.inner + (long long)g * 64 + c4 * 4;
         uint8_t* dst = stg_base + (item % kAxStages) * 32768;
 #pragma unroll
         for (int it = 0; it < kLdPerThread; ++it) {
-          const int i = kc * 64 + it * 16 + rsub;
-          const bool ok = live && i < p.n_in;
-          cp_async16(dst + it * (kLoaders * 16), ok ? (const void*)(src0 + (long long)i * p.inner) : (const void*)p.X,
-                     ok ? 16u : 0u);
+          const bool ok = live && (i0 + it * 16) < p.n_in;
+          cp_async16(dst + it * (kLoaders * 16), ok ? (const void*)src : (const void*)p.X, ok ? 16u : 0u);
+          src += row_step;
         }
       }
       cp_async_commit();
@@ -1027,45 +1027,57 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       const uint64_t dW1h = desc_kmajor(sW, 0), dW1l = desc_kmajor(sW + 32768u, 0);
       const uint64_t dW2h = desc_kmajor(sW + 65536u, 0), dW2l = desc_kmajor(sW + 98304u, 0);
       constexpr uint64_t kStage = 32768 >> 4, kHalf = 16384 >> 4, kBlk = 8192 >> 4;
+      // Software-pipelined issue order: G1 of tile n+1 is issued between the G2 chunks of tile n
+      //   G2_0(n) G2_1(n) | G1h0(n+1) | G2_2(n) G2_3(n) | G1h1(n+1)
+      // so the epilogue teams find the next D1 half ready as soon as they finish a tile (no G1 latency exposed).
+      auto issue_g1 = [&](int nn, int h) {
+        const int stn = nn & 1;
+        if (h == 0) mbar_wait(&a1_full[stn], (uint32_t)(nn >> 1) & 1u);
+        mbar_wait(&d1_empty[h], ((uint32_t)nn & 1u) ^ 1u);
+        tc_fence_after();
+        issue3_kmajor_elect<4>(tmem + (uint32_t)(h * 128), dA1h + stn * kStage, dA1l + stn * kStage, dW1h + h * kHalf,
+                               dW1l + h * kHalf, IDESC_G1, 0u);
+        umma_commit_elect(&d1_full[h]);
+        if (h == 1) umma_commit_elect(&a1_empty[stn]);
+      };
+      auto issue_g2 = [&](int nn, int j) {
+        const int team = j & 1, q = 2 * nn + (j >> 1), ds = nn & 1;
+        mbar_wait(&a2_full[team], (uint32_t)q & 1u);
+        if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(nn >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d2 = tmem + (uint32_t)(256 + ds * 64);
+        const uint32_t a_hi = tmem + (uint32_t)(384 + team * 64), a_lo = a_hi + 32u;
+        const uint64_t bh = dW2h + j * kBlk, bl = dW2l + j * kBlk;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = (pass == 2) ? a_lo : a_hi;
+          const uint64_t b = (pass == 1) ? bl : bh;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16_ts_elect(d2, a + (uint32_t)(ks * 8), b + (uint64_t)(ks * 2), IDESC_G2,
+                               (pass == 0 && ks == 0) ? (j > 0 ? 1u : 0u) : 1u);
+        }
+        umma_commit_elect(&a2_empty[team]);
+        if (j == 3) umma_commit_elect(&d2_full[ds]);
+      };
       int n = 0;
+      if ((int)blockIdx.x < n_tiles) {
+        issue_g1(0, 0);
+        issue_g1(0, 1);
+      }
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-        const int st = n & 1;
-        mbar_wait(&a1_full[st], (uint32_t)(n >> 1) & 1u);
+        const bool has_next = tile + (int)gridDim.x < n_tiles;
         if (lane == 0) TL(2, n, 0);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&d1_empty[h], ((uint32_t)n & 1u) ^ 1u);
-          tc_fence_after();
-          issue3_kmajor_elect<4>(tmem + (uint32_t)(h * 128), dA1h + st * kStage, dA1l + st * kStage, dW1h + h * kHalf,
-                                 dW1l + h * kHalf, IDESC_G1, 0u);
-          umma_commit_elect(&d1_full[h]);
-        }
-        umma_commit_elect(&a1_empty[st]);
+        issue_g2(n, 0);
+        issue_g2(n, 1);
         if (lane == 0) TL(2, n, 1);
-        const int ds = n & 1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int team = j & 1, q = 2 * n + (j >> 1);
-          mbar_wait(&a2_full[team], (uint32_t)q & 1u);
-          if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
-          tc_fence_after();
-          if (lane == 0) TL(2, n, 2 + j);
-          const uint32_t d2 = tmem + (uint32_t)(256 + ds * 64);
-          const uint32_t a_hi = tmem + (uint32_t)(384 + team * 64), a_lo = a_hi + 32u;
-          const uint64_t bh = dW2h + j * kBlk, bl = dW2l + j * kBlk;
-#pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a = (pass == 2) ? a_lo : a_hi;
-            const uint64_t b = (pass == 1) ? bl : bh;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_bf16_ts_elect(d2, a + (uint32_t)(ks * 8), b + (uint64_t)(ks * 2), IDESC_G2,
-                                 (pass == 0 && ks == 0) ? (j > 0 ? 1u : 0u) : 1u);
-          }
-          umma_commit_elect(&a2_empty[team]);
-        }
-        umma_commit_elect(&d2_full[ds]);
-        if (lane == 0) TL(2, n, 6);
+        if (has_next) issue_g1(n + 1, 0);
+        if (lane == 0) TL(2, n, 2);
+        issue_g2(n, 2);
+        issue_g2(n, 3);
+        if (lane == 0) TL(2, n, 3);
+        if (has_next) issue_g1(n + 1, 1);
+        if (lane == 0) TL(2, n, 4);
       }
     }
     __syncwarp();
