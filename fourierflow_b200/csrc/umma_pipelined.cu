@@ -116,8 +116,9 @@ __device__ __forceinline__ void store_split4_at(uint8_t* tile_hi, uint8_t* tile_
 constexpr int AXP_A_STAGE = 32768;                 // operand stage: hi 16 KB | lo 16 KB
 constexpr int AXP_BAR = 2 * AXP_A_STAGE;           // 65536
 constexpr int AXP_STAGING = AXP_BAR + 1024;        // kAxStages x 32 KB of raw FP32 (cp.async landing zone)
-constexpr int kAxStages = 3;
-constexpr int AXP_TABLE = AXP_STAGING + kAxStages * 32768;
+constexpr int kAxStages = 2;
+constexpr int AXP_OUT = AXP_STAGING + kAxStages * 32768;     // 2 teams x 16 KB output staging (32 columns x 128 floats)
+constexpr int AXP_TABLE = AXP_OUT + 32768;
 
 struct AxisSet {
   AxisXform ax[3];
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       mbar_init(&a_full[i], kLoaders);
       mbar_init(&a_empty[i], 1);
       mbar_init(&d_full[i], 1);
-      mbar_init(&d_empty[i], kEpiWarps * 32);
+      mbar_init(&d_empty[i], 128);
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -166,64 +167,63 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   const long long n_groups = p.outer * gpi;
 
   if (warp < kEpiWarps) {
-    // ---------------------------------------------------------------- epilogue: two teams, alternate 32-column chunks
+    // ---------------------------------------------------------------- epilogue: two teams on alternating tiles
+    // Team t owns accumulator stage t (tile n uses stage n & 1).  Each 32-column chunk goes TMEM -> registers ->
+    // transposed FP32 staging (column-major: 32 columns x 128 inner elements) -> float4 global stores, one column
+    // (two contiguous 256-byte runs) per warp instruction.
     const int team = warp >> 2, rt = tid & 127;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float* sOut = reinterpret_cast<float*>(smem + AXP_OUT + team * 16384);
+    const int total_chunks = (p.npad + 31) >> 5;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      const int ds = n & 1;
+      if ((n & 1) != team) continue;
+      const int ds = team;
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 0);
-      const long long G = (long long)tile * 2 + (rt >> 6);
-      const bool live = G < n_groups;
-      long long o = 0, g = 0;
-      if (live) {
-        const unsigned uo = (unsigned)G / (unsigned)gpi;
-        o = uo;
-        g = (unsigned)G - uo * (unsigned)gpi;
+      // the two 64-element groups of this tile (warp-uniform)
+      const long long G0 = (long long)tile * 2;
+      long long gbase[2];
+      bool glive[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const long long G = G0 + q;
+        glive[q] = G < n_groups;
+        const unsigned uo = glive[q] ? (unsigned)G / (unsigned)gpi : 0u;
+        const unsigned ug = glive[q] ? (unsigned)G - uo * (unsigned)gpi : 0u;
+        gbase[q] = ((long long)uo * p.n_out) * p.inner + (long long)ug * 64;
       }
-      float* ybase = p.Y + (o * p.n_out) * p.inner + g * 64 + (rt & 63);
-      const int n_chunks = p.npad >> 5;            // 32-column chunks (npad is a multiple of 16: last chunk may be half)
-      const int total_chunks = (p.npad + 31) >> 5;
-      (void)n_chunks;
-      bool released = false;
 #pragma unroll 1
-      for (int ch = team; ch < total_chunks; ch += 2) {
+      for (int ch = 0; ch < total_chunks; ++ch) {
         const int c0 = ch * 32;
         uint32_t v[32];
         tmem_ld32(tmem + lane_base + (uint32_t)(ds * stage_cols + c0), v);
         tmem_ld_wait();
-        if (ch + 2 >= total_chunks) {   // this team's last read of the stage
+        if (ch + 1 == total_chunks) {   // last read of this stage: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&d_empty[ds]);
-          released = true;
           if (warp == 0 && blockIdx.y == 0) TL(5, n, 1);
         }
-        if (live) {
-          float* dst = ybase + (long long)c0 * p.inner;
-          if (p.accumulate) {
 #pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 16) {
-              float old[16];
+        for (int j = 0; j < 32; ++j) sOut[j * 128 + rt] = __uint_as_float(v[j]);
+        if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
-              for (int j = 0; j < 16; ++j) old[j] = (c0 + j0 + j < p.n_out) ? dst[(long long)(j0 + j) * p.inner] : 0.f;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j0 + j < p.n_out) dst[(long long)(j0 + j) * p.inner] = __uint_as_float(v[j0 + j]) + old[j];
+        for (int it = 0; it < 8; ++it) {
+          const int idx = it * 128 + rt, col = idx >> 5, f4 = idx & 31, q = f4 >> 4;
+          if (glive[q] && c0 + col < p.n_out) {
+            float4 val = *reinterpret_cast<const float4*>(sOut + col * 128 + f4 * 4);
+            float* dst = p.Y + gbase[q] + (long long)(c0 + col) * p.inner + (f4 & 15) * 4;
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(dst);
+              val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (c0 + j < p.n_out) *dst = __uint_as_float(v[j]);
-              dst += p.inner;
-            }
+            *reinterpret_cast<float4*>(dst) = val;
           }
         }
-      }
-      if (!released) {                  // a team with no chunk in this tile still owes its arrivals
-        tc_fence_before();
-        mbar_arrive(&d_empty[ds]);
+        if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 2);
     }
@@ -857,7 +857,9 @@ constexpr int FF3_BIAS = FF3_OUT + 32768;          // 229376
 constexpr int FF3_BAR = FF3_BIAS + 320 * 4;        // 230656
 constexpr int FF3_TOTAL = FF3_BAR + 192;           // 230848 <= 232448
 
-__global__ void __launch_bounds__(kFFThreads, 1)
+constexpr int kFF3Threads = kFFLoaderThread0 + 256;      // 8 + 4 + 1 + 8 warps = 672 threads
+
+__global__ void __launch_bounds__(kFF3Threads, 1)
 ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
              const float* __restrict__ residual, float* __restrict__ x_out, float* __restrict__ b_out,
              const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2, long long P,
@@ -880,7 +882,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a1_full[i], 128);
+      mbar_init(&a1_full[i], 256);
       mbar_init(&a1_empty[i], 1);
       mbar_init(&d1_full[i], 1);
       mbar_init(&d1_empty[i], 256);
@@ -896,7 +898,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  for (int i = tid; i < 256; i += kFFThreads) sb1[i] = b1 ? b1[i] : 0.f;
+  for (int i = tid; i < 256; i += kFF3Threads) sb1[i] = b1 ? b1[i] : 0.f;
   if (tid < 64) sb2[tid] = b2 ? b2[tid] : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -1083,36 +1085,35 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- loaders: (s0 + s1 + s2) tile -> A1[stage]
-    const int lt = tid - kFFLoaderThread0;
+    // 8 warps; each thread owns 8 float4 of the tile and has all of its loads (every source) in flight at once
+    const int lt = tid - kFFLoaderThread0;          // 0..255
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       const long long row0 = (long long)tile * 128;
       const int st = n & 1;
       if (lt < 32) TL(3, n, 0);
-      float4 v[16];
+      float4 v[8], t1[8];
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
-        v[it] = (row0 + r < P) ? ldg_stream(s0 + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * 256 + lt, r = idx >> 4, c4 = idx & 15;
+        const bool ok = row0 + r < P;
+        const long long off = (row0 + r) * 64 + c4 * 4;
+        v[it] = ok ? ldg_stream(s0 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        t1[it] = (ok && s1) ? ldg_stream(s1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-#pragma unroll 1
-      for (int src = 1; src < 3; ++src) {
-        const float* sp = src == 1 ? s1 : s2;
-        if (!sp) continue;
+      if (s2) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float4 t[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int idx = (half * 8 + it) * 128 + lt, r = idx >> 4, c4 = idx & 15;
-            t[it] = (row0 + r < P) ? ldg_stream(sp + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            float4& a = v[half * 8 + it];
-            a.x += t[it].x; a.y += t[it].y; a.z += t[it].z; a.w += t[it].w;
+        for (int it = 0; it < 8; ++it) {
+          const int idx = it * 256 + lt, r = idx >> 4, c4 = idx & 15;
+          if (row0 + r < P) {
+            const float4 t2 = ldg_stream(s2 + (row0 + r) * 64 + c4 * 4);
+            v[it].x += t2.x; v[it].y += t2.y; v[it].z += t2.z; v[it].w += t2.w;
           }
         }
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        v[it].x += t1[it].x; v[it].y += t1[it].y; v[it].z += t1[it].z; v[it].w += t1[it].w;
       }
       if (lt < 32) TL(3, n, 1);
       mbar_wait(&a1_empty[st], ((uint32_t)(n >> 1) & 1u) ^ 1u);
@@ -1120,8 +1121,8 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       uint8_t* sA1h = smem + FF3_A1 + st * 32768;
       uint8_t* sA1l = sA1h + 16384;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * 256 + lt, r = idx >> 4, c4 = idx & 15;
         store_split4_at(sA1h, sA1l, kmajor_sw128_offset(r, c4 * 4), v[it]);
       }
       fence_proxy_async_smem();
@@ -1144,7 +1145,7 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
   }
   const int n_tiles = ceil_div(P, 128);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  ff_ts_kernel<<<grid, kFFThreads, FF3_TOTAL, st>>>(s0, s1, s2, residual, x_out, b_out, image, b1, b2, P, n_tiles);
+  ff_ts_kernel<<<grid, kFF3Threads, FF3_TOTAL, st>>>(s0, s1, s2, residual, x_out, b_out, image, b1, b2, P, n_tiles);
   ++g_launch_counter;
   FFNO_LAUNCH_CHECK("ff_ts_kernel");
   return FFNO_OK;
