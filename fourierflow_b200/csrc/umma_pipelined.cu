@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       mbar_init(&a_full[i], kLoaders);
       mbar_init(&a_empty[i], 1);
       mbar_init(&d_full[i], 1);
-      mbar_init(&d_empty[i], 128);
+      mbar_init(&d_empty[i], p.npad > 32 ? 256 : 128);   // see the epilogue: who drains a stage
     }
     mbar_init(bar_w, 1);
     fence_barrier_init();
@@ -167,23 +167,24 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   const long long n_groups = p.outer * gpi;
 
   if (warp < kEpiWarps) {
-    // ---------------------------------------------------------------- epilogue: two teams on alternating tiles
-    // Team t owns accumulator stage t (tile n uses stage n & 1).  Each 32-column chunk goes TMEM -> registers ->
-    // transposed FP32 staging (column-major: 32 columns x 128 inner elements) -> float4 global stores, one column
-    // (two contiguous 256-byte runs) per warp instruction.
+    // ---------------------------------------------------------------- epilogue: two teams of 4 warps
+    // One 32-column chunk goes TMEM -> registers -> transposed FP32 staging (32 columns x 128 inner elements) ->
+    // float4 global stores, one column (two contiguous 256-byte runs) per warp instruction.
+    //   npad <= 32 (one chunk per tile): the teams take alternate tiles, team t drains accumulator stage t alone;
+    //   npad  > 32: both teams work on every tile, team t takes chunks t, t+2, ... and both release the stage.
     const int team = warp >> 2, rt = tid & 127;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     float* sOut = reinterpret_cast<float*>(smem + AXP_OUT + team * 16384);
     const int total_chunks = (p.npad + 31) >> 5;
+    const bool split_tiles = total_chunks == 1;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      if ((n & 1) != team) continue;
-      const int ds = team;
+      const int ds = n & 1;
+      if (split_tiles && ds != team) continue;
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 0);
-      // the two 64-element groups of this tile (warp-uniform)
-      const long long G0 = (long long)tile * 2;
+      const long long G0 = (long long)tile * 2;                     // the two 64-element groups (warp-uniform)
       long long gbase[2];
       bool glive[2];
 #pragma unroll
@@ -194,15 +195,18 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
         const unsigned ug = glive[q] ? (unsigned)G - uo * (unsigned)gpi : 0u;
         gbase[q] = ((long long)uo * p.n_out) * p.inner + (long long)ug * 64;
       }
+      const int ch_begin = split_tiles ? 0 : team, ch_step = split_tiles ? 1 : 2;
+      bool released = false;
 #pragma unroll 1
-      for (int ch = 0; ch < total_chunks; ++ch) {
+      for (int ch = ch_begin; ch < total_chunks; ch += ch_step) {
         const int c0 = ch * 32;
         uint32_t v[32];
         tmem_ld32(tmem + lane_base + (uint32_t)(ds * stage_cols + c0), v);
         tmem_ld_wait();
-        if (ch + 1 == total_chunks) {   // last read of this stage: hand it back to the MMA warp
+        if (ch + ch_step >= total_chunks) {   // this team's last read of the stage
           tc_fence_before();
           mbar_arrive(&d_empty[ds]);
+          released = true;
           if (warp == 0 && blockIdx.y == 0) TL(5, n, 1);
         }
 #pragma unroll
@@ -224,6 +228,10 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
         }
         if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+      if (!split_tiles && !released) {        // a team with no chunk in this tile still owes its arrivals
+        tc_fence_before();
+        mbar_arrive(&d_empty[ds]);
       }
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 2);
     }
@@ -857,9 +865,7 @@ constexpr int FF3_BIAS = FF3_OUT + 32768;          // 229376
 constexpr int FF3_BAR = FF3_BIAS + 320 * 4;        // 230656
 constexpr int FF3_TOTAL = FF3_BAR + 192;           // 230848 <= 232448
 
-constexpr int kFF3Threads = kFFLoaderThread0 + 256;      // 8 + 4 + 1 + 8 warps = 672 threads
-
-__global__ void __launch_bounds__(kFF3Threads, 1)
+__global__ void __launch_bounds__(kFFThreads, 1)
 ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
              const float* __restrict__ residual, float* __restrict__ x_out, float* __restrict__ b_out,
              const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2, long long P,
@@ -882,7 +888,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a1_full[i], 256);
+      mbar_init(&a1_full[i], 128);
       mbar_init(&a1_empty[i], 1);
       mbar_init(&d1_full[i], 1);
       mbar_init(&d1_empty[i], 256);
@@ -898,7 +904,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  for (int i = tid; i < 256; i += kFF3Threads) sb1[i] = b1 ? b1[i] : 0.f;
+  for (int i = tid; i < 256; i += kFFThreads) sb1[i] = b1 ? b1[i] : 0.f;
   if (tid < 64) sb2[tid] = b2 ? b2[tid] : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -1085,35 +1091,36 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- loaders: (s0 + s1 + s2) tile -> A1[stage]
-    // 8 warps; each thread owns 8 float4 of the tile and has all of its loads (every source) in flight at once
-    const int lt = tid - kFFLoaderThread0;          // 0..255
+    const int lt = tid - kFFLoaderThread0;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       const long long row0 = (long long)tile * 128;
       const int st = n & 1;
       if (lt < 32) TL(3, n, 0);
-      float4 v[8], t1[8];
+      float4 v[16];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * 256 + lt, r = idx >> 4, c4 = idx & 15;
-        const bool ok = row0 + r < P;
-        const long long off = (row0 + r) * 64 + c4 * 4;
-        v[it] = ok ? ldg_stream(s0 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-        t1[it] = (ok && s1) ? ldg_stream(s1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < 16; ++it) {
+        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
+        v[it] = (row0 + r < P) ? ldg_stream(s0 + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (s2) {
+#pragma unroll 1
+      for (int src = 1; src < 3; ++src) {
+        const float* sp = src == 1 ? s1 : s2;
+        if (!sp) continue;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int idx = it * 256 + lt, r = idx >> 4, c4 = idx & 15;
-          if (row0 + r < P) {
-            const float4 t2 = ldg_stream(s2 + (row0 + r) * 64 + c4 * 4);
-            v[it].x += t2.x; v[it].y += t2.y; v[it].z += t2.z; v[it].w += t2.w;
+        for (int half = 0; half < 2; ++half) {
+          float4 t[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int idx = (half * 8 + it) * 128 + lt, r = idx >> 4, c4 = idx & 15;
+            t[it] = (row0 + r < P) ? ldg_stream(sp + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            float4& a = v[half * 8 + it];
+            a.x += t[it].x; a.y += t[it].y; a.z += t[it].z; a.w += t[it].w;
           }
         }
-      }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        v[it].x += t1[it].x; v[it].y += t1[it].y; v[it].z += t1[it].z; v[it].w += t1[it].w;
       }
       if (lt < 32) TL(3, n, 1);
       mbar_wait(&a1_empty[st], ((uint32_t)(n >> 1) & 1u) ^ 1u);
@@ -1121,8 +1128,8 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       uint8_t* sA1h = smem + FF3_A1 + st * 32768;
       uint8_t* sA1l = sA1h + 16384;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * 256 + lt, r = idx >> 4, c4 = idx & 15;
+      for (int it = 0; it < 16; ++it) {
+        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
         store_split4_at(sA1h, sA1l, kmajor_sw128_offset(r, c4 * 4), v[it]);
       }
       fence_proxy_async_smem();
@@ -1145,7 +1152,7 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
   }
   const int n_tiles = ceil_div(P, 128);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  ff_ts_kernel<<<grid, kFF3Threads, FF3_TOTAL, st>>>(s0, s1, s2, residual, x_out, b_out, image, b1, b2, P, n_tiles);
+  ff_ts_kernel<<<grid, kFFThreads, FF3_TOTAL, st>>>(s0, s1, s2, residual, x_out, b_out, image, b1, b2, P, n_tiles);
   ++g_launch_counter;
   FFNO_LAUNCH_CHECK("ff_ts_kernel");
   return FFNO_OK;
