@@ -324,13 +324,24 @@ int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, con
 
   float* cur = w.xa;
   float* nxt = w.xb;
+  bool head_fused = false;
   for (int l = 0; l < nl; ++l) {
     const LayerW& lw = p->layers[l];
     const bool last = (l == nl - 1);
     if (p->use_umma) {
-      FFNO_TRY(umma_layer_fwd(p->umma, l, cur, batch, nxt, w.s, w.b, w.F, w.R, w.umma,
-                              (taps && taps->spectral && taps->spectral[l]) || p->d.use_fork, last || p->d.use_fork,
-                              st));
+      const bool want_s = (taps && taps->spectral && taps->spectral[l]) || p->d.use_fork;
+      if (last && !taps && umma_can_fuse_head(p->umma, want_s)) {
+        // last layer: the FF store warps apply the folded head themselves — no `b` round trip, no head launch
+        UmmaFusedHead fh;
+        fh.w = p->head_w;
+        fh.b = p->head_b;
+        fh.forecast = forecast;
+        // (the residual stream is not needed after the last layer: no x_next store either)
+        FFNO_TRY(umma_layer_fwd(p->umma, l, cur, batch, nullptr, w.s, w.b, w.F, w.R, w.umma, false, false, st, &fh));
+        head_fused = true;
+      } else {
+        FFNO_TRY(umma_layer_fwd(p->umma, l, cur, batch, nxt, w.s, w.b, w.F, w.R, w.umma, want_s, last || p->d.use_fork, st));
+      }
     } else {
       const float* s = cur;
       if (p->d.spectral_mode != FFNO_MODE_NO_FOURIER) {
@@ -353,7 +364,7 @@ int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, con
     float* t = cur; cur = nxt; nxt = t;
   }
   if (taps && taps->b_last) FFNO_CUDA_CHECK(cudaMemcpyAsync(taps->b_last, w.b, Ubytes, cudaMemcpyDeviceToDevice, st));
-  if (!p->d.use_fork)
+  if (!p->d.use_fork && !head_fused)
     FFNO_TRY(launch_head(w.b, p->head_w, p->head_b, forecast, batch, g, p->d.out_features, false, st));
   return FFNO_OK;
 }
@@ -551,6 +562,9 @@ int ffno_plan_load_params(ffno_plan* p, const ffno_block_params* prm, void* stre
     }
     FFNO_TRY(umma_load_params(p->umma, srcs.data(), p->d_fwd, p->d_inv, st));
   }
+  // Forward kernels are launched with programmatic dependent launch and read these prepared parameters in their
+  // prologue, possibly before their stream predecessor has finished: make sure nothing of the load is still in flight.
+  FFNO_CUDA_CHECK(cudaStreamSynchronize(st));
   p->loaded = true;
   return FFNO_OK;
 }

@@ -53,8 +53,10 @@ int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b
 
 // v3 FF: hidden activations staged in tensor memory (TS-mode GEMM2), coalesced output through a smem staging tile,
 // loader sums up to three spectral partial outputs (s1 / s2 may be NULL).
+// head_w/head_b/forecast (optional): fused folded 1-output head on the FF output, forecast[p] = <b_p, head_w> + head_b.
 int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float* residual, float* x_out, float* b_out,
-                 const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st);
+                 const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st,
+                 const float* head_w = nullptr, const float* head_b = nullptr, float* forecast = nullptr);
 
 // Diagnostics: in-kernel clock64 timeline of block 0 of ff_pipe_kernel ([role 8][tile 16][event 8]).
 int debug_timeline(int enable, long long* host_out);

@@ -268,8 +268,14 @@ int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residua
   return launch_ff_ts(s_in, nullptr, nullptr, residual, xo, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
 }
 
+bool umma_can_fuse_head(const UmmaState* s, bool want_s) {
+  bool nopad = true;
+  for (int a = 0; a < s->d.ndim; ++a) nopad &= s->d.pad[a] == 0;
+  return !want_s && !s->v1 && !s->ff_v2 && all_axes_pipe(s) && s->d.out_features == 1 && nopad && !s->d.use_fork;
+}
+
 int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_next, float* s_out, float* b_out,
-                   float* F, float* R, float* ws, bool want_s, bool want_b, cudaStream_t st) {
+                   float* F, float* R, float* ws, bool want_s, bool want_b, cudaStream_t st, const UmmaFusedHead* head) {
   const UmmaLayer& L = s->layers[layer];
   long long P = batch;
   for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
@@ -279,8 +285,10 @@ int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_
     const size_t U = (size_t)P * kUmmaC;
     float* s_axis[3] = {s_out, ws, ws + U};
     FFNO_TRY(spectral_split(s, L, x, batch, s_axis, F, R, st));
-    return launch_ff_ts(s_axis[0], s->d.ndim > 1 ? s_axis[1] : nullptr, s->d.ndim > 2 ? s_axis[2] : nullptr, x, x_next, bo,
-                        L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+    return launch_ff_ts(s_axis[0], s->d.ndim > 1 ? s_axis[1] : nullptr, s->d.ndim > 2 ? s_axis[2] : nullptr,
+                        x_next ? x : nullptr, x_next, bo,
+                        L.ff_image, L.b1, L.b2, P, s->sm_count, st, head ? head->w : nullptr, head ? head->b : nullptr,
+                        head ? head->forecast : nullptr);
   }
   FFNO_TRY(umma_spectral_fwd(s, layer, x, batch, s_out, F, R, ws, st));
   if (s->v1) return launch_ff_umma(s_out, x, x_next, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);

@@ -26,8 +26,16 @@ size_t umma_workspace_floats(const UmmaState* s, int batch);
 
 // One full layer: x_next = x + FF(spectral(x)); optionally also materialises s (spectral output) and
 // b (FF output before the residual; the head input on the last layer).
+// Optional fused head (last layer, 1-output head, no padding): the FF writes forecast[p] = <b_p, w> + b directly.
+struct UmmaFusedHead {
+  const float* w = nullptr;
+  const float* b = nullptr;
+  float* forecast = nullptr;
+};
+bool umma_can_fuse_head(const UmmaState* s, bool want_s);
 int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_next, float* s_out, float* b_out,
-                   float* F, float* R, float* ws, bool want_s, bool want_b, cudaStream_t st);
+                   float* F, float* R, float* ws, bool want_s, bool want_b, cudaStream_t st,
+                   const UmmaFusedHead* head = nullptr);
 int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R,
                       float* ws, cudaStream_t st);
 int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* y, float* ws,

@@ -34,6 +34,26 @@ __device__ int g_timeline_on = 0;
 
 namespace {
 
+// Programmatic dependent launch: the kernel may begin (barrier init, TMEM allocation, constant-operand loads) while
+// its predecessor on the stream drains; griddepcontrol.wait then blocks until the predecessor has fully completed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // axis / mix kernels: 4 epilogue warps, 1 MMA warp, 16 loader-converter warps.  The FP32 -> BF16 hi/lo conversion is
 // ~25 instructions per float4 and is what bounds these kernels, so it is spread over as many warps as fit.
 constexpr int kLoaders = 512;
@@ -165,6 +185,8 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   const uint32_t tmem = *tmem_slot;
   const long long gpi = p.inner >> 6;
   const long long n_groups = p.outer * gpi;
+  pdl_launch_dependents();
+  if (warp != kMmaWarp) pdl_wait();     // the MMA warp first starts the (constant) table copy, then waits too
 
   if (warp < kEpiWarps) {
     // ---------------------------------------------------------------- epilogue: two teams of 4 warps
@@ -247,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
         }
       }
       __syncwarp();
+      pdl_wait();
       mbar_wait(bar_w, 0);
       const uint32_t idesc = make_idesc_bf16(128, p.npad, 1, 0);
       int item = 0, n = 0;
@@ -391,9 +414,8 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
   int per_axis = sm_count / n_axes;
   if (per_axis < 1) per_axis = 1;
   const int gx = max_tiles < per_axis ? max_tiles : per_axis;
-  axis_pipe_kernel<<<dim3(gx, n_axes), kThreads, smem, st>>>(set);
+  FFNO_CUDA_CHECK(launch_pdl(axis_pipe_kernel, dim3(gx, n_axes), dim3(kThreads), smem, st, set));
   ++g_launch_counter;
-  FFNO_LAUNCH_CHECK("axis_pipe_kernel");
   return FFNO_OK;
 }
 
@@ -455,6 +477,8 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const long long inner = ax.p_inner * 64;
+  pdl_launch_dependents();
+  if (warp != kMmaWarp) pdl_wait();
 
   if (warp < kEpiWarps) {
     // two epilogue teams: team 0 drains the real segment (columns 0..63), team 1 the imaginary one, each 32 columns
@@ -507,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
         bulk_g2s(sB + 32768, img + 32768, 32768, bar_w);
       }
       __syncwarp();
+      pdl_wait();
       mbar_wait(bar_w, 0);
       constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
       const uint64_t dBh = desc_kmajor(smem_u32(sB), 0), dBl = desc_kmajor(smem_u32(sB) + 32768u, 0);
@@ -604,9 +629,8 @@ int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t 
     const int gx = (int)((tiles + tpc - 1) / tpc);
     grid_x = gx > grid_x ? gx : grid_x;
   }
-  mix_pipe_kernel<<<dim3(grid_x, maxK, n_axes), kThreads, MXP_TOTAL, st>>>(set);
+  FFNO_CUDA_CHECK(launch_pdl(mix_pipe_kernel, dim3(grid_x, maxK, n_axes), dim3(kThreads), (size_t)MXP_TOTAL, st, set));
   ++g_launch_counter;
-  FFNO_LAUNCH_CHECK("mix_pipe_kernel");
   return FFNO_OK;
 }
 
@@ -863,13 +887,15 @@ constexpr int FF3_A1 = 131072;                     // 2 stages x (hi 16 KB | lo 
 constexpr int FF3_OUT = FF3_A1 + 65536;            // 196608: 128 rows x 256 B staging
 constexpr int FF3_BIAS = FF3_OUT + 32768;          // 229376
 constexpr int FF3_BAR = FF3_BIAS + 320 * 4;        // 230656
-constexpr int FF3_TOTAL = FF3_BAR + 192;           // 230848 <= 232448
+constexpr int FF3_HEAD = FF3_BAR + 192;            // 64 floats: folded head weights of a 1-output head
+constexpr int FF3_TOTAL = FF3_HEAD + 256;          // 231104 <= 232448
 
 __global__ void __launch_bounds__(kFFThreads, 1)
 ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
              const float* __restrict__ residual, float* __restrict__ x_out, float* __restrict__ b_out,
-             const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2, long long P,
-             int n_tiles) {
+             const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2,
+             const float* __restrict__ head_w, const float* __restrict__ head_b, float* __restrict__ forecast,
+             long long P, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* sb1 = reinterpret_cast<float*>(smem + FF3_BIAS);
   float* sb2 = sb1 + 256;
@@ -906,10 +932,14 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
   }
   for (int i = tid; i < 256; i += kFFThreads) sb1[i] = b1 ? b1[i] : 0.f;
   if (tid < 64) sb2[tid] = b2 ? b2[tid] : 0.f;
+  float* sHead = reinterpret_cast<float*>(smem + FF3_HEAD);
+  if (tid < 64) sHead[tid] = forecast ? head_w[tid] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_launch_dependents();
+  if (warp != kFFMmaWarp) pdl_wait();
 
   if (warp < 8) {
     // ---------------------------------------------------------------- chunk epilogue teams (thread = row)
@@ -982,6 +1012,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       mbar_wait(&d2_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
       if (warp == 8) TL(1, n, 1);
+      float hacc = 0.f;        // fused 1-output head on the last layer: forecast = <b_row, w_eff> + b_eff
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -1000,8 +1031,11 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           b.z = __uint_as_float(v[e * 4 + 2]) + sb2[c4 * 4 + 2];
           b.w = __uint_as_float(v[e * 4 + 3]) + sb2[c4 * 4 + 3];
           *reinterpret_cast<float4*>(sOut + rt * 256 + ((c4 ^ (rt & 15)) << 4)) = b;      // XOR swizzle: conflict-free
+          hacc = fmaf(b.x, sHead[c4 * 4 + 0], fmaf(b.y, sHead[c4 * 4 + 1],
+                 fmaf(b.z, sHead[c4 * 4 + 2], fmaf(b.w, sHead[c4 * 4 + 3], hacc))));
         }
       }
+      if (forecast && row0 + rt < P) forecast[row0 + rt] = hacc + head_b[0];
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 8) TL(1, n, 2);
 #pragma unroll
@@ -1027,6 +1061,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         for (int i = 0; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
       }
       __syncwarp();
+      pdl_wait();
       mbar_wait(bar_w, 0);
       constexpr uint32_t IDESC_G1 = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
@@ -1143,7 +1178,8 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
 }
 
 int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float* residual, float* x_out, float* b_out,
-                 const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st) {
+                 const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st,
+                 const float* head_w, const float* head_b, float* forecast) {
   if (P == 0) return FFNO_OK;
   static bool configured = false;
   if (!configured) {
@@ -1152,9 +1188,9 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
   }
   const int n_tiles = ceil_div(P, 128);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  ff_ts_kernel<<<grid, kFFThreads, FF3_TOTAL, st>>>(s0, s1, s2, residual, x_out, b_out, image, b1, b2, P, n_tiles);
+  FFNO_CUDA_CHECK(launch_pdl(ff_ts_kernel, dim3(grid), dim3(kFFThreads), (size_t)FF3_TOTAL, st, s0, s1, s2, residual, x_out,
+                             b_out, image, b1, b2, head_w, head_b, forecast, P, n_tiles));
   ++g_launch_counter;
-  FFNO_LAUNCH_CHECK("ff_ts_kernel");
   return FFNO_OK;
 }
 
