@@ -59,7 +59,8 @@ def test_grid2d_block_golden_per_layer(name, path, monkeypatch):
     plan = m.plan_for(x.device, x.shape[1:3])
     tol = tol_for(plan)
     errs = {"forecast": rel_err(out["forecast"], a["forecast"])}
-    assert torch.equal(out["forecast"], fc)
+    # plain forward = fused head inside the last FF; tapped forward = separate head kernel (different FMA order)
+    assert rel_err(out["forecast"], fc) < 1e-6
     for i, f in enumerate(out["forecast_list"]):
         errs[f"forecast_list{i}"] = rel_err(f, a[f"forecast_list{i}"])
     errs["lift"] = rel_err(taps["lift"], a["tap_lift"])
