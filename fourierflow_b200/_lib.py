@@ -73,6 +73,8 @@ EXPORTS = {
                                       C.c_void_p]),
     "ffno_spectral_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_size_t, C.c_void_p]),
+    "ffno_spectral_split_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p,
+                                          C.c_size_t, C.c_void_p]),
     "ffno_ff_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "ffno_linear_fwd": (C.c_int, [C.POINTER(LinearParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,

@@ -269,6 +269,19 @@ class StackPlan:
                                                   ws.numel(), _stream(self.device)), "ffno_spectral_fwd")
         return s
 
+    def spectral_split_forward(self, layer: int, x: torch.Tensor, out: Optional[List[torch.Tensor]] = None):
+        """The spectral operator as the layer loop runs it: one tensor per spatial axis, whose sum is forward_fourier(x)."""
+        B = x.shape[0]
+        nd = len(self.size)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(self.lib.ffno_workspace_bytes(self._plan, B))
+            if out is None:
+                out = [torch.empty_like(x) for _ in range(nd)]
+            ptrs = (C.c_void_p * 3)(*[t.data_ptr() for t in out], *([None] * (3 - nd)))
+            _lib.check(self.lib.ffno_spectral_split_fwd(self._plan, layer, x.data_ptr(), B, ptrs, ws.data_ptr(), ws.numel(),
+                                                        _stream(self.device)), "ffno_spectral_split_fwd")
+        return out
+
     def ff_forward(self, layer: int, which: int, s: torch.Tensor, residual: Optional[torch.Tensor]) -> torch.Tensor:
         B = s.shape[0]
         with torch.cuda.device(self.device):

@@ -628,6 +628,33 @@ int ffno_spectral_fwd(ffno_plan* p, int32_t layer, const float* x, int32_t batch
   return spectral_generic(p, p->layers[layer], x, batch, s, w.F, w.R, st);
 }
 
+int ffno_spectral_split_fwd(ffno_plan* p, int32_t layer, const float* x, int32_t batch, float* const* s_axis,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_workspace_bytes(p, batch)));
+  FFNO_REQUIRE(layer >= 0 && layer < p->d.n_layers, FFNO_ERR_BAD_ARG, "layer=%d", layer);
+  FFNO_REQUIRE(x && s_axis && s_axis[0], FFNO_ERR_BAD_ARG, "x/s_axis is NULL");
+  FFNO_REQUIRE(p->d.spectral_mode != FFNO_MODE_NO_FOURIER, FFNO_ERR_STATE, "plan was built with mode=no-fourier");
+  const Workspace w = carve(p, batch, workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (batch == 0) return FFNO_OK;
+  const long long before = g_launch_counter;
+  int status;
+  if (p->use_umma) {
+    for (int a = 1; a < p->d.ndim; ++a) FFNO_REQUIRE(s_axis[a], FFNO_ERR_BAD_ARG, "s_axis[%d] is NULL", a);
+    float* bufs[3] = {s_axis[0], p->d.ndim > 1 ? s_axis[1] : nullptr, p->d.ndim > 2 ? s_axis[2] : nullptr};
+    int n_written = 0;
+    status = umma_spectral_split_fwd(p->umma, layer, x, batch, bufs, w.F, w.R, w.umma, &n_written, st);
+    for (int a = n_written; status == FFNO_OK && a < p->d.ndim; ++a)       // summed fallback: the others contribute zero
+      FFNO_CUDA_CHECK(cudaMemsetAsync(bufs[a], 0, (size_t)batch * p->pts * p->d.width * 4, st));
+  } else {
+    status = spectral_generic(p, p->layers[layer], x, batch, s_axis[0], w.F, w.R, st);
+    for (int a = 1; status == FFNO_OK && a < p->d.ndim; ++a)
+      if (s_axis[a]) FFNO_CUDA_CHECK(cudaMemsetAsync(s_axis[a], 0, (size_t)batch * p->pts * p->d.width * 4, st));
+  }
+  p->last_launches = g_launch_counter - before;
+  return status;
+}
+
 int ffno_ff_fwd(ffno_plan* p, int32_t layer, int32_t which, const float* s, const float* residual, int32_t batch,
                 float* y, void* workspace, size_t workspace_bytes, void* stream) {
   FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_workspace_bytes(p, batch)));

@@ -256,6 +256,16 @@ static int spectral_split(UmmaState* s, const UmmaLayer& L, const float* x, int 
   return launch_axis_pipe(inv, s->d.ndim, s->sm_count, st);
 }
 
+int umma_spectral_split_fwd(UmmaState* s, int layer, const float* x, int batch, float* const s_axis[3], float* F, float* R,
+                            float* ws, int* n_written, cudaStream_t st) {
+  if (all_axes_pipe(s)) {
+    *n_written = s->d.ndim;
+    return spectral_split(s, s->layers[layer], x, batch, s_axis, F, R, st);
+  }
+  *n_written = 1;
+  return umma_spectral_fwd(s, layer, x, batch, s_axis[0], F, R, ws, st);
+}
+
 int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* y, float*,
                 cudaStream_t st) {
   const UmmaLayer& L = s->layers[layer];

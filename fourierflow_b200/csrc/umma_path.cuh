@@ -38,6 +38,10 @@ int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_
                    const UmmaFusedHead* head = nullptr);
 int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R,
                       float* ws, cudaStream_t st);
+// Per-axis outputs, no accumulation (falls back to the summed path into s_axis[0] when a kernel does not qualify;
+// returns the number of buffers written through *n_written).
+int umma_spectral_split_fwd(UmmaState* s, int layer, const float* x, int batch, float* const s_axis[3], float* F, float* R,
+                            float* ws, int* n_written, cudaStream_t st);
 int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* y, float* ws,
                 cudaStream_t st);
 

@@ -175,6 +175,13 @@ FFNO_API int ffno_spectral_fwd(ffno_plan* plan, int32_t layer, const float* x, i
 FFNO_API int ffno_ff_fwd(ffno_plan* plan, int32_t layer, int32_t which, const float* s, const float* residual,
                 int32_t batch, float* y, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The spectral operator exactly as the layer loop runs it (tcgen05 path: forward transforms of all axes, mode mixes of
+ * all axes, inverse transforms of all axes — 3 launches): s_axis[a] receives axis a's contribution; forward_fourier's
+ * result is their sum (grid_2d.py:94), which the FeedForward kernel forms while loading.  On plans that run the generic
+ * kernels only s_axis[0] is written (already summed) and the other pointers are ignored. */
+FFNO_API int ffno_spectral_split_fwd(ffno_plan* plan, int32_t layer, const float* x, int32_t batch, float* const* s_axis,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* Stateless WNLinear.forward (modules/linear.py:41-51): y[rows, out] = act(x[rows, in] @ W^T + b).
  * `scratch` (device, >= in*out*4 bytes) receives the folded, transposed weight. */
 FFNO_API int ffno_linear_fwd(const ffno_linear_params* lin, const float* x, int64_t rows, float* y, int32_t relu,

@@ -331,3 +331,16 @@ def test_full_size_rollout_is_deterministic_and_consistent():
         manual = torch.cat(outs, dim=-1)
     assert rel_err(preds, manual) < 1e-5
     assert len(step_losses) == 10 and torch.isfinite(loss)
+
+
+def test_spectral_split_sums_to_forward_fourier():
+    """ffno_spectral_split_fwd (the layer loop's launches) = per-axis parts whose sum is forward_fourier."""
+    m = _c2_model(n_layers=1).cuda()
+    layer = m.spectral_layers[0]
+    x = torch.randn(4, 64, 64, 64, device="cuda")
+    with torch.no_grad():
+        plan = layer._plan(x)
+        parts = plan.spectral_split_forward(0, x)
+        whole = plan.spectral_forward(0, x)
+    assert len(parts) == 2
+    assert rel_err(parts[0] + parts[1], whole) < 1e-6
