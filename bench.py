@@ -311,7 +311,8 @@ def run_ours(args, rank, world, local):
         "e2e": {"value": N * B / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                 "api": "ffno_block_fwd_host (pinned host buffers)"},
-        "gpu_launches": int(launches) * args.steps,
+        # this repo's kernels launched inside the timed region, all ranks (the sharded step adds one rel_l2 launch)
+        "gpu_launches": (int(launches) + (1 if N > 1 else 0)) * args.steps * N,
         "roofline": dominant, "roofline_spectral": roof_spec, "roofline_ff": roof_ff,
         "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{cpu_reps} forwards of {cpu_sample} samples through the 24-layer stack "
@@ -341,6 +342,7 @@ def main():
     if world > 1:
         from fourierflow_b200 import distributed as D
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         D.init_from_env("nccl")
     run_ours(args, rank, world, local)
     if world > 1:

@@ -46,8 +46,11 @@ int launch_axis_umma(const AxisXform& p, int sm_count, cudaStream_t st);
 
 // Warp-specialised, double-buffered versions (umma_pipelined.cu): same arithmetic, loads / MMAs / epilogues overlap.
 bool axis_pipe_fits(int n_in, int n_out);
-int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st);   // axes run concurrently
-int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st);
+// `reverse`: walk the tiles last-to-first.  Consecutive launches of the layer loop alternate the direction so that a
+// kernel starts with the data its predecessor wrote LAST (still resident in the 126 MB L2) instead of re-streaming it
+// in the producer's order, which is the LRU worst case for a ~100 MB working set.
+int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse = false);
+int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse = false);
 int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,
                    const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st);
 
@@ -56,7 +59,8 @@ int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b
 // head_w/head_b/forecast (optional): fused folded 1-output head on the FF output, forecast[p] = <b_p, head_w> + head_b.
 int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float* residual, float* x_out, float* b_out,
                  const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st,
-                 const float* head_w = nullptr, const float* head_b = nullptr, float* forecast = nullptr);
+                 const float* head_w = nullptr, const float* head_b = nullptr, float* forecast = nullptr,
+                 bool reverse = false);
 
 // Diagnostics: in-kernel clock64 timeline of block 0 of ff_pipe_kernel ([role 8][tile 16][event 8]).
 int debug_timeline(int enable, long long* host_out);

@@ -33,6 +33,7 @@ struct UmmaState {
   float* d_inv[3] = {nullptr, nullptr, nullptr};
   bool v1 = false;                                       // FFNO_UMMA_V1=1: non-pipelined kernels (cross-check)
   bool ff_v2 = false;                                    // FFNO_FF_V2=1: FF with hidden activations in smem (A/B)
+  bool zigzag = true;                                    // FFNO_ZIGZAG=0: every kernel walks its tiles first-to-last
   uint8_t* fwd_image[3] = {nullptr, nullptr, nullptr};   // tcgen05 table images (NULL -> FP32 table kernel)
   uint8_t* inv_image[3] = {nullptr, nullptr, nullptr};
 };
@@ -71,6 +72,8 @@ int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]) {
   s->v1 = v1 && v1[0] == '1';
   const char* v2 = getenv("FFNO_FF_V2");
   s->ff_v2 = v2 && v2[0] == '1';
+  const char* zz = getenv("FFNO_ZIGZAG");
+  s->zigzag = !(zz && zz[0] == '0');
   s->layers.resize(d->n_layers);
   *out = s;
   return FFNO_OK;
@@ -251,9 +254,11 @@ static int spectral_split(UmmaState* s, const UmmaLayer& L, const float* x, int 
     inv[a] = AxisXform{full ? Ra : Fa, s_axis[a], s->inv_image[a], outer, p_inner * kUmmaC, 2 * K, Ln, pad16i(Ln),
                        (2 * K + 63) / 64, 0};
   }
-  FFNO_TRY(launch_axis_pipe(fwd, s->d.ndim, s->sm_count, st));
-  if (full) FFNO_TRY(launch_mix_pipe(mix, s->d.ndim, s->sm_count, st));
-  return launch_axis_pipe(inv, s->d.ndim, s->sm_count, st);
+  // direction of the tile walk alternates launch to launch (fwd ->, mix <-, inv ->, FF <-): see umma_kernels.cuh
+  const bool zz = s->zigzag;
+  FFNO_TRY(launch_axis_pipe(fwd, s->d.ndim, s->sm_count, st, false));
+  if (full) FFNO_TRY(launch_mix_pipe(mix, s->d.ndim, s->sm_count, st, zz));
+  return launch_axis_pipe(inv, s->d.ndim, s->sm_count, st, false);
 }
 
 int umma_spectral_split_fwd(UmmaState* s, int layer, const float* x, int batch, float* const s_axis[3], float* F, float* R,
@@ -298,7 +303,7 @@ int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_
     return launch_ff_ts(s_axis[0], s->d.ndim > 1 ? s_axis[1] : nullptr, s->d.ndim > 2 ? s_axis[2] : nullptr,
                         x_next ? x : nullptr, x_next, bo,
                         L.ff_image, L.b1, L.b2, P, s->sm_count, st, head ? head->w : nullptr, head ? head->b : nullptr,
-                        head ? head->forecast : nullptr);
+                        head ? head->forecast : nullptr, s->zigzag);
   }
   FFNO_TRY(umma_spectral_fwd(s, layer, x, batch, s_out, F, R, ws, st));
   if (s->v1) return launch_ff_umma(s_out, x, x_next, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);

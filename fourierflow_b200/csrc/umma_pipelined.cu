@@ -144,6 +144,7 @@ struct AxisSet {
   AxisXform ax[3];
   int n_tiles[3];
   int tmem_cols[3];
+  int reverse;      // walk the tiles from the last to the first (see launch_axis_pipe)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
@@ -206,7 +207,8 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 0);
-      const long long G0 = (long long)tile * 2;                     // the two 64-element groups (warp-uniform)
+      const int ptile = set.reverse ? n_tiles - 1 - tile : tile;
+      const long long G0 = (long long)ptile * 2;                    // the two 64-element groups (warp-uniform)
       long long gbase[2];
       bool glive[2];
 #pragma unroll
@@ -330,7 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       if (item < n_items) {
         int tq = item, kc = 0;
         if (p.kchunks > 1) { tq = item / p.kchunks; kc = item - tq * p.kchunks; }
-        const int tile = (int)blockIdx.x + tq * (int)gridDim.x;
+        const int ltile = (int)blockIdx.x + tq * (int)gridDim.x;
+        const int tile = set.reverse ? n_tiles - 1 - ltile : ltile;
         const long long G = (long long)tile * 2 + gsel;
         const bool live = G < n_groups;
         const int o = live ? (int)((unsigned)G / (unsigned)gpi) : 0;
@@ -384,9 +387,10 @@ bool axis_pipe_fits(int n_in, int n_out) {
   return n_out <= 256 && AXP_TABLE + table_image_bytes(n_in, n_out) <= (size_t)227 * 1024;
 }
 
-int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st) {
+int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse) {
   FFNO_REQUIRE(n_axes >= 1 && n_axes <= 3, FFNO_ERR_BAD_ARG, "axis_pipe: n_axes=%d", n_axes);
   AxisSet set;
+  set.reverse = reverse ? 1 : 0;
   size_t smem = 0;
   int max_tiles = 0;
   for (int a = 0; a < n_axes; ++a) {
@@ -434,6 +438,7 @@ constexpr int MXP_TOTAL = MXP_OUT + 32768;                     // 230400 <= 2324
 struct MixSet {
   MixAxis ax[3];
   int tiles_per_cta[3];
+  int reverse;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
@@ -510,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int idx = it * 128 + rt, rr = idx >> 3, c4 = idx & 7;
-          const long long row = (long long)tile * 128 + rr;
+          const long long row = (long long)(set.reverse ? n_tiles - 1 - tile : tile) * 128 + rr;
           if (row < M) {
             const unsigned uo = (unsigned)row / (unsigned)ax.p_inner;
             const unsigned pp = (unsigned)row - uo * (unsigned)ax.p_inner;
@@ -562,7 +567,8 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
     uint8_t* stg_base = smem + MXP_STAGING + lt * 16;
     auto issue = [&](int item) {
       if (item < n_items) {
-        const int tile = tile_begin + (item >> 1), half = item & 1;
+        const int ltile = tile_begin + (item >> 1), half = item & 1;
+        const int tile = set.reverse ? n_tiles - 1 - ltile : ltile;
         uint8_t* dst = stg_base + (item % kMxStages) * 32768;
 #pragma unroll
         for (int it = 0; it < kLdPerThread; ++it) {
@@ -601,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st) {
+int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse) {
   FFNO_REQUIRE(n_axes >= 1 && n_axes <= 3, FFNO_ERR_BAD_ARG, "mix_pipe: n_axes=%d", n_axes);
   static bool configured = false;
   if (!configured) {
@@ -609,6 +615,7 @@ int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t 
     configured = true;
   }
   MixSet set;
+  set.reverse = reverse ? 1 : 0;
   int maxK = 0, total_modes = 0;
   long long total_tiles = 0;
   for (int a = 0; a < n_axes; ++a) {
@@ -895,7 +902,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
              const float* __restrict__ residual, float* __restrict__ x_out, float* __restrict__ b_out,
              const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2,
              const float* __restrict__ head_w, const float* __restrict__ head_b, float* __restrict__ forecast,
-             long long P, int n_tiles) {
+             long long P, int n_tiles, int reverse) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* sb1 = reinterpret_cast<float*>(smem + FF3_BIAS);
   float* sb2 = sb1 + 256;
@@ -995,7 +1002,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     uint8_t* sOut = smem + FF3_OUT;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      const long long row0 = (long long)tile * 128;
+      const long long row0 = (long long)(reverse ? n_tiles - 1 - tile : tile) * 128;
       if (warp == 8) TL(1, n, 0);
       float4 r[16];
       if (residual) {                      // coalesced prefetch, issued long before the accumulator is ready
@@ -1129,7 +1136,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     const int lt = tid - kFFLoaderThread0;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      const long long row0 = (long long)tile * 128;
+      const long long row0 = (long long)(reverse ? n_tiles - 1 - tile : tile) * 128;
       const int st = n & 1;
       if (lt < 32) TL(3, n, 0);
       float4 v[16];
@@ -1179,7 +1186,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
 
 int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float* residual, float* x_out, float* b_out,
                  const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st,
-                 const float* head_w, const float* head_b, float* forecast) {
+                 const float* head_w, const float* head_b, float* forecast, bool reverse) {
   if (P == 0) return FFNO_OK;
   static bool configured = false;
   if (!configured) {
@@ -1189,7 +1196,7 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
   const int n_tiles = ceil_div(P, 128);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
   FFNO_CUDA_CHECK(launch_pdl(ff_ts_kernel, dim3(grid), dim3(kFFThreads), (size_t)FF3_TOTAL, st, s0, s1, s2, residual, x_out,
-                             b_out, image, b1, b2, head_w, head_b, forecast, P, n_tiles));
+                             b_out, image, b1, b2, head_w, head_b, forecast, P, n_tiles, reverse ? 1 : 0));
   ++g_launch_counter;
   return FFNO_OK;
 }
