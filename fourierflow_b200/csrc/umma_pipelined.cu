@@ -897,7 +897,7 @@ constexpr int FF3_BAR = FF3_BIAS + 320 * 4;        // 230656
 constexpr int FF3_HEAD = FF3_BAR + 192;            // 64 floats: folded head weights of a 1-output head
 constexpr int FF3_TOTAL = FF3_HEAD + 256;          // 231104 <= 232448
 
-__global__ void __launch_bounds__(kFFThreads, 1)
+__global__ void __maxnreg__(120)        // 544 threads x 120 registers = 65 280 <= 65 536: one CTA per SM, no spills
 ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
              const float* __restrict__ residual, float* __restrict__ x_out, float* __restrict__ b_out,
              const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2,
