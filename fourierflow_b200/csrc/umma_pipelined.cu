@@ -897,7 +897,7 @@ constexpr int FF3_BAR = FF3_BIAS + 320 * 4;        // 230656
 constexpr int FF3_HEAD = FF3_BAR + 192;            // 64 floats: folded head weights of a 1-output head
 constexpr int FF3_TOTAL = FF3_HEAD + 256;          // 231104 <= 232448
 
-__global__ void __maxnreg__(120)        // 544 threads x 120 registers = 65 280 <= 65 536: one CTA per SM, no spills
+__global__ void __launch_bounds__(kFFThreads, 1)   // 17 warps are allocated as 20: 96 registers/thread is the cap
 ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
              const float* __restrict__ residual, float* __restrict__ x_out, float* __restrict__ b_out,
              const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2,
@@ -915,8 +915,9 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
   uint64_t* a2_empty = bars + 10;   // [2] commit
   uint64_t* d2_full = bars + 12;    // [2] commit
   uint64_t* d2_empty = bars + 14;   // [2] 128 (store warps)
-  uint64_t* bar_w = bars + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* bar_w = bars + 16;      // W1 image (first 64 KB) landed
+  uint64_t* bar_w2 = bars + 17;     // W2 image (second 64 KB) landed: only GEMM2 needs it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -931,6 +932,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       mbar_init(&d2_empty[i], 128);
     }
     mbar_init(bar_w, 1);
+    mbar_init(bar_w2, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -1064,8 +1066,10 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     // ---------------------------------------------------------------- MMA issuer
     {
       if (lane == 0) {
-        mbar_expect_tx(bar_w, 131072);
-        for (int i = 0; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
+        mbar_expect_tx(bar_w, 65536);
+        for (int i = 0; i < 2; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
+        mbar_expect_tx(bar_w2, 65536);
+        for (int i = 2; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w2);
       }
       __syncwarp();
       pdl_wait();
@@ -1115,6 +1119,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         issue_g1(0, 0);
         issue_g1(0, 1);
       }
+      mbar_wait(bar_w2, 0);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
         const bool has_next = tile + (int)gridDim.x < n_tiles;
         if (lane == 0) TL(2, n, 0);
