@@ -25,6 +25,17 @@ class PlanCacheMixin:
             self.__dict__["_plan_cache"] = d       # not a module attribute: skipped by state_dict/deepcopy hooks
         return d
 
+    def _flat_params(self):
+        """Parameter list in registration order, cached: walking a 24-layer module tree on every forward costs more
+        than the launch of the CUDA graph.  The Parameter objects survive load_state_dict / .cuda() / in-place
+        updates (their storage pointer and version counter are what StackPlan.sync_params watches)."""
+        cached = self.__dict__.get("_param_cache")
+        n = sum(1 for _ in self.parameters()) if cached is None else None
+        if cached is None or len(cached) != (n if n is not None else len(cached)):
+            cached = list(self.parameters())
+            self.__dict__["_param_cache"] = cached
+        return cached
+
     def __deepcopy__(self, memo):
         # plans hold raw device pointers of THIS module's parameters: never share them with a copy
         import copy
@@ -32,14 +43,15 @@ class PlanCacheMixin:
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k == "_plan_cache":
+            if k in ("_plan_cache", "_param_cache", "_spec_cache"):
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new
 
     def __getstate__(self):
         st = dict(self.__dict__)
-        st.pop("_plan_cache", None)
+        for k in ("_plan_cache", "_param_cache", "_spec_cache"):
+            st.pop(k, None)
         return st
 
     def _get_plan(self, device: torch.device, size: Sequence[int], **desc_kwargs) -> _ops.StackPlan:

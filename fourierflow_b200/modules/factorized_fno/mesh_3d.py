@@ -52,7 +52,7 @@ class SpectralConv2d(PlanCacheMixin, nn.Module):
             width=self.in_dim, in_features=1, append_grid=False, out_features=1, head_hidden=1, n_layers=1,
             ff_factor=self.factor, n_ff_layers=self.n_ff_layers, layer_norm=self.layer_norm,
             use_fork=self.use_fork, mode='full', path=default_path())
-        plan.sync_params(list(self.parameters()), None, None, [self.layer_spec()])
+        plan.sync_params(self._flat_params(), None, None, [self.layer_spec()])
         return plan
 
     def forward(self, x):
@@ -107,8 +107,11 @@ class FNOFactorizedMesh3D(PlanCacheMixin, nn.Module):
             width=self.width, in_features=self.input_dim - 3, append_grid=True, out_features=self.output_dim,
             head_hidden=128, n_layers=self.n_layers, ff_factor=self.factor, n_ff_layers=self.n_ff_layers,
             layer_norm=self.layer_norm, use_fork=False, mode='full', path=path or default_path())
-        plan.sync_params(list(self.parameters()), self.in_proj, self.out,
-                         [layer.layer_spec() for layer in self.spectral_layers])
+        specs = self.__dict__.get("_spec_cache")
+        if specs is None:
+            specs = [layer.layer_spec() for layer in self.spectral_layers]
+            self.__dict__["_spec_cache"] = specs
+        plan.sync_params(self._flat_params(), self.in_proj, self.out, specs)
         return plan
 
     def forward(self, x):
