@@ -46,7 +46,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {     // ~1 s at 2 GHz
+    if (clock64() - t0 > (1ll << 33)) {     // ~4 s at 2 GHz: far beyond any legitimate wait, still bounded
       atomicExch(&g_umma_timeout_flag, 1u);
       __trap();
     }
