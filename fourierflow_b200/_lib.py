@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libffno_b200.so")
+# FFNO_B200_LIB: load another build of the same library (the FFNO_TIMELINE=1 diagnostics build of tools/*_timeline.py)
+LIB_PATH = os.environ.get("FFNO_B200_LIB") or os.path.join(_HERE, "lib", "libffno_b200.so")
 
 ABI_VERSION = 1
 MAX_DIMS = 3

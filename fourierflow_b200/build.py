@@ -55,14 +55,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def _build_locked(verbose: bool) -> str:
-    objdir = os.path.join(LIBDIR, "obj")
+    timeline = os.environ.get("FFNO_TIMELINE") == "1"
+    lib = LIB[:-3] + "_timeline.so" if timeline else LIB      # diagnostics build lives beside the product, never replaces it
+    objdir = os.path.join(LIBDIR, "obj_timeline" if timeline else "obj")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc(), *ARCH, *FLAGS, "-c", src, "-o", obj]
-        if os.environ.get("FFNO_TIMELINE") == "1":      # diagnostics build: in-kernel clock64 stamps (tools/*_timeline.py)
+        if timeline:                                    # in-kernel clock64 stamps (tools/*_timeline.py, FFNO_B200_LIB=...)
             cmd.insert(1, "-DFFNO_TIMELINE")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -76,9 +78,9 @@ def _build_locked(verbose: bool) -> str:
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed (see log above)")
-    cmd = [nvcc(), *ARCH, "-shared", "-cudart", "static", "-o", LIB, *objs]
+    cmd = [nvcc(), *ARCH, "-shared", "-cudart", "static", "-o", lib, *objs]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

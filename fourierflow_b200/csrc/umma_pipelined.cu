@@ -25,7 +25,7 @@ __device__ int g_timeline_on = 0;
 #ifdef FFNO_TIMELINE
 #define TL(role, tile_n, ev)                                                                      \
   do {                                                                                            \
-    if (g_timeline_on && blockIdx.x == 0 && (tile_n) < 16 && (threadIdx.x & 31) == 0)             \
+    if (blockIdx.x == 0 && (tile_n) < 16 && (threadIdx.x & 31) == 0)    /* store only: no flag load */ \
       g_timeline[((role) * 16 + (tile_n)) * 8 + (ev)] = clock64();                                \
   } while (0)
 #else
@@ -80,6 +80,10 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
+}
+// Bulk L2 prefetch of a contiguous, 16-byte aligned range (no registers, no completion tracking).
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 // Ampere-style async copy (SASS: LDGSTS): 16 bytes global -> shared, L2-only; src_bytes = 0 zero-fills.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
@@ -137,8 +141,7 @@ constexpr int AXP_A_STAGE = 32768;                 // operand stage: hi 16 KB | 
 constexpr int AXP_BAR = 2 * AXP_A_STAGE;           // 65536
 constexpr int AXP_STAGING = AXP_BAR + 1024;        // kAxStages x 32 KB of raw FP32 (cp.async landing zone)
 constexpr int kAxStages = 2;
-constexpr int AXP_OUT = AXP_STAGING + kAxStages * 32768;     // 2 teams x 16 KB output staging (32 columns x 128 floats)
-constexpr int AXP_TABLE = AXP_OUT + 32768;
+constexpr int AXP_TABLE = AXP_STAGING + kAxStages * 32768;   // the DFT table image follows the ring
 
 struct AxisSet {
   AxisXform ax[3];
@@ -190,16 +193,19 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   if (warp != kMmaWarp) pdl_wait();     // the MMA warp first starts the (constant) table copy, then waits too
 
   if (warp < kEpiWarps) {
-    // ---------------------------------------------------------------- epilogue: two teams of 4 warps
-    // One 32-column chunk goes TMEM -> registers -> transposed FP32 staging (32 columns x 128 inner elements) ->
-    // float4 global stores, one column (two contiguous 256-byte runs) per warp instruction.
-    //   npad <= 32 (one chunk per tile): the teams take alternate tiles, team t drains accumulator stage t alone;
-    //   npad  > 32: both teams work on every tile, team t takes chunks t, t+2, ... and both release the stage.
-    const int team = warp >> 2, rt = tid & 127;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    float* sOut = reinterpret_cast<float*>(smem + AXP_OUT + team * 16384);
+    // ---------------------------------------------------------------- epilogue: 8 independent warps
+    // TMEM lane = inner element, column = output index, and inner is the contiguous dimension of Y: a warp's 32 lanes
+    // of one column are 128 contiguous bytes in global memory, so every warp drains its own lane quadrant straight
+    // from registers with one STG.32 per column (one full line per instruction, no staging, no block barrier).
+    //   npad <= 32 (one chunk per tile): warps 0-3 / 4-7 take alternate tiles, each drains a stage alone;
+    //   npad  > 32: both sets work on every tile, set t takes chunks t, t+2, ... and both release the stage.
+    const int team = warp >> 2, quad = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const int total_chunks = (p.npad + 31) >> 5;
     const bool split_tiles = total_chunks == 1;
+    const int gq = quad >> 1;                                  // which of the tile's two 64-element groups
+    const int in_group = (quad & 1) * 32 + lane;
+    const unsigned stride = (unsigned)p.inner;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       const int ds = n & 1;
@@ -208,17 +214,11 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       tc_fence_after();
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 0);
       const int ptile = set.reverse ? n_tiles - 1 - tile : tile;
-      const long long G0 = (long long)ptile * 2;                    // the two 64-element groups (warp-uniform)
-      long long gbase[2];
-      bool glive[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const long long G = G0 + q;
-        glive[q] = G < n_groups;
-        const unsigned uo = glive[q] ? (unsigned)G / (unsigned)gpi : 0u;
-        const unsigned ug = glive[q] ? (unsigned)G - uo * (unsigned)gpi : 0u;
-        gbase[q] = ((long long)uo * p.n_out) * p.inner + (long long)ug * 64;
-      }
+      const long long G = (long long)ptile * 2 + gq;             // warp-uniform
+      const bool live = G < n_groups;
+      const unsigned uo = live ? (unsigned)G / (unsigned)gpi : 0u;
+      const unsigned ug = live ? (unsigned)G - uo * (unsigned)gpi : 0u;
+      float* ybase = p.Y + ((long long)uo * p.n_out) * p.inner + (long long)ug * 64 + in_group;
       const int ch_begin = split_tiles ? 0 : team, ch_step = split_tiles ? 1 : 2;
       bool released = false;
 #pragma unroll 1
@@ -227,33 +227,29 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_base + (uint32_t)(ds * stage_cols + c0), v);
         tmem_ld_wait();
-        if (ch + ch_step >= total_chunks) {   // this team's last read of the stage
+        if (ch + ch_step >= total_chunks) {   // this warp's last read of the stage
           tc_fence_before();
           mbar_arrive(&d_empty[ds]);
           released = true;
           if (warp == 0 && blockIdx.y == 0) TL(5, n, 1);
         }
+        if (live) {
+          float* yp = ybase + (size_t)c0 * stride;
+          const int ncols = p.n_out - c0;                        // >= 32: full chunk
+          if (!p.accumulate && ncols >= 32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sOut[j * 128 + rt] = __uint_as_float(v[j]);
-        if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+            for (int j = 0; j < 32; ++j) yp[(size_t)j * stride] = __uint_as_float(v[j]);
+          } else {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int idx = it * 128 + rt, col = idx >> 5, f4 = idx & 31, q = f4 >> 4;
-          if (glive[q] && c0 + col < p.n_out) {
-            float4 val = *reinterpret_cast<const float4*>(sOut + col * 128 + f4 * 4);
-            float* dst = p.Y + gbase[q] + (long long)(c0 + col) * p.inner + (f4 & 15) * 4;
-            if (p.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(dst);
-              val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
-            }
-            *reinterpret_cast<float4*>(dst) = val;
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) {
+                float* dst = yp + (size_t)j * stride;
+                *dst = p.accumulate ? *dst + __uint_as_float(v[j]) : __uint_as_float(v[j]);
+              }
           }
         }
-        if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
-      if (!split_tiles && !released) {        // a team with no chunk in this tile still owes its arrivals
+      if (!split_tiles && !released) {        // a warp with no chunk in this tile still owes its arrivals
         tc_fence_before();
         mbar_arrive(&d_empty[ds]);
       }
@@ -395,7 +391,8 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
   int max_tiles = 0;
   for (int a = 0; a < n_axes; ++a) {
     const AxisXform& p = axes[a];
-    FFNO_REQUIRE(p.inner % 64 == 0, FFNO_ERR_UNSUPPORTED, "axis_pipe: inner=%lld not a multiple of 64", p.inner);
+    FFNO_REQUIRE(p.inner % 64 == 0 && p.inner < (1ll << 23), FFNO_ERR_UNSUPPORTED,
+                 "axis_pipe: inner=%lld must be a multiple of 64 below 2^23", p.inner);
     FFNO_REQUIRE(p.npad >= 16 && p.npad <= 256 && p.npad % 16 == 0, FFNO_ERR_UNSUPPORTED, "axis_pipe: npad=%d", p.npad);
     const size_t need = AXP_TABLE + table_image_bytes(p.n_in, p.n_out);
     FFNO_REQUIRE(need <= 227 * 1024, FFNO_ERR_UNSUPPORTED, "axis_pipe: table does not fit in shared memory");
@@ -896,8 +893,10 @@ constexpr int FF3_BIAS = FF3_OUT + 32768;          // 229376
 constexpr int FF3_BAR = FF3_BIAS + 320 * 4;        // 230656
 constexpr int FF3_HEAD = FF3_BAR + 192;            // 64 floats: folded head weights of a 1-output head
 constexpr int FF3_TOTAL = FF3_HEAD + 256;          // 231104 <= 232448
+constexpr int kFF3Threads = 576;                   // 8 chunk-epilogue + 4 store + G1 issuer + 4 loader + G2 issuer warps
+constexpr int kFF3G1Warp = 12, kFF3G2Warp = 17;
 
-__global__ void __launch_bounds__(kFFThreads, 1)   // 17 warps are allocated as 20: 96 registers/thread is the cap
+__global__ void __launch_bounds__(kFF3Threads, 1)  // 18 warps are allocated as 20: 96 registers/thread is the cap
 ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
              const float* __restrict__ residual, float* __restrict__ x_out, float* __restrict__ b_out,
              const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2,
@@ -939,7 +938,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  for (int i = tid; i < 256; i += kFFThreads) sb1[i] = b1 ? b1[i] : 0.f;
+  for (int i = tid; i < 256; i += kFF3Threads) sb1[i] = b1 ? b1[i] : 0.f;
   if (tid < 64) sb2[tid] = b2 ? b2[tid] : 0.f;
   float* sHead = reinterpret_cast<float*>(smem + FF3_HEAD);
   if (tid < 64) sHead[tid] = forecast ? head_w[tid] : 0.f;
@@ -948,7 +947,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_launch_dependents();
-  if (warp != kFFMmaWarp) pdl_wait();
+  if (warp != kFF3G1Warp && warp != kFF3G2Warp) pdl_wait();
 
   if (warp < 8) {
     // ---------------------------------------------------------------- chunk epilogue teams (thread = row)
@@ -999,24 +998,31 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     }
   } else if (warp < 12) {
     // ---------------------------------------------------------------- store warps
+    // Every address below is (tile base) + (per-thread constant) + (compile-time step): the role is one serial
+    // instruction stream per warp, so its speed is its instruction count.
     const int rt = tid - 256;
+    const int rq = rt >> 3, cq = rt & 7;       // coalesced phase: rows rq + 16 it, float4 column cq (+ 8 for half 1)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* sOut = smem + FF3_OUT;
+    uint8_t* so_wr = sOut + rt * 256;          // accumulator phase: thread = row rt, chunk c4 at ((c4 ^ (rt & 15)) << 4)
+    const uint32_t wsw = (uint32_t)(rt & 15) << 4;
+    const uint8_t* so_rd0 = sOut + rq * 256 + ((cq ^ rq) << 4);            // (rq + 16 it) & 15 == rq
+    const uint8_t* so_rd1 = sOut + rq * 256 + (((8 + cq) ^ rq) << 4);
+    const float hb = forecast ? head_b[0] : 0.f;
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       const long long row0 = (long long)(reverse ? n_tiles - 1 - tile : tile) * 128;
+      const int rows_left = (P - row0) < 128 ? (int)(P - row0) : 128;
+      const long long gofs = row0 * 64 + rq * 64 + cq * 4;
       if (warp == 8) TL(1, n, 0);
-      float4 r[16];
-      if (residual) {                      // coalesced prefetch, issued long before the accumulator is ready
+      // The tile is finished in two 32-channel halves so that only 8 float4 of the residual are live while the
+      // accumulator is in registers: half 0 is fetched before the wait (its rows were pulled into L2 by the loaders'
+      // bulk prefetch one tile earlier), half 1 once the accumulator registers are dead.
+      float4 r0[8], r1[8];
+      const float* rp = residual ? residual + gofs : s0 + gofs;
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int idx = it * 128 + rt, rr = idx >> 4, c4 = idx & 15;
-          r[it] = (row0 + rr < P) ? ldg_stream(residual + (row0 + rr) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      } else {
-#pragma unroll
-        for (int it = 0; it < 16; ++it) r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int it = 0; it < 8; ++it)
+        r0[it] = (residual && it * 16 + rq < rows_left) ? ldg_stream(rp + it * 1024) : make_float4(0.f, 0.f, 0.f, 0.f);
       const int ds = n & 1;
       mbar_wait(&d2_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
@@ -1034,72 +1040,113 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int c4 = half * 8 + e;
+          const float4 bb = *reinterpret_cast<const float4*>(sb2 + c4 * 4);
           float4 b;
-          b.x = __uint_as_float(v[e * 4 + 0]) + sb2[c4 * 4 + 0];
-          b.y = __uint_as_float(v[e * 4 + 1]) + sb2[c4 * 4 + 1];
-          b.z = __uint_as_float(v[e * 4 + 2]) + sb2[c4 * 4 + 2];
-          b.w = __uint_as_float(v[e * 4 + 3]) + sb2[c4 * 4 + 3];
-          *reinterpret_cast<float4*>(sOut + rt * 256 + ((c4 ^ (rt & 15)) << 4)) = b;      // XOR swizzle: conflict-free
-          hacc = fmaf(b.x, sHead[c4 * 4 + 0], fmaf(b.y, sHead[c4 * 4 + 1],
-                 fmaf(b.z, sHead[c4 * 4 + 2], fmaf(b.w, sHead[c4 * 4 + 3], hacc))));
+          b.x = __uint_as_float(v[e * 4 + 0]) + bb.x;
+          b.y = __uint_as_float(v[e * 4 + 1]) + bb.y;
+          b.z = __uint_as_float(v[e * 4 + 2]) + bb.z;
+          b.w = __uint_as_float(v[e * 4 + 3]) + bb.w;
+          *reinterpret_cast<float4*>(so_wr + (((uint32_t)c4 << 4) ^ wsw)) = b;      // XOR swizzle: conflict-free
+          if (forecast) {
+            const float4 hw = *reinterpret_cast<const float4*>(sHead + c4 * 4);
+            hacc = fmaf(b.x, hw.x, fmaf(b.y, hw.y, fmaf(b.z, hw.z, fmaf(b.w, hw.w, hacc))));
+          }
         }
       }
-      if (forecast && row0 + rt < P) forecast[row0 + rt] = hacc + head_b[0];
+      if (forecast && rt < rows_left) forecast[row0 + rt] = hacc + hb;
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        r1[it] = (residual && it * 16 + rq < rows_left) ? ldg_stream(rp + it * 1024 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 8) TL(1, n, 2);
+      if (b_out) {             // last layer only
+        float* bo = b_out + gofs;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int idx = it * 128 + rt, rr = idx >> 4, c4 = idx & 15;
-        const long long row = row0 + rr;
-        const float4 b = *reinterpret_cast<const float4*>(sOut + rr * 256 + ((c4 ^ (rr & 15)) << 4));
-        if (row < P) {
-          if (b_out) *reinterpret_cast<float4*>(b_out + row * 64 + c4 * 4) = b;
-          if (x_out)
-            *reinterpret_cast<float4*>(x_out + row * 64 + c4 * 4) =
-                make_float4(b.x + r[it].x, b.y + r[it].y, b.z + r[it].z, b.w + r[it].w);
+        for (int it = 0; it < 8; ++it)
+          if (it * 16 + rq < rows_left) {
+            *reinterpret_cast<float4*>(bo + it * 1024) = *reinterpret_cast<const float4*>(so_rd0 + it * 4096);
+            *reinterpret_cast<float4*>(bo + it * 1024 + 32) = *reinterpret_cast<const float4*>(so_rd1 + it * 4096);
+          }
+      }
+      if (x_out) {
+        float* xo = x_out + gofs;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float4 b = *reinterpret_cast<const float4*>(so_rd0 + it * 4096);
+          if (it * 16 + rq < rows_left)
+            *reinterpret_cast<float4*>(xo + it * 1024) =
+                make_float4(b.x + r0[it].x, b.y + r0[it].y, b.z + r0[it].z, b.w + r0[it].w);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const float4 b = *reinterpret_cast<const float4*>(so_rd1 + it * 4096);
+          if (it * 16 + rq < rows_left)
+            *reinterpret_cast<float4*>(xo + it * 1024 + 32) =
+                make_float4(b.x + r1[it].x, b.y + r1[it].y, b.z + r1[it].z, b.w + r1[it].w);
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 8) TL(1, n, 3);
     }
-  } else if (warp == kFFMmaWarp) {
-    // ---------------------------------------------------------------- MMA issuer
-    {
-      if (lane == 0) {
-        mbar_expect_tx(bar_w, 65536);
-        for (int i = 0; i < 2; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
-        mbar_expect_tx(bar_w2, 65536);
-        for (int i = 2; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w2);
-      }
-      __syncwarp();
-      pdl_wait();
-      mbar_wait(bar_w, 0);
-      constexpr uint32_t IDESC_G1 = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
-      const uint32_t sW = smem_u32(smem + FF3_W);
-      const uint64_t dA1h = desc_kmajor(smem_u32(smem + FF3_A1), 0), dA1l = desc_kmajor(smem_u32(smem + FF3_A1) + 16384u, 0);
-      const uint64_t dW1h = desc_kmajor(sW, 0), dW1l = desc_kmajor(sW + 32768u, 0);
-      const uint64_t dW2h = desc_kmajor(sW + 65536u, 0), dW2l = desc_kmajor(sW + 98304u, 0);
-      constexpr uint64_t kStage = 32768 >> 4, kHalf = 16384 >> 4, kBlk = 8192 >> 4;
-      // Software-pipelined issue order: G1 of tile n+1 is issued between the G2 chunks of tile n
-      //   G2_0(n) G2_1(n) | G1h0(n+1) | G2_2(n) G2_3(n) | G1h1(n+1)
-      // so the epilogue teams find the next D1 half ready as soon as they finish a tile (no G1 latency exposed).
-      auto issue_g1 = [&](int nn, int h) {
-        const int stn = nn & 1;
-        if (h == 0) mbar_wait(&a1_full[stn], (uint32_t)(nn >> 1) & 1u);
-        mbar_wait(&d1_empty[h], ((uint32_t)nn & 1u) ^ 1u);
+  } else if (warp == kFF3G1Warp) {
+    // ---------------------------------------------------------------- GEMM1 issuer
+    // GEMM1 and GEMM2 have independent dependency chains (A1/D1 vs A2/D2 barriers), so each gets its own issuing
+    // warp: the tensor pipe takes the instructions in arrival order, neither chain waits behind the other's
+    // operands, and the ~10 SASS instructions of descriptor set-up per tcgen05.mma are spread over two warps.
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, 65536);
+      for (int i = 0; i < 2; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
+    }
+    __syncwarp();
+    pdl_wait();
+    mbar_wait(bar_w, 0);
+    constexpr uint32_t IDESC_G1 = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t sW = smem_u32(smem + FF3_W);
+    const uint64_t dA1h = desc_kmajor(smem_u32(smem + FF3_A1), 0), dA1l = desc_kmajor(smem_u32(smem + FF3_A1) + 16384u, 0);
+    const uint64_t dW1h = desc_kmajor(sW, 0), dW1l = desc_kmajor(sW + 32768u, 0);
+    constexpr uint64_t kStage = 32768 >> 4, kHalf = 16384 >> 4;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      const int stn = n & 1;
+      mbar_wait(&a1_full[stn], (uint32_t)(n >> 1) & 1u);
+      if (lane == 0) TL(2, n, 0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&d1_empty[h], ((uint32_t)n & 1u) ^ 1u);
         tc_fence_after();
+        if (lane == 0) TL(2, n, 1 + 2 * h);
         issue3_kmajor_elect<4>(tmem + (uint32_t)(h * 128), dA1h + stn * kStage, dA1l + stn * kStage, dW1h + h * kHalf,
                                dW1l + h * kHalf, IDESC_G1, 0u);
         umma_commit_elect(&d1_full[h]);
         if (h == 1) umma_commit_elect(&a1_empty[stn]);
-      };
-      auto issue_g2 = [&](int nn, int j) {
-        const int team = j & 1, q = 2 * nn + (j >> 1), ds = nn & 1;
+        if (lane == 0) TL(2, n, 2 + 2 * h);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kFF3G2Warp) {
+    // ---------------------------------------------------------------- GEMM2 issuer (A operand from tensor memory)
+    if (lane == 0) {
+      mbar_expect_tx(bar_w2, 65536);
+      for (int i = 2; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w2);
+    }
+    __syncwarp();
+    pdl_wait();
+    mbar_wait(bar_w2, 0);
+    constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
+    const uint32_t sW = smem_u32(smem + FF3_W);
+    const uint64_t dW2h = desc_kmajor(sW + 65536u, 0), dW2l = desc_kmajor(sW + 98304u, 0);
+    constexpr uint64_t kBlk = 8192 >> 4;
+    int n = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      const int ds = n & 1;
+      const uint32_t d2 = tmem + (uint32_t)(256 + ds * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int team = j & 1, q = 2 * n + (j >> 1);
         mbar_wait(&a2_full[team], (uint32_t)q & 1u);
-        if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(nn >> 1) & 1u) ^ 1u);
+        if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d2 = tmem + (uint32_t)(256 + ds * 64);
+        if (lane == 0) TL(4, n, 2 * j);
         const uint32_t a_hi = tmem + (uint32_t)(384 + team * 64), a_lo = a_hi + 32u;
         const uint64_t bh = dW2h + j * kBlk, bl = dW2l + j * kBlk;
 #pragma unroll
@@ -1113,71 +1160,78 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         }
         umma_commit_elect(&a2_empty[team]);
         if (j == 3) umma_commit_elect(&d2_full[ds]);
-      };
-      int n = 0;
-      if ((int)blockIdx.x < n_tiles) {
-        issue_g1(0, 0);
-        issue_g1(0, 1);
-      }
-      mbar_wait(bar_w2, 0);
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-        const bool has_next = tile + (int)gridDim.x < n_tiles;
-        if (lane == 0) TL(2, n, 0);
-        issue_g2(n, 0);
-        issue_g2(n, 1);
-        if (lane == 0) TL(2, n, 1);
-        if (has_next) issue_g1(n + 1, 0);
-        if (lane == 0) TL(2, n, 2);
-        issue_g2(n, 2);
-        issue_g2(n, 3);
-        if (lane == 0) TL(2, n, 3);
-        if (has_next) issue_g1(n + 1, 1);
-        if (lane == 0) TL(2, n, 4);
+        if (lane == 0) TL(4, n, 2 * j + 1);
       }
     }
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- loaders: (s0 + s1 + s2) tile -> A1[stage]
-    const int lt = tid - kFFLoaderThread0;
+    // Two rounds of 8 float4 per source and thread (64 data registers live at most: more spills under the 96-register
+    // cap of a 17-warp CTA); the next tile of every source, and of the residual, is pulled into L2 by one bulk
+    // prefetch per buffer so that the rounds see L2 latency, not DRAM latency.
+    const int lt = tid - 13 * 32;        // warps 13..16
+    auto prefetch_tile = [&](int tile) {
+      const long long row0 = (long long)(reverse ? n_tiles - 1 - tile : tile) * 128;
+      const long long rows = (P - row0) < 128 ? (P - row0) : 128;
+      const uint32_t bytes = (uint32_t)rows * 256u;
+      prefetch_l2_bulk(s0 + row0 * 64, bytes);
+      if (s1) prefetch_l2_bulk(s1 + row0 * 64, bytes);
+      if (s2) prefetch_l2_bulk(s2 + row0 * 64, bytes);
+      if (residual) prefetch_l2_bulk(residual + row0 * 64, bytes);
+    };
+    if (lt == 0 && (int)blockIdx.x < n_tiles) prefetch_tile(blockIdx.x);
+    const int lr = lt >> 4, lc = lt & 15;      // rows lr + 8 i (i = 0..15), float4 column lc
+    const uint32_t a_off = (uint32_t)lr * 128u + (uint32_t)(((lc >> 1) ^ lr) << 4) + (uint32_t)(lc & 1) * 8u;   // + 1024 i
     int n = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       const long long row0 = (long long)(reverse ? n_tiles - 1 - tile : tile) * 128;
+      const int rows_left = (P - row0) < 128 ? (int)(P - row0) : 128;
+      const long long gofs = row0 * 64 + lr * 64 + lc * 4;
       const int st = n & 1;
       if (lt < 32) TL(3, n, 0);
-      float4 v[16];
+      if (lt == 0 && tile + (int)gridDim.x < n_tiles) prefetch_tile(tile + (int)gridDim.x);
+      uint8_t* sA1h = smem + FF3_A1 + st * 32768 + a_off;
+      uint8_t* sA1l = sA1h + 16384;
+      const float* p0 = s0 + gofs;
+      const float* p1 = s1 ? s1 + gofs : p0;
+      const float* p2 = s2 ? s2 + gofs : p0;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
-        v[it] = (row0 + r < P) ? ldg_stream(s0 + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll 1
-      for (int src = 1; src < 3; ++src) {
-        const float* sp = src == 1 ? s1 : s2;
-        if (!sp) continue;
+      for (int half = 0; half < 2; ++half) {
+        float4 v[8], t[8];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float4 t[8];
+        for (int it = 0; it < 8; ++it) {
+          const int i = half * 8 + it;
+          v[it] = (i * 8 + lr < rows_left) ? ldg_stream(p0 + i * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (s1) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int idx = (half * 8 + it) * 128 + lt, r = idx >> 4, c4 = idx & 15;
-            t[it] = (row0 + r < P) ? ldg_stream(sp + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int i = half * 8 + it;
+            t[it] = (i * 8 + lr < rows_left) ? ldg_stream(p1 + i * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            float4& a = v[half * 8 + it];
-            a.x += t[it].x; a.y += t[it].y; a.z += t[it].z; a.w += t[it].w;
+            v[it].x += t[it].x; v[it].y += t[it].y; v[it].z += t[it].z; v[it].w += t[it].w;
           }
         }
-      }
-      if (lt < 32) TL(3, n, 1);
-      mbar_wait(&a1_empty[st], ((uint32_t)(n >> 1) & 1u) ^ 1u);
-      if (lt < 32) TL(3, n, 2);
-      uint8_t* sA1h = smem + FF3_A1 + st * 32768;
-      uint8_t* sA1l = sA1h + 16384;
+        if (s2) {
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
-        store_split4_at(sA1h, sA1l, kmajor_sw128_offset(r, c4 * 4), v[it]);
+          for (int it = 0; it < 8; ++it) {
+            const int i = half * 8 + it;
+            t[it] = (i * 8 + lr < rows_left) ? ldg_stream(p2 + i * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            v[it].x += t[it].x; v[it].y += t[it].y; v[it].z += t[it].z; v[it].w += t[it].w;
+          }
+        }
+        if (half == 0) {
+          if (lt < 32) TL(3, n, 1);
+          mbar_wait(&a1_empty[st], ((uint32_t)(n >> 1) & 1u) ^ 1u);
+          if (lt < 32) TL(3, n, 2);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) store_split4_at(sA1h, sA1l, (uint32_t)(half * 8 + it) * 1024u, v[it]);
       }
       fence_proxy_async_smem();
       mbar_arrive(&a1_full[st]);
@@ -1200,7 +1254,7 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
   }
   const int n_tiles = ceil_div(P, 128);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  FFNO_CUDA_CHECK(launch_pdl(ff_ts_kernel, dim3(grid), dim3(kFFThreads), (size_t)FF3_TOTAL, st, s0, s1, s2, residual, x_out,
+  FFNO_CUDA_CHECK(launch_pdl(ff_ts_kernel, dim3(grid), dim3(kFF3Threads), (size_t)FF3_TOTAL, st, s0, s1, s2, residual, x_out,
                              b_out, image, b1, b2, head_w, head_b, forecast, P, n_tiles, reverse ? 1 : 0));
   ++g_launch_counter;
   return FFNO_OK;
