@@ -324,24 +324,37 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     const int gsel = (lt >> 4) & 1, c4 = lt & 15, rsub = lt >> 5;            // rsub: 0..15
     uint8_t* stg_base = smem + AXP_STAGING + lt * 16;
     const long long row_step = 16 * p.inner;                 // floats between the rows this thread copies
-    auto issue = [&](int item) {
-      if (item < n_items) {
-        int tq = item, kc = 0;
-        if (p.kchunks > 1) { tq = item / p.kchunks; kc = item - tq * p.kchunks; }
-        const int ltile = (int)blockIdx.x + tq * (int)gridDim.x;
-        const int tile = set.reverse ? n_tiles - 1 - ltile : ltile;
-        const long long G = (long long)tile * 2 + gsel;
-        const bool live = G < n_groups;
-        const int o = live ? (int)((unsigned)G / (unsigned)gpi) : 0;
-        const int g = live ? (int)((unsigned)G - (unsigned)o * (unsigned)gpi) : 0;
-        const int i0 = kc * 64 + rsub;
-        const float* src = p.X + ((long long)o * p.n_in + i0) * p.inner + (long long)g * 64 + c4 * 4;
-        uint8_t* dst = stg_base + (item % kAxStages) * 32768;
+    // The issue sequence walks this CTA's tiles in order, so the (outer, group) pair of the next tile follows from
+    // the previous one by a precomputed step: two divisions per kernel instead of two per work item.
+    const int sgn = set.reverse ? -1 : 1;
+    const unsigned step_groups = 2u * gridDim.x;
+    const int step_o = (int)(step_groups / (unsigned)gpi), step_g = (int)(step_groups % (unsigned)gpi);
+    long long curG = (long long)(set.reverse ? n_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * 2 + gsel;
+    // (a dead group G == n_groups of an odd tail still gets its true (outer, group): it is stepped from, never read)
+    int cur_o = (int)((unsigned)curG / (unsigned)gpi);
+    int cur_g = (int)((unsigned)curG - (unsigned)cur_o * (unsigned)gpi);
+    int iss_kc = 0, iss_left = n_items;
+    const long long thr_off = (long long)rsub * p.inner + c4 * 4;
+    auto issue = [&](int slot) {
+      if (iss_left > 0) {
+        --iss_left;
+        const bool live = curG < n_groups;
+        const int i0 = iss_kc * 64 + rsub;
+        const float* src = p.X + ((long long)cur_o * p.n_in + iss_kc * 64) * p.inner + (long long)cur_g * 64 + thr_off;
+        uint8_t* dst = stg_base + slot * 32768;
 #pragma unroll
         for (int it = 0; it < kLdPerThread; ++it) {
           const bool ok = live && (i0 + it * 16) < p.n_in;
           cp_async16(dst + it * (kLoaders * 16), ok ? (const void*)src : (const void*)p.X, ok ? 16u : 0u);
           src += row_step;
+        }
+        if (++iss_kc == p.kchunks) {
+          iss_kc = 0;
+          curG += sgn * (long long)step_groups;
+          cur_o += sgn * step_o;
+          cur_g += sgn * step_g;
+          if (cur_g >= (int)gpi) { cur_g -= (int)gpi; ++cur_o; }
+          if (cur_g < 0) { cur_g += (int)gpi; --cur_o; }
         }
       }
       cp_async_commit();
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       fence_proxy_async_smem();
       mbar_arrive(&a_full[as]);
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 2);
-      issue(item + kAxStages);
+      issue(item % kAxStages);       // refill the slot just drained with item + kAxStages
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 3);
     }
     cp_async_wait<0>();
@@ -488,6 +501,12 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
     const int team = warp >> 2, rt = tid & 127, seg = team;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* sOut = smem + MXP_OUT + team * 16384;
+    const int rq = rt >> 3, cq = rt & 7;                    // coalesced phase: rows rq + 16 it, float4 column cq
+    const uint8_t* so_rd = sOut + rq * 128 + ((cq ^ (rq & 7)) << 4);        // (rq + 16 it) & 7 == rq & 7
+    const unsigned p_in = (unsigned)ax.p_inner;
+    const unsigned q16 = 16u / p_in, r16 = 16u % p_in;
+    const long long o_stride = (long long)ax.K * 2 * inner;
+    float* out_seg = ax.R + ((long long)k * 2 + seg) * inner + cq * 4;
     int n = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
       const int ds = n & 1;
@@ -509,15 +528,21 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
                           __uint_as_float(v[e * 4 + 3]));
         if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
+        {
+          // rows rq + 16 it: (outer, position) of the first by one division, the rest by a constant step
+          const long long row_first = (long long)(set.reverse ? n_tiles - 1 - tile : tile) * 128 + rq;
+          const unsigned rf = row_first < M ? (unsigned)row_first : 0u;
+          unsigned uo = rf / p_in, pp = rf - uo * p_in;
+          const int rows_left = (M - row_first) > 0 ? (int)((M - row_first) < 128 ? (M - row_first) : 128) : 0;   // rows rq .. M-1
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int idx = it * 128 + rt, rr = idx >> 3, c4 = idx & 7;
-          const long long row = (long long)(set.reverse ? n_tiles - 1 - tile : tile) * 128 + rr;
-          if (row < M) {
-            const unsigned uo = (unsigned)row / (unsigned)ax.p_inner;
-            const unsigned pp = (unsigned)row - uo * (unsigned)ax.p_inner;
-            float* dst = ax.R + (((long long)uo * ax.K + k) * 2 + seg) * inner + (long long)pp * 64 + half * 32 + c4 * 4;
-            *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(sOut + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+          for (int it = 0; it < 8; ++it) {
+            if (it * 16 < rows_left) {
+              float* dst = out_seg + (long long)uo * o_stride + (long long)pp * 64 + half * 32;
+              *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(so_rd + it * 2048);
+            }
+            uo += q16;
+            pp += r16;
+            if (pp >= p_in) { pp -= p_in; ++uo; }
           }
         }
         if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -562,19 +587,27 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
     const int c4 = lt & 15, rsub = lt >> 4;                                   // rsub: 0..31
     const unsigned p_in = (unsigned)ax.p_inner;
     uint8_t* stg_base = smem + MXP_STAGING + lt * 16;
+    const unsigned q32 = 32u / p_in, r32 = 32u % p_in;
+    const long long o_stride = (long long)ax.K * 2 * inner;
+    const float* f_mode = ax.F + (long long)k * 2 * inner + c4 * 4;
     auto issue = [&](int item) {
       if (item < n_items) {
         const int ltile = tile_begin + (item >> 1), half = item & 1;
         const int tile = set.reverse ? n_tiles - 1 - ltile : ltile;
         uint8_t* dst = stg_base + (item % kMxStages) * 32768;
+        const long long row_first = (long long)tile * 128 + rsub;          // rows rsub + 32 it
+        const unsigned rf = row_first < M ? (unsigned)row_first : 0u;
+        unsigned o = rf / p_in, pp = rf - o * p_in;
+        const long long left = M - row_first;
+        const float* f_half = f_mode + (long long)half * inner;
 #pragma unroll
         for (int it = 0; it < kLdPerThread; ++it) {
-          const long long row = (long long)tile * 128 + it * 32 + rsub;
-          const bool ok = row < M;
-          const unsigned urow = ok ? (unsigned)row : 0u;
-          const unsigned o = urow / p_in, pp = urow - o * p_in;
-          const float* src = ax.F + (((long long)o * ax.K + k) * 2 + half) * inner + (long long)pp * 64 + c4 * 4;
+          const bool ok = it * 32 < left;
+          const float* src = f_half + (long long)o * o_stride + (long long)pp * 64;
           cp_async16(dst + it * (kLoaders * 16), ok ? (const void*)src : (const void*)ax.F, ok ? 16u : 0u);
+          o += q32;
+          pp += r32;
+          if (pp >= p_in) { pp -= p_in; ++o; }
         }
       }
       cp_async_commit();
