@@ -89,6 +89,22 @@ struct ffno_plan {
   GraphSlot g_block, g_rollout;
   bool graphs = true;
 
+  // Batch chunking of the stack forward (samples are independent): the batch is cut into chunks of
+  // `chunk` samples that run the whole layer stack one after the other on the same (small, L2-resident) workspace
+  // slot, or — with n_streams > 1 — side by side on forked streams, each kernel limited to 1/n_streams of the SMs so
+  // that one chunk's pipeline fill / drain overlaps the other's steady state.  0 = off.
+  int chunk = 0;
+  int n_streams = 1;
+  int sm_count = 148;
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  int chunk_for(int batch) const {
+    if (!use_umma) return 0;
+    int c = chunk;
+    if (c <= 0 && n_streams > 1) c = (batch + n_streams - 1) / n_streams;
+    return (c > 0 && c < batch) ? c : 0;
+  }
+
   LiftGeom geom() const {
     LiftGeom g;
     g.ndim = d.ndim;
@@ -310,7 +326,7 @@ int check_ready(const ffno_plan* p, int batch, const void* ws, size_t ws_bytes, 
   return FFNO_OK;
 }
 
-int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, const ffno_taps* taps,
+int block_fwd_core(ffno_plan* p, const float* x, int batch, float* forecast, const ffno_taps* taps,
                    void* workspace, cudaStream_t st) {
   const Workspace w = carve(p, batch, workspace);
   const LiftGeom g = p->geom();
@@ -340,7 +356,10 @@ int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, con
         FFNO_TRY(umma_layer_fwd(p->umma, l, cur, batch, nullptr, w.s, w.b, w.F, w.R, w.umma, false, false, st, &fh));
         head_fused = true;
       } else {
-        FFNO_TRY(umma_layer_fwd(p->umma, l, cur, batch, nxt, w.s, w.b, w.F, w.R, w.umma, want_s, last || p->d.use_fork, st));
+        // the residual stream is dead after the last layer (the head reads b): only a tap asks for it there
+        const bool want_x = !last || (taps && taps->x_after && taps->x_after[l]);
+        FFNO_TRY(umma_layer_fwd(p->umma, l, cur, batch, want_x ? nxt : nullptr, w.s, w.b, w.F, w.R, w.umma, want_s,
+                                last || p->d.use_fork, st));
       }
     } else {
       const float* s = cur;
@@ -369,6 +388,45 @@ int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, con
   return FFNO_OK;
 }
 
+
+// Bytes of the caller's workspace the stack forward may touch: the full-batch carve plus one slot per concurrent chunk.
+size_t stack_ws_bytes(const ffno_plan* p, int batch) {
+  size_t bytes = carve(p, batch, nullptr).bytes;
+  const int c = p->chunk_for(batch);
+  if (c > 0) bytes += (size_t)(p->n_streams > 1 ? p->n_streams : 1) * carve(p, c, nullptr).bytes;
+  return bytes;
+}
+
+int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, const ffno_taps* taps,
+                   void* workspace, cudaStream_t st) {
+  const int c = taps ? 0 : p->chunk_for(batch);
+  if (c == 0) return block_fwd_core(p, x, batch, forecast, taps, workspace, st);
+  const int S = p->n_streams > 1 ? p->n_streams : 1;
+  char* slots = static_cast<char*>(workspace) + carve(p, batch, nullptr).bytes;
+  const size_t slot_bytes = carve(p, c, nullptr).bytes;
+  const size_t in_stride = (size_t)p->pts_in * p->d.in_features, out_stride = (size_t)p->pts_in * p->d.out_features;
+  if (S > 1) {
+    umma_set_sm_limit(p->umma, 0);
+    FFNO_CUDA_CHECK(cudaEventRecord(p->ev_fork, st));
+    for (int i = 1; i < S; ++i) FFNO_CUDA_CHECK(cudaStreamWaitEvent(p->aux[i - 1], p->ev_fork, 0));
+  }
+  int status = FFNO_OK, n = 0;
+  for (int b0 = 0; b0 < batch && status == FFNO_OK; b0 += c, ++n) {
+    const int nb = batch - b0 < c ? batch - b0 : c;
+    const int lane = n % S;
+    if (S > 1) umma_set_sm_limit(p->umma, p->sm_count / S);
+    status = block_fwd_core(p, x + b0 * in_stride, nb, forecast + b0 * out_stride, nullptr, slots + lane * slot_bytes,
+                            lane == 0 ? st : p->aux[lane - 1]);
+  }
+  if (S > 1) {
+    umma_set_sm_limit(p->umma, 0);
+    for (int i = 1; i < S; ++i) {         // always join, also after an error: the forked streams must rejoin a capture
+      FFNO_CUDA_CHECK(cudaEventRecord(p->ev_join[i - 1], p->aux[i - 1]));
+      FFNO_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_join[i - 1], 0));
+    }
+  }
+  return status;
+}
 
 // Capture `body` (which only enqueues kernels on `st`) into an executable graph.  Returns false (and leaves the
 // stream usable) if capture is not possible; the caller then launches eagerly.
@@ -448,6 +506,22 @@ int ffno_device_ok(void) {
   return prop.major == 10 ? 1 : 0;
 }
 
+static int create_chunk_streams(ffno_plan* p) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+    p->sm_count = prop.multiProcessorCount;
+  else
+    cudaGetLastError();
+  if (!p->use_umma || p->n_streams <= 1) { p->n_streams = 1; return FFNO_OK; }
+  FFNO_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i + 1 < p->n_streams; ++i) {
+    FFNO_CUDA_CHECK(cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking));
+    FFNO_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+  }
+  return FFNO_OK;
+}
+
 int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
   FFNO_REQUIRE(out_plan != nullptr, FFNO_ERR_BAD_ARG, "out_plan is NULL");
   *out_plan = nullptr;
@@ -467,6 +541,15 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
     const char* g = getenv("FFNO_B200_GRAPH");
     p->graphs = !(g && g[0] == '0');
   }
+  {
+    const char* c = getenv("FFNO_B200_CHUNK");
+    const char* ns = getenv("FFNO_B200_STREAMS");
+    p->chunk = c ? atoi(c) : 0;
+    p->n_streams = ns ? atoi(ns) : 1;
+    if (p->n_streams < 1) p->n_streams = 1;
+    if (p->n_streams > 4) p->n_streams = 4;
+    if (p->chunk < 0) p->chunk = 0;
+  }
   p->layers.resize(desc->n_layers);
   int st = build_tables(p);
   if (st == FFNO_OK) {
@@ -476,6 +559,7 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
     p->use_umma = ok && desc->path != FFNO_PATH_GENERIC;
     if (st == FFNO_OK && p->use_umma) st = umma_create(&p->umma, desc, p->ext);
   }
+  if (st == FFNO_OK) st = create_chunk_streams(p);
   if (st != FFNO_OK) {
     ffno_plan_destroy(p);
     return st;
@@ -488,6 +572,11 @@ int ffno_plan_destroy(ffno_plan* plan) {
   if (!plan) return FFNO_OK;
   plan->g_block.reset();
   plan->g_rollout.reset();
+  for (int i = 0; i < 3; ++i) {
+    if (plan->aux[i]) cudaStreamDestroy(plan->aux[i]);
+    if (plan->ev_join[i]) cudaEventDestroy(plan->ev_join[i]);
+  }
+  if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
   if (plan->umma) umma_destroy(plan->umma);
   for (void* ptr : plan->owned) cudaFree(ptr);
   delete plan;
@@ -571,7 +660,7 @@ int ffno_plan_load_params(ffno_plan* p, const ffno_block_params* prm, void* stre
 
 size_t ffno_workspace_bytes(const ffno_plan* plan, int32_t batch) {
   if (!plan || batch < 0) return 0;
-  return carve(plan, batch, nullptr).bytes;
+  return stack_ws_bytes(plan, batch);
 }
 
 int ffno_block_fwd(ffno_plan* p, const float* x, int32_t batch, float* forecast, const ffno_taps* taps,
@@ -722,8 +811,9 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
   const Workspace w = carve(p, batch, workspace);
   char* base = static_cast<char*>(workspace);
   const size_t frame_b = (size_t)batch * X * Y * 4;
-  float* frame_st = reinterpret_cast<float*>(base + w.bytes);
-  float* preds_st = reinterpret_cast<float*>(base + w.bytes + (frame_b + 255) / 256 * 256);
+  const size_t stack_b = stack_ws_bytes(p, batch);
+  float* frame_st = reinterpret_cast<float*>(base + stack_b);
+  float* preds_st = reinterpret_cast<float*>(base + stack_b + (frame_b + 255) / 256 * 256);
   MeanStd3 ms;
   for (int i = 0; i < 3; ++i) { ms.m[i] = mean_host[i]; ms.s[i] = std_host[i]; }
 

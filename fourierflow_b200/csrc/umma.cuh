@@ -198,13 +198,41 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 }
 
 // ---- FP32 -> BF16 hi/lo split ---------------------------------------------------------------------------------
+// Packed FP32x2 arithmetic (sm_100 FADD2): one issue slot for two lanes of work — these conversion loops are bound by
+// instruction issue, not by the FP32 pipe.
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "sub.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   // packed conversions (F2FP.BF16.F32.PACK_AB): element 0 = a in the low half, element 1 = b in the high half
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   hi = *reinterpret_cast<const uint32_t*>(&h);
-  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xFFFF0000u);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
+  const float2 d = fsub2(make_float2(a, b), make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u)));
+  const __nv_bfloat162 l = __floats2bfloat162_rn(d.x, d.y);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// max(x, 0) and the split in one go: hi = bf16_rz(relu(x)) (F2FP.RELU...RZ), lo = bf16_rn(relu(x - hi)).
+// Truncating hi keeps x - hi >= 0 for x >= 0, so the second ReLU only ever clamps the x < 0 case (where hi = 0 and
+// x - hi = x < 0) — no separate FMNMX.  |x - hi - lo| <= 2^-17 |x|, the same order as the dropped lo*lo term.
+__device__ __forceinline__ void split2_relu(float2 x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x.y), "f"(x.x));
+  const float2 d = fsub2(x, make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u)));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d.y), "f"(d.x));
 }
 
 // Byte offset of element (row, k) inside a K-major SWIZZLE_128B tile whose rows hold 64 bf16:

@@ -24,7 +24,8 @@ struct UmmaLayer {
 struct UmmaState {
   ffno_desc d;
   int ext[3];
-  int sm_count = 148;
+  int sm_count = 148;                                    // CTAs a launch may use (<= hw_sm_count)
+  int hw_sm_count = 148;
   std::vector<UmmaLayer> layers;
   std::vector<void*> owned;
   std::map<std::pair<const void*, int>, uint8_t*> mix_cache;   // (source, axis) -> image
@@ -67,7 +68,7 @@ int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]) {
     return set_error(FFNO_ERR_UNSUPPORTED, "tcgen05 path needs compute capability 10.x, device is %d.%d", prop.major,
                      prop.minor);
   }
-  s->sm_count = prop.multiProcessorCount;
+  s->sm_count = s->hw_sm_count = prop.multiProcessorCount;
   const char* v1 = getenv("FFNO_UMMA_V1");
   s->v1 = v1 && v1[0] == '1';
   const char* v2 = getenv("FFNO_FF_V2");
@@ -77,6 +78,10 @@ int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]) {
   s->layers.resize(d->n_layers);
   *out = s;
   return FFNO_OK;
+}
+
+void umma_set_sm_limit(UmmaState* s, int n) {
+  s->sm_count = (n >= 1 && n < s->hw_sm_count) ? n : s->hw_sm_count;
 }
 
 void umma_destroy(UmmaState* s) {

@@ -20,6 +20,9 @@ bool umma_supported(const ffno_desc* d, const int ext[3]);
 const char* umma_why_not(const ffno_desc* d, const int ext[3]);
 int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]);
 void umma_destroy(UmmaState* s);
+// Persistent-kernel grid cap for the following launches (0 = all SMs): lets independent batch chunks on different
+// streams share the GPU side by side.
+void umma_set_sm_limit(UmmaState* s, int n);
 int umma_load_params(UmmaState* s, const UmmaLayerSrc* layers, float* const d_fwd[3], float* const d_inv[3],
                      cudaStream_t st);
 size_t umma_workspace_floats(const UmmaState* s, int batch);

@@ -943,13 +943,13 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
   uint64_t* a1_empty = bars + 2;    // [2] commit
   uint64_t* d1_full = bars + 4;     // [2] commit
   uint64_t* d1_empty = bars + 6;    // [2] 256 (both epilogue teams)
-  uint64_t* a2_full = bars + 8;     // [2] 128 (team t)
-  uint64_t* a2_empty = bars + 10;   // [2] commit
-  uint64_t* d2_full = bars + 12;    // [2] commit
-  uint64_t* d2_empty = bars + 14;   // [2] 128 (store warps)
-  uint64_t* bar_w = bars + 16;      // W1 image (first 64 KB) landed
-  uint64_t* bar_w2 = bars + 17;     // W2 image (second 64 KB) landed: only GEMM2 needs it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* a2_full = bars + 8;     // [4] 128 (team t, 32-column part p: stage 2 t + p)
+  uint64_t* a2_empty = bars + 12;   // [4] commit
+  uint64_t* d2_full = bars + 16;    // [2] commit
+  uint64_t* d2_empty = bars + 18;   // [2] 128 (store warps)
+  uint64_t* bar_w = bars + 20;      // W1 image (first 64 KB) landed
+  uint64_t* bar_w2 = bars + 21;     // W2 image (second 64 KB) landed: only GEMM2 needs it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -958,10 +958,12 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       mbar_init(&a1_empty[i], 1);
       mbar_init(&d1_full[i], 1);
       mbar_init(&d1_empty[i], 256);
-      mbar_init(&a2_full[i], 128);
-      mbar_init(&a2_empty[i], 1);
       mbar_init(&d2_full[i], 1);
       mbar_init(&d2_empty[i], 128);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&a2_full[i], 128);
+      mbar_init(&a2_empty[i], 1);
     }
     mbar_init(bar_w, 1);
     mbar_init(bar_w2, 1);
@@ -998,7 +1000,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         if (warp == 0) TL(0, n, h * 4 + 0);
         const float* bj = sb1 + j * 64;
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {      // 32 columns at a time keeps the live registers at ~64
+        for (int part = 0; part < 2; ++part) {      // 32 columns = one A2 stage at a time (~64 live registers)
           uint32_t v[32];
           tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + team * 64 + part * 32), v);
           tmem_ld_wait();
@@ -1009,23 +1011,25 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           }
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int col = part * 32 + 2 * e;
-            float a = __uint_as_float(v[2 * e]) + bj[col];
-            float b = __uint_as_float(v[2 * e + 1]) + bj[col + 1];
-            split2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[e], lo[e]);
+          for (int e = 0; e < 8; ++e) {             // +b1, ReLU, BF16 hi/lo: 6 instructions per element pair
+            const float4 bb = *reinterpret_cast<const float4*>(bj + part * 32 + 4 * e);
+            split2_relu(fadd2(make_float2(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1])), make_float2(bb.x, bb.y)),
+                        hi[2 * e], lo[2 * e]);
+            split2_relu(fadd2(make_float2(__uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3])), make_float2(bb.z, bb.w)),
+                        hi[2 * e + 1], lo[2 * e + 1]);
           }
-          if (part == 0) {
-            mbar_wait(&a2_empty[team], ((uint32_t)q & 1u) ^ 1u);
-            tc_fence_after();
-            if (warp == 0) TL(0, n, h * 4 + 2);
-          }
+          // each 32-column part is its own operand stage (K = 32 of GEMM2): the team only waits for the MMAs that
+          // read the same part of its PREVIOUS chunk, issued a whole part earlier than it needs the slot back
+          const int stage = team * 2 + part;
+          mbar_wait(&a2_empty[stage], ((uint32_t)q & 1u) ^ 1u);
+          tc_fence_after();
+          if (warp == 0 && part == 0) TL(0, n, h * 4 + 2);
           tmem_st16(a2_addr + (uint32_t)(part * 16), hi);
           tmem_st16(a2_addr + 32u + (uint32_t)(part * 16), lo);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&a2_full[stage]);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&a2_full[team]);
         if (warp == 0) TL(0, n, h * 4 + 3);
       }
     }
@@ -1176,22 +1180,28 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int team = j & 1, q = 2 * n + (j >> 1);
-        mbar_wait(&a2_full[team], (uint32_t)q & 1u);
-        if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        if (lane == 0) TL(4, n, 2 * j);
         const uint32_t a_hi = tmem + (uint32_t)(384 + team * 64), a_lo = a_hi + 32u;
         const uint64_t bh = dW2h + j * kBlk, bl = dW2l + j * kBlk;
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a = (pass == 2) ? a_lo : a_hi;
-          const uint64_t b = (pass == 1) ? bl : bh;
+        for (int part = 0; part < 2; ++part) {      // K = 32 per operand stage: 2 K steps x 3 passes
+          const int stage = team * 2 + part;
+          mbar_wait(&a2_full[stage], (uint32_t)q & 1u);
+          if (j == 0 && part == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          if (lane == 0 && part == 0) TL(4, n, 2 * j);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_bf16_ts_elect(d2, a + (uint32_t)(ks * 8), b + (uint64_t)(ks * 2), IDESC_G2,
-                               (pass == 0 && ks == 0) ? (j > 0 ? 1u : 0u) : 1u);
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? a_lo : a_hi;
+            const uint64_t b = (pass == 1) ? bl : bh;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const int kk = part * 2 + ks;
+              umma_bf16_ts_elect(d2, a + (uint32_t)(kk * 8), b + (uint64_t)(kk * 2), IDESC_G2,
+                                 (pass == 0 && ks == 0 && part == 0) ? (j > 0 ? 1u : 0u) : 1u);
+            }
+          }
+          umma_commit_elect(&a2_empty[stage]);
         }
-        umma_commit_elect(&a2_empty[team]);
         if (j == 3) umma_commit_elect(&d2_full[ds]);
         if (lane == 0) TL(4, n, 2 * j + 1);
       }
