@@ -997,7 +997,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         const int q = 2 * n + h;                 // running chunk index of this team (its A2 stage is `team`)
         mbar_wait(&d1_full[h], (uint32_t)n & 1u);
         tc_fence_after();
-        if (warp == 0) TL(0, n, h * 4 + 0);
+        if ((warp & 3) == 0) TL(team ? 5 : 0, n, h * 4 + 0);
         const float* bj = sb1 + j * 64;
 #pragma unroll
         for (int part = 0; part < 2; ++part) {      // 32 columns = one A2 stage at a time (~64 live registers)
@@ -1007,7 +1007,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           if (part == 1) {                          // D1 chunk fully read: release this half to the MMA warp
             tc_fence_before();
             mbar_arrive(&d1_empty[h]);
-            if (warp == 0) TL(0, n, h * 4 + 1);
+            if ((warp & 3) == 0) TL(team ? 5 : 0, n, h * 4 + 1);
           }
           uint32_t hi[16], lo[16];
 #pragma unroll
@@ -1023,14 +1023,14 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
           const int stage = team * 2 + part;
           mbar_wait(&a2_empty[stage], ((uint32_t)q & 1u) ^ 1u);
           tc_fence_after();
-          if (warp == 0 && part == 0) TL(0, n, h * 4 + 2);
+          if ((warp & 3) == 0 && part == 0) TL(team ? 5 : 0, n, h * 4 + 2);
           tmem_st16(a2_addr + (uint32_t)(part * 16), hi);
           tmem_st16(a2_addr + 32u + (uint32_t)(part * 16), lo);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&a2_full[stage]);
         }
-        if (warp == 0) TL(0, n, h * 4 + 3);
+        if ((warp & 3) == 0) TL(team ? 5 : 0, n, h * 4 + 3);
       }
     }
   } else if (warp < 12) {
@@ -1185,10 +1185,13 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
 #pragma unroll
         for (int part = 0; part < 2; ++part) {      // K = 32 per operand stage: 2 K steps x 3 passes
           const int stage = team * 2 + part;
+          if (lane == 0 && j == 0 && part == 0) TL(4, n, 0);
           mbar_wait(&a2_full[stage], (uint32_t)q & 1u);
+          if (lane == 0 && j == 0 && part == 0) TL(4, n, 1);
           if (j == 0 && part == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          if (lane == 0 && part == 0) TL(4, n, 2 * j);
+          if (lane == 0 && j == 0 && part == 0) TL(4, n, 2);
+          if (lane == 0 && j == 0 && part == 1) TL(4, n, 4);
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             const uint32_t a = (pass == 2) ? a_lo : a_hi;
@@ -1201,9 +1204,11 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
             }
           }
           umma_commit_elect(&a2_empty[stage]);
+          if (lane == 0 && j == 0) TL(4, n, part == 0 ? 3 : 5);
         }
         if (j == 3) umma_commit_elect(&d2_full[ds]);
-        if (lane == 0) TL(4, n, 2 * j + 1);
+        if (lane == 0 && j == 1) TL(4, n, 6);
+        if (lane == 0 && j == 3) TL(4, n, 7);
       }
     }
     __syncwarp();

@@ -1,0 +1,163 @@
+"""CPU: the hydra/omegaconf-free config loader (fourierflow_b200/config.py).
+
+The YAML below is written for this test in the schema of the reference's experiment files
+(experiments/torus_li/markov/24_layers/config.yaml, experiments/plasticity/ffno/24_layers/config.yaml): same block
+names, `_target_` paths, resolvers and hyper-parameters.  When the reference tree is mounted (this container only),
+every torus_li / plasticity F-FNO config in it is loaded as well.
+"""
+import functools
+import glob
+import os
+
+import pytest
+import torch
+
+from fourierflow_b200 import config as C
+from fourierflow_b200.modules import FNOFactorized2DBlock, FNOFactorizedMesh3D
+from fourierflow_b200.routines import Grid2DMarkovExperiment, StructuredMeshExperiment
+
+MARKOV_YAML = """
+wandb:
+  project: torus_li
+  group: markov/24_layers
+builder:
+  _target_: fourierflow.builders.NSMarkovBuilder
+  data_path: ${oc.env:DATA_ROOT}/zongyi/NavierStokes_V1e-5_N1200_T20.mat
+  train_size: 1000
+  test_size: 200
+  batch_size: 19
+routine:
+  _target_: fourierflow.routines.Grid2DMarkovExperiment
+  conv:
+    _target_: fourierflow.modules.FNOFactorized2DBlock
+    modes: 16
+    width: 64
+    n_layers: 24
+    input_dim: 3
+    share_weight: true
+    factor: 4
+    ff_weight_norm: true
+    gain: 0.1
+    dropout: 0.0
+    in_dropout: 0.0
+  n_steps: 10
+  max_accumulations: 1000
+  noise_std: 0.01
+  optimizer:
+    _target_: functools.partial
+    _args_: ["${get_method: torch.optim.AdamW}"]
+    lr: 0.0025
+    weight_decay: 0.0001
+  scheduler:
+    scheduler:
+      _target_: functools.partial
+      _args_: ["${get_method: fourierflow.schedulers.CosineWithWarmupScheduler}"]
+      num_warmup_steps: 500
+      num_training_steps: 100000
+      num_cycles: 0.5
+    name: learning_rate
+trainer:
+  accelerator: gpu
+  devices: 1
+  max_epochs: ${eval:1 + 100}
+callbacks:
+  - _target_: fourierflow.callbacks.CustomModelCheckpoint
+    save_top_k: 1
+  - _target_: pytorch_lightning.callbacks.ModelSummary
+    max_depth: 4
+"""
+
+MESH_YAML = """
+routine:
+  _target_: fourierflow.routines.StructuredMeshExperiment
+  model:
+    _target_: fourierflow.modules.FNOFactorizedMesh3D
+    modes_x: 12
+    modes_y: 12
+    modes_z: 8
+    width: 64
+    input_dim: 4
+    output_dim: 4
+    n_layers: 4
+    share_weight: false
+    factor: 4
+    ff_weight_norm: true
+    n_ff_layers: 2
+    layer_norm: false
+  optimizer:
+    _target_: functools.partial
+    _args_: ["${get_method: torch.optim.AdamW}"]
+    lr: ${lr}
+lr: 0.001
+"""
+
+
+def test_markov_routine_block_instantiates_unchanged():
+    torch.manual_seed(0)
+    routine, cfg = C.load_routine(MARKOV_YAML)
+    assert isinstance(routine, Grid2DMarkovExperiment)
+    assert isinstance(routine.conv, FNOFactorized2DBlock)
+    assert routine.n_steps == 10 and routine.conv.input_dim == 3
+    sd = routine.conv.state_dict()
+    assert len(sd) == 203                                   # 203 keys for the C2 model
+    assert sum(p.numel() for p in routine.conv.parameters()) == 1072834
+    assert sd["spectral_layers.3.backcast_ff.layers.0.0.weight_v"].shape == (256, 64)
+    # the rest of the file is carried along: resolvers evaluated, missing env var left as written
+    assert cfg["trainer"]["max_epochs"] == 101
+    assert cfg["builder"]["data_path"].startswith("${oc.env:DATA_ROOT}")
+
+
+def test_partials_and_out_of_scope_targets():
+    cfg = C.load_config(MARKOV_YAML)
+    opt = C.instantiate(cfg["routine"]["optimizer"])
+    assert isinstance(opt, functools.partial) and opt.func is torch.optim.AdamW and opt.keywords["lr"] == 0.0025
+    sched = C.instantiate(cfg["routine"]["scheduler"]["scheduler"])
+    assert isinstance(sched.func, C.MissingTarget)          # training harness: loads, raises only when used
+    with pytest.raises(RuntimeError, match="not available in fourierflow_b200"):
+        sched(None)
+    with pytest.raises(RuntimeError, match="fourierflow.callbacks.CustomModelCheckpoint"):
+        C.instantiate(cfg["callbacks"][0])
+
+
+def test_env_resolver_overrides_and_references(monkeypatch):
+    monkeypatch.setenv("DATA_ROOT", "/data")
+    cfg = C.load_config(MARKOV_YAML, overrides=["routine.conv.n_layers=4", "routine.n_steps=3", "+extra.flag=true"])
+    assert cfg["builder"]["data_path"] == "/data/zongyi/NavierStokes_V1e-5_N1200_T20.mat"
+    assert cfg["routine"]["conv"]["n_layers"] == 4 and cfg["routine"]["n_steps"] == 3 and cfg["extra"]["flag"] is True
+    routine, _ = C.load_routine(MESH_YAML)
+    assert isinstance(routine, StructuredMeshExperiment) and isinstance(routine.model, FNOFactorizedMesh3D)
+    assert C.instantiate(C.load_config(MESH_YAML)["routine"]["optimizer"]).keywords["lr"] == 0.001   # ${lr}
+    monkeypatch.delenv("DATA_ROOT")
+    with pytest.raises(KeyError, match="DATA_ROOT"):
+        C.load_config(MARKOV_YAML, strict=True)
+    assert C.load_config("v: ${oc.env:NOPE_NOT_SET,fallback}")["v"] == "fallback"
+
+
+def test_unknown_symbols_fail_loudly():
+    with pytest.raises(ImportError):
+        C.locate("no_such_package.thing")
+    # a reference operator outside the hot path (e.g. the geo-FNO baselines) is named in the error, not silently faked
+    with pytest.raises(RuntimeError, match="fourierflow.modules.FNOZongyi2DBlock.*not available"):
+        C.instantiate({"_target_": "fourierflow.modules.FNOZongyi2DBlock", "modes1": 12, "modes2": 12, "width": 20})
+
+
+REF_EXPERIMENTS = "/root/reference/experiments"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXPERIMENTS), reason="reference tree not mounted (GPU box)")
+def test_reference_ffno_configs_load_from_the_mounted_tree():
+    """Every shipped torus_li F-FNO (markov) config and the plasticity F-FNO configs: routine block -> our modules."""
+    paths = sorted(glob.glob(os.path.join(REF_EXPERIMENTS, "torus_li", "markov", "*", "config.yaml")) +
+                   glob.glob(os.path.join(REF_EXPERIMENTS, "plasticity", "ffno*", "*", "config.yaml")))
+    assert len(paths) >= 4
+    seen = 0
+    for p in paths:
+        raw = C.load_config(p, resolve=False)
+        tgt = raw["routine"].get("conv", raw["routine"].get("model", {})).get("_target_", "")
+        if not tgt.startswith("fourierflow.modules.FNOFactorized"):
+            continue
+        routine, _ = C.load_routine(p)
+        op = getattr(routine, "conv", None) or routine.model
+        assert type(op).__module__.startswith("fourierflow_b200.modules")
+        seen += 1
+    assert seen >= 4

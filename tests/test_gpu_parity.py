@@ -141,6 +141,27 @@ def test_rollout_golden(path, monkeypatch):
     assert rel_err(torch.stack(step_losses), a["step_losses"]) < 1e-4
 
 
+def test_config_built_routine_reproduces_the_golden_rollout():
+    """The routine block of an experiment YAML (reference schema, `_target_: fourierflow.*`) instantiated by
+    fourierflow_b200.config runs the rollout on the CUDA backend and matches the reference-driven fixture."""
+    from fourierflow_b200 import config as C
+    from test_config import MARKOV_YAML
+    kw, sd, a = load("rollout_c2arch_16")
+    n_steps = kw.pop("n_steps")
+    exp, _ = C.load_routine(MARKOV_YAML, overrides=[f"routine.conv.{k}={v}" for k, v in kw.items()] +
+                            [f"routine.n_steps={n_steps}"])
+    assert exp.n_steps == n_steps and len(exp.conv.spectral_layers) == kw["n_layers"]
+    exp.conv.load_state_dict(sd, strict=True)
+    exp = exp.cuda().eval()
+    exp.normalizer.sum.copy_(a["norm_sum"])
+    exp.normalizer.sum_squared.copy_(a["norm_sum_squared"])
+    exp.normalizer.count.copy_(a["norm_count"])
+    with torch.no_grad():
+        loss, _, preds, _ = exp({"data": a["data"].cuda()})
+    assert rel_err(preds, a["preds"]) < TOL_UMMA
+    assert abs(loss.item() - a["loss"].item()) < 1e-4 * abs(a["loss"].item())
+
+
 def _c2_model(n_layers=24, seed=0):
     torch.manual_seed(seed)
     return M().FNOFactorized2DBlock(modes=16, width=64, n_layers=n_layers, input_dim=3, share_weight=True, factor=4,

@@ -32,7 +32,7 @@ with torch.no_grad():
 t = buf.reshape(8, 16, 8)
 t0 = t[t > 0].min()
 rel = np.where(t > 0, t - t0, -1)
-names = {0: "epi1", 1: "store", 2: "g1", 3: "loader", 4: "g2"}
+names = {0: "epi_team0", 5: "epi_team1", 1: "store", 2: "g1", 3: "loader", 4: "g2"}
 out = {}
 for r, nm in names.items():
     out[nm] = rel[r, :8].tolist()
