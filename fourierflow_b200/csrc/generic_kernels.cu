@@ -251,24 +251,28 @@ __device__ __forceinline__ float linspace01(int i, int n) {
   return (float)((double)i * (1.0 / (double)(n - 1)));
 }
 
+// IDX = unsigned when the flattened index fits 32 bits (every BASELINE shape): the per-thread coordinate split is a
+// handful of 32-bit divisions instead of 64-bit ones, which were most of this kernel's time.
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 lift_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias,
             float4* __restrict__ out, long long total4, LiftGeom g) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total4) return;
-  const int C4 = g.C / 4;
-  int c4 = (int)(idx % C4);
-  long long pp = idx / C4;
+  const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx64 >= total4) return;
+  const IDX idx = (IDX)idx64;
+  const IDX C4 = (IDX)(g.C / 4);
+  const int c4 = (int)(idx % C4);
+  IDX rem = idx / C4;
   int coord[3] = {0, 0, 0};
-  long long rem = pp;
   bool in_pad = false;
   for (int a = g.ndim - 1; a >= 0; --a) {
-    int ext = g.size[a] + g.pad[a];
-    coord[a] = (int)(rem % ext);
-    rem /= ext;
+    const IDX ext = (IDX)(g.size[a] + g.pad[a]);
+    const IDX q = rem / ext;
+    coord[a] = (int)(rem - q * ext);
+    rem = q;
     in_pad |= coord[a] >= g.size[a];
   }
-  long long b = rem;
+  const long long b = (long long)rem;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!in_pad) {
     long long src = b;
@@ -290,7 +294,7 @@ lift_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const flo
       }
     }
   }
-  out[idx] = acc;
+  out[idx64] = acc;
 }
 
 int launch_lift(const float* x, const float* Wt, const float* bias, float* out, int batch, const LiftGeom& g,
@@ -300,7 +304,11 @@ int launch_lift(const float* x, const float* Wt, const float* bias, float* out, 
   for (int a = 0; a < g.ndim; ++a) pts *= (g.size[a] + g.pad[a]);
   long long total4 = pts * (g.C / 4);
   if (total4 == 0) return FFNO_OK;
-  lift_kernel<<<ceil_div(total4, 256), 256, 0, st>>>(x, Wt, bias, reinterpret_cast<float4*>(out), total4, g);
+  if (total4 < (1ll << 31))
+    lift_kernel<unsigned><<<ceil_div(total4, 256), 256, 0, st>>>(x, Wt, bias, reinterpret_cast<float4*>(out), total4, g);
+  else
+    lift_kernel<unsigned long long><<<ceil_div(total4, 256), 256, 0, st>>>(x, Wt, bias, reinterpret_cast<float4*>(out),
+                                                                          total4, g);
   ++g_launch_counter;
   FFNO_LAUNCH_CHECK("lift_kernel");
   return FFNO_OK;
