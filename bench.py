@@ -31,6 +31,18 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line.  Libraries write banners there (NCCL prints "NCCL version ..." to stdout at
+# NCCL_DEBUG=VERSION whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run and
+# the result line goes to a private duplicate of the original stdout.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 C2 = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4, ff_weight_norm=True, gain=0.1)
 GRID = 64
 BATCH_PER_GPU = 32
@@ -162,7 +174,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -318,7 +330,7 @@ def run_ours(args, rank, world, local):
                          "sample": f"{cpu_reps} forwards of {cpu_sample} samples through the 24-layer stack "
                                    "(torch-CPU oracle port of fourierflow.modules)"},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
