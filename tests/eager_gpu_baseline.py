@@ -1,7 +1,8 @@
 """Informational: the reference's op sequence (torch.fft.rfft / einsum / F.linear — the oracle port of
 fourierflow.modules) run EAGERLY on the B200 through torch's own CUDA kernels (cuFFT / cuBLAS), C2 shape.
 This is the "reference PyTorch-eager forward on 1xB200" denominator of the north star (>= 10x), measured
-with CUDA events; it is not part of the product or of bench.py."""
+with CUDA events; it is not part of the product or of bench.py.  It lives under tests/ because it executes oracle/
+(test infrastructure): only tests/, smoke() and bench.py's CPU baseline may do that.  Not a pytest module."""
 import json
 import os
 import sys
