@@ -139,14 +139,15 @@ __device__ __forceinline__ void store_split4_at(uint8_t* tile_hi, uint8_t* tile_
 // =======================================================================================================
 constexpr int AXP_A_STAGE = 32768;                 // operand stage: hi 16 KB | lo 16 KB
 constexpr int AXP_BAR = 2 * AXP_A_STAGE;           // 65536
-constexpr int AXP_STAGING = AXP_BAR + 1024;        // kAxStages x 32 KB of raw FP32 (cp.async landing zone)
-constexpr int kAxStages = 2;
-constexpr int AXP_TABLE = AXP_STAGING + kAxStages * 32768;   // the DFT table image follows the ring
+constexpr int AXP_STAGING = AXP_BAR + 1024;        // ring x 32 KB of raw FP32 (cp.async landing zone)
+constexpr int kAxStages = 2;                       // ring depth; 1 when a large table (C4: 128 KB) leaves no room for 2
+constexpr int axp_table_offset(int ring) { return AXP_STAGING + ring * 32768; }   // the DFT table image follows the ring
 
 struct AxisSet {
   AxisXform ax[3];
   int n_tiles[3];
   int tmem_cols[3];
+  int ring[3];      // cp.async staging ring depth of the axis (1 or 2)
   int reverse;      // walk the tiles from the last to the first (see launch_axis_pipe)
 };
 
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   uint64_t* d_empty = bars + 6;     // [2]
   uint64_t* bar_w = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  uint8_t* sB = smem + AXP_TABLE;
+  const int ring = set.ring[blockIdx.y];
+  uint8_t* sB = smem + axp_table_offset(ring);
   const uint32_t b_half = (uint32_t)p.kchunks * p.npad * 128u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -359,11 +361,11 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       }
       cp_async_commit();
     };
-    for (int q = 0; q < kAxStages; ++q) issue(q);
+    for (int q = 0; q < ring; ++q) issue(q);
     for (int item = 0; item < n_items; ++item) {
-      cp_async_wait<kAxStages - 1>();
+      if (ring == 2) cp_async_wait<1>(); else cp_async_wait<0>();      // warp-uniform
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 0);
-      const uint8_t* src = stg_base + (item % kAxStages) * 32768;
+      const uint8_t* src = stg_base + (item & (ring - 1)) * 32768;
       float4 v[kLdPerThread];
 #pragma unroll
       for (int it = 0; it < kLdPerThread; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * (kLoaders * 16));
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       fence_proxy_async_smem();
       mbar_arrive(&a_full[as]);
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 2);
-      issue(item % kAxStages);       // refill the slot just drained with item + kAxStages
+      issue(item & (ring - 1));      // refill the slot just drained with item + ring
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 3);
     }
     cp_async_wait<0>();
@@ -392,9 +394,12 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
 }
 
-bool axis_pipe_fits(int n_in, int n_out) {
-  return n_out <= 256 && AXP_TABLE + table_image_bytes(n_in, n_out) <= (size_t)227 * 1024;
+static int axis_ring_depth(int n_in, int n_out) {      // deepest staging ring that leaves room for the table, 0 = none
+  for (int ring = kAxStages; ring >= 1; --ring)
+    if (axp_table_offset(ring) + table_image_bytes(n_in, n_out) <= (size_t)227 * 1024) return ring;
+  return 0;
 }
+bool axis_pipe_fits(int n_in, int n_out) { return n_out <= 256 && axis_ring_depth(n_in, n_out) > 0; }
 
 int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse) {
   FFNO_REQUIRE(n_axes >= 1 && n_axes <= 3, FFNO_ERR_BAD_ARG, "axis_pipe: n_axes=%d", n_axes);
@@ -407,8 +412,10 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
     FFNO_REQUIRE(p.inner % 64 == 0 && p.inner < (1ll << 23), FFNO_ERR_UNSUPPORTED,
                  "axis_pipe: inner=%lld must be a multiple of 64 below 2^23", p.inner);
     FFNO_REQUIRE(p.npad >= 16 && p.npad <= 256 && p.npad % 16 == 0, FFNO_ERR_UNSUPPORTED, "axis_pipe: npad=%d", p.npad);
-    const size_t need = AXP_TABLE + table_image_bytes(p.n_in, p.n_out);
-    FFNO_REQUIRE(need <= 227 * 1024, FFNO_ERR_UNSUPPORTED, "axis_pipe: table does not fit in shared memory");
+    const int ring = axis_ring_depth(p.n_in, p.n_out);
+    FFNO_REQUIRE(ring > 0, FFNO_ERR_UNSUPPORTED, "axis_pipe: table does not fit in shared memory");
+    set.ring[a] = ring;
+    const size_t need = axp_table_offset(ring) + table_image_bytes(p.n_in, p.n_out);
     FFNO_REQUIRE(p.outer * (p.inner / 64) < (1ll << 31), FFNO_ERR_UNSUPPORTED, "axis_pipe: too many groups");
     smem = need > smem ? need : smem;
     set.ax[a] = p;
