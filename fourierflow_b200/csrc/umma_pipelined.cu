@@ -172,13 +172,24 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
+    // the (constant) table image first: its copy runs under TMEM allocation, barrier set-up and the wait for the
+    // predecessor grid instead of after them
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+    {
+      const uint32_t total = 2u * b_half;
+      mbar_expect_tx(bar_w, total);
+      for (uint32_t off = 0; off < total; off += 32768u) {
+        const uint32_t nb = (total - off) < 32768u ? (total - off) : 32768u;
+        bulk_g2s(sB + off, p.table + off, nb, bar_w);
+      }
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], kLoaders);
       mbar_init(&a_empty[i], 1);
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], p.npad > 32 ? 256 : 128);   // see the epilogue: who drains a stage
     }
-    mbar_init(bar_w, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -260,15 +271,6 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
     {   // the whole warp walks the schedule (warp-uniform); elect.sync picks the issuing lane per instruction
-      if (lane == 0) {
-        const uint32_t total = 2u * b_half;
-        mbar_expect_tx(bar_w, total);
-        for (uint32_t off = 0; off < total; off += 32768u) {
-          const uint32_t nb = (total - off) < 32768u ? (total - off) : 32768u;
-          bulk_g2s(sB + off, p.table + off, nb, bar_w);
-        }
-      }
-      __syncwarp();
       pdl_wait();
       mbar_wait(bar_w, 0);
       const uint32_t idesc = make_idesc_bf16(128, p.npad, 1, 0);
@@ -481,13 +483,20 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
+    mbar_init(bar_w, 1);                       // weight image first: see axis_pipe_kernel
+    fence_barrier_init();
+    {
+      mbar_expect_tx(bar_w, kMixImageBytes);
+      const uint8_t* img = ax.image + (long long)k * kMixImageBytes;
+      bulk_g2s(sB, img, 32768, bar_w);
+      bulk_g2s(sB + 32768, img + 32768, 32768, bar_w);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], kLoaders);
       mbar_init(&a_empty[i], 1);
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], kEpiWarps * 32);
     }
-    mbar_init(bar_w, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -558,13 +567,6 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
     }
   } else if (warp == kMmaWarp) {
     {
-      if (lane == 0) {
-        mbar_expect_tx(bar_w, kMixImageBytes);
-        const uint8_t* img = ax.image + (long long)k * kMixImageBytes;
-        bulk_g2s(sB, img, 32768, bar_w);
-        bulk_g2s(sB + 32768, img + 32768, 32768, bar_w);
-      }
-      __syncwarp();
       pdl_wait();
       mbar_wait(bar_w, 0);
       constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
@@ -960,6 +962,13 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
+    mbar_init(bar_w, 1);                       // weight images first: see axis_pipe_kernel
+    mbar_init(bar_w2, 1);
+    fence_barrier_init();
+    mbar_expect_tx(bar_w, 65536);
+    for (int i = 0; i < 2; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
+    mbar_expect_tx(bar_w2, 65536);
+    for (int i = 2; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w2);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a1_full[i], 128);
       mbar_init(&a1_empty[i], 1);
@@ -972,8 +981,6 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       mbar_init(&a2_full[i], 128);
       mbar_init(&a2_empty[i], 1);
     }
-    mbar_init(bar_w, 1);
-    mbar_init(bar_w2, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -1137,11 +1144,6 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     // GEMM1 and GEMM2 have independent dependency chains (A1/D1 vs A2/D2 barriers), so each gets its own issuing
     // warp: the tensor pipe takes the instructions in arrival order, neither chain waits behind the other's
     // operands, and the ~10 SASS instructions of descriptor set-up per tcgen05.mma are spread over two warps.
-    if (lane == 0) {
-      mbar_expect_tx(bar_w, 65536);
-      for (int i = 0; i < 2; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w);
-    }
-    __syncwarp();
     pdl_wait();
     mbar_wait(bar_w, 0);
     constexpr uint32_t IDESC_G1 = make_idesc_bf16(128, 128, 0, 0);
@@ -1169,11 +1171,6 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     __syncwarp();
   } else if (warp == kFF3G2Warp) {
     // ---------------------------------------------------------------- GEMM2 issuer (A operand from tensor memory)
-    if (lane == 0) {
-      mbar_expect_tx(bar_w2, 65536);
-      for (int i = 2; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, image + i * 32768, 32768, bar_w2);
-    }
-    __syncwarp();
     pdl_wait();
     mbar_wait(bar_w2, 0);
     constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
