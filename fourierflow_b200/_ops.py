@@ -113,6 +113,23 @@ def rel_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def velocity_features(w: torch.Tensor, length_x: float, length_y: float):
+    """(q, v) = (psi_y, −psi_x) of the vorticity ``w[B, X, Y]`` on a periodic ``length_x × length_y`` domain — the
+    ``use_velocity`` features of routines/grid_2d_markov.py:206-220 (ffno_velocity_fwd)."""
+    require_cuda(w, "velocity features")
+    lib = _lib.load()
+    w = w.contiguous()
+    B, X, Y = w.shape
+    q, v = torch.empty_like(w), torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        nbytes = lib.ffno_velocity_scratch_bytes(B, X, Y)
+        scratch = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=w.device)
+        _lib.check(lib.ffno_velocity_fwd(w.data_ptr(), X * Y, 1, B, X, Y, float(length_x), float(length_y), q.data_ptr(),
+                                         v.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream(w.device)),
+                   "ffno_velocity_fwd")
+    return q, v
+
+
 # ----------------------------------------------------------------------------------------------
 # A plan bound to one module tree (block or single spectral layer)
 # ----------------------------------------------------------------------------------------------
@@ -292,14 +309,19 @@ class StackPlan:
         return y
 
     def rollout_forward(self, frame0: torch.Tensor, n_steps: int, mean: Sequence[float], std: Sequence[float],
-                        low: float, high: float) -> torch.Tensor:
+                        low: float, high: float, domain: Optional[Sequence[float]] = None) -> torch.Tensor:
+        """``domain`` = (length_x, length_y) of the periodic box: only used by 5-feature (velocity) plans."""
         B = frame0.shape[0]
         X, Y = self.size
         with torch.cuda.device(self.device):
+            if domain is not None:
+                _lib.check(self.lib.ffno_plan_set_domain(self._plan, float(domain[0]), float(domain[1])),
+                           "ffno_plan_set_domain")
             ws = self._workspace(self.lib.ffno_rollout_workspace_bytes(self._plan, B, n_steps))
             preds = torch.empty(B, X, Y, n_steps, device=self.device, dtype=torch.float32)
-            m = (C.c_float * 3)(*[float(v) for v in mean])
-            s = (C.c_float * 3)(*[float(v) for v in std])
+            n_feat = len(mean)
+            m = (C.c_float * n_feat)(*[float(v) for v in mean])
+            s = (C.c_float * n_feat)(*[float(v) for v in std])
             _lib.check(self.lib.ffno_rollout_fwd(self._plan, frame0.data_ptr(), B, n_steps, m, s, float(low),
                                                  float(high), preds.data_ptr(), ws.data_ptr(), ws.numel(),
                                                  _stream(self.device)), "ffno_rollout_fwd")

@@ -117,15 +117,18 @@ def _resolve_str(text: str, root: Mapping, depth: int = 0) -> Any:
             return RESOLVERS[name.strip()](arg.strip())
         return _resolve(_select(root, expr.strip()), root, depth + 1)
 
-    m = _INTERP.fullmatch(text.strip())
-    if m:                                   # the whole value is one interpolation: keep the resolved type
-        return one(m.group(1))
+    # innermost interpolations first (``${eval:2 * ${import:numpy.pi}}``); when what is left is exactly one
+    # interpolation its resolved value keeps its type (float, callable, ...), otherwise values are spliced as text
     out = text
     while True:
+        m = _INTERP.fullmatch(out.strip())
+        if m:
+            return one(m.group(1))
         m = _INTERP.search(out)
         if not m:
             return out
-        out = out[:m.start()] + str(one(m.group(1))) + out[m.end():]
+        val = one(m.group(1))
+        out = out[:m.start()] + (repr(val) if isinstance(val, float) else str(val)) + out[m.end():]
 
 
 def _resolve(node: Any, root: Mapping, depth: int = 0, strict: bool = True) -> Any:

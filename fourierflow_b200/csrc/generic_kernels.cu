@@ -448,6 +448,167 @@ int launch_fold_head(const float* W0t, const float* b0, const float* W1t, const 
 }
 
 // ---- rollout glue --------------------------------------------------------------------------------
+// Velocity features of the torus_kochkov rollout (routines/grid_2d_markov.py:82-93, :206-220, :268-285):
+//   w_hat = rfftn(w, 'backward');  psi_hat = -w_hat / lap,  lap = (2 pi i)^2 (kx^2 + ky^2), lap[0,0] = 1
+//   q = irfftn(2 pi i ky psi_hat) = psi_y,   v = irfftn(-2 pi i kx psi_hat) = -psi_x
+// with kx = fftfreq(X, Lx/X), ky = rfftfreq(Y, Ly/Y).  With g = 1 / (2 pi (kx^2 + ky^2)) (0 at DC, where ky = kx = 0
+// kill the product anyway) this is q_hat = i ky g w_hat, v_hat = -i kx g w_hat.  One scalar field per sample — a
+// 1/64th of one axis of one layer — so the four separable passes are plain FP32 DFT sums over twiddles kept in shared
+// memory (exact for any X, Y); the C2R pass drops Im(DC) / Im(Nyquist) like torch's irfftn.
+namespace {
+
+constexpr int kVelMaxN = 1024;
+
+__device__ __forceinline__ void fill_twiddles(float* c, float* s, int N) {       // e^{+2 pi i r / N}, r = 0..N-1
+  for (int r = threadIdx.x; r < N; r += blockDim.x) sincospif(2.0f * (float)r / (float)N, &s[r], &c[r]);
+  __syncthreads();
+}
+
+// A[b][x][my] = sum_y w[b][x][y] e^{-2 pi i my y / Y},  my = 0..Y/2
+__global__ void __launch_bounds__(256)
+vel_fwd_y_kernel(const float* __restrict__ w, long long stride_b, long long stride_xy, float* __restrict__ Are,
+                 float* __restrict__ Aim, long long total, int X, int Y, int Yh) {
+  __shared__ float tc[kVelMaxN], ts[kVelMaxN];
+  fill_twiddles(tc, ts, Y);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int my = (int)(idx % Yh);
+  const long long bx = idx / Yh;
+  const long long b = bx / X;
+  const int x = (int)(bx - b * X);
+  const float* row = w + b * stride_b + (long long)x * Y * stride_xy;
+  float re = 0.f, im = 0.f;
+  int r = 0;
+  for (int y = 0; y < Y; ++y) {
+    const float v = row[(long long)y * stride_xy];
+    re = fmaf(v, tc[r], re);
+    im = fmaf(-v, ts[r], im);
+    r += my;
+    if (r >= Y) r -= Y;
+  }
+  Are[idx] = re;
+  Aim[idx] = im;
+}
+
+// W[b][mx][my] = sum_x A[b][x][my] e^{-2 pi i mx x / X};  Q = i ky g W,  V = -i kx g W
+__global__ void __launch_bounds__(256)
+vel_fwd_x_mul_kernel(const float* __restrict__ Are, const float* __restrict__ Aim, float* __restrict__ Qre,
+                     float* __restrict__ Qim, float* __restrict__ Vre, float* __restrict__ Vim, long long total, int X,
+                     int Yh, float Lx, float Ly) {
+  __shared__ float tc[kVelMaxN], ts[kVelMaxN];
+  fill_twiddles(tc, ts, X);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int my = (int)(idx % Yh);
+  const long long bm = idx / Yh;
+  const long long b = bm / X;
+  const int mx = (int)(bm - b * X);
+  const float* are = Are + b * X * Yh + my;
+  const float* aim = Aim + b * X * Yh + my;
+  float re = 0.f, im = 0.f;
+  int r = 0;
+  for (int x = 0; x < X; ++x) {
+    const float ar = are[(long long)x * Yh], ai = aim[(long long)x * Yh];
+    const float c = tc[r], s = ts[r];                 // (ar + i ai)(c - i s)
+    re = fmaf(ar, c, fmaf(ai, s, re));
+    im = fmaf(ai, c, fmaf(-ar, s, im));
+    r += mx;
+    if (r >= X) r -= X;
+  }
+  const int mxs = mx < (X + 1) / 2 ? mx : mx - X;     // fftfreq order: 0 .. ceil(X/2)-1, -floor(X/2) .. -1
+  const float kx = (float)mxs / Lx, ky = (float)my / Ly;
+  const float k2 = kx * kx + ky * ky;
+  const float g = k2 > 0.f ? 1.0f / (6.283185307179586f * k2) : 0.f;
+  const float gq = ky * g, gv = -kx * g;              // i g (re + i im) = g (-im + i re)
+  Qre[idx] = -gq * im;
+  Qim[idx] = gq * re;
+  Vre[idx] = -gv * im;
+  Vim[idx] = gv * re;
+}
+
+// B[b][x][my] = sum_mx F[b][mx][my] e^{+2 pi i mx x / X}  for F in {Q, V}
+__global__ void __launch_bounds__(256)
+vel_inv_x_kernel(const float* __restrict__ Qre, const float* __restrict__ Qim, const float* __restrict__ Vre,
+                 const float* __restrict__ Vim, float* __restrict__ BQre, float* __restrict__ BQim,
+                 float* __restrict__ BVre, float* __restrict__ BVim, long long total, int X, int Yh) {
+  __shared__ float tc[kVelMaxN], ts[kVelMaxN];
+  fill_twiddles(tc, ts, X);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int my = (int)(idx % Yh);
+  const long long bx = idx / Yh;
+  const long long b = bx / X;
+  const int x = (int)(bx - b * X);
+  const long long base = b * X * Yh + my;
+  float qr = 0.f, qi = 0.f, vr = 0.f, vi = 0.f;
+  int r = 0;
+  for (int mx = 0; mx < X; ++mx) {
+    const long long o = base + (long long)mx * Yh;
+    const float c = tc[r], s = ts[r];                 // (a + i b)(c + i s)
+    const float a0 = Qre[o], b0 = Qim[o], a1 = Vre[o], b1 = Vim[o];
+    qr = fmaf(a0, c, fmaf(-b0, s, qr));
+    qi = fmaf(b0, c, fmaf(a0, s, qi));
+    vr = fmaf(a1, c, fmaf(-b1, s, vr));
+    vi = fmaf(b1, c, fmaf(a1, s, vi));
+    r += x;
+    if (r >= X) r -= X;
+  }
+  BQre[idx] = qr; BQim[idx] = qi; BVre[idx] = vr; BVim[idx] = vi;
+}
+
+// C2R along y: f[b][x][y] = (1 / XY) sum_my c_my Re(B[b][x][my] e^{+2 pi i my y / Y}),  c = 1 (DC, Nyquist) or 2
+__global__ void __launch_bounds__(256)
+vel_inv_y_kernel(const float* __restrict__ BQre, const float* __restrict__ BQim, const float* __restrict__ BVre,
+                 const float* __restrict__ BVim, float* __restrict__ q, float* __restrict__ v, long long total, int X,
+                 int Y, int Yh) {
+  __shared__ float tc[kVelMaxN], ts[kVelMaxN];
+  fill_twiddles(tc, ts, Y);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int y = (int)(idx % Y);
+  const long long bx = idx / Y;
+  const long long base = bx * Yh;
+  float aq = 0.f, av = 0.f;
+  int r = 0;
+  for (int my = 0; my < Yh; ++my) {
+    const float cm = (my == 0 || (2 * my == Y)) ? 1.f : 2.f;
+    const float c = cm * tc[r], s = cm * ts[r];
+    aq = fmaf(BQre[base + my], c, fmaf(-BQim[base + my], s, aq));
+    av = fmaf(BVre[base + my], c, fmaf(-BVim[base + my], s, av));
+    r += y;
+    if (r >= Y) r -= Y;
+  }
+  const float scale = 1.0f / ((float)X * (float)Y);
+  q[idx] = aq * scale;
+  v[idx] = av * scale;
+}
+
+}  // namespace
+
+size_t velocity_scratch_floats(int batch, int X, int Y) { return (size_t)10 * batch * X * (Y / 2 + 1); }
+
+int launch_velocity(const float* w, long long stride_b, long long stride_xy, int batch, int X, int Y, float Lx, float Ly,
+                    float* q, float* v, float* scratch, cudaStream_t st) {
+  FFNO_REQUIRE(X >= 1 && Y >= 1 && X <= kVelMaxN && Y <= kVelMaxN, FFNO_ERR_UNSUPPORTED,
+               "velocity features: grid %dx%d exceeds %d per axis", X, Y, kVelMaxN);
+  FFNO_REQUIRE(Lx > 0.f && Ly > 0.f, FFNO_ERR_BAD_ARG, "velocity features: domain lengths must be positive");
+  if (batch == 0) return FFNO_OK;
+  const int Yh = Y / 2 + 1;
+  const long long nh = (long long)batch * X * Yh, nr = (long long)batch * X * Y;
+  float* a[10];
+  for (int i = 0; i < 10; ++i) a[i] = scratch + (size_t)i * nh;
+  vel_fwd_y_kernel<<<ceil_div(nh, 256), 256, 0, st>>>(w, stride_b, stride_xy, a[0], a[1], nh, X, Y, Yh);
+  FFNO_LAUNCH_CHECK("vel_fwd_y_kernel");
+  vel_fwd_x_mul_kernel<<<ceil_div(nh, 256), 256, 0, st>>>(a[0], a[1], a[2], a[3], a[4], a[5], nh, X, Yh, Lx, Ly);
+  FFNO_LAUNCH_CHECK("vel_fwd_x_mul_kernel");
+  vel_inv_x_kernel<<<ceil_div(nh, 256), 256, 0, st>>>(a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], nh, X, Yh);
+  FFNO_LAUNCH_CHECK("vel_inv_x_kernel");
+  vel_inv_y_kernel<<<ceil_div(nr, 256), 256, 0, st>>>(a[6], a[7], a[8], a[9], q, v, nr, X, Y, Yh);
+  FFNO_LAUNCH_CHECK("vel_inv_y_kernel");
+  g_launch_counter += 4;
+  return FFNO_OK;
+}
+
 __device__ __forceinline__ float torch_linspace(int i, int steps, float low, float high) {
   // torch.linspace float32 kernel: symmetric evaluation around the midpoint.
   if (steps <= 1) return low;
@@ -456,10 +617,12 @@ __device__ __forceinline__ float torch_linspace(int i, int steps, float low, flo
   return (i < half) ? (low + step * (float)i) : (high - step * (float)(steps - 1 - i));
 }
 
+// features of one rollout step, normalised: [w, (q, v,) gx, gy]
+template <int NF>
 __global__ void __launch_bounds__(256)
 rollout_features_kernel(const float* __restrict__ frame, long long stride_b, int stride_xy,
-                        float* __restrict__ feat, long long total, int X, int Y, float low, float high,
-                        MeanStd3 ms) {
+                        const float* __restrict__ q, const float* __restrict__ v, float* __restrict__ feat,
+                        long long total, int X, int Y, float low, float high, MeanStd ms) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   int y = (int)(idx % Y);
@@ -468,18 +631,28 @@ rollout_features_kernel(const float* __restrict__ frame, long long stride_b, int
   long long b = t / X;
   float w = frame[b * stride_b + ((long long)x * Y + y) * stride_xy];
   float gx = torch_linspace(x, X, low, high), gy = torch_linspace(y, Y, low, high);
-  feat[idx * 3 + 0] = (w - ms.m[0]) / ms.s[0];
-  feat[idx * 3 + 1] = (gx - ms.m[1]) / ms.s[1];
-  feat[idx * 3 + 2] = (gy - ms.m[2]) / ms.s[2];
+  float* f = feat + idx * NF;
+  int c = 0;
+  f[c] = (w - ms.m[c]) / ms.s[c]; ++c;
+  if (NF == 5) {
+    f[c] = (q[idx] - ms.m[c]) / ms.s[c]; ++c;
+    f[c] = (v[idx] - ms.m[c]) / ms.s[c]; ++c;
+  }
+  f[c] = (gx - ms.m[c]) / ms.s[c]; ++c;
+  f[c] = (gy - ms.m[c]) / ms.s[c];
 }
 
-int launch_rollout_features(const float* frame, long long frame_stride_b, int frame_stride_xy, float* feat,
-                            int batch, int X, int Y, float low, float high, const MeanStd3& mean_std,
-                            cudaStream_t st) {
+int launch_rollout_features(const float* frame, long long frame_stride_b, int frame_stride_xy, const float* q,
+                            const float* v, float* feat, int batch, int X, int Y, float low, float high,
+                            const MeanStd& mean_std, cudaStream_t st) {
   long long total = (long long)batch * X * Y;
   if (total == 0) return FFNO_OK;
-  rollout_features_kernel<<<ceil_div(total, 256), 256, 0, st>>>(frame, frame_stride_b, frame_stride_xy, feat,
-                                                                total, X, Y, low, high, mean_std);
+  if (q)
+    rollout_features_kernel<5><<<ceil_div(total, 256), 256, 0, st>>>(frame, frame_stride_b, frame_stride_xy, q, v, feat,
+                                                                     total, X, Y, low, high, mean_std);
+  else
+    rollout_features_kernel<3><<<ceil_div(total, 256), 256, 0, st>>>(frame, frame_stride_b, frame_stride_xy, q, v, feat,
+                                                                     total, X, Y, low, high, mean_std);
   ++g_launch_counter;
   FFNO_LAUNCH_CHECK("rollout_features_kernel");
   return FFNO_OK;
@@ -487,14 +660,14 @@ int launch_rollout_features(const float* frame, long long frame_stride_b, int fr
 
 __global__ void __launch_bounds__(256)
 rollout_denorm_kernel(const float* __restrict__ fc, float* __restrict__ preds, long long total, int n_steps,
-                      int t, MeanStd3 ms) {
+                      int t, MeanStd ms) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   preds[idx * n_steps + t] = fc[idx] * ms.s[0] + ms.m[0];
 }
 
 int launch_rollout_denorm(const float* forecast, float* preds, int batch, int XY, int n_steps, int t,
-                          const MeanStd3& mean_std, cudaStream_t st) {
+                          const MeanStd& mean_std, cudaStream_t st) {
   long long total = (long long)batch * XY;
   if (total == 0) return FFNO_OK;
   rollout_denorm_kernel<<<ceil_div(total, 256), 256, 0, st>>>(forecast, preds, total, n_steps, t, mean_std);

@@ -60,13 +60,19 @@ int launch_fold_head(const float* W0t /*[C][H]*/, const float* b0, const float* 
 
 // Rollout glue (routines/grid_2d_markov.py:286-306, modules/normalizer.py:51,62)
 //   feat[b][x][y][0] = (frame - mean0)/std0 ; feat[..][1] = (lin(x) - mean1)/std1 ; [2] likewise
-struct MeanStd3 { float m[3]; float s[3]; };   // passed by value: no device copy, graph-capturable
-int launch_rollout_features(const float* frame, long long frame_stride_b, int frame_stride_xy,
-                            float* feat, int batch, int X, int Y, float low, float high,
-                            const MeanStd3& ms, cudaStream_t st);
+struct MeanStd { float m[5]; float s[5]; };   // passed by value: no device copy, graph-capturable
+// q, v: velocity features of the frame (NULL: 3 features [w, gx, gy]; else 5: [w, q, v, gx, gy])
+int launch_rollout_features(const float* frame, long long frame_stride_b, int frame_stride_xy, const float* q,
+                            const float* v, float* feat, int batch, int X, int Y, float low, float high,
+                            const MeanStd& ms, cudaStream_t st);
+// (q, v) = (psi_y, -psi_x) from the vorticity w[b] at w + b * stride_b + (x * Y + y) * stride_xy on an Lx x Ly periodic
+// domain (routines/grid_2d_markov.py:206-220); scratch: velocity_scratch_floats(batch, X, Y) floats
+size_t velocity_scratch_floats(int batch, int X, int Y);
+int launch_velocity(const float* w, long long stride_b, long long stride_xy, int batch, int X, int Y, float Lx, float Ly,
+                    float* q, float* v, float* scratch, cudaStream_t st);
 //   preds[b][x][y][t] = fc[b][x][y] * std0 + mean0
 int launch_rollout_denorm(const float* forecast, float* preds, int batch, int XY, int n_steps, int t,
-                          const MeanStd3& ms, cudaStream_t st);
+                          const MeanStd& ms, cudaStream_t st);
 
 }  // namespace ffno
 

@@ -76,7 +76,7 @@ struct ffno_plan {
     cudaGraphExec_t exec = nullptr;
     int batch = -1, n_steps = 0, seen = 0;
     void* ws = nullptr;
-    MeanStd3 ms{};
+    MeanStd ms{};
     float low = 0.f, high = 0.f;
     int64_t launches = 0;
     void reset() {
@@ -88,6 +88,7 @@ struct ffno_plan {
   };
   GraphSlot g_block, g_rollout;
   bool graphs = true;
+  float domain[2] = {6.283185307179586f, 6.283185307179586f};   // periodic domain lengths of the velocity features
 
   // Batch chunking of the stack forward (samples are independent): the batch is cut into chunks of
   // `chunk` samples that run the whole layer stack one after the other on the same (small, L2-resident) workspace
@@ -792,7 +793,10 @@ size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch, int32_
   if (!plan || batch < 0 || n_steps < 0) return 0;
   size_t frame = ((size_t)batch * plan->pts_in * 4 + 255) / 256 * 256;
   size_t preds = ((size_t)batch * plan->pts_in * n_steps * 4 + 255) / 256 * 256;
-  return ffno_workspace_bytes(plan, batch) + frame + preds;
+  size_t vel = 0;
+  if (plan->d.in_features == 5 && plan->d.ndim == 2)      // q, v and the scratch of the four DFT passes
+    vel = 2 * frame + (velocity_scratch_floats(batch, plan->d.size[0], plan->d.size[1]) * 4 + 255) / 256 * 256;
+  return ffno_workspace_bytes(plan, batch) + frame + preds + vel;
 }
 
 int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n_steps, const float* mean_host,
@@ -801,9 +805,11 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
   FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_rollout_workspace_bytes(p, batch, n_steps)));
   if (batch == 0) { p->last_launches = 0; return FFNO_OK; }
   FFNO_REQUIRE(frame0 && preds && mean_host && std_host, FFNO_ERR_BAD_ARG, "NULL argument");
-  FFNO_REQUIRE(p->d.ndim == 2 && p->d.in_features == 3 && p->d.out_features == 1 && !p->d.append_grid &&
-                   p->d.pad[0] == 0 && p->d.pad[1] == 0 && !p->d.use_fork,
-               FFNO_ERR_UNSUPPORTED, "rollout needs the torus_li/markov layout (2-D grid, in=3, out=1)");
+  FFNO_REQUIRE(p->d.ndim == 2 && (p->d.in_features == 3 || p->d.in_features == 5) && p->d.out_features == 1 &&
+                   !p->d.append_grid && p->d.pad[0] == 0 && p->d.pad[1] == 0 && !p->d.use_fork,
+               FFNO_ERR_UNSUPPORTED,
+               "rollout needs the torus_li/markov (in=3) or torus_kochkov (in=5, velocity features) layout: 2-D grid, out=1");
+  const bool use_velocity = p->d.in_features == 5;
   FFNO_REQUIRE(n_steps >= 1, FFNO_ERR_BAD_ARG, "n_steps=%d", n_steps);
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -813,17 +819,26 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
   const size_t frame_b = (size_t)batch * X * Y * 4;
   const size_t stack_b = stack_ws_bytes(p, batch);
   float* frame_st = reinterpret_cast<float*>(base + stack_b);
-  float* preds_st = reinterpret_cast<float*>(base + stack_b + (frame_b + 255) / 256 * 256);
-  MeanStd3 ms;
-  for (int i = 0; i < 3; ++i) { ms.m[i] = mean_host[i]; ms.s[i] = std_host[i]; }
+  const size_t frame_al = (frame_b + 255) / 256 * 256;
+  const size_t preds_al = (frame_b * n_steps + 255) / 256 * 256;
+  float* preds_st = reinterpret_cast<float*>(base + stack_b + frame_al);
+  float* vel_q = use_velocity ? reinterpret_cast<float*>(base + stack_b + frame_al + preds_al) : nullptr;
+  float* vel_v = use_velocity ? reinterpret_cast<float*>(base + stack_b + 2 * frame_al + preds_al) : nullptr;
+  float* vel_scratch = use_velocity ? reinterpret_cast<float*>(base + stack_b + 3 * frame_al + preds_al) : nullptr;
+  MeanStd ms{};
+  for (int i = 0; i < p->d.in_features; ++i) { ms.m[i] = mean_host[i]; ms.s[i] = std_host[i]; }
 
   // the whole step loop: features -> layer stack -> de-normalise, each forecast feeding the next step
   // (routines/grid_2d_markov.py:263-321); every pointer it touches lives in the caller's workspace
   auto body = [&]() -> int {
     for (int t = 0; t < n_steps; ++t) {
-      if (t == 0) FFNO_TRY(launch_rollout_features(frame_st, (long long)X * Y, 1, w.io_in, batch, X, Y, low, high, ms, st));
-      else FFNO_TRY(launch_rollout_features(preds_st + (t - 1), (long long)X * Y * n_steps, n_steps, w.io_in, batch, X,
-                                            Y, low, high, ms, st));
+      // the frame fed to this step: ground truth at t = 0, then the previous (de-normalised) forecast
+      const float* frame = t == 0 ? frame_st : preds_st + (t - 1);
+      const long long fs_b = t == 0 ? (long long)X * Y : (long long)X * Y * n_steps;
+      const int fs_xy = t == 0 ? 1 : n_steps;
+      if (use_velocity)       // recomputed from every fed-back forecast (grid_2d_markov.py:268-285)
+        FFNO_TRY(launch_velocity(frame, fs_b, fs_xy, batch, X, Y, p->domain[0], p->domain[1], vel_q, vel_v, vel_scratch, st));
+      FFNO_TRY(launch_rollout_features(frame, fs_b, fs_xy, vel_q, vel_v, w.io_in, batch, X, Y, low, high, ms, st));
       FFNO_TRY(block_fwd_impl(p, w.io_in, batch, w.io_out, nullptr, workspace, st));
       FFNO_TRY(launch_rollout_denorm(w.io_out, preds_st, batch, X * Y, n_steps, t, ms, st));
     }
@@ -871,6 +886,32 @@ int ffno_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int32_t N
 
 int ffno_debug_timeline(int32_t enable, int64_t* host_out) {
   return debug_timeline(enable, reinterpret_cast<long long*>(host_out));
+}
+
+int ffno_plan_set_domain(ffno_plan* plan, float length_x, float length_y) {
+  FFNO_REQUIRE(plan != nullptr, FFNO_ERR_BAD_ARG, "plan is NULL");
+  FFNO_REQUIRE(length_x > 0.f && length_y > 0.f, FFNO_ERR_BAD_ARG, "domain lengths must be positive");
+  if (plan->domain[0] != length_x || plan->domain[1] != length_y) plan->g_rollout.reset();   // baked into the graph
+  plan->domain[0] = length_x;
+  plan->domain[1] = length_y;
+  return FFNO_OK;
+}
+
+size_t ffno_velocity_scratch_bytes(int32_t batch, int32_t X, int32_t Y) {
+  if (batch < 0 || X < 1 || Y < 1) return 0;
+  return velocity_scratch_floats(batch, X, Y) * sizeof(float);
+}
+
+int ffno_velocity_fwd(const float* w, int64_t stride_b, int64_t stride_xy, int32_t batch, int32_t X, int32_t Y,
+                      float length_x, float length_y, float* q, float* v, void* scratch, size_t scratch_bytes,
+                      void* stream) {
+  FFNO_REQUIRE(batch >= 0, FFNO_ERR_BAD_ARG, "batch=%d", batch);
+  if (batch == 0) return FFNO_OK;
+  FFNO_REQUIRE(w && q && v && scratch, FFNO_ERR_BAD_ARG, "NULL argument");
+  FFNO_REQUIRE(scratch_bytes >= ffno_velocity_scratch_bytes(batch, X, Y), FFNO_ERR_WORKSPACE, "scratch < %zu B",
+               ffno_velocity_scratch_bytes(batch, X, Y));
+  return launch_velocity(w, stride_b, stride_xy, batch, X, Y, length_x, length_y, q, v, static_cast<float*>(scratch),
+                         static_cast<cudaStream_t>(stream));
 }
 
 int64_t ffno_plan_last_launch_count(const ffno_plan* plan) { return plan ? plan->last_launches : 0; }

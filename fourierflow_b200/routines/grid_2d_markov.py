@@ -2,8 +2,9 @@
 
 The reference class is a pytorch_lightning ``Routine``; this mirror is a plain ``nn.Module`` with the same
 constructor keywords and the same ``forward(batch) -> (loss, step_losses, preds, pred_layer_list)``
-contract for the configuration the BASELINE names (torus_li/markov: position features, normaliser,
-no velocity / force / mu / grid shuffling / difference learning).  The step loop
+contract for the configurations the BASELINE names (torus_li/markov: position features + normaliser;
+torus_kochkov: additionally ``use_velocity`` — stream-function velocities recomputed from the vorticity at
+every step; no force / mu / grid shuffling / difference learning).  The step loop
 (``_valid_step``, grid_2d_markov.py:195-326) runs entirely in libffno_b200 (ffno_rollout_fwd): feature
 build → normalise → layer stack → de-normalise, feeding each forecast back, with no host round trip
 between steps.  The relative-L2 reduction (modules/loss.py:33-46) is ffno_rel_l2 per sample; the mean over
@@ -11,6 +12,7 @@ the batch is the only value a sharded run communicates (see fourierflow_b200/dis
 """
 from __future__ import annotations
 
+import math
 from typing import Optional
 
 import torch
@@ -27,14 +29,23 @@ class Grid2DMarkovExperiment(nn.Module):
                  append_mu: bool = False, max_accumulations: float = 1e6, should_normalize: bool = True,
                  use_fourier_position: bool = False, noise_std: float = 0.0, shuffle_grid: bool = False,
                  use_velocity: bool = False, learn_difference: bool = False, step_size: float = 1.0,
-                 n_test_steps_logged: Optional[int] = None, **kwargs):
+                 n_test_steps_logged: Optional[int] = None,
+                 domain=((0.0, 2 * math.pi), (0.0, 2 * math.pi)), **kwargs):
         super().__init__()
         unsupported = dict(append_force=append_force, append_mu=append_mu, use_fourier_position=use_fourier_position,
-                           shuffle_grid=shuffle_grid, use_velocity=use_velocity, learn_difference=learn_difference)
+                           shuffle_grid=shuffle_grid, learn_difference=learn_difference)
         bad = [k for k, v in unsupported.items() if v]
         if bad or not use_position or not should_normalize:
-            raise RuntimeError("Grid2DMarkovExperiment (B200 backend): only the torus_li/markov feature set is "
-                               f"implemented (use_position + should_normalize); unsupported: {bad}")
+            raise RuntimeError("Grid2DMarkovExperiment (B200 backend): only the torus_li/markov and torus_kochkov "
+                               "feature sets are implemented (use_position + should_normalize [+ use_velocity]); "
+                               f"unsupported: {bad}")
+        want = 5 if use_velocity else 3
+        if conv.input_dim != want:
+            raise RuntimeError(f"Grid2DMarkovExperiment: use_velocity={use_velocity} builds {want} input features, "
+                               f"conv.input_dim is {conv.input_dim}")
+        self.use_velocity = use_velocity
+        (x0, x1), (y0, y1) = domain                   # periodic box of the velocity features (grid_2d_markov.py:43,85)
+        self.domain_lengths = (float(x1) - float(x0), float(y1) - float(y0))
         self.conv = conv
         self.n_steps = n_steps
         self.l2_loss = LpLoss(size_average=True)
@@ -51,8 +62,13 @@ class Grid2DMarkovExperiment(nn.Module):
         """Fold every one-step input of ``data[B,X,Y,T]`` (frames 0..T-2 + position grid) into the normaliser."""
         B, X, Y, T = data.shape
         pos = self._positions(X, Y, data.device, data.dtype)
-        feats = torch.cat([data[..., :-1].unsqueeze(-1),
-                           pos[None, :, :, None, :].expand(B, X, Y, T - 1, 2)], dim=-1)
+        parts = [data[..., :-1].unsqueeze(-1)]
+        if self.use_velocity:                         # q, v of every input frame (:130-144), computed by the CUDA library
+            frames = data[..., :-1].permute(0, 3, 1, 2).reshape(B * (T - 1), X, Y)
+            q, v = _ops.velocity_features(frames, *self.domain_lengths)
+            parts += [t.reshape(B, T - 1, X, Y).permute(0, 2, 3, 1).unsqueeze(-1) for t in (q, v)]
+        parts.append(pos[None, :, :, None, :].expand(B, X, Y, T - 1, 2))
+        feats = torch.cat(parts, dim=-1)
         self.normalizer.accumulate(feats)
         self._ms_cache = None
 
@@ -79,7 +95,8 @@ class Grid2DMarkovExperiment(nn.Module):
         plan = self.conv.plan_for(data.device, (X, Y))
         mean, std = self._mean_std()
         frame0 = data[..., T - n_steps - 1].contiguous()
-        return plan.rollout_forward(frame0, n_steps, mean, std, self.low, self.high)
+        return plan.rollout_forward(frame0, n_steps, mean, std, self.low, self.high,
+                                    self.domain_lengths if self.use_velocity else None)
 
     def per_sample_losses(self, preds: torch.Tensor, data: torch.Tensor) -> torch.Tensor:
         """[n_steps, B] relative L2 of every rollout step against the last n_steps frames of ``data``."""

@@ -196,7 +196,8 @@ FFNO_API int ffno_rel_l2(const float* x, int64_t x_stride_b, int64_t x_stride_i,
                 int64_t y_stride_i, int32_t batch, int64_t n, float* out, void* stream);
 
 /* 10-step Markov rollout of Grid2DMarkovExperiment._valid_step (routines/grid_2d_markov.py:195-326)
- * for the torus_li/markov configuration (use_position, should_normalize; 2-D periodic grid only):
+ * for the torus_li/markov configuration (use_position, should_normalize; 2-D periodic grid only) and, for plans
+ * with in_features = 5, the torus_kochkov one (use_velocity: features [w, q, v, gx, gy], see ffno_velocity_fwd):
  *   frame0 [B, X, Y]        ground-truth vorticity fed to step 0
  *   mean/std [in_features]  Normalizer statistics (modules/normalizer.py:68-77), host pointers
  *   preds  [B, X, Y, n_steps]
@@ -206,6 +207,18 @@ FFNO_API int ffno_rollout_fwd(ffno_plan* plan, const float* frame0, int32_t batc
                      const float* mean_host, const float* std_host, float low, float high,
                      float* preds, void* workspace, size_t workspace_bytes, void* stream);
 FFNO_API size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch, int32_t n_steps);
+
+/* Velocity features of the torus_kochkov rollout (use_velocity=True, routines/grid_2d_markov.py:82-93, :206-220):
+ * (q, v) = (psi_y, -psi_x) of the stream function of the vorticity w (w = -laplace psi) on a periodic
+ * length_x x length_y domain, i.e. irfftn(+-2 pi i k psi_hat) with the reference's kx/ky/lap buffers.
+ *   w element (b, x, y) at w[b*stride_b + (x*Y + y)*stride_xy];  q, v: contiguous [B, X, Y].
+ * A plan built with in_features = 5 runs ffno_rollout_fwd with the features [w, q, v, gx, gy] and recomputes q, v from
+ * every fed-back forecast; ffno_plan_set_domain sets its domain lengths (default 2 pi x 2 pi, the reference default). */
+FFNO_API size_t ffno_velocity_scratch_bytes(int32_t batch, int32_t X, int32_t Y);
+FFNO_API int ffno_velocity_fwd(const float* w, int64_t stride_b, int64_t stride_xy, int32_t batch, int32_t X, int32_t Y,
+                      float length_x, float length_y, float* q, float* v, void* scratch, size_t scratch_bytes,
+                      void* stream);
+FFNO_API int ffno_plan_set_domain(ffno_plan* plan, float length_x, float length_y);
 
 /* Diagnostics: one tcgen05 product D[128][N] = A[128][K] * B[N][K]^T (bf16 bit patterns in, FP32 out) through
  * the operand layouts / descriptors the kernels use (a_mn / b_mn: operand stored MN-major; variant selects the

@@ -266,10 +266,48 @@ def position_features(dim_sizes: Sequence[int], low: float = 0.0, high: float = 
     return torch.stack(torch.meshgrid(*grids, indexing="ij"), dim=-1)
 
 
+def rfft_mesh(shape: Sequence[int], domain=((0.0, 2 * math.pi), (0.0, 2 * math.pi))):
+    """``jax_cfd.base.grids.Grid(shape, domain).rfft_mesh()`` — THIRD-PARTY arithmetic restated (jax-cfd rev eb4d723,
+    pyproject.toml:29 of the reference; the package is not installed here, so this one function is *unpinned* by
+    execution and follows its published definition):
+        kx, ky = meshgrid(fftfreq(nx, d=step_x), rfftfreq(ny, d=step_y), indexing='ij'),  step = domain length / n.
+    Used only to build the ``kx/ky/lap`` buffers of the velocity features (routines/grid_2d_markov.py:82-93)."""
+    (x0, x1), (y0, y1) = domain
+    nx, ny = shape
+    fx = torch.fft.fftfreq(nx, d=(x1 - x0) / nx, dtype=torch.float64)
+    fy = torch.fft.rfftfreq(ny, d=(y1 - y0) / ny, dtype=torch.float64)
+    return torch.meshgrid(fx, fy, indexing="ij")
+
+
+def velocity_features(w: torch.Tensor, domain=((0.0, 2 * math.pi), (0.0, 2 * math.pi))) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(q, v) = (psi_y, -psi_x) of the stream function of vorticity ``w[B, X, Y, ...]`` (transform over dims 1, 2).
+
+    Reference: fourierflow/routines/grid_2d_markov.py:82-93 (buffers: lap = (2 pi i)^2 (|kx|^2 + |ky|^2), lap[0,0] = 1)
+    and :206-220 / :268-285 (rfftn 'backward' -> psi_hat = -w_hat / lap -> 2 pi i ky psi_hat, -2 pi i kx psi_hat
+    -> irfftn).  Buffers are cast to the data precision exactly as ``register_buffer(torch.from_numpy(...))`` of the
+    float32 / complex64 jax arrays does."""
+    X, Y = w.shape[1], w.shape[2]
+    kx, ky = rfft_mesh((X, Y), domain)
+    lap = (2j * math.pi) ** 2 * (kx.abs() ** 2 + ky.abs() ** 2)
+    lap[0, 0] = 1
+    rdt = w.dtype
+    cdt = torch.complex64 if rdt == torch.float32 else torch.complex128
+    kx, ky, lap = kx.to(rdt), ky.to(rdt), lap.to(cdt)
+    extra = (1,) * (w.dim() - 3)
+    shp = (1, X, Y // 2 + 1) + extra
+    w_hat = torch.fft.rfftn(w, dim=[1, 2], norm="backward")
+    psi_hat = -w_hat / lap.reshape(shp)
+    q = torch.fft.irfftn(2 * math.pi * 1j * ky.reshape(shp) * psi_hat, s=(X, Y), dim=[1, 2], norm="backward")
+    v = torch.fft.irfftn(-2 * math.pi * 1j * kx.reshape(shp) * psi_hat, s=(X, Y), dim=[1, 2], norm="backward")
+    return q, v
+
+
 def markov_rollout(p: Params, data: torch.Tensor, stats: dict, *, modes: int, n_layers: int,
-                   n_steps: int = 10, low: float = 0.0, high: float = 1.0) -> dict:
+                   n_steps: int = 10, low: float = 0.0, high: float = 1.0, use_velocity: bool = False,
+                   domain=((0.0, 2 * math.pi), (0.0, 2 * math.pi))) -> dict:
     """``Grid2DMarkovExperiment._valid_step`` with the torus_li/markov config
-    (use_position, should_normalize; no velocity/force/mu/shuffle/difference).
+    (use_position, should_normalize; no force/mu/shuffle/difference) and, with ``use_velocity``, the torus_kochkov
+    feature set [w, q, v, gx, gy] (velocity recomputed from every fed-back forecast, :268-285).
 
     data:[B,X,Y,T].  Step 0 consumes the ground-truth frame T−n−1; later steps feed back the
     model's own de-normalised forecast, re-concatenated with the position grid.
@@ -284,6 +322,9 @@ def markov_rollout(p: Params, data: torch.Tensor, stats: dict, *, modes: int, n_
     step_losses, preds = [], []
     im = data[..., T - n_steps - 1].unsqueeze(-1)         # :236 / :265
     for t in range(n_steps):
+        if use_velocity:
+            q, v = velocity_features(im, domain)          # :206-220 / :268-285
+            im = torch.cat([im, q, v], dim=-1)
         x = torch.cat([im, pos], dim=-1)                  # :222-233 / :286-287
         x = (x - mean) / std                              # :296, normalizer.py:51
         im = block_grid2d_forward(p, x, modes=modes, n_layers=n_layers)["forecast"]   # :300-301

@@ -161,3 +161,40 @@ def test_reference_ffno_configs_load_from_the_mounted_tree():
         assert type(op).__module__.startswith("fourierflow_b200.modules")
         seen += 1
     assert seen >= 4
+
+
+KOCHKOV_YAML = """
+routine:
+  _target_: fourierflow.routines.Grid2DMarkovExperiment
+  conv:
+    _target_: fourierflow.modules.FNOFactorized2DBlock
+    modes: 64
+    width: 64
+    n_layers: 2
+    input_dim: 5
+    share_weight: true
+    factor: 4
+    ff_weight_norm: true
+    gain: 0.1
+  step_size: 0.28049934407051724
+  max_accumulations: 38736
+  noise_std: 0.01
+  use_velocity: true
+  grid_size: [256]
+  domain:
+    - [0, '${eval:2 * ${import:numpy.pi}}']
+    - [0, '${eval:2 * ${import:numpy.pi}}']
+"""
+
+
+def test_kochkov_routine_with_velocity_features_and_nested_interpolation():
+    """experiments/torus_kochkov/ffno/grid_sizes/256/config.yaml schema: nested ${eval:.. ${import:..}} keeps its
+    float type and use_velocity switches the routine to the 5-feature input [w, q, v, gx, gy]."""
+    import math
+    routine, cfg = C.load_routine(KOCHKOV_YAML)
+    assert cfg["routine"]["domain"][0][1] == pytest.approx(2 * math.pi) and isinstance(cfg["routine"]["domain"][0][1], float)
+    assert routine.use_velocity and routine.conv.input_dim == 5
+    assert routine.domain_lengths == (pytest.approx(2 * math.pi), pytest.approx(2 * math.pi))
+    assert routine.normalizer.sum.shape == (5,)
+    with pytest.raises(RuntimeError, match="input_dim"):
+        C.load_routine(KOCHKOV_YAML, overrides=["routine.use_velocity=false"])

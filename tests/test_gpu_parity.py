@@ -162,6 +162,53 @@ def test_config_built_routine_reproduces_the_golden_rollout():
     assert abs(loss.item() - a["loss"].item()) < 1e-4 * abs(a["loss"].item())
 
 
+@pytest.mark.parametrize("shape", [(4, 64, 64), (2, 256, 256), (3, 48, 40), (2, 33, 17)])
+def test_velocity_features_vs_oracle(shape):
+    """ffno_velocity_fwd (use_velocity features, routines/grid_2d_markov.py:206-220) against the torch.fft oracle:
+    square / non-square / odd grids, the 2 pi box and a stretched one, and a strided frame (a preds[..., t] slice)."""
+    import math
+    from fourierflow_b200 import _ops
+    from oracle import ffno_oracle as O
+    B, X, Y = shape
+    w = torch.randn(B, X, Y, generator=torch.Generator().manual_seed(3))
+    for dom in (((0.0, 2 * math.pi), (0.0, 2 * math.pi)), ((0.0, 1.0), (-1.0, 2.5))):
+        qr, vr = O.velocity_features(w.unsqueeze(-1).double(), dom)
+        q, v = _ops.velocity_features(w.cuda(), dom[0][1] - dom[0][0], dom[1][1] - dom[1][0])
+        assert rel_err(q, qr[..., 0]) < 2e-5 and rel_err(v, vr[..., 0]) < 2e-5
+    stacked = torch.randn(B, X, Y, 3, generator=torch.Generator().manual_seed(4)).cuda()
+    q, v = _ops.velocity_features(stacked[..., 1], 2 * math.pi, 2 * math.pi)      # made contiguous by the wrapper
+    qr, vr = O.velocity_features(stacked[..., 1:2].cpu().double())
+    assert rel_err(q, qr[..., 0]) < 2e-5 and rel_err(v, vr[..., 0]) < 2e-5
+
+
+@pytest.mark.parametrize("grid", [(32, 32), (64, 48)])
+def test_rollout_with_velocity_features_vs_oracle(grid):
+    """torus_kochkov feature set (use_velocity=True): [w, q, v, gx, gy], velocities recomputed from every fed-back
+    forecast (routines/grid_2d_markov.py:268-285), against the oracle's rollout on seeded weights and data."""
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    from oracle import ffno_oracle as O
+    X, Y = grid
+    torch.manual_seed(0)
+    conv = M().FNOFactorized2DBlock(modes=8, width=64, n_layers=3, input_dim=5, share_weight=True, factor=4,
+                                    ff_weight_norm=True, gain=0.1).eval()
+    sd = {k: v.detach().clone() for k, v in conv.state_dict().items()}
+    data = torch.randn(4, X, Y, 6, generator=torch.Generator().manual_seed(5))
+    exp = Grid2DMarkovExperiment(conv, n_steps=4, use_velocity=True).cuda().eval()
+    exp.accumulate_statistics(data.cuda())
+    # the same statistics on the oracle side: every one-step input [w, q, v, gx, gy] of frames 0..T-2
+    frames = data[..., :-1].unsqueeze(-1)
+    q, v = O.velocity_features(frames)
+    pos = O.position_features((X, Y), 0.0, 1.0, data.dtype)[None, :, :, None, :].expand(4, X, Y, 5, 2)
+    stats = O.normalizer_stats(torch.cat([frames, q, v, pos], dim=-1))
+    m_ref, s_ref = O.normalizer_mean_std(stats)
+    assert rel_err(exp.normalizer.mean, m_ref) < 1e-4 and rel_err(exp.normalizer.std, s_ref) < 1e-4
+    ref = O.markov_rollout(sd, data, stats, modes=8, n_layers=3, n_steps=4, use_velocity=True)
+    with torch.no_grad():
+        loss, step_losses, preds, _ = exp({"data": data.cuda()})
+    assert rel_err(preds, ref["preds"]) < TOL_UMMA
+    assert abs(loss.item() - ref["loss"].item()) < 2e-4 * abs(ref["loss"].item())
+
+
 def _c2_model(n_layers=24, seed=0):
     torch.manual_seed(seed)
     return M().FNOFactorized2DBlock(modes=16, width=64, n_layers=n_layers, input_dim=3, share_weight=True, factor=4,

@@ -94,3 +94,29 @@ def test_dft_matrices_match_torch_fft(L, K):
     r = torch.empty(2 * K, 3, dtype=torch.float64)
     r[0::2], r[1::2] = R.real, R.imag
     assert torch.allclose(E @ r, y, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (48, 40), (33, 17)])
+def test_velocity_features_restatement(shape):
+    """The use_velocity features (routines/grid_2d_markov.py:82-93, :206-220): for a stream function psi and
+    w = -laplace(psi) the oracle must return q = psi_y, v = -psi_x (its kx/ky/lap buffers restate jax-cfd's
+    rfft_mesh, which cannot be executed here: this analytic identity is what pins them)."""
+    import math
+    X, Y = shape
+    a, b = 3, 2
+    x = torch.arange(X, dtype=torch.float64) * 2 * math.pi / X
+    y = torch.arange(Y, dtype=torch.float64) * 2 * math.pi / Y
+    xx, yy = torch.meshgrid(x, y, indexing="ij")
+    psi = torch.sin(a * xx) * torch.cos(b * yy) + 0.5 * torch.cos(xx + 2 * yy)
+    w = (a * a + b * b) * torch.sin(a * xx) * torch.cos(b * yy) + 0.5 * 5 * torch.cos(xx + 2 * yy)
+    q, v = O.velocity_features(w[None, :, :, None])
+    psi_y = -b * torch.sin(a * xx) * torch.sin(b * yy) - 0.5 * 2 * torch.sin(xx + 2 * yy)
+    psi_x = a * torch.cos(a * xx) * torch.cos(b * yy) - 0.5 * torch.sin(xx + 2 * yy)
+    assert (q[0, ..., 0] - psi_y).abs().max() < 1e-12
+    assert (v[0, ..., 0] + psi_x).abs().max() < 1e-12
+    # a constant vorticity has no velocity (lap[0, 0] = 1 only avoids the division by zero), fp32 path included
+    q32, v32 = O.velocity_features(torch.ones(2, X, Y, 1))
+    assert q32.abs().max() < 1e-6 and v32.abs().max() < 1e-6
+    # domain scaling: on a box twice as long the same index-space field has velocities twice as large
+    q2, _ = O.velocity_features(w[None, :, :, None], domain=((0, 4 * math.pi), (0, 4 * math.pi)))
+    assert (q2 - 2 * q).abs().max() < 1e-10
