@@ -52,6 +52,18 @@ with torch.no_grad():
     x = torch.randn(8, 32, 32, 32, 1, device="cuda")
     ms = timed(lambda: m(x), n=5, warm=3)
     out["C5 Mesh3D 24 layers 32^3 (40^3 padded) batch 8"] = {"ms": ms, "samples_per_s": 8 / ms * 1e3}
+# 10-step rollouts through the routine mirror (one C-ABI call each): torus_li (3 features) and torus_kochkov
+# (use_velocity: 5 features, stream-function velocities recomputed every step)
+from fourierflow_b200.routines import Grid2DMarkovExperiment  # noqa: E402
+with torch.no_grad():
+    for name, kw, B, G, vel in (("torus_li 24 layers 64x64 batch 32", dict(modes=16, input_dim=3), 32, 64, False),
+                                ("torus_kochkov 24 layers 256x256 batch 2 (use_velocity)", dict(modes=64, input_dim=5), 2, 256, True)):
+        conv = FNOFactorized2DBlock(width=64, n_layers=24, share_weight=True, factor=4, ff_weight_norm=True, gain=0.1, **kw)
+        exp = Grid2DMarkovExperiment(conv, n_steps=10, use_velocity=vel).cuda().eval()
+        data = torch.randn(B, G, G, 12, device="cuda")
+        exp.accumulate_statistics(data)
+        ms = timed(lambda: exp.predict(data), n=5, warm=3)
+        out[f"rollout 10 steps: {name}"] = {"ms": ms, "ms_per_step": ms / 10, "sample_steps_per_s": B * 10 / ms * 1e3}
 for k, v in out.items():
     print(k, json.dumps(v))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
