@@ -583,6 +583,136 @@ vel_inv_y_kernel(const float* __restrict__ BQre, const float* __restrict__ BQim,
   v[idx] = av * scale;
 }
 
+// ---- shared-memory versions (X <= kVelTileX): one block per grid row for the y passes, one block per (sample, 4
+// ky columns) for the fused x passes (forward DFT, multiply, inverse DFT: W, Q, V never leave the SM)
+constexpr int kVelTileX = 256;
+constexpr int kVelTM = 4;
+
+__global__ void __launch_bounds__(128)
+vel_rows_fwd_kernel(const float* __restrict__ w, long long stride_b, long long stride_xy, float* __restrict__ Are,
+                    float* __restrict__ Aim, int X, int Y, int Yh) {
+  __shared__ float tc[kVelMaxN], ts[kVelMaxN], row[kVelMaxN];
+  const long long bx = blockIdx.x;
+  const long long b = bx / X;
+  const int x = (int)(bx - b * X);
+  const float* src = w + b * stride_b + (long long)x * Y * stride_xy;
+  for (int y = threadIdx.x; y < Y; y += blockDim.x) row[y] = src[(long long)y * stride_xy];
+  fill_twiddles(tc, ts, Y);                            // ends with __syncthreads()
+  for (int my = threadIdx.x; my < Yh; my += blockDim.x) {
+    float re = 0.f, im = 0.f;
+    int r = 0;
+    for (int y = 0; y < Y; ++y) {
+      re = fmaf(row[y], tc[r], re);
+      im = fmaf(-row[y], ts[r], im);
+      r += my;
+      if (r >= Y) r -= Y;
+    }
+    Are[bx * Yh + my] = re;
+    Aim[bx * Yh + my] = im;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+vel_cols_kernel(const float* __restrict__ Are, const float* __restrict__ Aim, float* __restrict__ BQre,
+                float* __restrict__ BQim, float* __restrict__ BVre, float* __restrict__ BVim, int X, int Yh, float Lx,
+                float Ly) {
+  __shared__ float tc[kVelTileX], ts[kVelTileX];
+  __shared__ float a_re[kVelTileX][kVelTM], a_im[kVelTileX][kVelTM];
+  __shared__ float q_re[kVelTileX][kVelTM], q_im[kVelTileX][kVelTM], v_re[kVelTileX][kVelTM], v_im[kVelTileX][kVelTM];
+  const int my0 = blockIdx.x * kVelTM;
+  const long long base = (long long)blockIdx.y * X * Yh;
+  for (int i = threadIdx.x; i < X * kVelTM; i += blockDim.x) {
+    const int x = i / kVelTM, j = i - x * kVelTM;
+    const bool ok = my0 + j < Yh;
+    a_re[x][j] = ok ? Are[base + (long long)x * Yh + my0 + j] : 0.f;
+    a_im[x][j] = ok ? Aim[base + (long long)x * Yh + my0 + j] : 0.f;
+  }
+  fill_twiddles(tc, ts, X);
+  for (int mx = threadIdx.x; mx < X; mx += blockDim.x) {          // W = forward DFT along x, then the multipliers
+    float re[kVelTM], im[kVelTM];
+#pragma unroll
+    for (int j = 0; j < kVelTM; ++j) re[j] = im[j] = 0.f;
+    int r = 0;
+    for (int x = 0; x < X; ++x) {
+      const float c = tc[r], s = ts[r];                             // (ar + i ai)(c - i s)
+#pragma unroll
+      for (int j = 0; j < kVelTM; ++j) {
+        re[j] = fmaf(a_re[x][j], c, fmaf(a_im[x][j], s, re[j]));
+        im[j] = fmaf(a_im[x][j], c, fmaf(-a_re[x][j], s, im[j]));
+      }
+      r += mx;
+      if (r >= X) r -= X;
+    }
+    const int mxs = mx < (X + 1) / 2 ? mx : mx - X;
+    const float kx = (float)mxs / Lx;
+#pragma unroll
+    for (int j = 0; j < kVelTM; ++j) {
+      const float ky = (float)(my0 + j) / Ly;
+      const float k2 = kx * kx + ky * ky;
+      const float g = k2 > 0.f ? 1.0f / (6.283185307179586f * k2) : 0.f;
+      const float gq = ky * g, gv = -kx * g;
+      q_re[mx][j] = -gq * im[j];
+      q_im[mx][j] = gq * re[j];
+      v_re[mx][j] = -gv * im[j];
+      v_im[mx][j] = gv * re[j];
+    }
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < X; x += blockDim.x) {             // inverse DFT along x of Q and V
+    float qr[kVelTM], qi[kVelTM], vr[kVelTM], vi[kVelTM];
+#pragma unroll
+    for (int j = 0; j < kVelTM; ++j) qr[j] = qi[j] = vr[j] = vi[j] = 0.f;
+    int r = 0;
+    for (int mx = 0; mx < X; ++mx) {
+      const float c = tc[r], s = ts[r];                             // (a + i b)(c + i s)
+#pragma unroll
+      for (int j = 0; j < kVelTM; ++j) {
+        qr[j] = fmaf(q_re[mx][j], c, fmaf(-q_im[mx][j], s, qr[j]));
+        qi[j] = fmaf(q_im[mx][j], c, fmaf(q_re[mx][j], s, qi[j]));
+        vr[j] = fmaf(v_re[mx][j], c, fmaf(-v_im[mx][j], s, vr[j]));
+        vi[j] = fmaf(v_im[mx][j], c, fmaf(v_re[mx][j], s, vi[j]));
+      }
+      r += x;
+      if (r >= X) r -= X;
+    }
+#pragma unroll
+    for (int j = 0; j < kVelTM; ++j)
+      if (my0 + j < Yh) {
+        const long long o = base + (long long)x * Yh + my0 + j;
+        BQre[o] = qr[j]; BQim[o] = qi[j]; BVre[o] = vr[j]; BVim[o] = vi[j];
+      }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+vel_rows_inv_kernel(const float* __restrict__ BQre, const float* __restrict__ BQim, const float* __restrict__ BVre,
+                    const float* __restrict__ BVim, float* __restrict__ q, float* __restrict__ v, int X, int Y, int Yh) {
+  __shared__ float tc[kVelMaxN], ts[kVelMaxN];
+  __shared__ float bq_re[kVelMaxN / 2 + 1], bq_im[kVelMaxN / 2 + 1], bv_re[kVelMaxN / 2 + 1], bv_im[kVelMaxN / 2 + 1];
+  const long long bx = blockIdx.x;
+  for (int my = threadIdx.x; my < Yh; my += blockDim.x) {
+    const float cm = (my == 0 || (2 * my == Y)) ? 1.f : 2.f;       // Hermitian half: bins >= 1 count twice
+    bq_re[my] = cm * BQre[bx * Yh + my];
+    bq_im[my] = cm * BQim[bx * Yh + my];
+    bv_re[my] = cm * BVre[bx * Yh + my];
+    bv_im[my] = cm * BVim[bx * Yh + my];
+  }
+  fill_twiddles(tc, ts, Y);
+  const float scale = 1.0f / ((float)X * (float)Y);
+  for (int y = threadIdx.x; y < Y; y += blockDim.x) {
+    float aq = 0.f, av = 0.f;
+    int r = 0;
+    for (int my = 0; my < Yh; ++my) {
+      aq = fmaf(bq_re[my], tc[r], fmaf(-bq_im[my], ts[r], aq));
+      av = fmaf(bv_re[my], tc[r], fmaf(-bv_im[my], ts[r], av));
+      r += y;
+      if (r >= Y) r -= Y;
+    }
+    q[bx * Y + y] = aq * scale;
+    v[bx * Y + y] = av * scale;
+  }
+}
+
 }  // namespace
 
 size_t velocity_scratch_floats(int batch, int X, int Y) { return (size_t)10 * batch * X * (Y / 2 + 1); }
@@ -597,6 +727,19 @@ int launch_velocity(const float* w, long long stride_b, long long stride_xy, int
   const long long nh = (long long)batch * X * Yh, nr = (long long)batch * X * Y;
   float* a[10];
   for (int i = 0; i < 10; ++i) a[i] = scratch + (size_t)i * nh;
+  if (X <= kVelTileX && batch <= 65535) {   // shared-memory passes: 3 launches, the x-direction spectra stay on chip
+    const long long rows = (long long)batch * X;
+    FFNO_REQUIRE(rows < (1ll << 31), FFNO_ERR_UNSUPPORTED, "velocity features: too many rows");
+    vel_rows_fwd_kernel<<<(unsigned)rows, 128, 0, st>>>(w, stride_b, stride_xy, a[0], a[1], X, Y, Yh);
+    FFNO_LAUNCH_CHECK("vel_rows_fwd_kernel");
+    vel_cols_kernel<<<dim3((unsigned)ceil_div(Yh, kVelTM), (unsigned)batch), 256, 0, st>>>(a[0], a[1], a[6], a[7], a[8],
+                                                                                        a[9], X, Yh, Lx, Ly);
+    FFNO_LAUNCH_CHECK("vel_cols_kernel");
+    vel_rows_inv_kernel<<<(unsigned)rows, 128, 0, st>>>(a[6], a[7], a[8], a[9], q, v, X, Y, Yh);
+    FFNO_LAUNCH_CHECK("vel_rows_inv_kernel");
+    g_launch_counter += 3;
+    return FFNO_OK;
+  }
   vel_fwd_y_kernel<<<ceil_div(nh, 256), 256, 0, st>>>(w, stride_b, stride_xy, a[0], a[1], nh, X, Y, Yh);
   FFNO_LAUNCH_CHECK("vel_fwd_y_kernel");
   vel_fwd_x_mul_kernel<<<ceil_div(nh, 256), 256, 0, st>>>(a[0], a[1], a[2], a[3], a[4], a[5], nh, X, Yh, Lx, Ly);

@@ -162,7 +162,7 @@ def test_config_built_routine_reproduces_the_golden_rollout():
     assert abs(loss.item() - a["loss"].item()) < 1e-4 * abs(a["loss"].item())
 
 
-@pytest.mark.parametrize("shape", [(4, 64, 64), (2, 256, 256), (3, 48, 40), (2, 33, 17)])
+@pytest.mark.parametrize("shape", [(4, 64, 64), (2, 256, 256), (3, 48, 40), (2, 33, 17), (1, 320, 96)])   # X > 256: untiled passes
 def test_velocity_features_vs_oracle(shape):
     """ffno_velocity_fwd (use_velocity features, routines/grid_2d_markov.py:206-220) against the torch.fft oracle:
     square / non-square / odd grids, the 2 pi box and a stretched one, and a strided frame (a preds[..., t] slice)."""
