@@ -20,10 +20,11 @@ import torch.nn as nn
 
 from .. import _ops
 from ..modules.loss import LpLoss
+from .base import RoutineMixin
 from ..modules.normalizer import Normalizer
 
 
-class Grid2DMarkovExperiment(nn.Module):
+class Grid2DMarkovExperiment(RoutineMixin, nn.Module):
     def __init__(self, conv: nn.Module, n_steps: Optional[int] = None, num_freq_bands: int = 8, freq_base: int = 2,
                  low: float = 0, high: float = 1, use_position: bool = True, append_force: bool = False,
                  append_mu: bool = False, max_accumulations: float = 1e6, should_normalize: bool = True,

@@ -6,9 +6,10 @@ import torch
 import torch.nn as nn
 
 from ..modules.loss import LpLoss
+from .base import RoutineMixin
 
 
-class StructuredMeshExperiment(nn.Module):
+class StructuredMeshExperiment(RoutineMixin, nn.Module):
     def __init__(self, model: nn.Module, loss_scale: float = 1.0, **kwargs):
         super().__init__()
         self.model = model

@@ -167,3 +167,33 @@ def test_normalizer_mirror_matches_oracle():
     n.eval()
     assert torch.allclose(n.inverse(y[..., :1], channel=0), x[..., :1], atol=1e-5)
     assert set(n.state_dict()) == {"count", "n_accumulations", "sum", "sum_squared", "one", "std_epsilon"}
+
+
+def test_routine_loads_a_reference_style_lightning_checkpoint(tmp_path):
+    """routines/base.py:79-102: checkpoint['state_dict'] with the reference's key names; the kx/ky/lap buffers of a
+    use_velocity routine are dropped (this backend computes them in ffno_velocity_fwd) and strict is relaxed only then."""
+    from fourierflow_b200.modules import FNOFactorized2DBlock
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+
+    def make(seed):
+        torch.manual_seed(seed)
+        conv = FNOFactorized2DBlock(modes=8, width=32, n_layers=2, input_dim=5, share_weight=True, factor=4,
+                                    ff_weight_norm=True, gain=0.1)
+        return Grid2DMarkovExperiment(conv, n_steps=3, use_velocity=True)
+
+    src, dst = make(0), make(1)
+    src.normalizer.sum += 3.0
+    src.normalizer.count += 7.0
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+    assert "conv.spectral_layers.1.backcast_ff.layers.0.0.weight_g" in sd and "normalizer.sum" in sd and "_float" in sd
+    sd.update({"kx_64": torch.zeros(64, 33), "ky_64": torch.zeros(64, 33), "lap_64": torch.zeros(64, 33, dtype=torch.complex64)})
+    path = tmp_path / "epoch=3.ckpt"
+    torch.save({"state_dict": sd, "epoch": 3}, path)
+    dst.load_lightning_model_state(str(path))
+    for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert torch.equal(a, b), k
+    # without removable keys the load is strict: a missing key must raise
+    bad = {k: v for k, v in src.state_dict().items() if k != "normalizer.sum"}
+    with pytest.raises(RuntimeError, match="normalizer.sum"):
+        make(2).load_lightning_model_state({"state_dict": bad})
+    assert make(3).infer.__func__ is src.infer.__func__ and src.warmup() is None
