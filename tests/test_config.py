@@ -198,3 +198,16 @@ def test_kochkov_routine_with_velocity_features_and_nested_interpolation():
     assert routine.normalizer.sum.shape == (5,)
     with pytest.raises(RuntimeError, match="input_dim"):
         C.load_routine(KOCHKOV_YAML, overrides=["routine.use_velocity=false"])
+
+
+def test_predict_command_parses_a_config_and_refuses_to_run_without_a_gpu(tmp_path, capsys):
+    """python -m fourierflow_b200.predict mirrors commands/predict.py:87-105; without a CUDA device it must stop loudly
+    after building the routine (there is no CPU path to time)."""
+    import torch
+    from fourierflow_b200 import predict
+    cfg = tmp_path / "config.yaml"
+    cfg.write_text(MARKOV_YAML)
+    if torch.cuda.is_available():
+        pytest.skip("covered by the gpu-marked test in test_gpu_parity.py")
+    with pytest.raises(SystemExit, match="no CUDA device"):
+        predict.main([str(cfg), "routine.conv.n_layers=2", "--samples", "4"])

@@ -209,6 +209,22 @@ def test_rollout_with_velocity_features_vs_oracle(grid):
     assert abs(loss.item() - ref["loss"].item()) < 2e-4 * abs(ref["loss"].item())
 
 
+def test_predict_command_reports_the_reference_inference_time(tmp_path, capsys):
+    """python -m fourierflow_b200.predict (commands/predict.py:87-105): config -> routine -> timed infer on synthetic
+    frames; the JSON carries the reference's metric, seconds per sample and simulated time unit."""
+    import json
+    from fourierflow_b200 import predict
+    from test_config import MARKOV_YAML
+    cfg = tmp_path / "config.yaml"
+    cfg.write_text(MARKOV_YAML)
+    assert predict.main([str(cfg), "routine.conv.n_layers=2", "routine.n_steps=3", "--samples", "4", "--grid", "32",
+                         "--frames", "6", "--repeats", "1"]) == 0
+    rec = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert rec["samples"] == 4 and rec["n_steps"] == 3 and rec["inference_time"] > 0
+    with pytest.raises(SystemExit, match="needs 11"):
+        predict.main([str(cfg), "routine.conv.n_layers=2", "--samples", "2", "--grid", "32", "--frames", "6"])
+
+
 def _c2_model(n_layers=24, seed=0):
     torch.manual_seed(seed)
     return M().FNOFactorized2DBlock(modes=16, width=64, n_layers=n_layers, input_dim=3, share_weight=True, factor=4,
