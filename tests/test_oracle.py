@@ -120,3 +120,34 @@ def test_velocity_features_restatement(shape):
     # domain scaling: on a box twice as long the same index-space field has velocities twice as large
     q2, _ = O.velocity_features(w[None, :, :, None], domain=((0, 4 * math.pi), (0, 4 * math.pi)))
     assert (q2 - 2 * q).abs().max() < 1e-10
+
+
+def test_three_pass_bf16_split_error_budget():
+    """The numerics claim behind the tcgen05 path: a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with
+    a_hi = bf16(a), a_lo = bf16(a - a_hi) and FP32 accumulation leaves errors of order 2^-16 |a||b| — two orders
+    below the rtol 1e-4 budget — while a single BF16 pass does not fit in it.  Emulated here on the FeedForward of
+    the C2 layer (64 -> 256 -> 64, ReLU) against float64."""
+    kw, sd, a = load("grid2d_c2arch_32")
+    p = "spectral_layers.0.backcast_ff."
+    w1 = O.weight_norm_fold(sd[p + "layers.0.0.weight_g"], sd[p + "layers.0.0.weight_v"])
+    w2 = O.weight_norm_fold(sd[p + "layers.1.0.weight_g"], sd[p + "layers.1.0.weight_v"])
+    b1, b2 = sd[p + "layers.0.0.bias"], sd[p + "layers.1.0.bias"]
+    x = torch.randn(4096, 64, generator=torch.Generator().manual_seed(0))
+
+    def split(t):
+        hi = t.to(torch.bfloat16).float()
+        return hi, (t - hi).to(torch.bfloat16).float()
+
+    def mm3(u, w):                       # u @ w.T in three BF16 x BF16 -> FP32 passes
+        uh, ul = split(u)
+        wh, wl = split(w)
+        return uh @ wh.T + uh @ wl.T + ul @ wh.T
+
+    ref = torch.relu(x.double() @ w1.double().T + b1.double()) @ w2.double().T + b2.double()
+    y3 = mm3(torch.relu(mm3(x, w1) + b1), w2) + b2
+    y1 = (torch.relu(split(x)[0] @ split(w1)[0].T + b1).to(torch.bfloat16).float() @ split(w2)[0].T) + b2
+    scale = ref.abs().max()
+    e3 = ((y3.double() - ref).abs().max() / scale).item()
+    e1 = ((y1.double() - ref).abs().max() / scale).item()
+    assert e3 < 2e-5, e3                 # ~8e-6 here; measured on the GPU path: <= 7e-6 per layer tap
+    assert e1 > 1e-4, e1                 # single-pass BF16 breaks the budget on one FeedForward already
