@@ -170,6 +170,36 @@ def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed):
     save(name, dict(kwargs, n_steps=n_steps), arrays)
 
 
+def grad_case(M, LpLoss, name, kwargs, shape, seed):
+    """Gradients of the reference's one-step training loss (routines/grid_2d_markov.py:172-193: forecast ->
+    LpLoss against the next frame) w.r.t. the input and every parameter, by the reference's own autograd graph —
+    the pin for the backward row: weight-norm (g, v), shared spectral weights accumulated over
+    layers, complex einsum / rfft / irfft adjoints."""
+    torch.manual_seed(seed)
+    m = M.FNOFactorized2DBlock(**kwargs).train()
+    perturb_(m, seed + 100)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(*shape, generator=g).requires_grad_(True)
+    y = torch.randn(*shape[:-1], 1, generator=g)
+    B = shape[0]
+    arrays = sd_np(m)
+    arrays["x"] = x.detach().numpy()
+    arrays["y"] = y.numpy()
+    forecast = m(x)["forecast"]
+    loss = LpLoss(size_average=True)(forecast.reshape(B, -1), y.reshape(B, -1))
+    loss.backward()
+    arrays["forecast"] = forecast.detach().numpy()
+    arrays["loss"] = loss.detach().numpy()
+    arrays["grad::x"] = x.grad.numpy()
+    seen = set()
+    for k, p_ in m.named_parameters():            # named_parameters de-duplicates the shared ParameterList
+        if id(p_) in seen:
+            continue
+        seen.add(id(p_))
+        arrays["grad::" + k] = p_.grad.detach().numpy()
+    save(name, kwargs, arrays)
+
+
 def init_case(M):
     """Seeded-construction checksums: the mirrors must draw the same random numbers in the same order."""
     cases = {
@@ -200,8 +230,19 @@ def init_case(M):
     print("init_parity.json written")
 
 
+def grad_cases(M, LpLoss):
+    # backward pins: shared weights + weight-norm (C2 architecture, reduced), and unshared weights without weight-norm
+    grad_case(M, LpLoss, "grad_c2arch_16", dict(modes=8, width=64, n_layers=3, input_dim=3, share_weight=True,
+              factor=4, ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0), (2, 16, 16, 3), seed=20)
+    grad_case(M, LpLoss, "grad_unshared_w32", dict(modes=5, width=32, n_layers=2, input_dim=4, share_weight=False,
+              factor=2, ff_weight_norm=False, gain=1), (2, 12, 10, 4), seed=21)
+
+
 def main():
     M, LpLoss = import_reference()
+    if "--only-grad" in sys.argv:
+        grad_cases(M, LpLoss)
+        return
     init_case(M)
     c2 = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4,
               ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0)
@@ -244,6 +285,8 @@ def main():
     # (10) 10-step Markov rollout with Normalizer / LpLoss
     rollout_case(M, LpLoss, "rollout_c2arch_16", dict(c2, n_layers=4, modes=8), B=2, X=16, T=12,
                  n_steps=10, seed=11)
+    # (11) gradients of the one-step training loss (backward row)
+    grad_cases(M, LpLoss)
 
 
 if __name__ == "__main__":

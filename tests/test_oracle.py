@@ -151,3 +151,35 @@ def test_three_pass_bf16_split_error_budget():
     e1 = ((y1.double() - ref).abs().max() / scale).item()
     assert e3 < 2e-5, e3                 # ~8e-6 here; measured on the GPU path: <= 7e-6 per layer tap
     assert e1 > 1e-4, e1                 # single-pass BF16 breaks the budget on one FeedForward already
+
+
+@pytest.mark.parametrize("name", ["grad_c2arch_16", "grad_unshared_w32"])
+def test_oracle_is_differentiable_and_matches_reference_gradients(name):
+    """Backward row groundwork: autograd through the oracle restatement reproduces the gradients the
+    executed reference computes for its one-step training loss (routines/grid_2d_markov.py:172-193) w.r.t. the input
+    and every parameter — weight-norm (g, v) pairs, spectral weights shared over layers, rfft/einsum/irfft adjoints.
+    A CUDA backward can then be checked against ``torch.autograd`` of the oracle at any size."""
+    kw, sd, a = load(name)
+    leaves = {}                         # keep the aliasing of a shared ParameterList: one leaf per distinct tensor
+    for k, v in sd.items():
+        if id(v) not in leaves:
+            leaves[id(v)] = v.clone().requires_grad_(True)
+    p = {k: leaves[id(v)] for k, v in sd.items()}
+    x = a["x"].clone().requires_grad_(True)
+    out = O.block_grid2d_forward(p, x, modes=kw["modes"], n_layers=kw["n_layers"],
+                                 n_ff_layers=kw.get("n_ff_layers", 2), layer_norm=kw.get("layer_norm", False))
+    B = x.shape[0]
+    loss = O.lp_loss_rel(out["forecast"].reshape(B, -1), a["y"].reshape(B, -1))
+    loss.backward()
+    assert rel_err(out["forecast"], a["forecast"]) < TOL
+    assert abs(loss.item() - a["loss"].item()) < 1e-6 * abs(a["loss"].item())
+    assert rel_err(x.grad, a["grad::x"]) < 2e-5
+    checked = 0
+    for k, ref in a.items():
+        if not k.startswith("grad::") or k == "grad::x":
+            continue
+        g = p[k[6:]].grad
+        assert g is not None, k
+        assert rel_err(g, ref) < 2e-5, k
+        checked += 1
+    assert checked >= 10
