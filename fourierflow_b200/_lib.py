@@ -95,6 +95,7 @@ EXPORTS = {
                                      C.c_int32, C.c_void_p]),
     "ffno_debug_timeline": (C.c_int, [C.c_int32, C.c_void_p]),
     "ffno_plan_last_launch_count": (C.c_int64, [C.c_void_p]),
+    "ffno_plan_graph_active": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

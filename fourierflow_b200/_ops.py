@@ -72,6 +72,9 @@ def linear_params(lin: nn.Linear, keep: list) -> _lib.LinearParams:
 def linear_forward(lin: nn.Linear, x: torch.Tensor, relu: bool = False) -> torch.Tensor:
     require_cuda(x, "WNLinear.forward")
     require_inference(lin, x)
+    if x.dim() < 1 or x.shape[-1] != lin.in_features:     # nn.Linear raises; a reshape(-1, in) would reinterpret rows
+        raise RuntimeError(f"WNLinear.forward: last dimension of the input is {tuple(x.shape)[-1:]}, "
+                           f"the layer has in_features={lin.in_features}")
     lib = _lib.load()
     keep: list = []
     with torch.cuda.device(x.device):
@@ -87,6 +90,9 @@ def linear_forward(lin: nn.Linear, x: torch.Tensor, relu: bool = False) -> torch
 
 def layernorm_forward(ln: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
     require_cuda(x, "LayerNorm")
+    if len(ln.normalized_shape) != 1 or x.dim() < 1 or x.shape[-1] != ln.normalized_shape[-1]:
+        raise RuntimeError(f"LayerNorm: input {tuple(x.shape)} does not end in normalized_shape={tuple(ln.normalized_shape)} "
+                           "(the B200 backend normalises the last dimension only)")
     lib = _lib.load()
     with torch.cuda.device(x.device):
         x2 = x.contiguous().reshape(-1, x.shape[-1])
@@ -192,6 +198,11 @@ class StackPlan:
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.ffno_plan_last_launch_count(self._plan))
+
+    @property
+    def graph_active(self) -> bool:
+        """True once the stack forward / rollout of this plan replays a captured CUDA graph."""
+        return bool(self.lib.ffno_plan_graph_active(self._plan))
 
     # ---- parameters ---------------------------------------------------------------------------
     def sync_params(self, params: List[torch.Tensor], in_proj, out, layers: List[LayerSpec]) -> None:

@@ -43,4 +43,13 @@ int set_error(int code, const char* fmt, ...);
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Opt a kernel into `bytes` of dynamic shared memory on the CURRENT device.  The attribute belongs to the
+// (function, device) pair, so what has been granted is remembered per pair, under a mutex: plans on several GPUs of
+// one process each get their opt-in, and concurrent callers do not race (include/ffno_b200.h: re-entrancy).
+int ensure_dynamic_smem(const void* func, size_t bytes);
+template <class... A>
+int ensure_dynamic_smem(void (*kernel)(A...), size_t bytes) {
+  return ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 }  // namespace ffno

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -28,6 +29,20 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(error_buffer(), 512, fmt, ap);
   va_end(ap);
   return code;
+}
+
+int ensure_dynamic_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  int dev = 0;
+  FFNO_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[std::make_pair(func, dev)];
+  if (bytes > have) {
+    FFNO_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return FFNO_OK;
 }
 
 struct Lin {
@@ -88,6 +103,12 @@ struct ffno_plan {
   };
   GraphSlot g_block, g_rollout;
   bool graphs = true;
+  int graph_failures = 0;          // refused captures; graphs are given up after kMaxGraphFailures of them
+  // Capture and replay need a capturable stream.  The legacy default stream (handle 0 — what
+  // torch.cuda.current_stream() is unless the caller opened a side stream) is not, so work arriving on it runs on this
+  // plan-owned non-blocking stream, fenced against the caller's stream with an event on either side.
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   float domain[2] = {6.283185307179586f, 6.283185307179586f};   // periodic domain lengths of the velocity features
 
   // Batch chunking of the stack forward (samples are independent): the batch is cut into chunks of
@@ -429,6 +450,33 @@ int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, con
   return status;
 }
 
+constexpr int kMaxGraphFailures = 3;
+
+bool is_legacy_stream(cudaStream_t st) { return st == nullptr || st == cudaStreamLegacy; }
+
+// The stream the forward actually runs on (see ffno_plan::own_stream), ordered after everything already enqueued on
+// the caller's stream.
+int fence_in(ffno_plan* p, cudaStream_t caller, cudaStream_t* run) {
+  *run = caller;
+  if (!p->graphs || !is_legacy_stream(caller)) return FFNO_OK;
+  if (!p->own_stream) {
+    FFNO_CUDA_CHECK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    FFNO_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+    FFNO_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
+  }
+  FFNO_CUDA_CHECK(cudaEventRecord(p->ev_in, caller));
+  FFNO_CUDA_CHECK(cudaStreamWaitEvent(p->own_stream, p->ev_in, 0));
+  *run = p->own_stream;
+  return FFNO_OK;
+}
+// ... and the caller's stream ordered after the forward.
+int fence_out(ffno_plan* p, cudaStream_t caller, cudaStream_t run) {
+  if (run == caller) return FFNO_OK;
+  FFNO_CUDA_CHECK(cudaEventRecord(p->ev_out, run));
+  FFNO_CUDA_CHECK(cudaStreamWaitEvent(caller, p->ev_out, 0));
+  return FFNO_OK;
+}
+
 // Capture `body` (which only enqueues kernels on `st`) into an executable graph.  Returns false (and leaves the
 // stream usable) if capture is not possible; the caller then launches eagerly.
 template <class Body>
@@ -458,7 +506,7 @@ bool capture_graph(cudaStream_t st, cudaGraphExec_t* exec, int64_t* launches, Bo
 }
 
 // Stack forward on the fixed staging buffers w.io_in -> w.io_out, replayed from a graph when possible.
-int block_fwd_staged(ffno_plan* p, int batch, void* workspace, cudaStream_t st) {
+int block_fwd_staged_on(ffno_plan* p, int batch, void* workspace, cudaStream_t st) {
   const Workspace w = carve(p, batch, workspace);
   ffno_plan::GraphSlot& g = p->g_block;
   if (p->graphs) {
@@ -473,7 +521,7 @@ int block_fwd_staged(ffno_plan* p, int batch, void* workspace, cudaStream_t st) 
         p->last_launches = g.launches;
         return FFNO_OK;
       }
-      p->graphs = false;       // capture refused: stay eager for the life of this plan
+      if (++p->graph_failures >= kMaxGraphFailures) p->graphs = false;   // capture keeps being refused: stay eager
     } else if (g.batch != batch || g.ws != workspace) {
       g.reset();
       g.batch = batch;
@@ -484,6 +532,14 @@ int block_fwd_staged(ffno_plan* p, int batch, void* workspace, cudaStream_t st) 
   const long long before = g_launch_counter;
   const int status = block_fwd_impl(p, w.io_in, batch, w.io_out, nullptr, workspace, st);
   p->last_launches = g_launch_counter - before;
+  return status;
+}
+
+int block_fwd_staged(ffno_plan* p, int batch, void* workspace, cudaStream_t caller) {
+  cudaStream_t run;
+  FFNO_TRY(fence_in(p, caller, &run));
+  const int status = block_fwd_staged_on(p, batch, workspace, run);
+  FFNO_TRY(fence_out(p, caller, run));
   return status;
 }
 
@@ -573,6 +629,9 @@ int ffno_plan_destroy(ffno_plan* plan) {
   if (!plan) return FFNO_OK;
   plan->g_block.reset();
   plan->g_rollout.reset();
+  if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
+  if (plan->ev_in) cudaEventDestroy(plan->ev_in);
+  if (plan->ev_out) cudaEventDestroy(plan->ev_out);
   for (int i = 0; i < 3; ++i) {
     if (plan->aux[i]) cudaStreamDestroy(plan->aux[i]);
     if (plan->ev_join[i]) cudaEventDestroy(plan->ev_join[i]);
@@ -812,7 +871,8 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
   const bool use_velocity = p->d.in_features == 5;
   FFNO_REQUIRE(n_steps >= 1, FFNO_ERR_BAD_ARG, "n_steps=%d", n_steps);
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStream_t caller = static_cast<cudaStream_t>(stream), st;
+  FFNO_TRY(fence_in(p, caller, &st));
   const int X = p->d.size[0], Y = p->d.size[1];
   const Workspace w = carve(p, batch, workspace);
   char* base = static_cast<char*>(workspace);
@@ -860,7 +920,7 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
         FFNO_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
         p->last_launches = g.launches;
         done = true;
-      } else {
+      } else if (++p->graph_failures >= kMaxGraphFailures) {
         p->graphs = false;
       }
     } else if (!same) {
@@ -875,7 +935,7 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
     p->last_launches = g_launch_counter - before;
   }
   FFNO_CUDA_CHECK(cudaMemcpyAsync(preds, preds_st, frame_b * n_steps, cudaMemcpyDeviceToDevice, st));
-  return FFNO_OK;
+  return fence_out(p, caller, st);
 }
 
 int ffno_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int32_t N, int32_t K, int32_t a_mn,
@@ -915,5 +975,9 @@ int ffno_velocity_fwd(const float* w, int64_t stride_b, int64_t stride_xy, int32
 }
 
 int64_t ffno_plan_last_launch_count(const ffno_plan* plan) { return plan ? plan->last_launches : 0; }
+
+int ffno_plan_graph_active(const ffno_plan* plan) {
+  return plan && (plan->g_block.exec || plan->g_rollout.exec) ? 1 : 0;
+}
 
 }  // extern "C"

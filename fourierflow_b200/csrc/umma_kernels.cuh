@@ -14,10 +14,6 @@ int launch_pack_ff_image(const float* w1t, const float* w2t, uint8_t* image, cud
 // Wblk [K][128][128] (real block form of the complex mode weights) -> K images of kMixImageBytes
 int launch_pack_mix_image(const float* wblk, uint8_t* image, int K, cudaStream_t st);
 
-// x_out[p] = residual[p] + W2 relu(W1 s[p] + b1) + b2,  b_out[p] = the FF output (either may be NULL)
-int launch_ff_umma(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,
-                   const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st);
-
 // Per-mode complex channel mix of one or more axes in one launch.
 struct MixAxis {
   const float* F;
@@ -26,7 +22,6 @@ struct MixAxis {
   long long outer, p_inner;
   int K;
 };
-int launch_mix_umma(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st);
 
 // Truncated real DFT along a strided axis on tcgen05 (forward and inverse are the same product with a
 // different table):   Y[o][j][inner] (+)= sum_i T[i][j] * X[o][i][inner],   inner % 64 == 0, n_out <= 256
@@ -42,19 +37,16 @@ struct AxisXform {
 size_t table_image_bytes(int n_in, int n_out);
 int launch_pack_table_image(const float* T /*[n_in][ldt]*/, int ldt, int n_in, int n_out, uint8_t* image,
                             cudaStream_t st);
-int launch_axis_umma(const AxisXform& p, int sm_count, cudaStream_t st);
 
-// Warp-specialised, double-buffered versions (umma_pipelined.cu): same arithmetic, loads / MMAs / epilogues overlap.
+// Warp-specialised, double-buffered kernels (umma_pipelined.cu): loads / MMAs / epilogues overlap.
 bool axis_pipe_fits(int n_in, int n_out);
 // `reverse`: walk the tiles last-to-first.  Consecutive launches of the layer loop alternate the direction so that a
 // kernel starts with the data its predecessor wrote LAST (still resident in the 126 MB L2) instead of re-streaming it
 // in the producer's order, which is the LRU worst case for a ~100 MB working set.
 int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse = false);
 int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse = false);
-int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,
-                   const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st);
 
-// v3 FF: hidden activations staged in tensor memory (TS-mode GEMM2), coalesced output through a smem staging tile,
+// FF: hidden activations staged in tensor memory (TS-mode GEMM2), coalesced output through a smem staging tile,
 // loader sums up to three spectral partial outputs (s1 / s2 may be NULL).
 // head_w/head_b/forecast (optional): fused folded 1-output head on the FF output, forecast[p] = <b_p, head_w> + head_b.
 int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float* residual, float* x_out, float* b_out,
@@ -62,7 +54,7 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
                  const float* head_w = nullptr, const float* head_b = nullptr, float* forecast = nullptr,
                  bool reverse = false);
 
-// Diagnostics: in-kernel clock64 timeline of block 0 of ff_pipe_kernel ([role 8][tile 16][event 8]).
+// Diagnostics: in-kernel clock64 timeline of block 0 of ff_ts_kernel ([role 8][tile 16][event 8]).
 int debug_timeline(int enable, long long* host_out);
 
 // Diagnostics: D[128][N] = A[128][K] * B[N][K]^T with bf16 inputs (raw ushort), one CTA, every layout variant

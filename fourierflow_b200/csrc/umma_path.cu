@@ -1,9 +1,10 @@
 // tcgen05 (UMMA) fast path of the F-FNO layer for width 64 / FF factor 4: state, parameter images, dispatch.
 //
-// v1 pipeline per layer (2-D: 7 launches):
-//   per axis:  truncated forward DFT (FP32 table kernel)  ->  per-mode complex mix on tcgen05 (3xBF16)
-//              ->  truncated inverse DFT accumulated into s (FP32 table kernel)
-//   then:      FeedForward + residual on tcgen05 (3xBF16, hidden activations never leave the SM)
+// Per layer (fast path, every axis on the pipelined kernels): all forward transforms -> all mode mixes -> all inverse
+// transforms (one output per axis) -> FeedForward (+ sum over axes, + residual), 4 launches; or the same stages as
+// persistent, flag-synchronised roles launched once per forward (umma_persistent.cu).  An axis whose DFT table does
+// not fit the pipelined transform kernel (n_out > 256 or a table image beyond shared memory) runs that transform on
+// the FP32 table kernel of generic_kernels.cu; its mix still runs on tcgen05.
 #include <cstdlib>
 #include <map>
 #include <vector>
@@ -32,17 +33,13 @@ struct UmmaState {
   std::map<const void*, uint8_t*> ff_cache;
   float* d_fwd[3] = {nullptr, nullptr, nullptr};
   float* d_inv[3] = {nullptr, nullptr, nullptr};
-  bool v1 = false;                                       // FFNO_UMMA_V1=1: non-pipelined kernels (cross-check)
-  bool ff_v2 = false;                                    // FFNO_FF_V2=1: FF with hidden activations in smem (A/B)
   bool zigzag = true;                                    // FFNO_ZIGZAG=0: every kernel walks its tiles first-to-last
   uint8_t* fwd_image[3] = {nullptr, nullptr, nullptr};   // tcgen05 table images (NULL -> FP32 table kernel)
   uint8_t* inv_image[3] = {nullptr, nullptr, nullptr};
 };
 
 static int pad16i(int n) { return (n + 15) / 16 * 16; }
-static bool axis_fits_umma(int n_in, int n_out) {
-  return n_out <= 256 && 32768 + 1024 + table_image_bytes(n_in, n_out) <= (size_t)227 * 1024;
-}
+static bool axis_fits_umma(int n_in, int n_out) { return axis_pipe_fits(n_in, n_out); }
 
 const char* umma_why_not(const ffno_desc* d, const int*) {
   if (d->width != kUmmaC) return "width != 64";
@@ -69,10 +66,6 @@ int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]) {
                      prop.minor);
   }
   s->sm_count = s->hw_sm_count = prop.multiProcessorCount;
-  const char* v1 = getenv("FFNO_UMMA_V1");
-  s->v1 = v1 && v1[0] == '1';
-  const char* v2 = getenv("FFNO_FF_V2");
-  s->ff_v2 = v2 && v2[0] == '1';
   const char* zz = getenv("FFNO_ZIGZAG");
   s->zigzag = !(zz && zz[0] == '0');
   s->layers.resize(d->n_layers);
@@ -164,29 +157,36 @@ static void axis_geom(const UmmaState* s, int batch, int a, long long* outer, lo
   for (int i = a + 1; i < s->d.ndim; ++i) *p_inner *= s->ext[i];
 }
 
-static int spectral_v1(UmmaState* s, const UmmaLayer& L, const float* x, int batch, float* s_out, float* F, float* R,
-                       cudaStream_t st) {
+// Summed spectral operator, one axis after the other (reference order: last axis first, grid_2d.py:57,75): used when
+// a caller wants the sum materialised (taps, the standalone ffno_spectral_fwd) or an axis does not fit the pipelined
+// transform kernel.
+int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R, float*,
+                      cudaStream_t st) {
+  const UmmaLayer& L = s->layers[layer];
+  const bool full = s->d.spectral_mode == FFNO_MODE_FULL;
   bool first = true;
   for (int a = s->d.ndim - 1; a >= 0; --a) {
     long long outer, p_inner;
     axis_geom(s, batch, a, &outer, &p_inner);
     const int Ln = s->ext[a], K = s->d.modes[a];
     const long long inner = p_inner * kUmmaC;
+    float* Fa = F + spec_offset(s, batch, a);
+    float* Ra = R + spec_offset(s, batch, a);
     if (s->fwd_image[a]) {
-      AxisXform t{x, F, s->fwd_image[a], outer, inner, Ln, 2 * K, pad16i(2 * K), (Ln + 63) / 64, 0};
-      FFNO_TRY(launch_axis_umma(t, s->sm_count, st));
+      AxisXform t{x, Fa, s->fwd_image[a], outer, inner, Ln, 2 * K, pad16i(2 * K), (Ln + 63) / 64, 0};
+      FFNO_TRY(launch_axis_pipe(&t, 1, s->sm_count, st));
     } else {
-      FFNO_TRY(launch_axis_transform(x, s->d_fwd[a], F, outer, Ln, 2 * K, inner, false, st));
+      FFNO_TRY(launch_axis_transform(x, s->d_fwd[a], Fa, outer, Ln, 2 * K, inner, false, st));
     }
-    const float* src = F;
-    if (s->d.spectral_mode == FFNO_MODE_FULL) {
-      MixAxis ax{F, R, L.mix_image[a], outer, p_inner, K};
-      FFNO_TRY(launch_mix_umma(&ax, 1, s->sm_count, st));
-      src = R;
+    const float* src = Fa;
+    if (full) {
+      MixAxis ax{Fa, Ra, L.mix_image[a], outer, p_inner, K};
+      FFNO_TRY(launch_mix_pipe(&ax, 1, s->sm_count, st));
+      src = Ra;
     }
     if (s->inv_image[a]) {
       AxisXform t{src, s_out, s->inv_image[a], outer, inner, 2 * K, Ln, pad16i(Ln), (2 * K + 63) / 64, first ? 0 : 1};
-      FFNO_TRY(launch_axis_umma(t, s->sm_count, st));
+      FFNO_TRY(launch_axis_pipe(&t, 1, s->sm_count, st));
     } else {
       FFNO_TRY(launch_axis_transform(src, s->d_inv[a], s_out, outer, 2 * K, Ln, inner, !first, st));
     }
@@ -195,51 +195,11 @@ static int spectral_v1(UmmaState* s, const UmmaLayer& L, const float* x, int bat
   return FFNO_OK;
 }
 
-// Pipelined path: all forward transforms in one launch, all mode mixes in one launch, then one inverse launch per
-// axis (the second and third accumulate into s).
-int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R, float*,
-                      cudaStream_t st) {
-  const UmmaLayer& L = s->layers[layer];
-  bool all_umma = true;
-  for (int a = 0; a < s->d.ndim; ++a)
-    all_umma &= (s->fwd_image[a] != nullptr) && (s->inv_image[a] != nullptr) &&
-                axis_pipe_fits(s->ext[a], 2 * s->d.modes[a]) && axis_pipe_fits(2 * s->d.modes[a], s->ext[a]);
-  if (s->v1 || !all_umma) return spectral_v1(s, L, x, batch, s_out, F, R, st);
-
-  AxisXform fwd[3];
-  MixAxis mix[3];
-  for (int a = 0; a < s->d.ndim; ++a) {
-    long long outer, p_inner;
-    axis_geom(s, batch, a, &outer, &p_inner);
-    const int Ln = s->ext[a], K = s->d.modes[a];
-    float* Fa = F + spec_offset(s, batch, a);
-    float* Ra = R + spec_offset(s, batch, a);
-    fwd[a] = AxisXform{x, Fa, s->fwd_image[a], outer, p_inner * kUmmaC, Ln, 2 * K, pad16i(2 * K), (Ln + 63) / 64, 0};
-    mix[a] = MixAxis{Fa, Ra, L.mix_image[a], outer, p_inner, K};
-  }
-  FFNO_TRY(launch_axis_pipe(fwd, s->d.ndim, s->sm_count, st));
-  const bool full = s->d.spectral_mode == FFNO_MODE_FULL;
-  if (full) FFNO_TRY(launch_mix_pipe(mix, s->d.ndim, s->sm_count, st));
-  bool first = true;
-  for (int a = s->d.ndim - 1; a >= 0; --a) {
-    long long outer, p_inner;
-    axis_geom(s, batch, a, &outer, &p_inner);
-    const int Ln = s->ext[a], K = s->d.modes[a];
-    const float* src = (full ? R : F) + spec_offset(s, batch, a);
-    AxisXform inv{src, s_out, s->inv_image[a], outer, p_inner * kUmmaC, 2 * K, Ln, pad16i(Ln), (2 * K + 63) / 64, first ? 0 : 1};
-    FFNO_TRY(launch_axis_pipe(&inv, 1, s->sm_count, st));
-    first = false;
-  }
-  return FFNO_OK;
-}
-
 // Per-axis spectral outputs (no accumulation): s_axis[a] receives the inverse transform of axis a; the FF loader sums
 // them.  3 launches per layer: all forward transforms, all mode mixes, all inverse transforms.
 static bool all_axes_pipe(const UmmaState* s) {
-  bool ok = !s->v1;
-  for (int a = 0; a < s->d.ndim; ++a)
-    ok &= (s->fwd_image[a] != nullptr) && (s->inv_image[a] != nullptr) && axis_pipe_fits(s->ext[a], 2 * s->d.modes[a]) &&
-          axis_pipe_fits(2 * s->d.modes[a], s->ext[a]);
+  bool ok = true;
+  for (int a = 0; a < s->d.ndim; ++a) ok &= (s->fwd_image[a] != nullptr) && (s->inv_image[a] != nullptr);
   return ok;
 }
 
@@ -283,15 +243,13 @@ int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residua
   for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
   float* xo = residual ? y : nullptr;
   float* bo = residual ? nullptr : y;
-  if (s->v1) return launch_ff_umma(s_in, residual, xo, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
-  if (s->ff_v2) return launch_ff_pipe(s_in, residual, xo, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
   return launch_ff_ts(s_in, nullptr, nullptr, residual, xo, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
 }
 
 bool umma_can_fuse_head(const UmmaState* s, bool want_s) {
   bool nopad = true;
   for (int a = 0; a < s->d.ndim; ++a) nopad &= s->d.pad[a] == 0;
-  return !want_s && !s->v1 && !s->ff_v2 && all_axes_pipe(s) && s->d.out_features == 1 && nopad && !s->d.use_fork;
+  return !want_s && all_axes_pipe(s) && s->d.out_features == 1 && nopad && !s->d.use_fork;
 }
 
 int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_next, float* s_out, float* b_out,
@@ -300,7 +258,7 @@ int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_
   long long P = batch;
   for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
   float* bo = want_b ? b_out : nullptr;
-  if (!want_s && !s->ff_v2 && all_axes_pipe(s)) {
+  if (!want_s && all_axes_pipe(s)) {
     // fast path: per-axis inverse outputs s_out (axis 0) and ws + (a-1) * U (axes 1, 2), summed by the FF loader
     const size_t U = (size_t)P * kUmmaC;
     float* s_axis[3] = {s_out, ws, ws + U};
@@ -311,8 +269,6 @@ int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_
                         head ? head->forecast : nullptr, s->zigzag);
   }
   FFNO_TRY(umma_spectral_fwd(s, layer, x, batch, s_out, F, R, ws, st));
-  if (s->v1) return launch_ff_umma(s_out, x, x_next, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
-  if (s->ff_v2) return launch_ff_pipe(s_out, x, x_next, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
   return launch_ff_ts(s_out, nullptr, nullptr, x, x_next, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
 }
 

@@ -6,8 +6,6 @@
 //   warps 5-8  loaders    (coalesced FP32 global loads -> BF16 hi/lo split -> swizzled operand tiles in smem)
 // Operand tiles in shared memory and accumulators in tensor memory are double-buffered and handed over with
 // full/empty mbarriers, so the global loads of tile t+1, the MMAs of tile t and the epilogue of tile t-1 overlap.
-// (The v1 kernels in umma_kernels.cu do the same arithmetic with one warpgroup and no overlap; they stay as the
-// cross-check, selectable with FFNO_UMMA_V1=1.)
 #include <type_traits>
 
 #include "umma.cuh"
@@ -429,11 +427,7 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
     max_tiles = set.n_tiles[a] > max_tiles ? set.n_tiles[a] : max_tiles;
   }
   if (max_tiles == 0) return FFNO_OK;
-  static size_t configured = 0;
-  if (smem > configured) {
-    FFNO_CUDA_CHECK(cudaFuncSetAttribute(axis_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  FFNO_TRY(ensure_dynamic_smem(axis_pipe_kernel, smem));
   int per_axis = sm_count / n_axes;
   if (per_axis < 1) per_axis = 1;
   const int gx = max_tiles < per_axis ? max_tiles : per_axis;
@@ -648,11 +642,7 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
 
 int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse) {
   FFNO_REQUIRE(n_axes >= 1 && n_axes <= 3, FFNO_ERR_BAD_ARG, "mix_pipe: n_axes=%d", n_axes);
-  static bool configured = false;
-  if (!configured) {
-    FFNO_CUDA_CHECK(cudaFuncSetAttribute(mix_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MXP_TOTAL));
-    configured = true;
-  }
+  FFNO_TRY(ensure_dynamic_smem(mix_pipe_kernel, MXP_TOTAL));
   MixSet set;
   set.reverse = reverse ? 1 : 0;
   int maxK = 0, total_modes = 0;
@@ -681,245 +671,7 @@ int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t 
 }
 
 // =======================================================================================================
-// FeedForward + residual, pipelined:
-//   G1 (two halves of 128 hidden units, N=128)  ->  epilogue-1 per 64-column chunk (+b1, ReLU, split -> A2[2 stages])
-//   G2 per chunk (N=64, accumulating into D2[2 stages])  ->  final epilogue (+b2, +residual, store)
-// =======================================================================================================
-constexpr int FFP_W = 0;                           // 128 KB image
-constexpr int FFP_A1 = 131072;                     // hi 16 | lo 16
-constexpr int FFP_A2 = FFP_A1 + 32768;             // 2 stages x (hi 16 | lo 16)
-constexpr int FFP_BIAS = FFP_A2 + 65536;           // 229376
-constexpr int FFP_BAR = FFP_BIAS + 320 * 4;        // 230656
-constexpr int FFP_TOTAL = FFP_BAR + 160;           // 230816 <= 232448
-
-// Roles (17 warps): 0-3 / 4-7 two chunk-epilogue teams (team t turns the odd/even 64-column chunks of D1 into the
-// A2 stage t: +b1, ReLU, BF16 hi/lo split), 8-11 store warps (prefetch the residual rows, then D2 + b2 + residual ->
-// global), 12 MMA issuer, 13-16 loaders (s tile -> A1, next tile's loads in flight in registers).
-// The per-element epilogue arithmetic (~7 instructions) is what bounds this kernel, hence 12 of 17 warps do it.
-constexpr int kFFThreads = 544;
-constexpr int kFFMmaWarp = 12;
-constexpr int kFFLoaderThread0 = 416;
-
-__global__ void __launch_bounds__(kFFThreads, 1)
-ff_pipe_kernel(const float* __restrict__ s, const float* __restrict__ residual, float* __restrict__ x_out,
-               float* __restrict__ b_out, const uint8_t* __restrict__ image, const float* __restrict__ b1,
-               const float* __restrict__ b2, long long P, int n_tiles) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  float* sb1 = reinterpret_cast<float*>(smem + FFP_BIAS);
-  float* sb2 = sb1 + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FFP_BAR);
-  uint64_t* a1_full = bars;        // count 128 (loaders)
-  uint64_t* a1_empty = bars + 1;   // commit
-  uint64_t* d1_full = bars + 2;    // [2] commit
-  uint64_t* d1_empty = bars + 4;   // [2] 256 (both chunk-epilogue teams)
-  uint64_t* a2_full = bars + 6;    // [2] 128 (team t)
-  uint64_t* a2_empty = bars + 8;   // [2] commit
-  uint64_t* d2_full = bars + 10;   // [2] commit
-  uint64_t* d2_empty = bars + 12;  // [2] 128 (store warps)
-  uint64_t* bar_w = bars + 14;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    mbar_init(a1_full, 128);
-    mbar_init(a1_empty, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&d1_full[i], 1);
-      mbar_init(&d1_empty[i], 256);
-      mbar_init(&a2_full[i], 128);
-      mbar_init(&a2_empty[i], 1);
-      mbar_init(&d2_full[i], 1);
-      mbar_init(&d2_empty[i], 128);
-    }
-    mbar_init(bar_w, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  for (int i = tid; i < 256; i += kFFThreads) sb1[i] = b1 ? b1[i] : 0.f;
-  if (tid < 64) sb2[tid] = b2 ? b2[tid] : 0.f;
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  // TMEM columns: D1 half h at h*128 (128 cols each), D2 stage t at 256 + t*64
-  const uint32_t sW1h = smem_u32(smem + FFP_W), sW1l = sW1h + 32768u, sW2h = sW1h + 65536u, sW2l = sW1h + 98304u;
-
-  if (warp < 8) {
-    // ---------------------------------------------------------------- chunk epilogue teams (thread = row)
-    const int team = warp >> 2, rt = tid & 127;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint8_t* sA2h = smem + FFP_A2 + team * 32768;
-    uint8_t* sA2l = sA2h + 16384;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int j = 2 * h + team;              // this team's chunk of D1 half h: columns team*64 .. +63
-        const int q = 2 * n + h;                 // running index of this team's chunks (A2 stage = team)
-        mbar_wait(&d1_full[h], (uint32_t)n & 1u);
-        tc_fence_after();
-        if (warp == 0) TL(0, n, h == 0 ? 0 : 4);
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + team * 64), v0);
-        tmem_ld32(tmem + lane_base + (uint32_t)(h * 128 + team * 64 + 32), v1);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&d1_empty[h]);
-        if (warp == 0) TL(0, n, h == 0 ? 1 : 5);
-        mbar_wait(&a2_empty[team], ((uint32_t)q & 1u) ^ 1u);
-        if (warp == 0) TL(0, n, h == 0 ? 2 : 6);
-        const float* bj = sb1 + j * 64;
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int col = cc * 8 + e * 2;
-            float a = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]) + bj[col];
-            float b = __uint_as_float(col + 1 < 32 ? v0[col + 1] : v1[col + 1 - 32]) + bj[col + 1];
-            split2(fmaxf(a, 0.f), fmaxf(b, 0.f), hi[e], lo[e]);
-          }
-          const uint32_t off = (uint32_t)rt * 128u + (uint32_t)((cc ^ (rt & 7)) << 4);
-          *reinterpret_cast<uint4*>(sA2h + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(sA2l + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&a2_full[team]);
-        if (warp == 0) TL(0, n, h == 0 ? 3 : 7);
-      }
-    }
-  } else if (warp < 12) {
-    // ---------------------------------------------------------------- store warps (thread = row)
-    const int rt = tid - 256;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      const long long row = (long long)tile * 128 + rt;
-      const bool live = row < P;
-      if (warp == 8) TL(1, n, 0);
-      float4 r[16];
-      if (residual && live) {              // issued before the accumulator is ready: latency hides behind the MMAs
-#pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) r[c4] = ldg_stream(residual + row * 64 + c4 * 4);
-      } else {
-#pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) r[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      const int ds = n & 1;
-      mbar_wait(&d2_full[ds], (uint32_t)(n >> 1) & 1u);
-      tc_fence_after();
-      if (warp == 8) TL(1, n, 1);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld32(tmem + lane_base + (uint32_t)(256 + ds * 64 + half * 32), v);
-        tmem_ld_wait();
-        if (warp == 8 && half == 0) TL(1, n, 2);
-        if (half == 1) {
-          tc_fence_before();
-          mbar_arrive(&d2_empty[ds]);
-        }
-        if (live) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c4 = half * 8 + e;
-            float4 b;
-            b.x = __uint_as_float(v[e * 4 + 0]) + sb2[c4 * 4 + 0];
-            b.y = __uint_as_float(v[e * 4 + 1]) + sb2[c4 * 4 + 1];
-            b.z = __uint_as_float(v[e * 4 + 2]) + sb2[c4 * 4 + 2];
-            b.w = __uint_as_float(v[e * 4 + 3]) + sb2[c4 * 4 + 3];
-            if (b_out) *reinterpret_cast<float4*>(b_out + row * 64 + c4 * 4) = b;
-            if (x_out) {
-              float4 o = make_float4(b.x + r[c4].x, b.y + r[c4].y, b.z + r[c4].z, b.w + r[c4].w);
-              *reinterpret_cast<float4*>(x_out + row * 64 + c4 * 4) = o;
-            }
-          }
-        }
-      }
-      if (warp == 8) TL(1, n, 3);
-    }
-  } else if (warp == kFFMmaWarp) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      mbar_expect_tx(bar_w, 131072);
-      for (int i = 0; i < 4; ++i) bulk_g2s(smem + FFP_W + i * 32768, image + i * 32768, 32768, bar_w);
-      mbar_wait(bar_w, 0);
-      constexpr uint32_t IDESC_G1 = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t IDESC_G2 = make_idesc_bf16(128, 64, 0, 0);
-      // every operand descriptor of the tile loop, built once
-      const uint64_t dA1h = desc_kmajor(smem_u32(smem + FFP_A1), 0), dA1l = desc_kmajor(smem_u32(smem + FFP_A1) + 16384u, 0);
-      const uint64_t dW1h = desc_kmajor(sW1h, 0), dW1l = desc_kmajor(sW1l, 0);
-      const uint64_t dW2h = desc_kmajor(sW2h, 0), dW2l = desc_kmajor(sW2l, 0);
-      const uint64_t dA2h0 = desc_kmajor(smem_u32(smem + FFP_A2), 0), dA2l0 = desc_kmajor(smem_u32(smem + FFP_A2) + 16384u, 0);
-      constexpr uint64_t kStage = 32768 >> 4, kHalf = 16384 >> 4, kBlk = 8192 >> 4;   // descriptor address units (16 B)
-      int n = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-        mbar_wait(a1_full, (uint32_t)n & 1u);
-        TL(2, n, 0);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&d1_empty[h], ((uint32_t)n & 1u) ^ 1u);
-          tc_fence_after();
-          issue3_kmajor<4>(tmem + (uint32_t)(h * 128), dA1h, dA1l, dW1h + h * kHalf, dW1l + h * kHalf, IDESC_G1, 0u);
-          umma_commit(&d1_full[h]);
-        }
-        umma_commit(a1_empty);
-        TL(2, n, 1);
-        const int ds = n & 1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int team = j & 1, q = 2 * n + (j >> 1);
-          mbar_wait(&a2_full[team], (uint32_t)q & 1u);
-          if (j == 0) mbar_wait(&d2_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
-          tc_fence_after();
-          TL(2, n, 2 + j);
-          issue3_kmajor<4>(tmem + (uint32_t)(256 + ds * 64), dA2h0 + team * kStage, dA2l0 + team * kStage, dW2h + j * kBlk,
-                           dW2l + j * kBlk, IDESC_G2, j > 0 ? 1u : 0u);
-          umma_commit(&a2_empty[team]);
-        }
-        umma_commit(&d2_full[ds]);
-        TL(2, n, 6);
-      }
-    }
-    __syncwarp();
-  } else {
-    // ---------------------------------------------------------------- loaders: s tile -> A1
-    const int lt = tid - kFFLoaderThread0;
-    uint8_t* sA1h = smem + FFP_A1;
-    uint8_t* sA1l = sA1h + 16384;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      const long long row0 = (long long)tile * 128;
-      if (lt < 32) TL(3, n, 0);
-      float4 v[16];
-#pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
-        v[it] = (row0 + r < P) ? ldg_stream(s + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      mbar_wait(a1_empty, ((uint32_t)n & 1u) ^ 1u);
-      if (lt < 32) TL(3, n, 1);
-#pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int idx = it * 128 + lt, r = idx >> 4, c4 = idx & 15;
-        store_split4_at(sA1h, sA1l, kmajor_sw128_offset(r, c4 * 4), v[it]);
-      }
-      if (lt < 32) TL(3, n, 2);
-      fence_proxy_async_smem();
-      mbar_arrive(a1_full);
-      if (lt < 32) TL(3, n, 3);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-// =======================================================================================================
-// FeedForward + residual, v3: the hidden activations never touch shared memory.
+// FeedForward + residual: the hidden activations never touch shared memory.
 //   G1   : D1[128 x 256] = A1 (smem, 2 stages) x W1 (smem)                       (SS, N = 128 halves)
 //   epi  : D1 chunk -> +b1, ReLU, BF16 hi/lo -> tcgen05.st into TMEM operand stage A2[team]
 //   G2   : D2[128 x 64] += A2 (TMEM) x W2 (smem)                                  (TS: A operand from tensor memory)
@@ -1299,11 +1051,7 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
                  const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st,
                  const float* head_w, const float* head_b, float* forecast, bool reverse) {
   if (P == 0) return FFNO_OK;
-  static bool configured = false;
-  if (!configured) {
-    FFNO_CUDA_CHECK(cudaFuncSetAttribute(ff_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF3_TOTAL));
-    configured = true;
-  }
+  FFNO_TRY(ensure_dynamic_smem(ff_ts_kernel, FF3_TOTAL));
   const int n_tiles = ceil_div(P, 128);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
   FFNO_CUDA_CHECK(launch_pdl(ff_ts_kernel, dim3(grid), dim3(kFF3Threads), (size_t)FF3_TOTAL, st, s0, s1, s2, residual, x_out,
@@ -1319,22 +1067,6 @@ int debug_timeline(int enable, long long* host_out /*[1024] or NULL*/) {
     FFNO_CUDA_CHECK(cudaMemcpyToSymbol(g_timeline, zero, sizeof(zero)));
     FFNO_CUDA_CHECK(cudaMemcpyToSymbol(g_timeline_on, &enable, sizeof(int)));
   }
-  return FFNO_OK;
-}
-
-int launch_ff_pipe(const float* s, const float* residual, float* x_out, float* b_out, const uint8_t* image,
-                   const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st) {
-  if (P == 0) return FFNO_OK;
-  static bool configured = false;
-  if (!configured) {
-    FFNO_CUDA_CHECK(cudaFuncSetAttribute(ff_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFP_TOTAL));
-    configured = true;
-  }
-  const int n_tiles = ceil_div(P, 128);
-  const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  ff_pipe_kernel<<<grid, kFFThreads, FFP_TOTAL, st>>>(s, residual, x_out, b_out, image, b1, b2, P, n_tiles);
-  ++g_launch_counter;
-  FFNO_LAUNCH_CHECK("ff_pipe_kernel");
   return FFNO_OK;
 }
 

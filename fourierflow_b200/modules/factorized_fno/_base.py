@@ -26,15 +26,41 @@ class PlanCacheMixin:
         return d
 
     def _flat_params(self):
-        """Parameter list in registration order, cached: walking a 24-layer module tree on every forward costs more
-        than the launch of the CUDA graph.  The Parameter objects survive load_state_dict / .cuda() / in-place
-        updates (their storage pointer and version counter are what StackPlan.sync_params watches)."""
+        """Distinct parameters of the module tree, cached — walking a 24-layer tree with ``parameters()`` on every
+        forward costs more than launching the CUDA graph.  The cache is re-validated on every call by identity: each
+        cached Parameter must still be the object registered under its owner's name and each owner must still have
+        the same children, so ``load_state_dict(..., assign=True)``, ``.to()`` / ``_apply`` replacements, swapped
+        sub-modules and added layers are all picked up (the reference re-folds weight-norm from the live parameters
+        on every forward, linear.py:49).  In-place edits through ``p.data`` bump no version counter and cannot be seen
+        from here: call ``invalidate_plans()`` after such an edit."""
         cached = self.__dict__.get("_param_cache")
-        n = sum(1 for _ in self.parameters()) if cached is None else None
-        if cached is None or len(cached) != (n if n is not None else len(cached)):
-            cached = list(self.parameters())
-            self.__dict__["_param_cache"] = cached
-        return cached
+        if cached is not None:
+            owners, children, params = cached
+            if all(mod._parameters.get(name) is p for mod, name, p in owners) and \
+                    all(len(kids) == len(mod._modules) and all(a is b for a, b in zip(kids, mod._modules.values()))
+                        for mod, kids in children):
+                return params
+        owners, children, params, seen = [], [], [], set()
+        for mod in self.modules():
+            children.append((mod, tuple(mod._modules.values())))
+            for name, p in mod._parameters.items():
+                if p is None:
+                    continue
+                owners.append((mod, name, p))
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    params.append(p)
+        self.__dict__["_param_cache"] = (owners, children, params)
+        self.__dict__.pop("_spec_cache", None)          # layer specs hold Parameter references too
+        return params
+
+    def invalidate_plans(self) -> None:
+        """Force the next forward to re-read, re-fold and re-pack every parameter (needed only after in-place edits
+        through ``p.data``, which no version counter records)."""
+        self.__dict__.pop("_param_cache", None)
+        self.__dict__.pop("_spec_cache", None)
+        for plan in self._plans().values():
+            plan._version_key = None
 
     def __deepcopy__(self, memo):
         # plans hold raw device pointers of THIS module's parameters: never share them with a copy

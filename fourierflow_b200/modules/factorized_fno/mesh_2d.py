@@ -108,11 +108,12 @@ class FNOFactorizedMesh2D(PlanCacheMixin, nn.Module):
             in_features=self.input_dim - 2, append_grid=True, out_features=1, head_hidden=128,
             n_layers=self.n_layers, ff_factor=self.factor, n_ff_layers=self.n_ff_layers,
             layer_norm=self.layer_norm, use_fork=False, mode='full', path=path or default_path())
+        params = self._flat_params()                   # validates the caches first (may drop a stale _spec_cache)
         specs = self.__dict__.get("_spec_cache")
         if specs is None:
             specs = [layer.layer_spec() for layer in self.spectral_layers]
             self.__dict__["_spec_cache"] = specs
-        plan.sync_params(self._flat_params(), self.in_proj, self.out, specs)
+        plan.sync_params(params, self.in_proj, self.out, specs)
         return plan
 
     def forward(self, x):

@@ -93,6 +93,9 @@ class Grid2DMarkovExperiment(RoutineMixin, nn.Module):
         _ops.require_cuda(data, "Grid2DMarkovExperiment")
         B, X, Y, T = data.shape
         n_steps = n_steps or self.n_steps or T - 1
+        if not 1 <= n_steps <= T - 1:      # a negative frame index below would silently wrap to the end of the series
+            raise RuntimeError(f"Grid2DMarkovExperiment: a {n_steps}-step rollout needs {n_steps + 1} frames, "
+                               f"data has T={T}")
         plan = self.conv.plan_for(data.device, (X, Y))
         mean, std = self._mean_std()
         frame0 = data[..., T - n_steps - 1].contiguous()
@@ -113,4 +116,6 @@ class Grid2DMarkovExperiment(RoutineMixin, nn.Module):
         losses = self.per_sample_losses(preds, data)            # [n_steps, B]
         step_losses = list(losses.mean(dim=1))                  # LpLoss(size_average) per step (:313)
         loss = losses.mean(dim=1).sum()                         # loss += l (:315)
-        return loss, step_losses, preds, []
+        # one (empty) per-layer forecast list per step, as `pred_layer_list.append(out['forecast_list'])` builds it for
+        # a conv without use_fork (grid_2d_markov.py:320-321)
+        return loss, step_losses, preds, [[] for _ in range(preds.shape[-1])]

@@ -233,6 +233,13 @@ FFNO_API int ffno_debug_timeline(int32_t enable, int64_t* host_out);
 /* Number of kernel launches the last ffno_block_fwd / ffno_rollout_fwd on this plan enqueued. */
 FFNO_API int64_t ffno_plan_last_launch_count(const ffno_plan* plan);
 
+/* 1 once a CUDA graph of the stack forward (ffno_block_fwd without taps, ffno_block_fwd_host) or of the rollout
+ * (ffno_rollout_fwd) has been captured and is what the next identical call replays; 0 while calls still launch
+ * kernel by kernel (first two calls of a shape, FFNO_B200_GRAPH=0, or capture refused).  Work submitted on the
+ * legacy default stream is captured and replayed on a plan-owned stream fenced with events, since that stream
+ * cannot be captured. */
+FFNO_API int ffno_plan_graph_active(const ffno_plan* plan);
+
 #ifdef __cplusplus
 }
 #endif

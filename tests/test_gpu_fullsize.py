@@ -1,0 +1,234 @@
+"""GPU (B200): parity of the CUDA path against the CPU oracle, run on the box, AT THE SIZES THAT ARE TIMED —
+the full BASELINE configurations, not scaled-down stand-ins ("What's weak" 1a/1c):
+
+  C2  torus_li/markov/24_layers: B=32, 64x64, 24 layers — per-layer x_l taps, last b, forecast
+      and the 10-step Markov rollout of the same model (per step)
+  C4  torus_kochkov 256x256, modes 64, input_dim 5, B=2: 12 layers and the 24 the config ships
+  C5  Mesh3D 32^3 -> 40^3 padded, modes (12,12,8), B=8, 24 layers, unshared weights
+  Mesh2D width 64 on the tcgen05 path: airfoil shape 221x51 -> 229x59, modes 32/16
+  Mesh3D at the real plasticity shape 101x31x20 -> 109x39x28, modes (32,12,8), B=2
+
+Tolerance: the north star's rtol 1e-4, measured as max|y-ref| / max|ref| per tap and per rollout step
+(SURVEY.md §8c); the oracle is fp32 torch-CPU (its own distance to float64 is ~5e-7 over 24 layers).
+Reference lines: grid_2d.py:154-177, mesh_2d.py:149-165, mesh_3d.py:160-176, routines/grid_2d_markov.py:263-321.
+"""
+import pytest
+import torch
+
+from golden_util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.set_num_threads(16)          # the oracle legs run on the host cores
+
+
+def M():
+    import fourierflow_b200.modules as m
+    return m
+
+
+def sd_of(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def c2_model(seed=0, n_layers=24):
+    torch.manual_seed(seed)
+    return M().FNOFactorized2DBlock(modes=16, width=64, n_layers=n_layers, input_dim=3, share_weight=True, factor=4,
+                                    ff_weight_norm=True, gain=0.1).eval()
+
+
+def test_c2_full_size_per_layer_vs_oracle():
+    """B=32, 64x64, 24 layers: lift, every x_l, the last b and the forecast against the oracle; the plain forward
+    (the launch sequence bench.py times, fused head) against the same oracle forecast."""
+    from oracle import ffno_oracle as O
+    m = c2_model()
+    x = torch.randn(32, 64, 64, 3, generator=torch.Generator().manual_seed(1))     # bench.py's rank-0 input
+    taps = {}
+    with torch.no_grad():
+        ref = O.block_grid2d_forward(sd_of(m), x, modes=16, n_layers=24, taps=taps)["forecast"]
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())["forecast"]
+        y2 = mc(x.cuda())["forecast"]
+        y3 = mc(x.cuda())["forecast"]            # third call: CUDA-graph replay
+        fc, t = mc.forward_with_taps(x.cuda())
+    plan = mc.plan_for(y.device, (64, 64))
+    assert plan.uses_umma and plan.graph_active
+    errs = {"forecast": rel_err(y, ref), "forecast_replay": rel_err(y3, ref), "forecast_tapped": rel_err(fc, ref),
+            "lift": rel_err(t["lift"], taps["lift"]), "b_last": rel_err(t["b_last"], taps["b23"])}
+    for l in range(24):
+        errs[f"x{l}"] = rel_err(t["x"][l], taps[f"x{l}"])
+        errs[f"s{l}"] = rel_err(t["s"][l], taps[f"s{l}"])
+    print("C2 full size", {k: f"{v:.1e}" for k, v in errs.items() if k in ("forecast", "x0", "x11", "x23", "s23", "b_last")},
+          "worst", max(errs, key=errs.get), f"{max(errs.values()):.2e}")
+    assert torch.equal(y2, y3)
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
+
+
+def test_c2_full_size_10_step_rollout_vs_oracle():
+    """The 10-step rollout of the 24-layer model at 64x64, B=32 (routines/grid_2d_markov.py:263-321), per step."""
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    from oracle import ffno_oracle as O
+    conv = c2_model(seed=2)
+    sd = sd_of(conv)
+    g = torch.Generator().manual_seed(22)
+    data = torch.randn(32, 64, 64, 1, generator=g) + 0.2 * torch.cumsum(torch.randn(32, 64, 64, 12, generator=g), dim=-1)
+    exp = Grid2DMarkovExperiment(conv, n_steps=10).cuda().eval()
+    exp.accumulate_statistics(data.cuda())
+    frames = data[..., :-1].unsqueeze(-1)
+    pos = O.position_features((64, 64), 0.0, 1.0, data.dtype)[None, :, :, None, :].expand(32, 64, 64, 11, 2)
+    stats = O.normalizer_stats(torch.cat([frames, pos], dim=-1))
+    with torch.no_grad():
+        ref = O.markov_rollout(sd, data, stats, modes=16, n_layers=24, n_steps=10)
+        loss, step_losses, preds, layer_list = exp({"data": data.cuda()})
+        exp({"data": data.cuda()})
+        loss3, _, preds3, _ = exp({"data": data.cuda()})        # graph replay
+    per_step = [rel_err(preds[..., t], ref["preds"][..., t]) for t in range(10)]
+    print("rollout full size per step", [f"{e:.1e}" for e in per_step], f"loss {loss.item():.6f} vs {ref['loss'].item():.6f}")
+    assert max(per_step) < TOL
+    assert torch.equal(preds, preds3)
+    assert abs(loss.item() - ref["loss"].item()) < 1e-4 * abs(ref["loss"].item())
+    assert rel_err(torch.stack(step_losses), ref["step_losses"]) < 1e-4
+    assert len(layer_list) == 10 and all(entry == [] for entry in layer_list)
+    assert conv.plan_for(preds.device, (64, 64)).graph_active
+
+
+@pytest.mark.parametrize("n_layers", [12, 24])
+def test_c4_full_size_vs_oracle(n_layers):
+    """BASELINE configs[3]: Kochkov 256x256, modes 64, input_dim 5, batch 2; 12 layers and the 24 the config ships."""
+    from oracle import ffno_oracle as O
+    torch.manual_seed(31)
+    m = M().FNOFactorized2DBlock(modes=64, width=64, n_layers=n_layers, input_dim=5, share_weight=True, factor=4,
+                                 ff_weight_norm=True, gain=0.1).eval()
+    x = torch.randn(2, 256, 256, 5, generator=torch.Generator().manual_seed(32))
+    taps = {}
+    with torch.no_grad():
+        ref = O.block_grid2d_forward(sd_of(m), x, modes=64, n_layers=n_layers, taps=taps)["forecast"]
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())["forecast"]
+        fc, t = mc.forward_with_taps(x.cuda())
+    assert mc.plan_for(y.device, (256, 256)).uses_umma
+    errs = {"forecast": rel_err(y, ref), "forecast_tapped": rel_err(fc, ref)}
+    for l in range(n_layers):
+        errs[f"x{l}"] = rel_err(t["x"][l], taps[f"x{l}"])
+    print("C4", n_layers, "worst", max(errs, key=errs.get), f"{max(errs.values()):.2e}", f"forecast {errs['forecast']:.2e}")
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
+
+
+def test_c5_full_size_vs_oracle():
+    """BASELINE configs[4]: FNOFactorizedMesh3D, 32^3 cube (40^3 padded), modes (12,12,8), batch 8, 24 layers."""
+    from oracle import ffno_oracle as O
+    torch.manual_seed(41)
+    m = M().FNOFactorizedMesh3D(modes_x=12, modes_y=12, modes_z=8, width=64, input_dim=4, output_dim=4, n_layers=24,
+                                share_weight=False, factor=4, ff_weight_norm=True, n_ff_layers=2, layer_norm=False).eval()
+    x = torch.randn(8, 32, 32, 32, 1, generator=torch.Generator().manual_seed(42))
+    with torch.no_grad():
+        ref = O.block_mesh_forward(sd_of(m), x, modes=(12, 12, 8), n_layers=24)
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())
+    assert mc.plan_for(y.device, (32, 32, 32)).uses_umma
+    e = rel_err(y, ref)
+    print("C5 full size", f"{e:.2e}")
+    assert y.shape == ref.shape and e < TOL
+
+
+def test_mesh2d_width64_airfoil_shape_vs_oracle():
+    """FNOFactorizedMesh2D on the tcgen05 path (width 64): the airfoil shape 221x51 (229x59 padded: odd, non-power-of-two),
+    modes 32/16 (experiments/airfoil/ffno), 4 layers, unshared weights."""
+    from oracle import ffno_oracle as O
+    torch.manual_seed(51)
+    m = M().FNOFactorizedMesh2D(modes_x=32, modes_y=16, width=64, input_dim=4, n_layers=4, share_weight=False, factor=4,
+                                ff_weight_norm=True, n_ff_layers=2, layer_norm=False).eval()
+    x = torch.randn(3, 221, 51, 2, generator=torch.Generator().manual_seed(52))
+    with torch.no_grad():
+        ref = O.block_mesh_forward(sd_of(m), x, modes=(32, 16), n_layers=4)
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())
+    assert mc.plan_for(y.device, (221, 51)).uses_umma
+    e = rel_err(y, ref)
+    print("mesh2d w64 airfoil", f"{e:.2e}")
+    assert y.shape == ref.shape and e < TOL
+
+
+def test_mesh3d_real_plasticity_shape_vs_oracle():
+    """The real plasticity shape (SURVEY §8d stretch): 101x31x20 -> 109 (prime) x 39 x 28, modes (32,12,8), batch 2."""
+    from oracle import ffno_oracle as O
+    torch.manual_seed(61)
+    m = M().FNOFactorizedMesh3D(modes_x=32, modes_y=12, modes_z=8, width=64, input_dim=4, output_dim=4, n_layers=4,
+                                share_weight=False, factor=4, ff_weight_norm=True, n_ff_layers=2, layer_norm=False).eval()
+    x = torch.randn(2, 101, 31, 20, 1, generator=torch.Generator().manual_seed(62))
+    with torch.no_grad():
+        ref = O.block_mesh_forward(sd_of(m), x, modes=(32, 12, 8), n_layers=4)
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())
+    assert mc.plan_for(y.device, (101, 31, 20)).uses_umma
+    e = rel_err(y, ref)
+    print("mesh3d plasticity shape", f"{e:.2e}")
+    assert y.shape == ref.shape and e < TOL
+
+
+def test_axis_beyond_the_pipelined_transform_falls_back_per_axis():
+    """An axis whose inverse table does not fit the pipelined tcgen05 transform (length 264 > 256 output rows) runs that
+    transform on the FP32 table kernel while the other axis, every mix and the FF stay on tcgen05."""
+    from oracle import ffno_oracle as O
+    torch.manual_seed(71)
+    m = M().FNOFactorized2DBlock(modes=16, width=64, n_layers=2, input_dim=3, share_weight=True, factor=4,
+                                 ff_weight_norm=True, gain=0.1).eval()
+    x = torch.randn(2, 264, 64, 3, generator=torch.Generator().manual_seed(72))
+    with torch.no_grad():
+        ref = O.block_grid2d_forward(sd_of(m), x, modes=16, n_layers=2)["forecast"]
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())["forecast"]
+    assert mc.plan_for(y.device, (264, 64)).uses_umma
+    e = rel_err(y, ref)
+    print("fallback axis", f"{e:.2e}")
+    assert e < TOL
+
+
+def test_host_side_contracts_on_the_device():
+    """stale parameter caches, .data edits, wrong trailing dimensions, rollout length."""
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    m = c2_model(n_layers=1).cuda()
+    x = torch.randn(1, 64, 64, 3, device="cuda")
+    with torch.no_grad():
+        y0 = m(x)["forecast"].clone()
+        sd = {k: (v.clone() * 1.25 if k.endswith("weight_g") else v.clone()) for k, v in m.state_dict().items()}
+        m.load_state_dict(sd, assign=True)                       # replaces every Parameter object
+        y1 = m(x)["forecast"].clone()
+        assert rel_err(y1, y0) > 1e-3
+        m.spectral_layers[0].backcast_ff.layers[1][0].weight_g.data.mul_(2.0)    # no version bump
+        m.invalidate_plans()
+        assert rel_err(m(x)["forecast"], y1) > 1e-3
+        lin = M().WNLinear(3, 8, wnorm=True).cuda()
+        with pytest.raises(RuntimeError, match="in_features"):
+            lin(torch.randn(4, 6, device="cuda"))                # 6 = 2 x 3 would silently become 8 rows
+        exp = Grid2DMarkovExperiment(m, n_steps=6).cuda().eval()
+        with pytest.raises(RuntimeError, match="needs 7 frames"):
+            exp.predict(torch.randn(1, 64, 64, 5, device="cuda"))
+
+
+def test_plans_on_two_devices_in_one_process():
+    """The dynamic shared-memory opt-in is per device: a second GPU used from the same process must get its own."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run by bench.py --selftest-multidev on the scaling box)")
+    m0 = c2_model(n_layers=2).to("cuda:0")
+    m1 = c2_model(n_layers=2).to("cuda:1")
+    x = torch.randn(2, 64, 64, 3)
+    with torch.no_grad():
+        y0 = m0(x.to("cuda:0"))["forecast"]
+        y1 = m1(x.to("cuda:1"))["forecast"]
+    assert rel_err(y1.cpu(), y0.cpu()) < 1e-6

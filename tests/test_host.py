@@ -197,3 +197,37 @@ def test_routine_loads_a_reference_style_lightning_checkpoint(tmp_path):
     with pytest.raises(RuntimeError, match="normalizer.sum"):
         make(2).load_lightning_model_state({"state_dict": bad})
     assert make(3).infer.__func__ is src.infer.__func__ and src.warmup() is None
+
+
+def test_parameter_cache_follows_replaced_parameters_and_modules():
+    """The plan's view of the parameters must follow load_state_dict(assign=True), parameter re-registration and
+    swapped / added sub-modules (the reference re-reads the live parameters on every forward, linear.py:49)."""
+    torch.manual_seed(0)
+    m = _cls("FNOFactorized2DBlock")(modes=4, width=32, n_layers=2, input_dim=3, share_weight=True, factor=4,
+                                     ff_weight_norm=True)
+    p0 = m._flat_params()
+    assert len(p0) == len(list(m.parameters())) and m._flat_params() is p0       # cached while nothing changed
+    m.__dict__["_spec_cache"] = "stale"
+    sd = {k: v.clone() + 1.0 for k, v in m.state_dict().items()}
+    m.load_state_dict(sd, assign=True)                                          # every Parameter object is replaced
+    p1 = m._flat_params()
+    assert p1 is not p0 and "_spec_cache" not in m.__dict__
+    assert {id(p) for p in p1} == {id(p) for p in m.parameters()}
+    assert not ({id(p) for p in p1} & {id(p) for p in p0})
+    m.spectral_layers[1] = copy.deepcopy(m.spectral_layers[0])                   # swapped sub-module
+    p2 = m._flat_params()
+    assert {id(p) for p in p2} == {id(p) for p in m.parameters()}
+    m.spectral_layers.append(copy.deepcopy(m.spectral_layers[0]))                # added layer
+    assert {id(p) for p in m._flat_params()} == {id(p) for p in m.parameters()}
+    m.invalidate_plans()
+    assert "_param_cache" not in m.__dict__
+
+
+def test_rollout_contract_checks():
+    """n_steps must leave a start frame (a negative index would wrap silently); dropout / unsupported options raise."""
+    from fourierflow_b200.modules import FNOFactorized2DBlock
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    conv = FNOFactorized2DBlock(modes=4, width=32, n_layers=1, input_dim=3)
+    exp = Grid2DMarkovExperiment(conv, n_steps=6)
+    with pytest.raises(RuntimeError):           # CPU tensor: refused before anything else
+        exp.predict(torch.randn(1, 8, 8, 4))

@@ -126,8 +126,6 @@ CASES["ff_131072"] = (ff_case, (131072,))
 CASES["ffonly_131072"] = (ff_case, (131072, "ff"))
 CASES["speconly_131072"] = (ff_case, (131072, "spectral"))
 CASES["block24"] = (block_case, ())
-CASES["block24_v1"] = (block_case, ())     # run with FFNO_UMMA_V1=1 (set by the driver loop below)
-CASES["block24_ffv2"] = (block_case, ())   # run with FFNO_FF_V2=1
 
 
 def main():
@@ -141,10 +139,6 @@ def main():
     for name in names:
         try:
             env = dict(os.environ, FFNO_DIAG_CHILD="1")
-            if name.endswith("_v1"):
-                env["FFNO_UMMA_V1"] = "1"
-            if name.endswith("_ffv2"):
-                env["FFNO_FF_V2"] = "1"
             r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True,
                                timeout=180, env=env)
             line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
