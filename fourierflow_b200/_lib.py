@@ -96,6 +96,8 @@ EXPORTS = {
     "ffno_debug_timeline": (C.c_int, [C.c_int32, C.c_void_p]),
     "ffno_plan_last_launch_count": (C.c_int64, [C.c_void_p]),
     "ffno_plan_graph_active": (C.c_int, [C.c_void_p]),
+    "ffno_plan_pipeline_unit": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ffno_debug_pipe_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
 }
 
 _lib = None

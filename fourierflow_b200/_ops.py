@@ -199,6 +199,10 @@ class StackPlan:
     def last_launch_count(self) -> int:
         return int(self.lib.ffno_plan_last_launch_count(self._plan))
 
+    def pipeline_unit(self, batch: int) -> int:
+        """Samples per unit of the stage-pipelined forward for this batch size; 0 = one launch per stage and layer."""
+        return int(self.lib.ffno_plan_pipeline_unit(self._plan, int(batch)))
+
     @property
     def graph_active(self) -> bool:
         """True once the stack forward / rollout of this plan replays a captured CUDA graph."""

@@ -360,6 +360,15 @@ int block_fwd_core(ffno_plan* p, const float* x, int batch, float* forecast, con
   FFNO_TRY(launch_lift(x, p->lift.wt, p->lift.bias, w.xa, batch, g, st));
   if (taps && taps->lift) FFNO_CUDA_CHECK(cudaMemcpyAsync(taps->lift, w.xa, Ubytes, cudaMemcpyDeviceToDevice, st));
 
+  if (p->use_umma && !taps && umma_pipeline_unit(p->umma, batch) > 0) {
+    // every layer in four stage-pipelined launches (umma_pipelined.cu: PipeDesc); the last FF applies the head
+    UmmaFusedHead fh;
+    fh.w = p->head_w;
+    fh.b = p->head_b;
+    fh.forecast = forecast;
+    return umma_stack_fwd_pipelined(p->umma, w.xa, w.xb, batch, w.s, w.F, w.R, w.umma, fh, st);
+  }
+
   float* cur = w.xa;
   float* nxt = w.xb;
   bool head_fused = false;
@@ -452,6 +461,42 @@ int block_fwd_impl(ffno_plan* p, const float* x, int batch, float* forecast, con
 
 constexpr int kMaxGraphFailures = 3;
 
+// Two stage-pipelined forwards must never be in flight at once on one device: each needs ALL of its four kernels
+// resident (they wait for each other), and two half-resident sets would wait forever.  Forwards of this process are
+// therefore chained through one event per device: a forward starts after the previous one has ended, whatever streams
+// the callers use.  (Skipped while the caller's stream is being captured: the events would become part of that graph.)
+struct SerialGuard {
+  std::mutex mu;
+  std::map<int, cudaEvent_t> ev;
+  cudaEvent_t get() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    cudaEvent_t& e = ev[dev];
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) e = nullptr;
+    return e;
+  }
+};
+SerialGuard& serial_guard() {
+  static SerialGuard g;
+  return g;
+}
+bool stream_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+int guard_begin(const ffno_plan* p, cudaStream_t st) {
+  if (!p->use_umma || stream_is_capturing(st)) return FFNO_OK;
+  if (cudaEvent_t e = serial_guard().get()) FFNO_CUDA_CHECK(cudaStreamWaitEvent(st, e, 0));
+  return FFNO_OK;
+}
+int guard_end(const ffno_plan* p, cudaStream_t st) {
+  if (!p->use_umma || stream_is_capturing(st)) return FFNO_OK;
+  if (cudaEvent_t e = serial_guard().get()) FFNO_CUDA_CHECK(cudaEventRecord(e, st));
+  return FFNO_OK;
+}
+
 bool is_legacy_stream(cudaStream_t st) { return st == nullptr || st == cudaStreamLegacy; }
 
 // The stream the forward actually runs on (see ffno_plan::own_stream), ordered after everything already enqueued on
@@ -509,7 +554,7 @@ bool capture_graph(cudaStream_t st, cudaGraphExec_t* exec, int64_t* launches, Bo
 int block_fwd_staged_on(ffno_plan* p, int batch, void* workspace, cudaStream_t st) {
   const Workspace w = carve(p, batch, workspace);
   ffno_plan::GraphSlot& g = p->g_block;
-  if (p->graphs) {
+  if (p->graphs && !stream_is_capturing(st)) {      // (a caller capturing its own graph gets the plain launches)
     if (g.exec && g.batch == batch && g.ws == workspace) {
       FFNO_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
       p->last_launches = g.launches;
@@ -538,7 +583,9 @@ int block_fwd_staged_on(ffno_plan* p, int batch, void* workspace, cudaStream_t s
 int block_fwd_staged(ffno_plan* p, int batch, void* workspace, cudaStream_t caller) {
   cudaStream_t run;
   FFNO_TRY(fence_in(p, caller, &run));
+  FFNO_TRY(guard_begin(p, run));
   const int status = block_fwd_staged_on(p, batch, workspace, run);
+  FFNO_TRY(guard_end(p, run));
   FFNO_TRY(fence_out(p, caller, run));
   return status;
 }
@@ -740,8 +787,10 @@ int ffno_block_fwd(ffno_plan* p, const float* x, int32_t batch, float* forecast,
     return FFNO_OK;
   }
   const long long before = g_launch_counter;
+  FFNO_TRY(guard_begin(p, cst));
   int st = block_fwd_impl(p, x, batch, forecast, taps, workspace, cst);
   p->last_launches = g_launch_counter - before;
+  FFNO_TRY(guard_end(p, cst));
   return st;
 }
 
@@ -906,9 +955,10 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
   };
 
   FFNO_CUDA_CHECK(cudaMemcpyAsync(frame_st, frame0, frame_b, cudaMemcpyDeviceToDevice, st));
+  FFNO_TRY(guard_begin(p, st));
   ffno_plan::GraphSlot& g = p->g_rollout;
   bool done = false;
-  if (p->graphs) {
+  if (p->graphs && !stream_is_capturing(st)) {
     const bool same = g.batch == batch && g.ws == workspace && g.n_steps == n_steps && g.low == low && g.high == high &&
                       memcmp(&g.ms, &ms, sizeof(ms)) == 0;
     if (same && g.exec) {
@@ -934,6 +984,7 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
     FFNO_TRY(body());
     p->last_launches = g_launch_counter - before;
   }
+  FFNO_TRY(guard_end(p, st));
   FFNO_CUDA_CHECK(cudaMemcpyAsync(preds, preds_st, frame_b * n_steps, cudaMemcpyDeviceToDevice, st));
   return fence_out(p, caller, st);
 }
@@ -975,6 +1026,15 @@ int ffno_velocity_fwd(const float* w, int64_t stride_b, int64_t stride_xy, int32
 }
 
 int64_t ffno_plan_last_launch_count(const ffno_plan* plan) { return plan ? plan->last_launches : 0; }
+
+int ffno_debug_pipe_stats(const ffno_plan* plan, uint64_t* host_out, int32_t n_words) {
+  FFNO_REQUIRE(plan && plan->use_umma && host_out && n_words > 0, FFNO_ERR_BAD_ARG, "bad argument");
+  return umma_pipe_debug(plan->umma, reinterpret_cast<unsigned long long*>(host_out), n_words);
+}
+
+int ffno_plan_pipeline_unit(const ffno_plan* plan, int32_t batch) {
+  return plan && plan->use_umma && batch > 0 ? umma_pipeline_unit(plan->umma, batch) : 0;
+}
 
 int ffno_plan_graph_active(const ffno_plan* plan) {
   return plan && (plan->g_block.exec || plan->g_rollout.exec) ? 1 : 0;

@@ -54,6 +54,38 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
                  const float* head_w = nullptr, const float* head_b = nullptr, float* forecast = nullptr,
                  bool reverse = false);
 
+// ---- stage-pipelined forward of the whole layer stack (umma_pipelined.cu: PipeDesc) -----------------------------
+// Per-layer FeedForward parameters (device array, one entry per layer).
+struct FFLayerArgs {
+  const uint8_t* image;
+  const float* b1;
+  const float* b2;
+};
+struct StackPipeArgs {
+  int n_layers, n_axes, n_units;
+  AxisXform fwd[3];            // X = residual-stream buffer of the EVEN layers (xbuf[0]), Y = F of the axis
+  const float* x_odd;          // residual-stream buffer of the odd layers (xbuf[1])
+  MixAxis mix[3];              // image = the mode weights shared by every layer
+  AxisXform inv[3];            // X = R of the axis, Y = the axis' spectral output s_a
+  float* xbuf[2];
+  const FFLayerArgs* ff_layers;
+  const float* head_w;
+  const float* head_b;
+  float* forecast;
+  long long P;                 // points of the whole batch
+  unsigned* counters;          // stack_pipe_counter_bytes(n_units) of arrival counters (zeroed by the call)
+  unsigned long long* dbg;     // diagnostics buffer or NULL
+  int only_stage;              // diagnostics: >= 0 runs that stage alone with its dependencies pre-satisfied; -1 = all
+  int sms[4];                  // CTAs of the forward-transform / mix / inverse-transform / FF stage
+  cudaStream_t streams[4];     // [0] = the caller's stream; the others are forked from it and joined back
+  cudaEvent_t fork, join[3];
+};
+size_t stack_pipe_counter_bytes(int n_units);
+bool stack_pipe_geometry_ok(const AxisXform* fwd, const MixAxis* mix, int n_axes, long long P, int n_units);
+int launch_stack_pipe(const StackPipeArgs& a);
+// Do kernels of two streams really run at the same time in this process (false under serialising profilers)?
+int probe_stream_concurrency(cudaStream_t s0, cudaStream_t s1, unsigned* dev_flags4, bool* concurrent);
+
 // Diagnostics: in-kernel clock64 timeline of block 0 of ff_ts_kernel ([role 8][tile 16][event 8]).
 int debug_timeline(int enable, long long* host_out);
 

@@ -36,9 +36,23 @@ struct UmmaState {
   bool zigzag = true;                                    // FFNO_ZIGZAG=0: every kernel walks its tiles first-to-last
   uint8_t* fwd_image[3] = {nullptr, nullptr, nullptr};   // tcgen05 table images (NULL -> FP32 table kernel)
   uint8_t* inv_image[3] = {nullptr, nullptr, nullptr};
+  // stage-pipelined forward (launch_stack_pipe): FFNO_B200_PERSIST=1 turns it on, FFNO_B200_PIPE_SMS=f,m,i,ff sets
+  // the CTAs per stage
+  bool persist_env = false;
+  bool concurrent = false;                               // probe_stream_concurrency at parameter load
+  bool mix_shared = false;                               // every layer uses the same mode-weight images
+  cudaStream_t pstream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t pfork = nullptr, pjoin[3] = {nullptr, nullptr, nullptr};
+  unsigned* counters = nullptr;
+  int counter_units = 0;
+  FFLayerArgs* ff_layers_dev = nullptr;
+  int pipe_sms[4] = {0, 0, 0, 0};
+  unsigned long long* pipe_dbg = nullptr;                // FFNO_B200_PIPE_DEBUG=1: per-CTA wait statistics
 };
 
 static int pad16i(int n) { return (n + 15) / 16 * 16; }
+constexpr int kPipeDebugWords = 8 + 4 * 256 + 4 * 64;
+static int alloc_bytes(UmmaState* s, size_t bytes, uint8_t** out);
 static bool axis_fits_umma(int n_in, int n_out) { return axis_pipe_fits(n_in, n_out); }
 
 const char* umma_why_not(const ffno_desc* d, const int*) {
@@ -68,6 +82,18 @@ int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]) {
   s->sm_count = s->hw_sm_count = prop.multiProcessorCount;
   const char* zz = getenv("FFNO_ZIGZAG");
   s->zigzag = !(zz && zz[0] == '0');
+  const char* pe = getenv("FFNO_B200_PERSIST");
+  s->persist_env = pe && pe[0] == '1';       // opt-in: measured slower than one launch per stage and layer
+  const char* pd = getenv("FFNO_B200_PIPE_DEBUG");
+  if (pd && pd[0] == '1') {
+    uint8_t* raw = nullptr;
+    if (alloc_bytes(s, kPipeDebugWords * 8, &raw) == FFNO_OK) {
+      s->pipe_dbg = reinterpret_cast<unsigned long long*>(raw);
+      cudaMemset(raw, 0, kPipeDebugWords * 8);
+    }
+  }
+  const char* ps = getenv("FFNO_B200_PIPE_SMS");
+  if (ps) sscanf(ps, "%d,%d,%d,%d", &s->pipe_sms[0], &s->pipe_sms[1], &s->pipe_sms[2], &s->pipe_sms[3]);
   s->layers.resize(d->n_layers);
   *out = s;
   return FFNO_OK;
@@ -79,6 +105,11 @@ void umma_set_sm_limit(UmmaState* s, int n) {
 
 void umma_destroy(UmmaState* s) {
   if (!s) return;
+  for (int i = 0; i < 3; ++i) {
+    if (s->pstream[i]) cudaStreamDestroy(s->pstream[i]);
+    if (s->pjoin[i]) cudaEventDestroy(s->pjoin[i]);
+  }
+  if (s->pfork) cudaEventDestroy(s->pfork);
   for (void* p : s->owned) cudaFree(p);
   delete s;
 }
@@ -131,6 +162,31 @@ int umma_load_params(UmmaState* s, const UmmaLayerSrc* layers, float* const d_fw
     L.ff_image = img;
     L.b1 = src.b1;
     L.b2 = src.b2;
+  }
+  // ---- stage-pipelined forward: per-layer FF table on the device, side streams, concurrency probe ----------------
+  s->mix_shared = s->d.spectral_mode == FFNO_MODE_FULL;
+  for (int l = 1; l < s->d.n_layers; ++l)
+    for (int a = 0; a < s->d.ndim; ++a) s->mix_shared &= s->layers[l].mix_image[a] == s->layers[0].mix_image[a];
+  if (s->persist_env && s->d.ndim == 2) {
+    if (!s->ff_layers_dev) {
+      uint8_t* raw = nullptr;
+      FFNO_TRY(alloc_bytes(s, sizeof(FFLayerArgs) * s->d.n_layers, &raw));
+      s->ff_layers_dev = reinterpret_cast<FFLayerArgs*>(raw);
+    }
+    std::vector<FFLayerArgs> host(s->d.n_layers);
+    for (int l = 0; l < s->d.n_layers; ++l) host[l] = FFLayerArgs{s->layers[l].ff_image, s->layers[l].b1, s->layers[l].b2};
+    FFNO_CUDA_CHECK(cudaStreamSynchronize(st));
+    FFNO_CUDA_CHECK(cudaMemcpy(s->ff_layers_dev, host.data(), sizeof(FFLayerArgs) * host.size(), cudaMemcpyHostToDevice));
+    if (!s->pfork) {
+      FFNO_CUDA_CHECK(cudaEventCreateWithFlags(&s->pfork, cudaEventDisableTiming));
+      for (int i = 0; i < 3; ++i) {
+        FFNO_CUDA_CHECK(cudaStreamCreateWithFlags(&s->pstream[i], cudaStreamNonBlocking));
+        FFNO_CUDA_CHECK(cudaEventCreateWithFlags(&s->pjoin[i], cudaEventDisableTiming));
+      }
+      uint8_t* flags = nullptr;
+      FFNO_TRY(alloc_bytes(s, 4 * sizeof(unsigned), &flags));
+      FFNO_TRY(probe_stream_concurrency(s->pstream[0], s->pstream[1], reinterpret_cast<unsigned*>(flags), &s->concurrent));
+    }
   }
   return FFNO_OK;
 }
@@ -244,6 +300,116 @@ int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residua
   float* xo = residual ? y : nullptr;
   float* bo = residual ? nullptr : y;
   return launch_ff_ts(s_in, nullptr, nullptr, residual, xo, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
+}
+
+// ---- stage-pipelined forward ---------------------------------------------------------------------------------------
+// Samples per unit: the smallest group whose tiles align in every stage (0 = this batch cannot be pipelined).
+int umma_pipeline_unit(const UmmaState* s, int batch) {
+  bool nopad = true;
+  for (int a = 0; a < s->d.ndim; ++a) nopad &= s->d.pad[a] == 0;
+  if (!s->persist_env || !s->concurrent || !s->mix_shared || s->d.ndim != 2 || !all_axes_pipe(s) || !nopad ||
+      s->d.out_features != 1 || s->d.use_fork || s->ff_layers_dev == nullptr || s->sm_count != s->hw_sm_count)
+    return 0;
+  int mix_ctas = 0;
+  for (int a = 0; a < s->d.ndim; ++a) mix_ctas = s->d.modes[a] > mix_ctas ? s->d.modes[a] : mix_ctas;
+  mix_ctas *= s->d.ndim;
+  if (mix_ctas + 3 * s->d.ndim > s->hw_sm_count) return 0;
+  for (int u = 1; u <= 8; u *= 2) {
+    if (batch % u != 0 || batch / u < 4) continue;
+    AxisXform fwd[3];
+    MixAxis mix[3];
+    long long P = batch;
+    for (int a = 0; a < s->d.ndim; ++a) {
+      long long outer, p_inner;
+      axis_geom(s, batch, a, &outer, &p_inner);
+      fwd[a] = AxisXform{nullptr, nullptr, nullptr, outer, p_inner * kUmmaC, s->ext[a], 2 * s->d.modes[a], 0, 0, 0};
+      mix[a] = MixAxis{nullptr, nullptr, nullptr, outer, p_inner, s->d.modes[a]};
+      P *= s->ext[a];
+    }
+    if (stack_pipe_geometry_ok(fwd, mix, s->d.ndim, P, batch / u)) return u;
+  }
+  return 0;
+}
+
+// The whole layer stack on the lifted activations in xa: four launches (forward transforms, mode mixes, inverse
+// transforms, FeedForward + residual + fused head on the last layer), each walking every layer.
+int umma_stack_fwd_pipelined(UmmaState* s, float* xa, float* xb, int batch, float* s_out, float* F, float* R, float* ws,
+                             const UmmaFusedHead& head, cudaStream_t st) {
+  const int u = umma_pipeline_unit(s, batch);
+  FFNO_REQUIRE(u > 0, FFNO_ERR_STATE, "stage-pipelined forward requested for a batch that does not qualify");
+  const int n_units = batch / u;
+  if (s->counter_units < n_units) {
+    uint8_t* raw = nullptr;
+    FFNO_TRY(alloc_bytes(s, stack_pipe_counter_bytes(n_units), &raw));
+    s->counters = reinterpret_cast<unsigned*>(raw);
+    s->counter_units = n_units;
+  }
+  StackPipeArgs A{};
+  A.n_layers = s->d.n_layers;
+  A.n_axes = s->d.ndim;
+  A.n_units = n_units;
+  long long P = batch;
+  size_t U = (size_t)batch * kUmmaC;
+  for (int a = 0; a < s->d.ndim; ++a) { P *= s->ext[a]; U *= s->ext[a]; }
+  float* s_axis[3] = {s_out, ws, ws + U};
+  int maxK = 0;
+  for (int a = 0; a < s->d.ndim; ++a) {
+    long long outer, p_inner;
+    axis_geom(s, batch, a, &outer, &p_inner);
+    const int Ln = s->ext[a], K = s->d.modes[a];
+    float* Fa = F + spec_offset(s, batch, a);
+    float* Ra = R + spec_offset(s, batch, a);
+    A.fwd[a] = AxisXform{xa, Fa, s->fwd_image[a], outer, p_inner * kUmmaC, Ln, 2 * K, pad16i(2 * K), (Ln + 63) / 64, 0};
+    A.mix[a] = MixAxis{Fa, Ra, s->layers[0].mix_image[a], outer, p_inner, K};
+    A.inv[a] = AxisXform{Ra, s_axis[a], s->inv_image[a], outer, p_inner * kUmmaC, 2 * K, Ln, pad16i(Ln), (2 * K + 63) / 64, 0};
+    maxK = K > maxK ? K : maxK;
+  }
+  A.x_odd = xb;
+  A.xbuf[0] = xa;
+  A.xbuf[1] = xb;
+  A.ff_layers = s->ff_layers_dev;
+  A.head_w = head.w;
+  A.head_b = head.b;
+  A.forecast = head.forecast;
+  A.P = P;
+  A.counters = s->counters;
+  A.dbg = s->pipe_dbg;
+  {
+    const char* os = getenv("FFNO_B200_PIPE_ONLY");      // diagnostics (tools/pipe_stage_alone.py); results are garbage
+    A.only_stage = os ? atoi(os) : -1;
+  }
+  if (s->pipe_sms[0] > 0 && s->pipe_sms[2] > 0 && s->pipe_sms[3] > 0) {
+    for (int i = 0; i < 4; ++i) A.sms[i] = s->pipe_sms[i];
+  } else {
+    // One CTA per (axis, mode) mixes; the other SMs are shared in proportion to the stages' measured steady-state
+    // tile costs inside the pipeline (B200, 64 x 64 grid, tools/pipe_stats.py: 0.95 us per forward-transform tile,
+    // 1.4 us per inverse-transform tile, 2.5 us per FF tile — DESIGN.md §5).
+    const int mix_ctas = maxK * s->d.ndim, rest = s->hw_sm_count - mix_ctas, nd = s->d.ndim;
+    double tiles_ax = 0.0;
+    for (int a = 0; a < nd; ++a) tiles_ax += (double)(A.fwd[a].outer * (A.fwd[a].inner / 64) / 2);
+    const double w_f = 0.95 * tiles_ax, w_i = 1.4 * tiles_ax, w_ff = 2.5 * (double)(P / 128), tot = w_f + w_i + w_ff;
+    int f = (int)(rest * w_f / tot + 0.5) / nd * nd, i = (int)(rest * w_i / tot + 0.5) / nd * nd;
+    if (f < nd) f = nd;
+    if (i < nd) i = nd;
+    A.sms[0] = f;
+    A.sms[1] = mix_ctas;
+    A.sms[2] = i;
+    A.sms[3] = rest - f - i;
+  }
+  FFNO_REQUIRE(A.sms[0] + maxK * s->d.ndim + A.sms[2] + A.sms[3] <= s->hw_sm_count && A.sms[3] >= 1, FFNO_ERR_BAD_ARG,
+               "stage-pipelined forward: %d + %d + %d + %d CTAs exceed the %d SMs (all stages must be resident at once)",
+               A.sms[0], maxK * s->d.ndim, A.sms[2], A.sms[3], s->hw_sm_count);
+  A.streams[0] = st;
+  for (int i = 0; i < 3; ++i) { A.streams[i + 1] = s->pstream[i]; A.join[i] = s->pjoin[i]; }
+  A.fork = s->pfork;
+  return launch_stack_pipe(A);
+}
+
+int umma_pipe_debug(const UmmaState* s, unsigned long long* host_out, int n_words) {
+  FFNO_REQUIRE(s->pipe_dbg != nullptr, FFNO_ERR_STATE, "plan was not created with FFNO_B200_PIPE_DEBUG=1");
+  const int n = n_words < kPipeDebugWords ? n_words : kPipeDebugWords;
+  FFNO_CUDA_CHECK(cudaMemcpy(host_out, s->pipe_dbg, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return n;
 }
 
 bool umma_can_fuse_head(const UmmaState* s, bool want_s) {

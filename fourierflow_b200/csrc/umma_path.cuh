@@ -36,6 +36,14 @@ struct UmmaFusedHead {
   float* forecast = nullptr;
 };
 bool umma_can_fuse_head(const UmmaState* s, bool want_s);
+// Stage-pipelined forward of the whole stack (four persistent, flag-synchronised launches per forward instead of four
+// per layer).  umma_pipeline_unit: samples per pipeline unit for this batch, 0 when the plan / batch does not qualify
+// (3-D, padded or forked stacks, unshared mode weights, fewer than 4 units, kernels of different streams not running
+// concurrently in this process, FFNO_B200_PERSIST=0).
+int umma_pipeline_unit(const UmmaState* s, int batch);
+int umma_pipe_debug(const UmmaState* s, unsigned long long* host_out, int n_words);   // diagnostics, see ffno_debug_pipe_stats
+int umma_stack_fwd_pipelined(UmmaState* s, float* xa, float* xb, int batch, float* s_out, float* F, float* R, float* ws,
+                             const UmmaFusedHead& head, cudaStream_t st);
 int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_next, float* s_out, float* b_out,
                    float* F, float* R, float* ws, bool want_s, bool want_b, cudaStream_t st,
                    const UmmaFusedHead* head = nullptr);

@@ -6,6 +6,7 @@
 //   warps 5-8  loaders    (coalesced FP32 global loads -> BF16 hi/lo split -> swizzled operand tiles in smem)
 // Operand tiles in shared memory and accumulators in tensor memory are double-buffered and handed over with
 // full/empty mbarriers, so the global loads of tile t+1, the MMAs of tile t and the epilogue of tile t-1 overlap.
+#include <cstdlib>
 #include <type_traits>
 
 #include "umma.cuh"
@@ -59,6 +60,8 @@ constexpr int kEpiWarps = 8;                   // two teams of 4 (one per TMEM l
 constexpr int kMmaWarp = kEpiWarps;
 constexpr int kLoaderThread0 = (kEpiWarps + 1) * 32;
 constexpr int kThreads = kLoaderThread0 + kLoaders;       // 800
+constexpr int kPollWarp = kThreads / 32, kPubWarp = kPollWarp + 1;   // pipelined kernels: +2 synchronisation warps
+constexpr int kPipeThreads = kThreads + 64;
 constexpr int kLdPerThread = 2048 / kLoaders;  // float4 per thread per 32 KB work item
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -130,6 +133,121 @@ __device__ __forceinline__ void store_split4_at(uint8_t* tile_hi, uint8_t* tile_
   *reinterpret_cast<uint2*>(tile_lo + off) = make_uint2(l0, l1);
 }
 
+
+// =======================================================================================================
+// Stage-pipelined execution (launch_stack_pipe): the transform / mix / inverse / FF kernels are launched ONCE per
+// forward, side by side on disjoint SMs, and each walks the whole (layer, tile) sequence of its stage.  A "unit" is the
+// smallest group of samples whose tiles align in every stage (two samples on the 64 x 64 grid); a stage may start a
+// unit of layer l when its producer's arrival counter of that unit has reached the layer's target:
+//     forward transforms <- FF of layer l-1      mode mix <- forward transforms      inverse <- mode mix      FF <- inverse
+// Counters are cumulative over the layers of one forward (zeroed by a memset before the kernels), bumped once per
+// epilogue warp and finished tile with a gpu-scope release, read with a gpu-scope acquire.  Every dependency points to
+// an earlier element of the (layer, unit, stage) order, every CTA walks its tiles in that order and all CTAs of the
+// four kernels are resident at once (grid sizes add up to at most the SM count, one CTA per SM), so waits always end;
+// the chain FF(l-1,u) -> fwd(l,u) -> mix -> inv -> FF(l,u) also orders every reuse of the F / R / s / x buffers.
+// =======================================================================================================
+struct PipeDesc {
+  int n_layers;                  // 0 = plain single-launch behaviour, everything below ignored
+  int tiles_per_unit[3];         // per axis: tiles of this kernel (per mode for the mix) that make up one unit
+  int wait_lag;                  // the loader of (layer l, unit u) waits for wait_ctr[u] >= (l + wait_lag) * wait_count
+  unsigned wait_count[3];        // per axis: arrivals the producer posts per layer and unit
+  const unsigned* wait_ctr[3];   // per axis: the producer's counters [unit]; NULL = nothing to wait for
+  unsigned* done_ctr[3];         // per axis: this stage's counters [unit]
+  unsigned long long* dbg_ts;    // diagnostics: [64] globaltimer at which CTA 0's loaders found (layer, unit) ready
+  unsigned long long* dbg;       // diagnostics (FFNO_B200_PIPE_DEBUG=1): per CTA {cycles blocked on the producer, cycles
+                                 // in the kernel, start, end (globaltimer ns)} of the polling loader warp; NULL = off
+};
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr int kCtrStride = 32;     // unsigned per counter: every counter has its own 128-byte line (no false sharing
+                                   // between the line a producer bumps and the lines other consumers poll)
+// One thread: block until *ctr >= target (bounded, like the mbarrier waits: a protocol bug must surface as an error).
+// Relaxed polls + one acquire fence at the end: a gpu-scope acquire invalidates the SM's L1, once per wait is enough.
+__device__ __forceinline__ void pipe_wait(const unsigned* ctr, unsigned target) {
+  if (target == 0u) return;
+  if (ld_relaxed_gpu(ctr) < target) {
+    const long long t0 = clock64();
+    while (ld_relaxed_gpu(ctr) < target) {
+      __nanosleep(100);
+      if (clock64() - t0 > (1ll << 33)) {
+        atomicExch(&g_umma_timeout_flag, 2u);
+        __trap();
+      }
+    }
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+// Synchronisation is kept off the working warps: in the pipelined kernels two extra warps do it.
+//  * The POLLER warp walks the CTA's tile sequence ahead of the loaders, waits (gpu-scope acquire) for each new unit's
+//    producer counter and publishes the unit's sequence number in a shared-memory word; loaders / store warps only
+//    watch that word (cta-scope acquire), so no gpu-scope fence ever stalls a warp with copies or stores in flight.
+//  * The PUBLISHER warp waits until the epilogue warps have issued a tile's global stores (a shared-memory counter
+//    they bump with cta-scope release after their last store), then posts ONE arrival for the tile with a gpu-scope
+//    release.  The release is cumulative over the epilogue warps' stores (the same pattern as a grid barrier:
+//    bar / cta-scope synchronisation first, one thread fences and signals), and only the publisher waits for them to
+//    drain.
+__device__ __forceinline__ int ld_acquire_cta_smem(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_smem(int* p, int v) {
+  asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// one thread: block until the shared-memory word reaches `want` (bounded)
+__device__ __forceinline__ void smem_wait_ge(const int* p, int want) {
+  if (ld_acquire_cta_smem(p) >= want) return;
+  const long long tb = clock64();
+  while (ld_acquire_cta_smem(p) < want) {
+    __nanosleep(40);
+    if (clock64() - tb > (1ll << 33)) {
+      atomicExch(&g_umma_timeout_flag, 3u);
+      __trap();
+    }
+  }
+}
+// Whole warp (warp-uniform arguments): wait until the poller has seen unit `seq` ready.  Returns the cycles lane 0 waited.
+__device__ __forceinline__ long long wait_unit_ready(const int* s_seq, int seq) {
+  long long blocked = 0;
+  if ((threadIdx.x & 31) == 0) {
+    const long long ta = clock64();
+    smem_wait_ge(s_seq, seq);
+    blocked = clock64() - ta;
+  }
+  __syncwarp();
+  return blocked;
+}
+// Whole epilogue warp, after its last global store of a tile: tell the publisher (cta-scope release).
+__device__ __forceinline__ void stores_issued(int* s_pub) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) asm volatile("red.release.cta.shared::cta.add.s32 [%0], %1;" ::"r"(smem_u32(s_pub)), "r"(1) : "memory");
+}
+// Publisher thread: one arrival on the stage counter (gpu-scope release, cumulative over what it has observed).
+__device__ __forceinline__ void pipe_publish(unsigned* ctr) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+}
+// Coherent streaming load (L2 only): data written by another kernel DURING this kernel's lifetime must not come from
+// the non-coherent path or from a stale L1 line.
+__device__ __forceinline__ float4 ldg_cg(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 }  // namespace
 
 // =======================================================================================================
@@ -138,7 +256,9 @@ __device__ __forceinline__ void store_split4_at(uint8_t* tile_hi, uint8_t* tile_
 constexpr int AXP_A_STAGE = 32768;                 // operand stage: hi 16 KB | lo 16 KB
 constexpr int AXP_BAR = 2 * AXP_A_STAGE;           // 65536
 constexpr int AXP_STAGING = AXP_BAR + 1024;        // ring x 32 KB of raw FP32 (cp.async landing zone)
-constexpr int kAxStages = 2;                       // ring depth; 1 when a large table (C4: 128 KB) leaves no room for 2
+constexpr int kAxStages = 4;                       // deepest staging ring (power of two); shallower when a large table
+                                                   // (C4: 128 KB) leaves no room.  The ring depth x 32 KB is what a CTA
+                                                   // keeps in flight: the loaders are bound by latency / depth
 constexpr int axp_table_offset(int ring) { return AXP_STAGING + ring * 32768; }   // the DFT table image follows the ring
 
 struct AxisSet {
@@ -147,12 +267,19 @@ struct AxisSet {
   int tmem_cols[3];
   int ring[3];      // cp.async staging ring depth of the axis (1 or 2)
   int reverse;      // walk the tiles from the last to the first (see launch_axis_pipe)
+  const float* X_odd[3];   // kPipe: input of the odd layers (the residual stream ping-pongs between two buffers)
+  PipeDesc pipe;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
+// kPipe: the CTA walks tile, tile + grid, ... of every layer back to back (grid <= n_tiles, n_groups even), its loaders
+// wait for the unit's producer and its epilogue warps post the unit's completion (see PipeDesc).
+template <bool kPipe>
+__global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) axis_pipe_kernel(AxisSet set) {
   const AxisXform& p = set.ax[blockIdx.y];
   const int n_tiles = set.n_tiles[blockIdx.y];
   if ((int)blockIdx.x >= n_tiles) return;
+  const int n_layers = kPipe ? set.pipe.n_layers : 1;
+  const int my_tiles = (int)(((long long)n_layers * n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
   const int tmem_cols = set.tmem_cols[blockIdx.y];
   const int stage_cols = tmem_cols >> 1;
 
@@ -164,12 +291,16 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
   uint64_t* d_empty = bars + 6;     // [2]
   uint64_t* bar_w = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  int* s_seq = reinterpret_cast<int*>(bars + 10);      // kPipe: last unit the poller has seen ready
+  int* s_pub = s_seq + 1;                              // [2] kPipe: warps of epilogue team t that have issued their stores
   const int ring = set.ring[blockIdx.y];
   uint8_t* sB = smem + axp_table_offset(ring);
   const uint32_t b_half = (uint32_t)p.kchunks * p.npad * 128u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
+    *s_seq = -1;
+    s_pub[0] = s_pub[1] = 0;
     // the (constant) table image first: its copy runs under TMEM allocation, barrier set-up and the wait for the
     // predecessor grid instead of after them
     mbar_init(bar_w, 1);
@@ -217,14 +348,16 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     const int gq = quad >> 1;                                  // which of the tile's two 64-element groups
     const int in_group = (quad & 1) * 32 + lane;
     const unsigned stride = (unsigned)p.inner;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+    int tile = (int)blockIdx.x - (int)gridDim.x;
+    for (int n = 0; n < my_tiles; ++n) {
+      tile += gridDim.x;
+      if (kPipe && tile >= n_tiles) tile -= n_tiles;       // next layer
       const int ds = n & 1;
       if (split_tiles && ds != team) continue;
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 0);
-      const int ptile = set.reverse ? n_tiles - 1 - tile : tile;
+      const int ptile = (!kPipe && set.reverse) ? n_tiles - 1 - tile : tile;
       const long long G = (long long)ptile * 2 + gq;             // warp-uniform
       const bool live = G < n_groups;
       const unsigned uo = live ? (unsigned)G / (unsigned)gpi : 0u;
@@ -264,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
         tc_fence_before();
         mbar_arrive(&d_empty[ds]);
       }
+      if (kPipe) stores_issued(&s_pub[team]);
       if (warp == 0 && blockIdx.y == 0) TL(5, n, 2);
     }
   } else if (warp == kMmaWarp) {
@@ -272,8 +406,8 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       pdl_wait();
       mbar_wait(bar_w, 0);
       const uint32_t idesc = make_idesc_bf16(128, p.npad, 1, 0);
-      int item = 0, n = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      int item = 0;
+      for (int n = 0; n < my_tiles; ++n) {
         const int ds = n & 1;
         mbar_wait(&d_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
         const uint32_t d_addr = tmem + (uint32_t)(ds * stage_cols);
@@ -314,6 +448,39 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       }
     }
     __syncwarp();
+  } else if (kPipe && warp == kPollWarp) {
+    // ---------------------------------------------------------------- poller (see wait_unit_ready)
+    if (lane == 0) {
+      const unsigned* ctr = set.pipe.wait_ctr[blockIdx.y];
+      const unsigned cnt = set.pipe.wait_count[blockIdx.y];
+      const int tpu = set.pipe.tiles_per_unit[blockIdx.y];
+      int tile = (int)blockIdx.x - (int)gridDim.x, layer = 0, last = -1;
+      for (int n = 0; n < my_tiles; ++n) {
+        tile += gridDim.x;
+        if (tile >= n_tiles) { tile -= n_tiles; ++layer; }
+        const int unit = tile / tpu, seq = layer * (n_tiles + 1) + unit;
+        if (seq != last) {
+          pipe_wait(ctr + unit * kCtrStride, (unsigned)(layer + set.pipe.wait_lag) * cnt);
+          st_release_cta_smem(s_seq, seq);
+          last = seq;
+        }
+      }
+    }
+  } else if (kPipe && warp == kPubWarp) {
+    // ---------------------------------------------------------------- publisher (see pipe_publish)
+    if (lane == 0) {
+      const bool split_tiles = p.npad <= 32;       // one team stores a tile (teams alternate), else both do
+      unsigned* ctr = set.pipe.done_ctr[blockIdx.y];
+      const int tpu = set.pipe.tiles_per_unit[blockIdx.y];
+      int tile = (int)blockIdx.x - (int)gridDim.x, need0 = 0, need1 = 0;
+      for (int n = 0; n < my_tiles; ++n) {
+        tile += gridDim.x;
+        if (tile >= n_tiles) tile -= n_tiles;
+        if (!split_tiles || (n & 1) == 0) { need0 += 4; smem_wait_ge(&s_pub[0], need0); }
+        if (!split_tiles || (n & 1) == 1) { need1 += 4; smem_wait_ge(&s_pub[1], need1); }
+        pipe_publish(ctr + (tile / tpu) * kCtrStride);
+      }
+    }
   } else {
     // ---------------------------------------------------------------- loaders
     // Each thread streams its own 16 x 16 B of every work item through a private slice of the staging ring with
@@ -321,17 +488,21 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     // landed: FP32 -> BF16 hi/lo, MN-major SWIZZLE_128B operand stage.  A thread only ever reads what it copied,
     // so the ring needs no cross-thread synchronisation (per-thread cp.async groups).
     const int lt = tid - kLoaderThread0;
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_items = my_tiles * p.kchunks;
     const int gsel = (lt >> 4) & 1, c4 = lt & 15, rsub = lt >> 5;            // rsub: 0..15
     uint8_t* stg_base = smem + AXP_STAGING + lt * 16;
     const long long row_step = 16 * p.inner;                 // floats between the rows this thread copies
     // The issue sequence walks this CTA's tiles in order, so the (outer, group) pair of the next tile follows from
     // the previous one by a precomputed step: two divisions per kernel instead of two per work item.
-    const int sgn = set.reverse ? -1 : 1;
+    const int sgn = (!kPipe && set.reverse) ? -1 : 1;
     const unsigned step_groups = 2u * gridDim.x;
     const int step_o = (int)(step_groups / (unsigned)gpi), step_g = (int)(step_groups % (unsigned)gpi);
-    long long curG = (long long)(set.reverse ? n_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * 2 + gsel;
+    long long curG = (long long)((!kPipe && set.reverse) ? n_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * 2 + gsel;
+    int iss_tile = blockIdx.x, iss_layer = 0, ready_seq = -1;     // kPipe: tile / layer of the next issue, last unit seen ready
+    const float* Xl = p.X;
+    long long dbg_blocked = 0;
+    const long long dbg_c0 = kPipe ? clock64() : 0;
+    const unsigned long long dbg_t0 = kPipe ? globaltimer_ns() : 0ull;
     // (a dead group G == n_groups of an odd tail still gets its true (outer, group): it is stepped from, never read)
     int cur_o = (int)((unsigned)curG / (unsigned)gpi);
     int cur_g = (int)((unsigned)curG - (unsigned)cur_o * (unsigned)gpi);
@@ -340,9 +511,21 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
     auto issue = [&](int slot) {
       if (iss_left > 0) {
         --iss_left;
+        if (kPipe && iss_kc == 0) {       // first chunk of a tile: its unit's inputs must be complete (warp-uniform)
+          const int unit = iss_tile / set.pipe.tiles_per_unit[blockIdx.y];
+          const int seq = iss_layer * (n_tiles + 1) + unit;
+          if (seq != ready_seq) {
+            dbg_blocked += wait_unit_ready(s_seq, seq);
+            ready_seq = seq;
+            if (set.pipe.dbg_ts && lt == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+              const int q = iss_layer * (n_tiles / set.pipe.tiles_per_unit[0]) + unit;
+              if (q < 64) set.pipe.dbg_ts[q] = globaltimer_ns();
+            }
+          }
+        }
         const bool live = curG < n_groups;
         const int i0 = iss_kc * 64 + rsub;
-        const float* src = p.X + ((long long)cur_o * p.n_in + iss_kc * 64) * p.inner + (long long)cur_g * 64 + thr_off;
+        const float* src = Xl + ((long long)cur_o * p.n_in + iss_kc * 64) * p.inner + (long long)cur_g * 64 + thr_off;
         uint8_t* dst = stg_base + slot * 32768;
 #pragma unroll
         for (int it = 0; it < kLdPerThread; ++it) {
@@ -357,13 +540,25 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
           cur_g += sgn * step_g;
           if (cur_g >= (int)gpi) { cur_g -= (int)gpi; ++cur_o; }
           if (cur_g < 0) { cur_g += (int)gpi; --cur_o; }
+          if (kPipe) {
+            iss_tile += gridDim.x;
+            if (iss_tile >= n_tiles) {      // wrap into the next layer: n_groups == 2 n_tiles == outer * gpi
+              iss_tile -= n_tiles;
+              ++iss_layer;
+              curG -= n_groups;
+              cur_o -= (int)p.outer;
+              Xl = (iss_layer & 1) ? set.X_odd[blockIdx.y] : p.X;
+            }
+          }
         }
       }
       cp_async_commit();
     };
     for (int q = 0; q < ring; ++q) issue(q);
     for (int item = 0; item < n_items; ++item) {
-      if (ring == 2) cp_async_wait<1>(); else cp_async_wait<0>();      // warp-uniform
+      if (ring == 4) cp_async_wait<3>();                                 // warp-uniform
+      else if (ring == 2) cp_async_wait<1>();
+      else cp_async_wait<0>();
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 0);
       const uint8_t* src = stg_base + (item & (ring - 1)) * 32768;
       float4 v[kLdPerThread];
@@ -388,6 +583,13 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 3);
     }
     cp_async_wait<0>();
+    if (kPipe && lt == 0 && set.pipe.dbg) {
+      unsigned long long* d = set.pipe.dbg + 4 * (blockIdx.y * gridDim.x + blockIdx.x);
+      d[0] = (unsigned long long)dbg_blocked;
+      d[1] = (unsigned long long)(clock64() - dbg_c0);
+      d[2] = dbg_t0;
+      d[3] = globaltimer_ns();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -395,7 +597,12 @@ __global__ void __launch_bounds__(kThreads, 1) axis_pipe_kernel(AxisSet set) {
 }
 
 static int axis_ring_depth(int n_in, int n_out) {      // deepest staging ring that leaves room for the table, 0 = none
-  for (int ring = kAxStages; ring >= 1; --ring)
+  static const int max_ring = [] {
+    const char* e = getenv("FFNO_B200_AXIS_RING");       // A/B switch: 1, 2 or 4
+    const int v = e ? atoi(e) : kAxStages;
+    return (v == 1 || v == 2 || v == 4) ? v : kAxStages;
+  }();
+  for (int ring = max_ring; ring >= 1; ring >>= 1)
     if (axp_table_offset(ring) + table_image_bytes(n_in, n_out) <= (size_t)227 * 1024) return ring;
   return 0;
 }
@@ -427,11 +634,12 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
     max_tiles = set.n_tiles[a] > max_tiles ? set.n_tiles[a] : max_tiles;
   }
   if (max_tiles == 0) return FFNO_OK;
-  FFNO_TRY(ensure_dynamic_smem(axis_pipe_kernel, smem));
+  FFNO_TRY(ensure_dynamic_smem(axis_pipe_kernel<false>, smem));
   int per_axis = sm_count / n_axes;
   if (per_axis < 1) per_axis = 1;
   const int gx = max_tiles < per_axis ? max_tiles : per_axis;
-  FFNO_CUDA_CHECK(launch_pdl(axis_pipe_kernel, dim3(gx, n_axes), dim3(kThreads), smem, st, set));
+  set.pipe = PipeDesc{};
+  FFNO_CUDA_CHECK(launch_pdl(axis_pipe_kernel<false>, dim3(gx, n_axes), dim3(kThreads), smem, st, set));
   ++g_launch_counter;
   return FFNO_OK;
 }
@@ -452,9 +660,13 @@ struct MixSet {
   MixAxis ax[3];
   int tiles_per_cta[3];
   int reverse;
+  PipeDesc pipe;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
+// kPipe: the CTA of (axis, mode) walks its row tiles of every layer back to back with its weight image stationary
+// (the mode weights must be shared by the layers), waits for the unit's forward transforms and posts completion.
+template <bool kPipe>
+__global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_kernel(MixSet set) {
   const MixAxis& ax = set.ax[blockIdx.z];
   const int k = blockIdx.y;
   if (k >= ax.K) return;
@@ -464,6 +676,8 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
   const int tile_begin = blockIdx.x * tpc;
   if (tile_begin >= n_tiles) return;
   const int tile_end = min(n_tiles, tile_begin + tpc);
+  const int n_layers = kPipe ? set.pipe.n_layers : 1;
+  const int my_tiles = (tile_end - tile_begin) * n_layers;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sB = smem + MXP_B;
@@ -474,9 +688,13 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
   uint64_t* d_empty = bars + 6;
   uint64_t* bar_w = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  int* s_seq = reinterpret_cast<int*>(bars + 10);
+  int* s_pub = s_seq + 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
+    *s_seq = -1;
+    s_pub[0] = s_pub[1] = 0;
     mbar_init(bar_w, 1);                       // weight image first: see axis_pipe_kernel
     fence_barrier_init();
     {
@@ -517,8 +735,9 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
     const unsigned q16 = 16u / p_in, r16 = 16u % p_in;
     const long long o_stride = (long long)ax.K * 2 * inner;
     float* out_seg = ax.R + ((long long)k * 2 + seg) * inner + cq * 4;
-    int n = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
+    int tile = tile_begin - 1;
+    for (int n = 0; n < my_tiles; ++n) {
+      if (++tile == tile_end) tile = tile_begin;         // kPipe: next layer
       const int ds = n & 1;
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
@@ -540,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         {
           // rows rq + 16 it: (outer, position) of the first by one division, the rest by a constant step
-          const long long row_first = (long long)(set.reverse ? n_tiles - 1 - tile : tile) * 128 + rq;
+          const long long row_first = (long long)((!kPipe && set.reverse) ? n_tiles - 1 - tile : tile) * 128 + rq;
           const unsigned rf = row_first < M ? (unsigned)row_first : 0u;
           unsigned uo = rf / p_in, pp = rf - uo * p_in;
           const int rows_left = (M - row_first) > 0 ? (int)((M - row_first) < 128 ? (M - row_first) : 128) : 0;   // rows rq .. M-1
@@ -558,6 +777,7 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
         if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
+      if (kPipe) stores_issued(&s_pub[team]);
     }
   } else if (warp == kMmaWarp) {
     {
@@ -566,8 +786,8 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
       constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
       const uint64_t dBh = desc_kmajor(smem_u32(sB), 0), dBl = desc_kmajor(smem_u32(sB) + 32768u, 0);
       const uint64_t dAh = desc_kmajor(smem_u32(smem), 0), dAl = desc_kmajor(smem_u32(smem) + 16384u, 0);
-      int item = 0, n = 0;
-      for (int tile = tile_begin; tile < tile_end; ++tile, ++n) {
+      int item = 0;
+      for (int n = 0; n < my_tiles; ++n) {
         const int ds = n & 1;
         mbar_wait(&d_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
         const uint32_t d_addr = tmem + (uint32_t)(ds * 128);
@@ -583,11 +803,44 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
       }
     }
     __syncwarp();
+  } else if (kPipe && warp == kPollWarp) {
+    if (lane == 0) {      // poller
+      const unsigned* ctr = set.pipe.wait_ctr[blockIdx.z];
+      const unsigned cnt = set.pipe.wait_count[blockIdx.z];
+      const int tpu = set.pipe.tiles_per_unit[blockIdx.z];
+      int tile = tile_begin - 1, layer = 0, last = -1;
+      for (int n = 0; n < my_tiles; ++n) {
+        if (++tile == tile_end) { tile = tile_begin; ++layer; }
+        const int unit = tile / tpu, seq = layer * (n_tiles + 1) + unit;
+        if (seq != last) {
+          pipe_wait(ctr + unit * kCtrStride, (unsigned)(layer + set.pipe.wait_lag) * cnt);
+          st_release_cta_smem(s_seq, seq);
+          last = seq;
+        }
+      }
+    }
+  } else if (kPipe && warp == kPubWarp) {
+    if (lane == 0) {      // publisher: both teams store a part of every tile
+      unsigned* ctr = set.pipe.done_ctr[blockIdx.z];
+      const int tpu = set.pipe.tiles_per_unit[blockIdx.z];
+      int tile = tile_begin - 1, need = 0;
+      for (int n = 0; n < my_tiles; ++n) {
+        if (++tile == tile_end) tile = tile_begin;
+        need += 4;
+        smem_wait_ge(&s_pub[0], need);
+        smem_wait_ge(&s_pub[1], need);
+        pipe_publish(ctr + (tile / tpu) * kCtrStride);
+      }
+    }
   } else {
     // cp.async staging ring, one private slice per thread (see axis_pipe_kernel)
     const int lt = tid - kLoaderThread0;
-    const int n_items = (tile_end - tile_begin) * 2;
+    const int n_items = my_tiles * 2;
     const int c4 = lt & 15, rsub = lt >> 4;                                   // rsub: 0..31
+    int iss_tile = tile_begin, iss_layer = 0, ready_seq = -1;                 // tile / layer of the next issue
+    long long dbg_blocked = 0;
+    const long long dbg_c0 = kPipe ? clock64() : 0;
+    const unsigned long long dbg_t0 = kPipe ? globaltimer_ns() : 0ull;
     const unsigned p_in = (unsigned)ax.p_inner;
     uint8_t* stg_base = smem + MXP_STAGING + lt * 16;
     const unsigned q32 = 32u / p_in, r32 = 32u % p_in;
@@ -595,8 +848,21 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
     const float* f_mode = ax.F + (long long)k * 2 * inner + c4 * 4;
     auto issue = [&](int item) {
       if (item < n_items) {
-        const int ltile = tile_begin + (item >> 1), half = item & 1;
-        const int tile = set.reverse ? n_tiles - 1 - ltile : ltile;
+        const int ltile = iss_tile, half = item & 1;
+        if (kPipe && half == 0) {         // first half of a tile: the unit's forward transforms must be complete
+          const int unit = ltile / set.pipe.tiles_per_unit[blockIdx.z];
+          const int seq = iss_layer * (n_tiles + 1) + unit;
+          if (seq != ready_seq) {
+            dbg_blocked += wait_unit_ready(s_seq, seq);
+            ready_seq = seq;
+            if (set.pipe.dbg_ts && lt == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+              const int q = iss_layer * (n_tiles / set.pipe.tiles_per_unit[0]) + unit;
+              if (q < 64) set.pipe.dbg_ts[q] = globaltimer_ns();
+            }
+          }
+        }
+        if (half == 1 && ++iss_tile == tile_end) { iss_tile = tile_begin; ++iss_layer; }
+        const int tile = (!kPipe && set.reverse) ? n_tiles - 1 - ltile : ltile;
         uint8_t* dst = stg_base + (item % kMxStages) * 32768;
         const long long row_first = (long long)tile * 128 + rsub;          // rows rsub + 32 it
         const unsigned rf = row_first < M ? (unsigned)row_first : 0u;
@@ -634,6 +900,13 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
       issue(item + kMxStages);
     }
     cp_async_wait<0>();
+    if (kPipe && lt == 0 && set.pipe.dbg) {
+      unsigned long long* d = set.pipe.dbg + 4 * (blockIdx.z * gridDim.y + blockIdx.y);
+      d[0] = (unsigned long long)dbg_blocked;
+      d[1] = (unsigned long long)(clock64() - dbg_c0);
+      d[2] = dbg_t0;
+      d[3] = globaltimer_ns();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -642,8 +915,9 @@ __global__ void __launch_bounds__(kThreads, 1) mix_pipe_kernel(MixSet set) {
 
 int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse) {
   FFNO_REQUIRE(n_axes >= 1 && n_axes <= 3, FFNO_ERR_BAD_ARG, "mix_pipe: n_axes=%d", n_axes);
-  FFNO_TRY(ensure_dynamic_smem(mix_pipe_kernel, MXP_TOTAL));
+  FFNO_TRY(ensure_dynamic_smem(mix_pipe_kernel<false>, MXP_TOTAL));
   MixSet set;
+  set.pipe = PipeDesc{};
   set.reverse = reverse ? 1 : 0;
   int maxK = 0, total_modes = 0;
   long long total_tiles = 0;
@@ -665,7 +939,7 @@ int launch_mix_pipe(const MixAxis* axes, int n_axes, int sm_count, cudaStream_t 
     const int gx = (int)((tiles + tpc - 1) / tpc);
     grid_x = gx > grid_x ? gx : grid_x;
   }
-  FFNO_CUDA_CHECK(launch_pdl(mix_pipe_kernel, dim3(grid_x, maxK, n_axes), dim3(kThreads), (size_t)MXP_TOTAL, st, set));
+  FFNO_CUDA_CHECK(launch_pdl(mix_pipe_kernel<false>, dim3(grid_x, maxK, n_axes), dim3(kThreads), (size_t)MXP_TOTAL, st, set));
   ++g_launch_counter;
   return FFNO_OK;
 }
@@ -684,18 +958,47 @@ constexpr int FF3_W = 0;
 constexpr int FF3_A1 = 131072;                     // 2 stages x (hi 16 KB | lo 16 KB)
 constexpr int FF3_OUT = FF3_A1 + 65536;            // 196608: 128 rows x 256 B staging
 constexpr int FF3_BIAS = FF3_OUT + 32768;          // 229376
-constexpr int FF3_BAR = FF3_BIAS + 320 * 4;        // 230656
-constexpr int FF3_HEAD = FF3_BAR + 192;            // 64 floats: folded head weights of a 1-output head
-constexpr int FF3_TOTAL = FF3_HEAD + 256;          // 231104 <= 232448
+constexpr int FF3_BAR = FF3_BIAS + 2 * 320 * 4;    // 231936: two bias sets (kPipe: the layer's parity selects the live one)
+constexpr int FF3_HEAD = FF3_BAR + 208;            // 64 floats: folded head weights of a 1-output head
+constexpr int FF3_TOTAL = FF3_HEAD + 256;          // 232400 <= 232448
 constexpr int kFF3Threads = 576;                   // 8 chunk-epilogue + 4 store + G1 issuer + 4 loader + G2 issuer warps
 constexpr int kFF3G1Warp = 12, kFF3G2Warp = 17;
+constexpr int kFF3PollWarp = 18, kFF3PubWarp = 19, kFF3PipeThreads = kFF3Threads + 64;   // pipelined kernel only
 
-__global__ void __launch_bounds__(kFF3Threads, 1)  // 18 warps are allocated as 20: 96 registers/thread is the cap
-ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
-             const float* __restrict__ residual, float* __restrict__ x_out, float* __restrict__ b_out,
-             const uint8_t* __restrict__ image, const float* __restrict__ b1, const float* __restrict__ b2,
-             const float* __restrict__ head_w, const float* __restrict__ head_b, float* __restrict__ forecast,
-             long long P, int n_tiles, int reverse) {
+struct FFArgs {
+  const float *s0, *s1, *s2, *residual;
+  float *x_out, *b_out;
+  const uint8_t* image;
+  const float *b1, *b2, *head_w, *head_b;
+  float* forecast;
+  long long P;
+  int n_tiles, reverse;
+  // kPipe: every layer in one launch.  Layer l reads the residual stream from xbuf[l & 1] and writes xbuf[(l + 1) & 1]
+  // (nothing on the last layer, whose store warps apply the fused head instead); weights / biases come from layers[l].
+  const FFLayerArgs* layers;
+  float* xbuf[2];
+  PipeDesc pipe;
+};
+
+template <bool kPipe>
+__global__ void __launch_bounds__(kPipe ? kFF3PipeThreads : kFF3Threads, 1)  // 18 warps are allocated as 20: 96 registers/thread
+ff_ts_kernel(const FFArgs a) {
+  const float* __restrict__ s0 = a.s0;
+  const float* __restrict__ s1 = a.s1;
+  const float* __restrict__ s2 = a.s2;
+  const float* __restrict__ residual = a.residual;
+  float* __restrict__ x_out = a.x_out;
+  float* __restrict__ b_out = a.b_out;
+  const uint8_t* __restrict__ image = kPipe ? a.layers[0].image : a.image;
+  const float* __restrict__ b1 = kPipe ? a.layers[0].b1 : a.b1;
+  const float* __restrict__ b2 = kPipe ? a.layers[0].b2 : a.b2;
+  const float* __restrict__ head_w = a.head_w;
+  const float* __restrict__ head_b = a.head_b;
+  float* __restrict__ forecast = a.forecast;
+  const long long P = a.P;
+  const int n_tiles = a.n_tiles, reverse = kPipe ? 0 : a.reverse;
+  const int n_layers = kPipe ? a.pipe.n_layers : 1;
+  const int my_tiles = (int)(((long long)n_layers * n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
   extern __shared__ __align__(1024) uint8_t smem[];
   float* sb1 = reinterpret_cast<float*>(smem + FF3_BIAS);
   float* sb2 = sb1 + 256;
@@ -710,7 +1013,10 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
   uint64_t* d2_empty = bars + 18;   // [2] 128 (store warps)
   uint64_t* bar_w = bars + 20;      // W1 image (first 64 KB) landed
   uint64_t* bar_w2 = bars + 21;     // W2 image (second 64 KB) landed: only GEMM2 needs it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* w_free = bars + 22;     // [2] kPipe: every GEMM1 / GEMM2 MMA issued so far has retired (W1 / W2 may be replaced)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  int* s_seq = reinterpret_cast<int*>(tmem_slot + 1);      // kPipe: last unit the poller has seen ready
+  int* s_pub = s_seq + 1;                                  // kPipe: store warps that have issued their tile's stores
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -733,6 +1039,10 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       mbar_init(&a2_full[i], 128);
       mbar_init(&a2_empty[i], 1);
     }
+    mbar_init(&w_free[0], 1);
+    mbar_init(&w_free[1], 1);
+    *s_seq = -1;
+    *s_pub = 0;
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -755,8 +1065,18 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     const int team = warp >> 2;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t a2_addr = tmem + lane_base + (uint32_t)(384 + team * 64);
-    int n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+    int tile = (int)blockIdx.x - (int)gridDim.x, layer = 0;
+    for (int n = 0; n < my_tiles; ++n) {
+      tile += gridDim.x;
+      if (kPipe && tile >= n_tiles) { tile -= n_tiles; ++layer; }
+      if (kPipe && tile < (int)gridDim.x && layer > 0) {
+        // first tile of a new layer: its b1 goes into the bias set of the layer's parity (the other set may still be
+        // read by a slower warp of the role; the gpu-scope acquires of the loaders keep invalidating L1, so the hot
+        // loop must not read biases from global memory)
+        sb1[(layer & 1) * 320 + tid] = __ldg(a.layers[layer].b1 + tid);
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
+      const float* bl = sb1 + (kPipe ? (layer & 1) * 320 : 0);
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const int j = 2 * h + team;              // chunk of hidden units j*64 .. j*64+63
@@ -764,7 +1084,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         mbar_wait(&d1_full[h], (uint32_t)n & 1u);
         tc_fence_after();
         if ((warp & 3) == 0) TL(team ? 5 : 0, n, h * 4 + 0);
-        const float* bj = sb1 + j * 64;
+        const float* bj = bl + j * 64;
 #pragma unroll
         for (int part = 0; part < 2; ++part) {      // 32 columns = one A2 stage at a time (~64 live registers)
           uint32_t v[32];
@@ -812,8 +1132,30 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     const uint8_t* so_rd0 = sOut + rq * 256 + ((cq ^ rq) << 4);            // (rq + 16 it) & 15 == rq
     const uint8_t* so_rd1 = sOut + rq * 256 + (((8 + cq) ^ rq) << 4);
     const float hb = forecast ? head_b[0] : 0.f;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+    int tile = (int)blockIdx.x - (int)gridDim.x, layer = 0, ready_seq = -1;
+    const float* b2l = sb2;
+    for (int n = 0; n < my_tiles; ++n) {
+      tile += gridDim.x;
+      if (kPipe && tile >= n_tiles) { tile -= n_tiles; ++layer; }
+      if (kPipe) {
+        // this layer's buffers; the fused head replaces the residual-stream store on the last layer
+        const bool last = layer == n_layers - 1;
+        residual = a.xbuf[layer & 1];
+        x_out = last ? nullptr : a.xbuf[(layer + 1) & 1];
+        forecast = last ? a.forecast : nullptr;
+        if (tile < (int)gridDim.x && layer > 0) {       // first tile of a new layer: b2 into the parity's bias set
+          if (rt < 64) sb2[(layer & 1) * 320 + rt] = __ldg(a.layers[layer].b2 + rt);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        b2l = sb2 + (layer & 1) * 320;
+        // the rows read (residual) and overwritten (x of layer l - 1) below belong to FF(l - 1, unit): it must be complete
+        const int unit = tile / a.pipe.tiles_per_unit[0];
+        const int seq = layer * (n_tiles + 1) + unit;
+        if (seq != ready_seq) {      // (ready inverse transforms of (l, unit) imply a complete FF(l - 1, unit))
+          wait_unit_ready(s_seq, seq);
+          ready_seq = seq;
+        }
+      }
       const long long row0 = (long long)(reverse ? n_tiles - 1 - tile : tile) * 128;
       const int rows_left = (P - row0) < 128 ? (int)(P - row0) : 128;
       const long long gofs = row0 * 64 + rq * 64 + cq * 4;
@@ -825,7 +1167,8 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       const float* rp = residual ? residual + gofs : s0 + gofs;
 #pragma unroll
       for (int it = 0; it < 8; ++it)
-        r0[it] = (residual && it * 16 + rq < rows_left) ? ldg_stream(rp + it * 1024) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r0[it] = (residual && it * 16 + rq < rows_left) ? (kPipe ? ldg_cg(rp + it * 1024) : ldg_stream(rp + it * 1024))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
       const int ds = n & 1;
       mbar_wait(&d2_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
@@ -843,7 +1186,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int c4 = half * 8 + e;
-          const float4 bb = *reinterpret_cast<const float4*>(sb2 + c4 * 4);
+          const float4 bb = *reinterpret_cast<const float4*>(b2l + c4 * 4);
           float4 b;
           b.x = __uint_as_float(v[e * 4 + 0]) + bb.x;
           b.y = __uint_as_float(v[e * 4 + 1]) + bb.y;
@@ -859,7 +1202,8 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       if (forecast && rt < rows_left) forecast[row0 + rt] = hacc + hb;
 #pragma unroll
       for (int it = 0; it < 8; ++it)
-        r1[it] = (residual && it * 16 + rq < rows_left) ? ldg_stream(rp + it * 1024 + 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r1[it] = (residual && it * 16 + rq < rows_left) ? (kPipe ? ldg_cg(rp + it * 1024 + 32) : ldg_stream(rp + it * 1024 + 32))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 8) TL(1, n, 2);
       if (b_out) {             // last layer only
@@ -889,6 +1233,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (kPipe) stores_issued(s_pub);
       if (warp == 8) TL(1, n, 3);
     }
   } else if (warp == kFF3G1Warp) {
@@ -903,8 +1248,27 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     const uint64_t dA1h = desc_kmajor(smem_u32(smem + FF3_A1), 0), dA1l = desc_kmajor(smem_u32(smem + FF3_A1) + 16384u, 0);
     const uint64_t dW1h = desc_kmajor(sW, 0), dW1l = desc_kmajor(sW + 32768u, 0);
     constexpr uint64_t kStage = 32768 >> 4, kHalf = 16384 >> 4;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+    int tile = (int)blockIdx.x - (int)gridDim.x, layer = 0;
+    uint32_t w_phase = 1u, free_phase = 0u;
+    for (int n = 0; n < my_tiles; ++n) {
+      tile += gridDim.x;
+      if (kPipe && tile >= n_tiles) {
+        // next layer: once every GEMM1 issued so far has retired, replace the W1 image (the GEMM2s, chunk epilogues and
+        // stores of the previous tile keep running meanwhile) and wait for it to land
+        tile -= n_tiles;
+        ++layer;
+        umma_commit_elect(&w_free[0]);
+        mbar_wait(&w_free[0], free_phase);
+        free_phase ^= 1u;
+        if (lane == 0) {
+          mbar_expect_tx(bar_w, 65536);
+          const uint8_t* img = a.layers[layer].image;
+          for (int i = 0; i < 2; ++i) bulk_g2s(smem + FF3_W + i * 32768, img + i * 32768, 32768, bar_w);
+        }
+        __syncwarp();
+        mbar_wait(bar_w, w_phase);
+        w_phase ^= 1u;
+      }
       const int stn = n & 1;
       mbar_wait(&a1_full[stn], (uint32_t)(n >> 1) & 1u);
       if (lane == 0) TL(2, n, 0);
@@ -929,8 +1293,25 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
     const uint32_t sW = smem_u32(smem + FF3_W);
     const uint64_t dW2h = desc_kmajor(sW + 65536u, 0), dW2l = desc_kmajor(sW + 98304u, 0);
     constexpr uint64_t kBlk = 8192 >> 4;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+    int tile = (int)blockIdx.x - (int)gridDim.x, layer = 0;
+    uint32_t w_phase = 1u, free_phase = 0u;
+    for (int n = 0; n < my_tiles; ++n) {
+      tile += gridDim.x;
+      if (kPipe && tile >= n_tiles) {             // next layer: same hand-over for the W2 image
+        tile -= n_tiles;
+        ++layer;
+        umma_commit_elect(&w_free[1]);
+        mbar_wait(&w_free[1], free_phase);
+        free_phase ^= 1u;
+        if (lane == 0) {
+          mbar_expect_tx(bar_w2, 65536);
+          const uint8_t* img = a.layers[layer].image;
+          for (int i = 2; i < 4; ++i) bulk_g2s(smem + FF3_W + i * 32768, img + i * 32768, 32768, bar_w2);
+        }
+        __syncwarp();
+        mbar_wait(bar_w2, w_phase);
+        w_phase ^= 1u;
+      }
       const int ds = n & 1;
       const uint32_t d2 = tmem + (uint32_t)(256 + ds * 64);
 #pragma unroll
@@ -968,6 +1349,34 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       }
     }
     __syncwarp();
+  } else if (kPipe && warp == kFF3PollWarp) {
+    if (lane == 0) {      // poller: the unit's inverse transforms of every axis
+      const int tpu = a.pipe.tiles_per_unit[0];
+      int tile = (int)blockIdx.x - (int)gridDim.x, layer = 0, last = -1;
+      for (int n = 0; n < my_tiles; ++n) {
+        tile += gridDim.x;
+        if (tile >= n_tiles) { tile -= n_tiles; ++layer; }
+        const int unit = tile / tpu, seq = layer * (n_tiles + 1) + unit;
+        if (seq != last) {
+          pipe_wait(a.pipe.wait_ctr[0] + unit * kCtrStride, (unsigned)(layer + 1) * a.pipe.wait_count[0]);
+          pipe_wait(a.pipe.wait_ctr[1] + unit * kCtrStride, (unsigned)(layer + 1) * a.pipe.wait_count[1]);
+          st_release_cta_smem(s_seq, seq);
+          last = seq;
+        }
+      }
+    }
+  } else if (kPipe && warp == kFF3PubWarp) {
+    if (lane == 0) {      // publisher
+      const int tpu = a.pipe.tiles_per_unit[0];
+      int tile = (int)blockIdx.x - (int)gridDim.x, need = 0;
+      for (int n = 0; n < my_tiles; ++n) {
+        tile += gridDim.x;
+        if (tile >= n_tiles) tile -= n_tiles;
+        need += 4;
+        smem_wait_ge(s_pub, need);
+        pipe_publish(a.pipe.done_ctr[0] + (tile / tpu) * kCtrStride);
+      }
+    }
   } else {
     // ---------------------------------------------------------------- loaders: (s0 + s1 + s2) tile -> A1[stage]
     // Two rounds of 8 float4 per source and thread (64 data registers live at most: more spills under the 96-register
@@ -983,17 +1392,34 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       if (s2) prefetch_l2_bulk(s2 + row0 * 64, bytes);
       if (residual) prefetch_l2_bulk(residual + row0 * 64, bytes);
     };
-    if (lt == 0 && (int)blockIdx.x < n_tiles) prefetch_tile(blockIdx.x);
+    if (!kPipe && lt == 0 && (int)blockIdx.x < n_tiles) prefetch_tile(blockIdx.x);
     const int lr = lt >> 4, lc = lt & 15;      // rows lr + 8 i (i = 0..15), float4 column lc
     const uint32_t a_off = (uint32_t)lr * 128u + (uint32_t)(((lc >> 1) ^ lr) << 4) + (uint32_t)(lc & 1) * 8u;   // + 1024 i
-    int n = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+    int tile = (int)blockIdx.x - (int)gridDim.x, layer = 0, ready_seq = -1;
+    long long dbg_blocked = 0;
+    const long long dbg_c0 = kPipe ? clock64() : 0;
+    const unsigned long long dbg_t0 = kPipe ? globaltimer_ns() : 0ull;
+    for (int n = 0; n < my_tiles; ++n) {
+      tile += gridDim.x;
+      if (kPipe && tile >= n_tiles) { tile -= n_tiles; ++layer; }
+      if (kPipe) {      // the unit's inverse transforms of every axis must be complete
+        const int unit = tile / a.pipe.tiles_per_unit[0];
+        const int seq = layer * (n_tiles + 1) + unit;
+        if (seq != ready_seq) {
+          dbg_blocked += wait_unit_ready(s_seq, seq);
+          ready_seq = seq;
+          if (a.pipe.dbg_ts && lt == 0 && blockIdx.x == 0) {
+            const int q = layer * (n_tiles / a.pipe.tiles_per_unit[0]) + unit;
+            if (q < 64) a.pipe.dbg_ts[q] = globaltimer_ns();
+          }
+        }
+      }
       const long long row0 = (long long)(reverse ? n_tiles - 1 - tile : tile) * 128;
       const int rows_left = (P - row0) < 128 ? (int)(P - row0) : 128;
       const long long gofs = row0 * 64 + lr * 64 + lc * 4;
       const int st = n & 1;
       if (lt < 32) TL(3, n, 0);
-      if (lt == 0 && tile + (int)gridDim.x < n_tiles) prefetch_tile(tile + (int)gridDim.x);
+      if (!kPipe && lt == 0 && tile + (int)gridDim.x < n_tiles) prefetch_tile(tile + (int)gridDim.x);
       uint8_t* sA1h = smem + FF3_A1 + st * 32768 + a_off;
       uint8_t* sA1l = sA1h + 16384;
       const float* p0 = s0 + gofs;
@@ -1005,13 +1431,13 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int i = half * 8 + it;
-          v[it] = (i * 8 + lr < rows_left) ? ldg_stream(p0 + i * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[it] = (i * 8 + lr < rows_left) ? (kPipe ? ldg_cg(p0 + i * 512) : ldg_stream(p0 + i * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (s1) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int i = half * 8 + it;
-            t[it] = (i * 8 + lr < rows_left) ? ldg_stream(p1 + i * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+            t[it] = (i * 8 + lr < rows_left) ? (kPipe ? ldg_cg(p1 + i * 512) : ldg_stream(p1 + i * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -1022,7 +1448,7 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int i = half * 8 + it;
-            t[it] = (i * 8 + lr < rows_left) ? ldg_stream(p2 + i * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+            t[it] = (i * 8 + lr < rows_left) ? (kPipe ? ldg_cg(p2 + i * 512) : ldg_stream(p2 + i * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
@@ -1041,6 +1467,13 @@ ff_ts_kernel(const float* __restrict__ s0, const float* __restrict__ s1, const f
       mbar_arrive(&a1_full[st]);
       if (lt < 32) TL(3, n, 3);
     }
+    if (kPipe && lt == 0 && a.pipe.dbg) {
+      unsigned long long* d = a.pipe.dbg + 4 * blockIdx.x;
+      d[0] = (unsigned long long)dbg_blocked;
+      d[1] = (unsigned long long)(clock64() - dbg_c0);
+      d[2] = dbg_t0;
+      d[3] = globaltimer_ns();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1051,12 +1484,219 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
                  const uint8_t* image, const float* b1, const float* b2, long long P, int sm_count, cudaStream_t st,
                  const float* head_w, const float* head_b, float* forecast, bool reverse) {
   if (P == 0) return FFNO_OK;
-  FFNO_TRY(ensure_dynamic_smem(ff_ts_kernel, FF3_TOTAL));
+  FFNO_TRY(ensure_dynamic_smem(ff_ts_kernel<false>, FF3_TOTAL));
   const int n_tiles = ceil_div(P, 128);
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  FFNO_CUDA_CHECK(launch_pdl(ff_ts_kernel, dim3(grid), dim3(kFF3Threads), (size_t)FF3_TOTAL, st, s0, s1, s2, residual, x_out,
-                             b_out, image, b1, b2, head_w, head_b, forecast, P, n_tiles, reverse ? 1 : 0));
+  FFArgs a{};
+  a.s0 = s0; a.s1 = s1; a.s2 = s2; a.residual = residual; a.x_out = x_out; a.b_out = b_out;
+  a.image = image; a.b1 = b1; a.b2 = b2; a.head_w = head_w; a.head_b = head_b; a.forecast = forecast;
+  a.P = P; a.n_tiles = n_tiles; a.reverse = reverse ? 1 : 0;
+  FFNO_CUDA_CHECK(launch_pdl(ff_ts_kernel<false>, dim3(grid), dim3(kFF3Threads), (size_t)FF3_TOTAL, st, a));
   ++g_launch_counter;
+  return FFNO_OK;
+}
+
+
+// =======================================================================================================
+// Stage-pipelined forward of the whole layer stack: four launches per forward (see PipeDesc).
+// =======================================================================================================
+static int pipe_axis_set(const AxisXform* axes, int n_axes, int n_units, AxisSet* set, size_t* smem, int* max_tiles) {
+  *smem = 0;
+  *max_tiles = 0;
+  set->reverse = 0;
+  for (int a = 0; a < n_axes; ++a) {
+    const AxisXform& p = axes[a];
+    FFNO_REQUIRE(p.inner % 64 == 0 && p.inner < (1ll << 23) && p.npad >= 16 && p.npad <= 256 && p.npad % 16 == 0,
+                 FFNO_ERR_UNSUPPORTED, "stack_pipe: axis %d geometry", a);
+    const int ring = axis_ring_depth(p.n_in, p.n_out);
+    FFNO_REQUIRE(ring > 0, FFNO_ERR_UNSUPPORTED, "stack_pipe: table does not fit in shared memory");
+    set->ring[a] = ring;
+    const size_t need = axp_table_offset(ring) + table_image_bytes(p.n_in, p.n_out);
+    *smem = need > *smem ? need : *smem;
+    set->ax[a] = p;
+    const long long n_groups = p.outer * (p.inner / 64);
+    FFNO_REQUIRE(n_groups % (2 * n_units) == 0 && n_groups < (1ll << 31), FFNO_ERR_UNSUPPORTED,
+                 "stack_pipe: %lld groups of axis %d do not split into %d units of whole tiles", n_groups, a, n_units);
+    set->n_tiles[a] = (int)(n_groups / 2);
+    set->pipe.tiles_per_unit[a] = set->n_tiles[a] / n_units;
+    int cols = 32;
+    while (cols < 2 * p.npad) cols *= 2;
+    set->tmem_cols[a] = cols;
+    *max_tiles = set->n_tiles[a] > *max_tiles ? set->n_tiles[a] : *max_tiles;
+  }
+  return FFNO_OK;
+}
+
+
+size_t stack_pipe_counter_bytes(int n_units) { return (size_t)10 * n_units * kCtrStride * sizeof(unsigned); }
+
+bool stack_pipe_geometry_ok(const AxisXform* fwd, const MixAxis* mix, int n_axes, long long P, int n_units) {
+  if (n_axes != 2 || n_units < 4 || P % (128ll * n_units) != 0) return false;
+  for (int a = 0; a < n_axes; ++a) {
+    const long long n_groups = fwd[a].outer * (fwd[a].inner / 64);
+    if (fwd[a].inner % 64 != 0 || n_groups % (2 * n_units) != 0) return false;
+    const long long rows = mix[a].outer * mix[a].p_inner;
+    if (rows % (128ll * n_units) != 0) return false;
+  }
+  return true;
+}
+
+int launch_stack_pipe(const StackPipeArgs& A) {
+  const int n_units = A.n_units, na = A.n_axes, L = A.n_layers;
+  FFNO_REQUIRE(na == 2, FFNO_ERR_UNSUPPORTED, "stack_pipe: %d axes", na);
+  FFNO_REQUIRE(stack_pipe_geometry_ok(A.fwd, A.mix, na, A.P, n_units), FFNO_ERR_UNSUPPORTED, "stack_pipe: geometry");
+  const size_t cs = (size_t)n_units * kCtrStride;          // one 128-byte line per counter
+  unsigned* ctr_fwd[3], *ctr_mix[3], *ctr_inv[3], *ctr_ff = A.counters + 9 * cs;
+  for (int a = 0; a < 3; ++a) {
+    ctr_fwd[a] = A.counters + a * cs;
+    ctr_mix[a] = A.counters + (3 + a) * cs;
+    ctr_inv[a] = A.counters + (6 + a) * cs;
+  }
+  const int ff_tiles = (int)(A.P / 128), ff_tpu = ff_tiles / n_units;
+  const unsigned ff_arrivals = (unsigned)ff_tpu;              // the publisher warps post one arrival per finished tile
+
+  AxisSet fset{}, iset{};
+  size_t fsmem, ismem;
+  int fmax, imax;
+  FFNO_TRY(pipe_axis_set(A.fwd, na, n_units, &fset, &fsmem, &fmax));
+  FFNO_TRY(pipe_axis_set(A.inv, na, n_units, &iset, &ismem, &imax));
+  MixSet mset{};
+  int maxK = 0;
+  unsigned fwd_arr[3] = {0, 0, 0}, mix_arr[3] = {0, 0, 0}, inv_arr[3] = {0, 0, 0};
+  for (int a = 0; a < na; ++a) {
+    mset.ax[a] = A.mix[a];
+    const int tiles = (int)(A.mix[a].outer * A.mix[a].p_inner / 128);
+    mset.tiles_per_cta[a] = tiles;
+    mset.pipe.tiles_per_unit[a] = tiles / n_units;
+    maxK = A.mix[a].K > maxK ? A.mix[a].K : maxK;
+    fwd_arr[a] = (unsigned)fset.pipe.tiles_per_unit[a];
+    mix_arr[a] = (unsigned)A.mix[a].K * (unsigned)mset.pipe.tiles_per_unit[a];
+    inv_arr[a] = (unsigned)iset.pipe.tiles_per_unit[a];
+  }
+  // forward transforms: wait for the FF of the previous layer (nothing at layer 0), read x of the layer's parity
+  fset.pipe.n_layers = L;
+  fset.pipe.wait_lag = 0;
+  for (int a = 0; a < na; ++a) {
+    fset.pipe.wait_ctr[a] = ctr_ff;
+    fset.pipe.wait_count[a] = ff_arrivals;
+    fset.pipe.done_ctr[a] = ctr_fwd[a];
+    fset.X_odd[a] = A.x_odd;
+    iset.X_odd[a] = A.inv[a].X;
+  }
+  mset.reverse = 0;
+  mset.pipe.n_layers = L;
+  mset.pipe.wait_lag = 1;
+  iset.pipe.n_layers = L;
+  iset.pipe.wait_lag = 1;
+  for (int a = 0; a < na; ++a) {
+    mset.pipe.wait_ctr[a] = ctr_fwd[a];
+    mset.pipe.wait_count[a] = fwd_arr[a];
+    mset.pipe.done_ctr[a] = ctr_mix[a];
+    iset.pipe.wait_ctr[a] = ctr_mix[a];
+    iset.pipe.wait_count[a] = mix_arr[a];
+    iset.pipe.done_ctr[a] = ctr_inv[a];
+  }
+  FFArgs fa{};
+  fa.s0 = A.inv[0].Y;
+  fa.s1 = A.inv[1].Y;
+  fa.s2 = nullptr;
+  fa.head_w = A.head_w;
+  fa.head_b = A.head_b;
+  fa.forecast = A.forecast;
+  fa.P = A.P;
+  fa.n_tiles = ff_tiles;
+  fa.layers = A.ff_layers;
+  fa.xbuf[0] = A.xbuf[0];
+  fa.xbuf[1] = A.xbuf[1];
+  fa.pipe.n_layers = L;
+  fa.pipe.tiles_per_unit[0] = ff_tpu;
+  fa.pipe.wait_lag = 1;
+  fa.pipe.wait_ctr[0] = ctr_inv[0];
+  fa.pipe.wait_ctr[1] = ctr_inv[1];
+  fa.pipe.wait_count[0] = inv_arr[0];
+  fa.pipe.wait_count[1] = inv_arr[1];
+  fa.pipe.done_ctr[0] = ctr_ff;
+
+  // SM budget: one CTA per (axis, mode) for the mix; the rest split between the three streaming stages
+  int g_fwd = A.sms[0] / na, g_inv = A.sms[2] / na, g_ff = A.sms[3];
+  g_fwd = g_fwd < 1 ? 1 : (g_fwd > fmax ? fmax : g_fwd);
+  g_inv = g_inv < 1 ? 1 : (g_inv > imax ? imax : g_inv);
+  g_ff = g_ff < 1 ? 1 : (g_ff > ff_tiles ? ff_tiles : g_ff);
+  for (int a = 0; a < na; ++a)
+    FFNO_REQUIRE(g_fwd <= fset.n_tiles[a] && g_inv <= iset.n_tiles[a], FFNO_ERR_UNSUPPORTED, "stack_pipe: grid > tiles");
+
+  FFNO_TRY(ensure_dynamic_smem(axis_pipe_kernel<true>, fsmem > ismem ? fsmem : ismem));
+  FFNO_TRY(ensure_dynamic_smem(mix_pipe_kernel<true>, MXP_TOTAL));
+  FFNO_TRY(ensure_dynamic_smem(ff_ts_kernel<true>, FF3_TOTAL));
+
+  if (A.dbg) {
+    unsigned long long* d = A.dbg;
+    d += 8;                                     // header written by the host wrapper: grid sizes
+    fset.pipe.dbg = d;
+    d += 4 * na * g_fwd;
+    mset.pipe.dbg = d;
+    d += 4 * na * maxK;
+    iset.pipe.dbg = d;
+    d += 4 * na * g_inv;
+    fa.pipe.dbg = d;
+    unsigned long long* ts = A.dbg + 8 + 4 * 256;
+    fset.pipe.dbg_ts = ts;
+    mset.pipe.dbg_ts = ts + 64;
+    iset.pipe.dbg_ts = ts + 128;
+    fa.pipe.dbg_ts = ts + 192;
+    const unsigned long long hdr[8] = {(unsigned long long)(na * g_fwd), (unsigned long long)(na * maxK),
+                                       (unsigned long long)(na * g_inv), (unsigned long long)g_ff, 0, 0, 0, 0};
+    FFNO_CUDA_CHECK(cudaMemcpyAsync(A.dbg, hdr, sizeof(hdr), cudaMemcpyHostToDevice, A.streams[0]));
+  }
+  cudaStream_t st = A.streams[0];
+  // diagnostics (A.only_stage >= 0): one stage alone with every dependency pre-satisfied — its raw throughput
+  FFNO_CUDA_CHECK(cudaMemsetAsync(A.counters, A.only_stage >= 0 ? 0x3f : 0, stack_pipe_counter_bytes(n_units), st));
+  FFNO_CUDA_CHECK(cudaEventRecord(A.fork, st));
+  for (int i = 1; i < 4; ++i) FFNO_CUDA_CHECK(cudaStreamWaitEvent(A.streams[i], A.fork, 0));
+  const int only = A.only_stage;
+  if (only < 0 || only == 0) axis_pipe_kernel<true><<<dim3(g_fwd, na), kPipeThreads, fsmem, A.streams[0]>>>(fset);
+  if (only < 0 || only == 1) mix_pipe_kernel<true><<<dim3(1, maxK, na), kPipeThreads, MXP_TOTAL, A.streams[1]>>>(mset);
+  if (only < 0 || only == 2) axis_pipe_kernel<true><<<dim3(g_inv, na), kPipeThreads, ismem, A.streams[2]>>>(iset);
+  if (only < 0 || only == 3) ff_ts_kernel<true><<<dim3(g_ff), kFF3PipeThreads, FF3_TOTAL, A.streams[3]>>>(fa);
+  g_launch_counter += 4;
+  const cudaError_t e = cudaGetLastError();
+  for (int i = 1; i < 4; ++i) {          // always rejoin (a forked stream must rejoin a capture even after an error)
+    cudaEventRecord(A.join[i - 1], A.streams[i]);
+    cudaStreamWaitEvent(st, A.join[i - 1], 0);
+  }
+  if (e != cudaSuccess) return set_error(FFNO_ERR_CUDA, "stack_pipe launch failed: %s", cudaGetErrorString(e));
+  return FFNO_OK;
+}
+
+// Two tiny kernels that can only both succeed when they run at the same time (each raises its flag and waits ~1 ms for
+// the other's): tells whether kernels of different streams really execute concurrently in this process — they do not
+// under a profiler that serialises launches or with CUDA_LAUNCH_BLOCKING=1, where the stage-pipelined forward must not
+// be used (its stages wait for each other).
+__global__ void concurrency_probe_kernel(unsigned* flags, int me) {
+  atomicExch(&flags[me], 1u);
+  __threadfence();
+  const long long t0 = clock64();
+  unsigned seen = 0;
+  while (clock64() - t0 < 2000000ll) {
+    seen = ld_acquire_gpu(&flags[1 - me]);
+    if (seen) break;
+    __nanosleep(200);
+  }
+  flags[2 + me] = seen;
+}
+int probe_stream_concurrency(cudaStream_t s0, cudaStream_t s1, unsigned* dev_flags4, bool* concurrent) {
+  *concurrent = false;
+  FFNO_CUDA_CHECK(cudaMemsetAsync(dev_flags4, 0, 4 * sizeof(unsigned), s0));
+  FFNO_CUDA_CHECK(cudaStreamSynchronize(s0));
+  concurrency_probe_kernel<<<1, 1, 0, s0>>>(dev_flags4, 0);
+  concurrency_probe_kernel<<<1, 1, 0, s1>>>(dev_flags4, 1);
+  g_launch_counter += 2;
+  FFNO_LAUNCH_CHECK("concurrency_probe_kernel");
+  FFNO_CUDA_CHECK(cudaStreamSynchronize(s0));
+  FFNO_CUDA_CHECK(cudaStreamSynchronize(s1));
+  unsigned h[4] = {0, 0, 0, 0};
+  FFNO_CUDA_CHECK(cudaMemcpy(h, dev_flags4, sizeof(h), cudaMemcpyDeviceToHost));
+  *concurrent = h[2] != 0 && h[3] != 0;
   return FFNO_OK;
 }
 

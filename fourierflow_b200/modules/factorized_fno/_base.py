@@ -10,6 +10,20 @@ import torch.nn as nn
 from ... import _ops
 
 
+# Bumped whenever ANY nn.Module in the process registers a sub-module or a parameter (torch's global registration
+# hooks): the cheap way to know that a cached parameter list may no longer describe the module tree.
+_STRUCTURE_EPOCH = [0]
+
+
+def _bump_structure_epoch(*_args):
+    _STRUCTURE_EPOCH[0] += 1
+    return None
+
+
+torch.nn.modules.module.register_module_module_registration_hook(_bump_structure_epoch)
+torch.nn.modules.module.register_module_parameter_registration_hook(_bump_structure_epoch)
+
+
 def default_path() -> str:
     """`FFNO_B200_PATH=generic|umma|auto` overrides the kernel family (testing / profiling)."""
     return os.environ.get("FFNO_B200_PATH", "auto")
@@ -27,22 +41,24 @@ class PlanCacheMixin:
 
     def _flat_params(self):
         """Distinct parameters of the module tree, cached — walking a 24-layer tree with ``parameters()`` on every
-        forward costs more than launching the CUDA graph.  The cache is re-validated on every call by identity: each
-        cached Parameter must still be the object registered under its owner's name and each owner must still have
-        the same children, so ``load_state_dict(..., assign=True)``, ``.to()`` / ``_apply`` replacements, swapped
-        sub-modules and added layers are all picked up (the reference re-folds weight-norm from the live parameters
-        on every forward, linear.py:49).  In-place edits through ``p.data`` bump no version counter and cannot be seen
-        from here: call ``invalidate_plans()`` after such an edit."""
+        forward costs more than launching the CUDA graph.  The cache is re-validated on every call: (i) each cached
+        Parameter must still be the object registered under its owner's name (``load_state_dict(assign=True)``,
+        re-registration, ``_apply`` replacements), and (ii) no module or parameter may have been registered anywhere in
+        the process since the cache was built (swapped sub-modules, added layers) — torch's global registration hooks
+        bump ``_STRUCTURE_EPOCH``.  The reference re-folds weight-norm from the live parameters on every forward
+        (linear.py:49); this is the same guarantee at ~15 us per call.  In-place edits through ``p.data`` bump no
+        version counter and cannot be seen from here: call ``invalidate_plans()`` after such an edit."""
         cached = self.__dict__.get("_param_cache")
         if cached is not None:
-            owners, children, params = cached
-            if all(mod._parameters.get(name) is p for mod, name, p in owners) and \
-                    all(len(kids) == len(mod._modules) and all(a is b for a, b in zip(kids, mod._modules.values()))
-                        for mod, kids in children):
-                return params
-        owners, children, params, seen = [], [], [], set()
+            epoch, owners, params = cached
+            if epoch == _STRUCTURE_EPOCH[0]:
+                for mod, name, p in owners:
+                    if mod._parameters.get(name) is not p:
+                        break
+                else:
+                    return params
+        owners, params, seen = [], [], set()
         for mod in self.modules():
-            children.append((mod, tuple(mod._modules.values())))
             for name, p in mod._parameters.items():
                 if p is None:
                     continue
@@ -50,7 +66,7 @@ class PlanCacheMixin:
                 if id(p) not in seen:
                     seen.add(id(p))
                     params.append(p)
-        self.__dict__["_param_cache"] = (owners, children, params)
+        self.__dict__["_param_cache"] = (_STRUCTURE_EPOCH[0], owners, params)
         self.__dict__.pop("_spec_cache", None)          # layer specs hold Parameter references too
         return params
 

@@ -240,6 +240,21 @@ FFNO_API int64_t ffno_plan_last_launch_count(const ffno_plan* plan);
  * cannot be captured. */
 FFNO_API int ffno_plan_graph_active(const ffno_plan* plan);
 
+/* Samples per pipeline unit when ffno_block_fwd / ffno_rollout_fwd run `batch` samples through the STAGE-PIPELINED
+ * forward — the transform / mix / inverse / FeedForward kernels launched once per forward as persistent,
+ * flag-synchronised stages on disjoint SMs (replaces the layer loop of grid_2d.py:160-169 as a whole) — or 0 when this
+ * plan and batch use one launch per stage and layer (3-D, padded or forked stacks, unshared mode weights, fewer than
+ * four units, FFNO_B200_PERSIST not set to 1 (the path is opt-in), or a process whose kernels do not run concurrently,
+ * e.g. under a profiler). */
+FFNO_API int ffno_plan_pipeline_unit(const ffno_plan* plan, int32_t batch);
+
+/* Diagnostics of the stage-pipelined forward (plans created with FFNO_B200_PIPE_DEBUG=1, FFNO_B200_GRAPH=0): copies
+ * up to n_words 64-bit words to the host — 8 header words {CTAs of the forward-transform, mix, inverse-transform and
+ * FF stage, 0...} followed, stage after stage, by 4 words per CTA of the last forward: SM cycles its loaders spent
+ * blocked on the producer stage, SM cycles in the kernel, start and end time (globaltimer ns).  Returns the number
+ * of words written, or a negative status. */
+FFNO_API int ffno_debug_pipe_stats(const ffno_plan* plan, uint64_t* host_out, int32_t n_words);
+
 #ifdef __cplusplus
 }
 #endif

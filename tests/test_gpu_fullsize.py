@@ -232,3 +232,44 @@ def test_plans_on_two_devices_in_one_process():
         y0 = m0(x.to("cuda:0"))["forecast"]
         y1 = m1(x.to("cuda:1"))["forecast"]
     assert rel_err(y1.cpu(), y0.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("batch", [8, 32, 256])
+def test_stage_pipelined_forward_is_bit_identical_to_one_launch_per_layer(batch, monkeypatch):
+    """The stage-pipelined forward (four persistent, flag-synchronised launches per forward) runs the same tile
+    arithmetic as the launch-per-stage-and-layer path: outputs must be identical bit for bit, call after call."""
+    x = torch.randn(batch, 64, 64, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(81))
+    monkeypatch.setenv("FFNO_B200_PERSIST", "1")
+    m = c2_model().cuda()
+    with torch.no_grad():
+        ys = [m(x)["forecast"].clone() for _ in range(4)]          # eager, eager, captured, replayed
+    plan = m.plan_for(x.device, (64, 64))
+    assert plan.pipeline_unit(batch) == 2 and plan.pipeline_unit(6) == 0 and plan.pipeline_unit(2) == 0
+    assert plan.last_launch_count <= 8, plan.last_launch_count       # lift + 4 stage kernels (+ probes), not 97
+    monkeypatch.setenv("FFNO_B200_PERSIST", "0")
+    m2 = c2_model().cuda()
+    with torch.no_grad():
+        y2 = m2(x)["forecast"]
+    plan2 = m2.plan_for(x.device, (64, 64))
+    assert plan2.pipeline_unit(batch) == 0 and plan2.last_launch_count > 90
+    for y in ys:
+        assert torch.equal(y, y2)
+    assert torch.isfinite(y2).all()
+
+
+def test_stage_pipelined_rollout_matches_the_launch_per_layer_rollout(monkeypatch):
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    g = torch.Generator(device="cuda").manual_seed(82)
+    data = torch.randn(8, 64, 64, 1, device="cuda", generator=g) + 0.2 * torch.cumsum(
+        torch.randn(8, 64, 64, 8, device="cuda", generator=g), dim=-1)
+    outs = []
+    for persist in ("1", "0"):
+        monkeypatch.setenv("FFNO_B200_PERSIST", persist)
+        exp = Grid2DMarkovExperiment(c2_model(n_layers=6).cuda(), n_steps=5).cuda().eval()
+        exp.accumulate_statistics(data)
+        with torch.no_grad():
+            for _ in range(3):
+                loss, _, preds, _ = exp({"data": data})
+        outs.append((loss.item(), preds.clone(), exp.conv.plan_for(data.device, (64, 64)).pipeline_unit(8)))
+    assert outs[0][2] == 2 and outs[1][2] == 0
+    assert torch.equal(outs[0][1], outs[1][1]) and outs[0][0] == outs[1][0]
