@@ -6,6 +6,8 @@
 //   warps 5-8  loaders    (coalesced FP32 global loads -> BF16 hi/lo split -> swizzled operand tiles in smem)
 // Operand tiles in shared memory and accumulators in tensor memory are double-buffered and handed over with
 // full/empty mbarriers, so the global loads of tile t+1, the MMAs of tile t and the epilogue of tile t-1 overlap.
+#include <cuda.h>
+
 #include <cstdlib>
 #include <type_traits>
 
@@ -62,6 +64,10 @@ constexpr int kLoaderThread0 = (kEpiWarps + 1) * 32;
 constexpr int kThreads = kLoaderThread0 + kLoaders;       // 800
 constexpr int kPollWarp = kThreads / 32, kPubWarp = kPollWarp + 1;   // pipelined kernels: +2 synchronisation warps
 constexpr int kPipeThreads = kThreads + 64;
+// axis transform: the activation tiles arrive by TMA, issued by one producer warp (which in the pipelined kernel also
+// does the poller's job); the pipelined kernel adds the publisher warp
+constexpr int kAxProdWarp = kThreads / 32, kAxPubWarp = kAxProdWarp + 1;
+constexpr int kAxThreads = kThreads + 32, kAxPipeThreads = kThreads + 64;
 constexpr int kLdPerThread = 2048 / kLoaders;  // float4 per thread per 32 KB work item
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -74,6 +80,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// TMA tile load (SASS: UTMALDG): one 4-D box of the tensor described by `tmap` -> shared memory, completion (bytes) on
+// an mbarrier.  Out-of-range coordinates read as zeros, which is how tails and dead groups are padded.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 __device__ __forceinline__ float4 ldg_stream(const float* p) {
   float4 v;
@@ -269,12 +287,15 @@ struct AxisSet {
   int reverse;      // walk the tiles from the last to the first (see launch_axis_pipe)
   const float* X_odd[3];   // kPipe: input of the odd layers (the residual stream ping-pongs between two buffers)
   PipeDesc pipe;
+  // TMA descriptors of the inputs, viewed as [outer][n_in][inner / 64][64] floats with a box of one 64 x 64 group
+  alignas(64) CUtensorMap tm[3];
+  alignas(64) CUtensorMap tm_odd[3];
 };
 
 // kPipe: the CTA walks tile, tile + grid, ... of every layer back to back (grid <= n_tiles, n_groups even), its loaders
 // wait for the unit's producer and its epilogue warps post the unit's completion (see PipeDesc).
 template <bool kPipe>
-__global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) axis_pipe_kernel(AxisSet set) {
+__global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_pipe_kernel(const __grid_constant__ AxisSet set) {
   const AxisXform& p = set.ax[blockIdx.y];
   const int n_tiles = set.n_tiles[blockIdx.y];
   if ((int)blockIdx.x >= n_tiles) return;
@@ -291,15 +312,16 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) axis_pipe_
   uint64_t* d_empty = bars + 6;     // [2]
   uint64_t* bar_w = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  int* s_seq = reinterpret_cast<int*>(bars + 10);      // kPipe: last unit the poller has seen ready
-  int* s_pub = s_seq + 1;                              // [2] kPipe: warps of epilogue team t that have issued their stores
+  int* s_pub = reinterpret_cast<int*>(bars + 10);      // [2] kPipe: warps of epilogue team t that have issued their stores
+  uint64_t* stg_full = bars + 12;   // [4] staging slot landed (TMA transaction bytes)
+  uint64_t* stg_empty = bars + 16;  // [4] every converter thread has taken its part of the slot
   const int ring = set.ring[blockIdx.y];
+  const int ring_log2 = ring == 4 ? 2 : (ring == 2 ? 1 : 0);
   uint8_t* sB = smem + axp_table_offset(ring);
   const uint32_t b_half = (uint32_t)p.kchunks * p.npad * 128u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    *s_seq = -1;
     s_pub[0] = s_pub[1] = 0;
     // the (constant) table image first: its copy runs under TMEM allocation, barrier set-up and the wait for the
     // predecessor grid instead of after them
@@ -318,6 +340,10 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) axis_pipe_
       mbar_init(&a_empty[i], 1);
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], p.npad > 32 ? 256 : 128);   // see the epilogue: who drains a stage
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&stg_full[i], 1);
+      mbar_init(&stg_empty[i], kLoaders);
     }
     fence_barrier_init();
   }
@@ -448,25 +474,66 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) axis_pipe_
       }
     }
     __syncwarp();
-  } else if (kPipe && warp == kPollWarp) {
-    // ---------------------------------------------------------------- poller (see wait_unit_ready)
+  } else if (warp == kAxProdWarp) {
+    // ---------------------------------------------------------------- TMA producer (+ kPipe: dependency waits)
+    // One thread walks the CTA's tile sequence `ring` items ahead of the converters: it waits until every converter
+    // has taken its part of a staging slot, (kPipe) until the tile's unit is complete in the producer stage, then
+    // fetches the item's two 64 x 64 groups with one tensor-map load each.  Rows beyond n_in and groups beyond the
+    // tensor read as zeros.
     if (lane == 0) {
+      const CUtensorMap* tm = &set.tm[blockIdx.y];
+      tma_prefetch_desc(tm);
+      if (kPipe) tma_prefetch_desc(&set.tm_odd[blockIdx.y]);
+      pdl_wait();
       const unsigned* ctr = set.pipe.wait_ctr[blockIdx.y];
       const unsigned cnt = set.pipe.wait_count[blockIdx.y];
-      const int tpu = set.pipe.tiles_per_unit[blockIdx.y];
-      int tile = (int)blockIdx.x - (int)gridDim.x, layer = 0, last = -1;
+      const int tpu = kPipe ? set.pipe.tiles_per_unit[blockIdx.y] : 1;
+      long long dbg_blocked = 0;
+      const long long dbg_c0 = kPipe ? clock64() : 0;
+      const unsigned long long dbg_t0 = kPipe ? globaltimer_ns() : 0ull;
+      int tile = (int)blockIdx.x - (int)gridDim.x, layer = 0, last = -1, j = 0;
       for (int n = 0; n < my_tiles; ++n) {
         tile += gridDim.x;
-        if (tile >= n_tiles) { tile -= n_tiles; ++layer; }
-        const int unit = tile / tpu, seq = layer * (n_tiles + 1) + unit;
-        if (seq != last) {
-          pipe_wait(ctr + unit * kCtrStride, (unsigned)(layer + set.pipe.wait_lag) * cnt);
-          st_release_cta_smem(s_seq, seq);
-          last = seq;
+        if (kPipe && tile >= n_tiles) {
+          tile -= n_tiles;
+          ++layer;
+          tm = (layer & 1) ? &set.tm_odd[blockIdx.y] : &set.tm[blockIdx.y];
+        }
+        if (kPipe) {
+          const int unit = tile / tpu, seq = layer * (n_tiles + 1) + unit;
+          if (seq != last) {
+            const long long ta = clock64();
+            pipe_wait(ctr + unit * kCtrStride, (unsigned)(layer + set.pipe.wait_lag) * cnt);
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes of the producer stage -> TMA reads
+            dbg_blocked += clock64() - ta;
+            last = seq;
+            if (set.pipe.dbg_ts && blockIdx.x == 0 && blockIdx.y == 0) {
+              const int q = layer * (n_tiles / tpu) + unit;
+              if (q < 64) set.pipe.dbg_ts[q] = globaltimer_ns();
+            }
+          }
+        }
+        const unsigned G0 = 2u * (unsigned)((!kPipe && set.reverse) ? n_tiles - 1 - tile : tile), G1 = G0 + 1u;
+        const unsigned o0 = G0 / (unsigned)gpi, u0 = G0 - o0 * (unsigned)gpi;
+        const unsigned o1 = G1 / (unsigned)gpi, u1 = G1 - o1 * (unsigned)gpi;     // o1 == outer for a dead group: zeros
+        for (int kc = 0; kc < p.kchunks; ++kc, ++j) {
+          const int slot = j & (ring - 1), use = j >> ring_log2;
+          if (use > 0) mbar_wait(&stg_empty[slot], (uint32_t)(use - 1) & 1u);
+          uint8_t* dst = smem + AXP_STAGING + slot * 32768;
+          mbar_expect_tx(&stg_full[slot], 32768u);
+          tma_load_4d(dst, tm, 0, (int)u0, kc * 64, (int)o0, &stg_full[slot]);
+          tma_load_4d(dst + 16384, tm, 0, (int)u1, kc * 64, (int)o1, &stg_full[slot]);
         }
       }
+      if (kPipe && set.pipe.dbg) {
+        unsigned long long* d = set.pipe.dbg + 4 * (blockIdx.y * gridDim.x + blockIdx.x);
+        d[0] = (unsigned long long)dbg_blocked;
+        d[1] = (unsigned long long)(clock64() - dbg_c0);
+        d[2] = dbg_t0;
+        d[3] = globaltimer_ns();
+      }
     }
-  } else if (kPipe && warp == kPubWarp) {
+  } else if (kPipe && warp == kAxPubWarp) {
     // ---------------------------------------------------------------- publisher (see pipe_publish)
     if (lane == 0) {
       const bool split_tiles = p.npad <= 32;       // one team stores a tile (teams alternate), else both do
@@ -481,89 +548,23 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) axis_pipe_
         pipe_publish(ctr + (tile / tpu) * kCtrStride);
       }
     }
-  } else {
-    // ---------------------------------------------------------------- loaders
-    // Each thread streams its own 16 x 16 B of every work item through a private slice of the staging ring with
-    // cp.async (kAxStages items = 96 KB in flight per CTA, no registers held), then converts the item that has
-    // landed: FP32 -> BF16 hi/lo, MN-major SWIZZLE_128B operand stage.  A thread only ever reads what it copied,
-    // so the ring needs no cross-thread synchronisation (per-thread cp.async groups).
+  } else if (warp > kMmaWarp && warp < kAxProdWarp) {
+    // ---------------------------------------------------------------- converters
+    // A staging slot holds one item as the TMA delivers it: [group 2][axis index 64][64 floats].  Every thread takes
+    // four float4 of it into registers, releases the slot, and — once the MMA warp has retired the operand stage —
+    // writes them as BF16 hi / lo into the MN-major SWIZZLE_128B operand tiles.
     const int lt = tid - kLoaderThread0;
     const int n_items = my_tiles * p.kchunks;
     const int gsel = (lt >> 4) & 1, c4 = lt & 15, rsub = lt >> 5;            // rsub: 0..15
-    uint8_t* stg_base = smem + AXP_STAGING + lt * 16;
-    const long long row_step = 16 * p.inner;                 // floats between the rows this thread copies
-    // The issue sequence walks this CTA's tiles in order, so the (outer, group) pair of the next tile follows from
-    // the previous one by a precomputed step: two divisions per kernel instead of two per work item.
-    const int sgn = (!kPipe && set.reverse) ? -1 : 1;
-    const unsigned step_groups = 2u * gridDim.x;
-    const int step_o = (int)(step_groups / (unsigned)gpi), step_g = (int)(step_groups % (unsigned)gpi);
-    long long curG = (long long)((!kPipe && set.reverse) ? n_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x) * 2 + gsel;
-    int iss_tile = blockIdx.x, iss_layer = 0, ready_seq = -1;     // kPipe: tile / layer of the next issue, last unit seen ready
-    const float* Xl = p.X;
-    long long dbg_blocked = 0;
-    const long long dbg_c0 = kPipe ? clock64() : 0;
-    const unsigned long long dbg_t0 = kPipe ? globaltimer_ns() : 0ull;
-    // (a dead group G == n_groups of an odd tail still gets its true (outer, group): it is stepped from, never read)
-    int cur_o = (int)((unsigned)curG / (unsigned)gpi);
-    int cur_g = (int)((unsigned)curG - (unsigned)cur_o * (unsigned)gpi);
-    int iss_kc = 0, iss_left = n_items;
-    const long long thr_off = (long long)rsub * p.inner + c4 * 4;
-    auto issue = [&](int slot) {
-      if (iss_left > 0) {
-        --iss_left;
-        if (kPipe && iss_kc == 0) {       // first chunk of a tile: its unit's inputs must be complete (warp-uniform)
-          const int unit = iss_tile / set.pipe.tiles_per_unit[blockIdx.y];
-          const int seq = iss_layer * (n_tiles + 1) + unit;
-          if (seq != ready_seq) {
-            dbg_blocked += wait_unit_ready(s_seq, seq);
-            ready_seq = seq;
-            if (set.pipe.dbg_ts && lt == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-              const int q = iss_layer * (n_tiles / set.pipe.tiles_per_unit[0]) + unit;
-              if (q < 64) set.pipe.dbg_ts[q] = globaltimer_ns();
-            }
-          }
-        }
-        const bool live = curG < n_groups;
-        const int i0 = iss_kc * 64 + rsub;
-        const float* src = Xl + ((long long)cur_o * p.n_in + iss_kc * 64) * p.inner + (long long)cur_g * 64 + thr_off;
-        uint8_t* dst = stg_base + slot * 32768;
-#pragma unroll
-        for (int it = 0; it < kLdPerThread; ++it) {
-          const bool ok = live && (i0 + it * 16) < p.n_in;
-          cp_async16(dst + it * (kLoaders * 16), ok ? (const void*)src : (const void*)p.X, ok ? 16u : 0u);
-          src += row_step;
-        }
-        if (++iss_kc == p.kchunks) {
-          iss_kc = 0;
-          curG += sgn * (long long)step_groups;
-          cur_o += sgn * step_o;
-          cur_g += sgn * step_g;
-          if (cur_g >= (int)gpi) { cur_g -= (int)gpi; ++cur_o; }
-          if (cur_g < 0) { cur_g += (int)gpi; --cur_o; }
-          if (kPipe) {
-            iss_tile += gridDim.x;
-            if (iss_tile >= n_tiles) {      // wrap into the next layer: n_groups == 2 n_tiles == outer * gpi
-              iss_tile -= n_tiles;
-              ++iss_layer;
-              curG -= n_groups;
-              cur_o -= (int)p.outer;
-              Xl = (iss_layer & 1) ? set.X_odd[blockIdx.y] : p.X;
-            }
-          }
-        }
-      }
-      cp_async_commit();
-    };
-    for (int q = 0; q < ring; ++q) issue(q);
+    const uint8_t* stg_thr = smem + AXP_STAGING + gsel * 16384 + rsub * 256 + c4 * 16;     // + it * 4096: rows rsub + 16 it
     for (int item = 0; item < n_items; ++item) {
-      if (ring == 4) cp_async_wait<3>();                                 // warp-uniform
-      else if (ring == 2) cp_async_wait<1>();
-      else cp_async_wait<0>();
+      const int slot = item & (ring - 1);
+      mbar_wait(&stg_full[slot], (uint32_t)(item >> ring_log2) & 1u);
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 0);
-      const uint8_t* src = stg_base + (item & (ring - 1)) * 32768;
+      const uint8_t* src = stg_thr + slot * 32768;
       float4 v[kLdPerThread];
 #pragma unroll
-      for (int it = 0; it < kLdPerThread; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * (kLoaders * 16));
+      for (int it = 0; it < kLdPerThread; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * 4096);
       const int as = item & 1;
       mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 1);
@@ -576,24 +577,51 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) axis_pipe_
                              (uint32_t)(((c4 >> 1) ^ (il & 7)) << 4) + (uint32_t)(c4 & 1) * 8u;
         store_split4_at(sAh, sAl, off, v[it]);
       }
+      // The slot is released only now: mbarrier operations are not ordered behind shared-memory loads still in flight,
+      // so the arrival must come after instructions that consumed the loaded registers (measured: releasing right after
+      // the LDS lets the next TMA overwrite data that has not been read yet).
+      mbar_arrive(&stg_empty[slot]);
       fence_proxy_async_smem();
       mbar_arrive(&a_full[as]);
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 2);
-      issue(item & (ring - 1));      // refill the slot just drained with item + ring
-      if (lt < 32 && blockIdx.y == 0) TL(7, item, 3);
-    }
-    cp_async_wait<0>();
-    if (kPipe && lt == 0 && set.pipe.dbg) {
-      unsigned long long* d = set.pipe.dbg + 4 * (blockIdx.y * gridDim.x + blockIdx.x);
-      d[0] = (unsigned long long)dbg_blocked;
-      d[1] = (unsigned long long)(clock64() - dbg_c0);
-      d[2] = dbg_t0;
-      d[3] = globaltimer_ns();
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
+// ---- TMA descriptors (host) ------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+// Input of an axis transform, X[outer][n_in][inner] FP32, as the 4-D tensor [outer][n_in][inner / 64][64] with a box
+// of one group: 64 axis indices x 64 contiguous floats (16 KB).  Coordinates past n_in / outer read as zeros.
+static int encode_axis_tmap(CUtensorMap* tm, const float* X, long long outer, int n_in, long long inner) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  FFNO_REQUIRE(fn != nullptr, FFNO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  FFNO_REQUIRE(((uintptr_t)X & 15) == 0, FFNO_ERR_BAD_ARG, "axis transform input must be 16-byte aligned");
+  const cuuint64_t dims[4] = {64, (cuuint64_t)(inner / 64), (cuuint64_t)n_in, (cuuint64_t)outer};
+  const cuuint64_t strides[3] = {256, (cuuint64_t)inner * 4, (cuuint64_t)n_in * (cuuint64_t)inner * 4};
+  const cuuint32_t box[4] = {64, 1, 64, 1}, estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(X), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FFNO_REQUIRE(r == CUDA_SUCCESS, FFNO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%lld][%d][%lld]", (int)r, outer,
+               n_in, inner);
+  return FFNO_OK;
 }
 
 static int axis_ring_depth(int n_in, int n_out) {      // deepest staging ring that leaves room for the table, 0 = none
@@ -610,7 +638,7 @@ bool axis_pipe_fits(int n_in, int n_out) { return n_out <= 256 && axis_ring_dept
 
 int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream_t st, bool reverse) {
   FFNO_REQUIRE(n_axes >= 1 && n_axes <= 3, FFNO_ERR_BAD_ARG, "axis_pipe: n_axes=%d", n_axes);
-  AxisSet set;
+  AxisSet set{};
   set.reverse = reverse ? 1 : 0;
   size_t smem = 0;
   int max_tiles = 0;
@@ -632,6 +660,7 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
     while (cols < 2 * p.npad) cols *= 2;
     set.tmem_cols[a] = cols;
     max_tiles = set.n_tiles[a] > max_tiles ? set.n_tiles[a] : max_tiles;
+    if (n_groups > 0) FFNO_TRY(encode_axis_tmap(&set.tm[a], p.X, p.outer, p.n_in, p.inner));
   }
   if (max_tiles == 0) return FFNO_OK;
   FFNO_TRY(ensure_dynamic_smem(axis_pipe_kernel<false>, smem));
@@ -639,7 +668,7 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
   if (per_axis < 1) per_axis = 1;
   const int gx = max_tiles < per_axis ? max_tiles : per_axis;
   set.pipe = PipeDesc{};
-  FFNO_CUDA_CHECK(launch_pdl(axis_pipe_kernel<false>, dim3(gx, n_axes), dim3(kThreads), smem, st, set));
+  FFNO_CUDA_CHECK(launch_pdl(axis_pipe_kernel<false>, dim3(gx, n_axes), dim3(kAxThreads), smem, st, set));
   ++g_launch_counter;
   return FFNO_OK;
 }
@@ -1500,7 +1529,8 @@ int launch_ff_ts(const float* s0, const float* s1, const float* s2, const float*
 // =======================================================================================================
 // Stage-pipelined forward of the whole layer stack: four launches per forward (see PipeDesc).
 // =======================================================================================================
-static int pipe_axis_set(const AxisXform* axes, int n_axes, int n_units, AxisSet* set, size_t* smem, int* max_tiles) {
+static int pipe_axis_set(const AxisXform* axes, int n_axes, int n_units, const float* x_odd, AxisSet* set, size_t* smem,
+                         int* max_tiles) {
   *smem = 0;
   *max_tiles = 0;
   set->reverse = 0;
@@ -1519,6 +1549,8 @@ static int pipe_axis_set(const AxisXform* axes, int n_axes, int n_units, AxisSet
                  "stack_pipe: %lld groups of axis %d do not split into %d units of whole tiles", n_groups, a, n_units);
     set->n_tiles[a] = (int)(n_groups / 2);
     set->pipe.tiles_per_unit[a] = set->n_tiles[a] / n_units;
+    FFNO_TRY(encode_axis_tmap(&set->tm[a], p.X, p.outer, p.n_in, p.inner));
+    FFNO_TRY(encode_axis_tmap(&set->tm_odd[a], x_odd ? x_odd : p.X, p.outer, p.n_in, p.inner));
     int cols = 32;
     while (cols < 2 * p.npad) cols *= 2;
     set->tmem_cols[a] = cols;
@@ -1558,8 +1590,8 @@ int launch_stack_pipe(const StackPipeArgs& A) {
   AxisSet fset{}, iset{};
   size_t fsmem, ismem;
   int fmax, imax;
-  FFNO_TRY(pipe_axis_set(A.fwd, na, n_units, &fset, &fsmem, &fmax));
-  FFNO_TRY(pipe_axis_set(A.inv, na, n_units, &iset, &ismem, &imax));
+  FFNO_TRY(pipe_axis_set(A.fwd, na, n_units, A.x_odd, &fset, &fsmem, &fmax));
+  FFNO_TRY(pipe_axis_set(A.inv, na, n_units, nullptr, &iset, &ismem, &imax));
   MixSet mset{};
   int maxK = 0;
   unsigned fwd_arr[3] = {0, 0, 0}, mix_arr[3] = {0, 0, 0}, inv_arr[3] = {0, 0, 0};
@@ -1654,9 +1686,9 @@ int launch_stack_pipe(const StackPipeArgs& A) {
   FFNO_CUDA_CHECK(cudaEventRecord(A.fork, st));
   for (int i = 1; i < 4; ++i) FFNO_CUDA_CHECK(cudaStreamWaitEvent(A.streams[i], A.fork, 0));
   const int only = A.only_stage;
-  if (only < 0 || only == 0) axis_pipe_kernel<true><<<dim3(g_fwd, na), kPipeThreads, fsmem, A.streams[0]>>>(fset);
+  if (only < 0 || only == 0) axis_pipe_kernel<true><<<dim3(g_fwd, na), kAxPipeThreads, fsmem, A.streams[0]>>>(fset);
   if (only < 0 || only == 1) mix_pipe_kernel<true><<<dim3(1, maxK, na), kPipeThreads, MXP_TOTAL, A.streams[1]>>>(mset);
-  if (only < 0 || only == 2) axis_pipe_kernel<true><<<dim3(g_inv, na), kPipeThreads, ismem, A.streams[2]>>>(iset);
+  if (only < 0 || only == 2) axis_pipe_kernel<true><<<dim3(g_inv, na), kAxPipeThreads, ismem, A.streams[2]>>>(iset);
   if (only < 0 || only == 3) ff_ts_kernel<true><<<dim3(g_ff), kFF3PipeThreads, FF3_TOTAL, A.streams[3]>>>(fa);
   g_launch_counter += 4;
   const cudaError_t e = cudaGetLastError();
