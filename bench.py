@@ -13,8 +13,14 @@ samples per GPU (weak scaling: 32 samples per rank; N=8 is configs[2], batch 256
           copied H2D, forward, forecast copied D2H, all inside the timed region.
   roofline / cpu_baseline : see DESIGN.md §Measurement.
 
-`--impl reference` times the reference's own CPU path (the torch-CPU oracle port of it — the Python reference tree
-cannot travel to the GPU box) on the host cores, same metric and config, on a bounded sample per step.
+  parity : the timed kernels' forecast of the first 8 samples of rank 0 against the reference's own modules run on
+          the host cores on the same input and weights (max|y-ref| / max|ref|); the line is refused above 1e-4.
+  eager_gpu / vs_eager : the reference's own FNOFactorized2DBlock (oracle/_ref, unmodified) moved to the same GPU,
+          TF32 off, eager PyTorch, timed in this run — the north star's ">= 10x reference eager" denominator.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref: the unmodified fourierflow.modules
+files, copied there by oracle/make_ref.sh; the torch-CPU oracle port only if that copy is missing) on the host cores,
+same metric and config, all 32 samples per step.
 """
 from __future__ import annotations
 
@@ -113,18 +119,44 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU path (oracle port) on the host cores
 # --------------------------------------------------------------------------------------------------
-def oracle_setup(sample_batch: int):
-    from oracle import ffno_oracle as O          # the one place bench.py touches oracle/: the CPU baseline
+def reference_model(state_dict=None):
+    """The reference's own FNOFactorized2DBlock (oracle/_ref, see oracle/make_ref.sh) with the C2 arguments and the
+    seed-0 initialisation; None when the copy is not there.  Only bench legs that TIME or CHECK use it."""
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_root, "fourierflow", "modules", "factorized_fno", "grid_2d.py")):
+        return None
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    import warnings
+    warnings.filterwarnings("ignore")
+    from fourierflow.modules.factorized_fno.grid_2d import FNOFactorized2DBlock as RefBlock
+    torch.manual_seed(0)
+    m = RefBlock(**C2).eval()
+    if state_dict is not None:
+        m.load_state_dict(state_dict, strict=True)
+    return m
+
+
+def oracle_setup(sample_batch: int, seed: int = 1):
+    """(step, kind): one forward of `sample_batch` samples of the seed-`seed` input on the host cores through the
+    reference modules ("reference") or, without oracle/_ref, the oracle port ("port")."""
     from fourierflow_b200.modules import FNOFactorized2DBlock
     torch.manual_seed(0)
     m = FNOFactorized2DBlock(**C2).eval()
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
-    x = torch.randn(sample_batch, GRID, GRID, 3, generator=torch.Generator().manual_seed(1))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(BATCH_PER_GPU, GRID, GRID, 3, generator=torch.Generator().manual_seed(seed))[:sample_batch]
+    ref = reference_model(sd)
+    if ref is not None:
+        def step():
+            with torch.no_grad():
+                return ref(x)["forecast"]
+        return step, "reference"
+    from oracle import ffno_oracle as O          # the one other place bench.py touches oracle/: the CPU baseline
 
     def step():
         with torch.no_grad():
             return O.block_grid2d_forward(sd, x, modes=C2["modes"], n_layers=C2["n_layers"])["forecast"]
-    return step
+    return step, "port"
 
 
 def pick_cpu_threads(step):
@@ -153,8 +185,8 @@ def pick_cpu_threads(step):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    sample = 8
-    step = oracle_setup(sample)
+    sample = BATCH_PER_GPU
+    step, kind = oracle_setup(sample)
     cores = pick_cpu_threads(step)
     for _ in range(args.warmup):
         step()
@@ -163,14 +195,15 @@ def run_reference(args, rank, world):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     v = sample / dt
+    what = ("the reference's own FNOFactorized2DBlock (oracle/_ref, unmodified fourierflow.modules files)" if kind == "reference"
+            else "torch CPU oracle port of fourierflow.modules (oracle/_ref missing)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} of the 32 samples per step (CPU)"},
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample}-sample forward of the 24-layer stack per step, torch CPU oracle port "
-                                   f"of fourierflow.modules (the Python reference tree cannot travel to the GPU box)"},
+        "config": {"workload": WORKLOAD, "global_batch": sample, "grid": [GRID, GRID], "n_layers": 24},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": f"all {sample} samples of one step per forward of the 24-layer stack, {what}"},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -220,6 +253,9 @@ def run_ours(args, rank, world, local):
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     plan = model.plan_for(dev, (GRID, GRID))
     loss_fn = LpLoss()
+    # the one collective of a sharded run: per-sample losses for the LpLoss mean, gathered on a side stream into
+    # preallocated buffers so that the (latency-bound) all-gather overlaps the next step's kernels
+    gatherer = D.LossGatherer(1, B, B * world, dev) if world > 1 else None
 
     def flush():
         flush_buf.zero_()
@@ -227,9 +263,8 @@ def run_ours(args, rank, world, local):
     def step():
         with torch.no_grad():
             y = model(x)["forecast"]
-            if world > 1:     # the one collective of a sharded run: per-sample losses for the LpLoss mean
-                per = loss_fn.rel_per_sample(y, target).unsqueeze(0)
-                D.gather_sample_losses(per, B * world)
+            if gatherer is not None:
+                gatherer.submit(loss_fn.rel_per_sample(y, target).unsqueeze(0))
         return y
 
     def step_e2e():
@@ -245,6 +280,8 @@ def run_ours(args, rank, world, local):
         sampler = ClockSampler(local)
         sampler.start()
         ms = timed(step, args.steps, args.warmup, flush)
+        if gatherer is not None:
+            gatherer.result()                 # every gather of the timed steps has completed
         launches = plan.last_launch_count
         ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup), flush)
         barrier()
@@ -295,40 +332,81 @@ def run_ours(args, rank, world, local):
     # the spectral operator is the kernel family the north star names and holds the larger share of the step
     dominant = roof_spec if 1.0 * t_spec >= t_ff else roof_ff
 
+    # ---- the reference's own module, eager PyTorch on this GPU (rank 0; TF32 off: the reference's default) ------
+    eager = None
+    y_gpu_first8 = None
+    if rank == 0:
+        with torch.no_grad():
+            y_gpu_first8 = model(x)["forecast"][:8].float().cpu()
+        ref = None if args.no_eager_gpu else reference_model({k: v.detach().cpu() for k, v in model.state_dict().items()})
+        if ref is not None:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            ref = ref.to(dev)
+            eager_steps = max(10, min(args.steps, 100))
+            sampler = ClockSampler(local)
+            sampler.start()
+            with torch.no_grad():
+                ms_eager = timed(lambda: ref(x)["forecast"], eager_steps, 10, flush)
+                y_eager = ref(x)["forecast"][:8].float().cpu()
+            eager_clocks = sampler.stop()
+            scale = y_eager.abs().max().clamp(min=1e-30)
+            eager = {"value": B / (ms_eager * 1e-3), "unit": "samples/s", "ms_per_step": ms_eager, "steps": eager_steps,
+                     "warmup": 10, "kind": "reference", "allow_tf32": False, "clocks": eager_clocks,
+                     "what": "oracle/_ref FNOFactorized2DBlock(**C2).cuda(), eager PyTorch, same input and weights, L2 "
+                             "flushed between timed forwards, CUDA events",
+                     "max_rel_diff_vs_ours": float((y_gpu_first8 - y_eager).abs().max() / scale)}
+            del ref
+
+    if world > 1:
+        dist.barrier()                    # the other ranks leave here; rank 0's CPU leg below holds no GPU busy
+        dist.destroy_process_group()
     if rank != 0:
         return
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample -------------------------------
+    # ---- CPU baseline + parity gate: the reference modules on the host cores, bounded sample -------------------
     cpu_sample, cpu_reps = 8, 3
+    parity = None
     if args.no_cpu_baseline:
-        cores, cpu_v = 0, None
+        cores, cpu_v, cpu_kind = 0, None, None
     else:
-        cstep = oracle_setup(cpu_sample)
+        cstep, cpu_kind = oracle_setup(cpu_sample, seed=1)        # rank 0's input: seed 1 + rank
         cores = pick_cpu_threads(cstep)
         t0 = time.perf_counter()
         for _ in range(cpu_reps):
-            cstep()
+            y_ref = cstep()
         cpu_v = cpu_sample * cpu_reps / (time.perf_counter() - t0)
+        err = float((y_gpu_first8.double() - y_ref.double()).abs().max() / y_ref.double().abs().max())
+        parity = {"max_rel_err": err, "n": cpu_sample, "tolerance": 1e-4, "against": cpu_kind,
+                  "what": "forecast of the first 8 samples of the timed batch: CUDA path vs the reference modules on the "
+                          "host cores, max|y-ref|/max|ref|"}
+        if not err < 1e-4:
+            raise SystemExit(f"bench.py: parity gate failed — max|y-ref|/max|ref| = {err:.3e} over the first {cpu_sample} "
+                             "samples exceeds 1e-4; no value is reported for kernels that compute the wrong answer")
 
     N = world
+    value = N * B / (ms * 1e-3)
     line = {
-        "metric": METRIC, "value": N * B / (ms * 1e-3), "unit": "samples/s", "n_gpus": N, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": N, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": N * B, "grid": [GRID, GRID], "n_layers": 24,
                    "parallelism": f"dp{N} (batch shards, no data-path collective; loss all-gather only)",
                    "l2": "flushed between timed steps (256 MiB memset outside the timed events)",
-                   "kernel_path": "tcgen05" if plan.uses_umma else "generic-fp32"},
+                   "kernel_path": "tcgen05" if plan.uses_umma else "generic-fp32",
+                   "stage_pipelined": plan.pipeline_unit(B) > 0, "cuda_graph": plan.graph_active},
         "clocks": clocks,
         "e2e": {"value": N * B / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
                 "api": "ffno_block_fwd_host (pinned host buffers)"},
         # this repo's kernels launched inside the timed region, all ranks (the sharded step adds one rel_l2 launch)
         "gpu_launches": (int(launches) + (1 if N > 1 else 0)) * args.steps * N,
+        "parity": parity,
+        "eager_gpu": eager, "vs_eager": (value / N / eager["value"]) if eager else None,
         "roofline": dominant, "roofline_spectral": roof_spec, "roofline_ff": roof_ff,
-        "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": cpu_kind,
                          "sample": f"{cpu_reps} forwards of {cpu_sample} samples through the 24-layer stack "
-                                   "(torch-CPU oracle port of fourierflow.modules)"},
+                                   "(the reference modules of oracle/_ref on the host cores; 'port' = oracle restatement)"},
     }
     emit(line)
 
@@ -339,7 +417,8 @@ def main():
     ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 100; reference arm: 5)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs under ncu)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg and the parity gate (profiling runs under ncu)")
+    ap.add_argument("--no-eager-gpu", action="store_true", help="skip the reference-eager-on-GPU leg (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.steps is None:
@@ -358,11 +437,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         D.init_from_env("nccl")
-    run_ours(args, rank, world, local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    run_ours(args, rank, world, local)          # (destroys the process group itself, before rank 0's CPU leg)
 
 
 if __name__ == "__main__":

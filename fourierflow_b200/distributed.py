@@ -62,6 +62,54 @@ def gather_sample_losses(local: torch.Tensor, n_global: int) -> torch.Tensor:
     return torch.cat(pieces, dim=1)
 
 
+class LossGatherer:
+    """The loss all-gather off the compute stream: ``submit(local[n_steps, B_local])`` copies the per-sample losses
+    into a preallocated (padded) send buffer and enqueues ``all_gather_into_tensor`` on a side stream that waits only
+    for the kernel that produced ``local``; ``result()`` joins the side stream and returns ``[n_steps, n_global]``.
+    No allocation, slicing or concatenation per call — the collective is a few hundred bytes and latency-bound, so
+    what matters is that it neither blocks the next forward nor is rebuilt around it."""
+
+    def __init__(self, n_steps: int, b_local: int, n_global: int, device: torch.device):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.n_steps, self.n_global = n_steps, n_global
+        self.width = -(-n_global // self.world)
+        self.send = torch.zeros(n_steps, self.width, device=device)
+        self.recv = torch.empty(self.world * n_steps, self.width, device=device)
+        self.cuda = device.type == "cuda"
+        self.stream = torch.cuda.Stream(device) if self.cuda else None
+        self.pending = False
+
+    def submit(self, local: torch.Tensor) -> None:
+        if self.world == 1:
+            self.send[:, :local.shape[1]].copy_(local)
+            self.pending = True
+            return
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream(local.device))
+            with torch.cuda.stream(self.stream):
+                self.send[:, :local.shape[1]].copy_(local, non_blocking=True)
+                dist.all_gather_into_tensor(self.recv, self.send)
+            local.record_stream(self.stream)
+        else:
+            self.send[:, :local.shape[1]].copy_(local)
+            dist.all_gather_into_tensor(self.recv, self.send)
+        self.pending = True
+
+    def result(self) -> torch.Tensor:
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream(self.send.device).wait_stream(self.stream)
+        if self.world == 1:
+            return self.send[:, :self.n_global]
+        out = self.recv.view(self.world, self.n_steps, self.width)
+        if self.n_global % self.world == 0:
+            return out.permute(1, 0, 2).reshape(self.n_steps, self.n_global)
+        pieces = []
+        for r in range(self.world):
+            lo, hi = shard_bounds(self.n_global, r, self.world)
+            pieces.append(out[r, :, :hi - lo])
+        return torch.cat(pieces, dim=1)
+
+
 def rollout_loss(local: torch.Tensor, n_global: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """(loss, step_losses) over the GLOBAL batch from per-rank per-sample losses: mean over samples per step,
     summed over steps (routines/grid_2d_markov.py:313-315)."""

@@ -27,6 +27,12 @@ def _worker(rank, world, port, n_global, n_steps, q):
     local = full[:, lo:hi].contiguous()
     loss, step = D.rollout_loss(local, n_global)
     gathered = D.gather_sample_losses(local, n_global)
+    # the side-stream gatherer bench.py uses (preallocated buffers; here on CPU: same collective, same layout)
+    g = D.LossGatherer(n_steps, hi - lo, n_global, torch.device("cpu"))
+    for _ in range(2):                       # reused buffers: a second submit must give the same answer
+        g.submit(local)
+        again = g.result()
+    assert torch.equal(again, gathered), (again, gathered)
     q.put((rank, loss.item(), step.tolist(), gathered.tolist()))
     dist.barrier()
     dist.destroy_process_group()
