@@ -1449,6 +1449,14 @@ ff_ts_kernel(const FFArgs a) {
       const int st = n & 1;
       if (lt < 32) TL(3, n, 0);
       if (!kPipe && lt == 0 && tile + (int)gridDim.x < n_tiles) prefetch_tile(tile + (int)gridDim.x);
+      if (kPipe && lt == 0 && n + 1 < my_tiles) {
+        // pull the residual rows of this CTA's next tile into L2: they were written a whole layer ago (evicted since),
+        // and the store warps read them inside their serial per-tile chain.  (Across a layer boundary the rows may
+        // still be in the making: a prefetch of a line that is rewritten later is harmless, L2 is the coherence point.)
+        int nt = tile + (int)gridDim.x, nl = layer;
+        if (nt >= n_tiles) { nt -= n_tiles; ++nl; }
+        prefetch_l2_bulk(a.xbuf[nl & 1] + (long long)nt * 128 * 64, 128u * 256u);
+      }
       uint8_t* sA1h = smem + FF3_A1 + st * 32768 + a_off;
       uint8_t* sA1l = sA1h + 16384;
       const float* p0 = s0 + gofs;
