@@ -297,6 +297,37 @@ lift_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const flo
   out[idx64] = acc;
 }
 
+// Periodic grids (no padding, no appended coordinates — FNOFactorized2DBlock, grid_2d.py:157): the lift is a plain
+// [points x in] x [in x C] product.  One thread keeps its float4 column of the weights and the bias in registers and
+// walks kLiftPts points, so the kernel is a streaming write of the activations instead of a division per float4.
+constexpr int kLiftPts = 8, kLiftMaxIn = 8;
+__global__ void __launch_bounds__(256)
+lift_plain_kernel(const float* __restrict__ x, const float* __restrict__ Wt, const float* __restrict__ bias,
+                  float4* __restrict__ out, long long pts, int in_features, int C4) {
+  const int c4 = threadIdx.x % C4, sub = threadIdx.x / C4, per_block = blockDim.x / C4;
+  float4 w[kLiftMaxIn];
+#pragma unroll
+  for (int j = 0; j < kLiftMaxIn; ++j)
+    w[j] = j < in_features ? __ldg(reinterpret_cast<const float4*>(Wt + (long long)j * C4 * 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long p0 = ((long long)blockIdx.x * per_block + sub) * kLiftPts;
+#pragma unroll
+  for (int i = 0; i < kLiftPts; ++i) {
+    const long long pt = p0 + i;
+    if (pt >= pts) return;
+    const float* xr = x + pt * in_features;
+    float4 acc = b;
+#pragma unroll
+    for (int j = 0; j < kLiftMaxIn; ++j)
+      if (j < in_features) {
+        const float v = __ldg(xr + j);
+        acc.x = fmaf(v, w[j].x, acc.x); acc.y = fmaf(v, w[j].y, acc.y);
+        acc.z = fmaf(v, w[j].z, acc.z); acc.w = fmaf(v, w[j].w, acc.w);
+      }
+    out[pt * C4 + c4] = acc;
+  }
+}
+
 int launch_lift(const float* x, const float* Wt, const float* bias, float* out, int batch, const LiftGeom& g,
                 cudaStream_t st) {
   FFNO_REQUIRE(g.C % 4 == 0, FFNO_ERR_UNSUPPORTED, "lift: width %d not a multiple of 4", g.C);
@@ -304,6 +335,16 @@ int launch_lift(const float* x, const float* Wt, const float* bias, float* out, 
   for (int a = 0; a < g.ndim; ++a) pts *= (g.size[a] + g.pad[a]);
   long long total4 = pts * (g.C / 4);
   if (total4 == 0) return FFNO_OK;
+  bool plain = !g.append_grid && g.in_features <= kLiftMaxIn && 256 % (g.C / 4) == 0;
+  for (int a = 0; a < g.ndim; ++a) plain &= g.pad[a] == 0;
+  if (plain) {
+    const int C4 = g.C / 4, per_block = 256 / C4;
+    lift_plain_kernel<<<ceil_div(pts, (long long)per_block * kLiftPts), 256, 0, st>>>(x, Wt, bias, reinterpret_cast<float4*>(out),
+                                                                                      pts, g.in_features, C4);
+    ++g_launch_counter;
+    FFNO_LAUNCH_CHECK("lift_plain_kernel");
+    return FFNO_OK;
+  }
   if (total4 < (1ll << 31))
     lift_kernel<unsigned><<<ceil_div(total4, 256), 256, 0, st>>>(x, Wt, bias, reinterpret_cast<float4*>(out), total4, g);
   else

@@ -24,9 +24,12 @@ using namespace umma;
 __device__ long long g_timeline[8 * 16 * 8];
 __device__ int g_timeline_on = 0;
 #ifdef FFNO_TIMELINE
+// g_timeline_on selects the kernel that records: 1 FF, 2 forward transforms, 3 inverse transforms, 4 mode mix
+// (tl_on is read from g_timeline_on ONCE at kernel start: a flag load per stamp would put an L2 round trip in front of
+// every clock read and distort the very timeline it records)
 #define TL(role, tile_n, ev)                                                                      \
   do {                                                                                            \
-    if (blockIdx.x == 0 && (tile_n) < 16 && (threadIdx.x & 31) == 0)    /* store only: no flag load */ \
+    if (tl_on && blockIdx.x == 0 && (tile_n) < 16 && (threadIdx.x & 31) == 0)                     \
       g_timeline[((role) * 16 + (tile_n)) * 8 + (ev)] = clock64();                                \
   } while (0)
 #else
@@ -59,8 +62,12 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 // ~25 instructions per float4 and is what bounds these kernels, so it is spread over as many warps as fit.
 constexpr int kLoaders = 512;
 constexpr int kEpiWarps = 8;                   // two teams of 4 (one per TMEM lane quadrant), splitting the columns
-constexpr int kMmaWarp = kEpiWarps;
-constexpr int kLoaderThread0 = (kEpiWarps + 1) * 32;
+// Warp order: epilogue warps first, then the MMA issuer, then the converter / loader warps.  (Tried: converters
+// first so that the short, latency-critical roles get the higher warp ids, which the warp schedulers of this
+// architecture family are said to favour — 1.90 -> 2.01 ms per forward, rejected.)
+constexpr int kEpiWarp0 = 0;                              // warps 0..7 (warp & 3 = TMEM lane quadrant)
+constexpr int kMmaWarp = kEpiWarp0 + kEpiWarps;           // warp 8
+constexpr int kLoaderThread0 = (kMmaWarp + 1) * 32;       // warps 9..24
 constexpr int kThreads = kLoaderThread0 + kLoaders;       // 800
 constexpr int kPollWarp = kThreads / 32, kPubWarp = kPollWarp + 1;   // pipelined kernels: +2 synchronisation warps
 constexpr int kPipeThreads = kThreads + 64;
@@ -303,6 +310,7 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
   const int my_tiles = (int)(((long long)n_layers * n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
   const int tmem_cols = set.tmem_cols[blockIdx.y];
   const int stage_cols = tmem_cols >> 1;
+  [[maybe_unused]] const bool tl_on = g_timeline_on == (p.n_in >= p.n_out ? 2 : 3);      // timeline build: forward / inverse
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AXP_BAR);
@@ -360,14 +368,14 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
   pdl_launch_dependents();
   if (warp != kMmaWarp) pdl_wait();     // the MMA warp first starts the (constant) table copy, then waits too
 
-  if (warp < kEpiWarps) {
+  if (warp >= kEpiWarp0 && warp < kMmaWarp) {
     // ---------------------------------------------------------------- epilogue: 8 independent warps
     // TMEM lane = inner element, column = output index, and inner is the contiguous dimension of Y: a warp's 32 lanes
     // of one column are 128 contiguous bytes in global memory, so every warp drains its own lane quadrant straight
     // from registers with one STG.32 per column (one full line per instruction, no staging, no block barrier).
     //   npad <= 32 (one chunk per tile): warps 0-3 / 4-7 take alternate tiles, each drains a stage alone;
     //   npad  > 32: both sets work on every tile, set t takes chunks t, t+2, ... and both release the stage.
-    const int team = warp >> 2, quad = warp & 3;
+    const int team = (warp - kEpiWarp0) >> 2, quad = warp & 3;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const int total_chunks = (p.npad + 31) >> 5;
     const bool split_tiles = total_chunks == 1;
@@ -380,28 +388,34 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
       if (kPipe && tile >= n_tiles) tile -= n_tiles;       // next layer
       const int ds = n & 1;
       if (split_tiles && ds != team) continue;
-      mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
-      tc_fence_after();
-      if (warp == 0 && blockIdx.y == 0) TL(5, n, 0);
+      // Where the tile goes, BEFORE waiting for its accumulator: the division and the 64-bit multiplies are a
+      // dependent chain of several hundred cycles (in-kernel timeline: 750-950 between the accumulator becoming ready
+      // and the tcgen05.ld when computed after the wait) that belongs under the wait, not behind it.
       const int ptile = (!kPipe && set.reverse) ? n_tiles - 1 - tile : tile;
       const long long G = (long long)ptile * 2 + gq;             // warp-uniform
       const bool live = G < n_groups;
       const unsigned uo = live ? (unsigned)G / (unsigned)gpi : 0u;
       const unsigned ug = live ? (unsigned)G - uo * (unsigned)gpi : 0u;
       float* ybase = p.Y + ((long long)uo * p.n_out) * p.inner + (long long)ug * 64 + in_group;
+      mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
+      tc_fence_after();
+      if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 0);
       const int ch_begin = split_tiles ? 0 : team, ch_step = split_tiles ? 1 : 2;
       bool released = false;
 #pragma unroll 1
       for (int ch = ch_begin; ch < total_chunks; ch += ch_step) {
         const int c0 = ch * 32;
         uint32_t v[32];
+        if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 3);
         tmem_ld32(tmem + lane_base + (uint32_t)(ds * stage_cols + c0), v);
+        if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 4);
         tmem_ld_wait();
+        if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 5);
         if (ch + ch_step >= total_chunks) {   // this warp's last read of the stage
           tc_fence_before();
           mbar_arrive(&d_empty[ds]);
           released = true;
-          if (warp == 0 && blockIdx.y == 0) TL(5, n, 1);
+          if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 1);
         }
         if (live) {
           float* yp = ybase + (size_t)c0 * stride;
@@ -424,7 +438,7 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
         mbar_arrive(&d_empty[ds]);
       }
       if (kPipe) stores_issued(&s_pub[team]);
-      if (warp == 0 && blockIdx.y == 0) TL(5, n, 2);
+      if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 2);
     }
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
@@ -707,6 +721,8 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
   const int tile_end = min(n_tiles, tile_begin + tpc);
   const int n_layers = kPipe ? set.pipe.n_layers : 1;
   const int my_tiles = (tile_end - tile_begin) * n_layers;
+  [[maybe_unused]] const bool tl_on = g_timeline_on == 4;
+  [[maybe_unused]] const bool tl_cta = blockIdx.y == 0 && blockIdx.z == 0;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sB = smem + MXP_B;
@@ -752,10 +768,10 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
   pdl_launch_dependents();
   if (warp != kMmaWarp) pdl_wait();
 
-  if (warp < kEpiWarps) {
+  if (warp >= kEpiWarp0 && warp < kMmaWarp) {
     // two epilogue teams: team 0 drains the real segment (columns 0..63), team 1 the imaginary one, each 32 columns
     // at a time through its own swizzled 16 KB staging tile so the global stores are full 128-byte lines
-    const int team = warp >> 2, rt = tid & 127, seg = team;
+    const int team = (warp - kEpiWarp0) >> 2, rt = tid & 127, seg = team;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* sOut = smem + MXP_OUT + team * 16384;
     const int rq = rt >> 3, cq = rt & 7;                    // coalesced phase: rows rq + 16 it, float4 column cq
@@ -768,8 +784,10 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
     for (int n = 0; n < my_tiles; ++n) {
       if (++tile == tile_end) tile = tile_begin;         // kPipe: next layer
       const int ds = n & 1;
+      if (tl_cta && (warp & 3) == 0) TL(team ? 6 : 5, n, 0);
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
+      if (tl_cta && (warp & 3) == 0) TL(team ? 6 : 5, n, 1);
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -788,6 +806,8 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         {
           // rows rq + 16 it: (outer, position) of the first by one division, the rest by a constant step
+          // (kept inside the drain: hoisting the eight row pointers above the accumulator wait costs 16 registers the
+          // kernel does not have — it spilled and the forward got slower, 1.90 -> 1.97 ms)
           const long long row_first = (long long)((!kPipe && set.reverse) ? n_tiles - 1 - tile : tile) * 128 + rq;
           const unsigned rf = row_first < M ? (unsigned)row_first : 0u;
           unsigned uo = rf / p_in, pp = rf - uo * p_in;
@@ -806,6 +826,7 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
         if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
+      if (tl_cta && (warp & 3) == 0) TL(team ? 6 : 5, n, 2);
       if (kPipe) stores_issued(&s_pub[team]);
     }
   } else if (warp == kMmaWarp) {
@@ -824,6 +845,7 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
           const int as = item & 1;
           mbar_wait(&a_full[as], (uint32_t)(item >> 1) & 1u);
           tc_fence_after();
+          if (tl_cta) TL(4, n, kb);
           const uint64_t a_off = (uint64_t)(as * (MXP_A_STAGE >> 4)), b_off = (uint64_t)(kb * (16384 >> 4));
           issue3_kmajor_elect<4>(d_addr, dAh + a_off, dAl + a_off, dBh + b_off, dBl + b_off, IDESC, kb > 0 ? 1u : 0u);
           umma_commit_elect(&a_empty[as]);
@@ -913,6 +935,7 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
     for (int q = 0; q < kMxStages; ++q) issue(q);
     for (int item = 0; item < n_items; ++item) {
       cp_async_wait<kMxStages - 1>();
+      if (tl_cta && lt < 32) TL(7, item, 0);
       const uint8_t* src = stg_base + (item % kMxStages) * 32768;
       float4 v[kLdPerThread];
 #pragma unroll
@@ -926,7 +949,9 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
         store_split4_at(sAh, sAl, kmajor_sw128_offset(it * 32 + rsub, c4 * 4), v[it]);
       fence_proxy_async_smem();
       mbar_arrive(&a_full[as]);
+      if (tl_cta && lt < 32) TL(7, item, 1);
       issue(item + kMxStages);
+      if (tl_cta && lt < 32) TL(7, item, 2);
     }
     cp_async_wait<0>();
     if (kPipe && lt == 0 && set.pipe.dbg) {
@@ -1028,6 +1053,7 @@ ff_ts_kernel(const FFArgs a) {
   const int n_tiles = a.n_tiles, reverse = kPipe ? 0 : a.reverse;
   const int n_layers = kPipe ? a.pipe.n_layers : 1;
   const int my_tiles = (int)(((long long)n_layers * n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+  [[maybe_unused]] const bool tl_on = g_timeline_on == 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* sb1 = reinterpret_cast<float*>(smem + FF3_BIAS);
   float* sb2 = sb1 + 256;
