@@ -56,8 +56,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 def _build_locked(verbose: bool) -> str:
     timeline = os.environ.get("FFNO_TIMELINE") == "1"
-    lib = LIB[:-3] + "_timeline.so" if timeline else LIB      # diagnostics build lives beside the product, never replaces it
-    objdir = os.path.join(LIBDIR, "obj_timeline" if timeline else "obj")
+    tag = os.environ.get("FFNO_BUILD_TAG", "")              # experiment builds: FFNO_BUILD_TAG=name FFNO_BUILD_DEFS="-DX=1 ..."
+    extra = os.environ.get("FFNO_BUILD_DEFS", "").split() if tag else []
+    suffix = ("_timeline" if timeline else "") + (f"_{tag}" if tag else "")
+    lib = LIB[:-3] + suffix + ".so" if suffix else LIB      # diagnostics builds live beside the product, never replace it
+    objdir = os.path.join(LIBDIR, "obj" + suffix)
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -66,6 +69,8 @@ def _build_locked(verbose: bool) -> str:
         cmd = [nvcc(), *ARCH, *FLAGS, "-c", src, "-o", obj]
         if timeline:                                    # in-kernel clock64 stamps (tools/*_timeline.py, FFNO_B200_LIB=...)
             cmd.insert(1, "-DFFNO_TIMELINE")
+        for d in extra:
+            cmd.insert(1, d)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -136,11 +136,17 @@ __device__ __forceinline__ void issue3_kmajor(uint32_t tmem_d, uint64_t a_hi, ui
   }
 }
 
+#ifndef FFNO_KO
+#define FFNO_KO 0
+#endif
+#define KO_TILES(x) ((FFNO_KO & 1) ? 0 : (x))
+#define KO_PASSES(bit) ((FFNO_KO & (bit)) ? 1 : 3)
 template <int KSTEPS>
 __device__ __forceinline__ void issue3_kmajor_elect(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
-                                                    uint64_t b_lo, uint32_t idesc, uint32_t acc_first) {
+                                                    uint64_t b_lo, uint32_t idesc, uint32_t acc_first, int npass = 3) {
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
+    if (pass >= npass) break;
     const uint64_t a = (pass == 2) ? a_lo : a_hi;
     const uint64_t b = (pass == 1) ? b_lo : b_hi;
 #pragma unroll
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
   const int n_tiles = set.n_tiles[blockIdx.y];
   if ((int)blockIdx.x >= n_tiles) return;
   const int n_layers = kPipe ? set.pipe.n_layers : 1;
-  const int my_tiles = (int)(((long long)n_layers * n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+  const int my_tiles = KO_TILES((int)(((long long)n_layers * n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x));
   const int tmem_cols = set.tmem_cols[blockIdx.y];
   const int stage_cols = tmem_cols >> 1;
   [[maybe_unused]] const bool tl_on = g_timeline_on == (p.n_in >= p.n_out ? 2 : 3);      // timeline build: forward / inverse
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
       // and the tcgen05.ld when computed after the wait) that belongs under the wait, not behind it.
       const int ptile = (!kPipe && set.reverse) ? n_tiles - 1 - tile : tile;
       const long long G = (long long)ptile * 2 + gq;             // warp-uniform
-      const bool live = G < n_groups;
+      const bool live = (FFNO_KO & 2) ? false : G < n_groups;
       const unsigned uo = live ? (unsigned)G / (unsigned)gpi : 0u;
       const unsigned ug = live ? (unsigned)G - uo * (unsigned)gpi : 0u;
       float* ybase = p.Y + ((long long)uo * p.n_out) * p.inner + (long long)ug * 64 + in_group;
@@ -467,7 +473,7 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
           auto issue = [&](auto KS) {
             constexpr int kSteps = decltype(KS)::value;
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
+            for (int pass = 0; pass < KO_PASSES(8); ++pass) {
               const uint64_t a = (pass == 2) ? dAl : dAh, b = (pass == 1) ? dBl : dBh;
 #pragma unroll
               for (int ks = 0; ks < kSteps; ++ks)
@@ -578,7 +584,7 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
       const uint8_t* src = stg_thr + slot * 32768;
       float4 v[kLdPerThread];
 #pragma unroll
-      for (int it = 0; it < kLdPerThread; ++it) v[it] = *reinterpret_cast<const float4*>(src + it * 4096);
+      for (int it = 0; it < kLdPerThread; ++it) v[it] = (FFNO_KO & 4) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(src + it * 4096);
       const int as = item & 1;
       mbar_wait(&a_empty[as], ((uint32_t)(item >> 1) & 1u) ^ 1u);
       if (lt < 32 && blockIdx.y == 0) TL(7, item, 1);
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
         const int il = it * 16 + rsub;
         const uint32_t off = (uint32_t)gsel * 8192u + (uint32_t)(il >> 3) * 1024u + (uint32_t)(il & 7) * 128u +
                              (uint32_t)(((c4 >> 1) ^ (il & 7)) << 4) + (uint32_t)(c4 & 1) * 8u;
-        store_split4_at(sAh, sAl, off, v[it]);
+        if (!(FFNO_KO & 4)) store_split4_at(sAh, sAl, off, v[it]);
       }
       // The slot is released only now: mbarrier operations are not ordered behind shared-memory loads still in flight,
       // so the arrival must come after instructions that consumed the loaded registers (measured: releasing right after
@@ -720,7 +726,7 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
   if (tile_begin >= n_tiles) return;
   const int tile_end = min(n_tiles, tile_begin + tpc);
   const int n_layers = kPipe ? set.pipe.n_layers : 1;
-  const int my_tiles = (tile_end - tile_begin) * n_layers;
+  const int my_tiles = KO_TILES((tile_end - tile_begin) * n_layers);
   [[maybe_unused]] const bool tl_on = g_timeline_on == 4;
   [[maybe_unused]] const bool tl_cta = blockIdx.y == 0 && blockIdx.z == 0;
 
@@ -811,7 +817,7 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
           const long long row_first = (long long)((!kPipe && set.reverse) ? n_tiles - 1 - tile : tile) * 128 + rq;
           const unsigned rf = row_first < M ? (unsigned)row_first : 0u;
           unsigned uo = rf / p_in, pp = rf - uo * p_in;
-          const int rows_left = (M - row_first) > 0 ? (int)((M - row_first) < 128 ? (M - row_first) : 128) : 0;   // rows rq .. M-1
+          const int rows_left = (FFNO_KO & 128) ? 0 : ((M - row_first) > 0 ? (int)((M - row_first) < 128 ? (M - row_first) : 128) : 0);   // rows rq .. M-1
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             if (it * 16 < rows_left) {
@@ -847,7 +853,7 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
           tc_fence_after();
           if (tl_cta) TL(4, n, kb);
           const uint64_t a_off = (uint64_t)(as * (MXP_A_STAGE >> 4)), b_off = (uint64_t)(kb * (16384 >> 4));
-          issue3_kmajor_elect<4>(d_addr, dAh + a_off, dAl + a_off, dBh + b_off, dBl + b_off, IDESC, kb > 0 ? 1u : 0u);
+          issue3_kmajor_elect<4>(d_addr, dAh + a_off, dAl + a_off, dBh + b_off, dBl + b_off, IDESC, kb > 0 ? 1u : 0u, KO_PASSES(256));
           umma_commit_elect(&a_empty[as]);
         }
         umma_commit_elect(&d_full[ds]);
@@ -922,7 +928,7 @@ __global__ void __launch_bounds__(kPipe ? kPipeThreads : kThreads, 1) mix_pipe_k
         const float* f_half = f_mode + (long long)half * inner;
 #pragma unroll
         for (int it = 0; it < kLdPerThread; ++it) {
-          const bool ok = it * 32 < left;
+          const bool ok = (FFNO_KO & 512) ? false : it * 32 < left;
           const float* src = f_half + (long long)o * o_stride + (long long)pp * 64;
           cp_async16(dst + it * (kLoaders * 16), ok ? (const void*)src : (const void*)ax.F, ok ? 16u : 0u);
           o += q32;
@@ -1052,7 +1058,7 @@ ff_ts_kernel(const FFArgs a) {
   const long long P = a.P;
   const int n_tiles = a.n_tiles, reverse = kPipe ? 0 : a.reverse;
   const int n_layers = kPipe ? a.pipe.n_layers : 1;
-  const int my_tiles = (int)(((long long)n_layers * n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+  const int my_tiles = KO_TILES((int)(((long long)n_layers * n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x));
   [[maybe_unused]] const bool tl_on = g_timeline_on == 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* sb1 = reinterpret_cast<float*>(smem + FF3_BIAS);
@@ -1212,7 +1218,7 @@ ff_ts_kernel(const FFArgs a) {
         }
       }
       const long long row0 = (long long)(reverse ? n_tiles - 1 - tile : tile) * 128;
-      const int rows_left = (P - row0) < 128 ? (int)(P - row0) : 128;
+      const int rows_left = (FFNO_KO & 16) ? 0 : ((P - row0) < 128 ? (int)(P - row0) : 128);
       const long long gofs = row0 * 64 + rq * 64 + cq * 4;
       if (warp == 8) TL(1, n, 0);
       // The tile is finished in two 32-channel halves so that only 8 float4 of the residual are live while the
@@ -1333,7 +1339,7 @@ ff_ts_kernel(const FFArgs a) {
         tc_fence_after();
         if (lane == 0) TL(2, n, 1 + 2 * h);
         issue3_kmajor_elect<4>(tmem + (uint32_t)(h * 128), dA1h + stn * kStage, dA1l + stn * kStage, dW1h + h * kHalf,
-                               dW1l + h * kHalf, IDESC_G1, 0u);
+                               dW1l + h * kHalf, IDESC_G1, 0u, KO_PASSES(32));
         umma_commit_elect(&d1_full[h]);
         if (h == 1) umma_commit_elect(&a1_empty[stn]);
         if (lane == 0) TL(2, n, 2 + 2 * h);
@@ -1385,7 +1391,7 @@ ff_ts_kernel(const FFArgs a) {
           if (lane == 0 && j == 0 && part == 0) TL(4, n, 2);
           if (lane == 0 && j == 0 && part == 1) TL(4, n, 4);
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {
+          for (int pass = 0; pass < KO_PASSES(32); ++pass) {
             const uint32_t a = (pass == 2) ? a_lo : a_hi;
             const uint64_t b = (pass == 1) ? bl : bh;
 #pragma unroll
@@ -1494,9 +1500,17 @@ ff_ts_kernel(const FFArgs a) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int i = half * 8 + it;
+#if FFNO_KO & 64
+          v[it] = make_float4(0.1f * (float)lr, 0.2f, 0.3f, 0.4f);
+#else
           v[it] = (i * 8 + lr < rows_left) ? (kPipe ? ldg_cg(p0 + i * 512) : ldg_stream(p0 + i * 512)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
         }
+#if FFNO_KO & 64
+        if (false) {
+#else
         if (s1) {
+#endif
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int i = half * 8 + it;
