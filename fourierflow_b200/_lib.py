@@ -52,6 +52,10 @@ class BlockParams(C.Structure):
                 ("layers", C.POINTER(LayerParams)), ("n_layers", C.c_int32)]
 
 
+class RolloutExtras(C.Structure):
+    _fields_ = [("use_velocity", C.c_int32), ("force_steps", C.c_int32), ("force", C.c_void_p), ("mu", C.c_void_p)]
+
+
 class Taps(C.Structure):
     _fields_ = [("lift", C.c_void_p), ("x_after", C.POINTER(C.c_void_p)), ("spectral", C.POINTER(C.c_void_p)),
                 ("b_last", C.c_void_p), ("forecast_list", C.POINTER(C.c_void_p))]
@@ -87,6 +91,10 @@ EXPORTS = {
     "ffno_rollout_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
     "ffno_rollout_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p,
                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ffno_rollout_workspace_bytes_ex": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "ffno_rollout_fwd_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p,
+                                      C.c_float, C.c_float, C.POINTER(RolloutExtras), C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
     "ffno_velocity_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "ffno_velocity_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -324,20 +324,31 @@ class StackPlan:
         return y
 
     def rollout_forward(self, frame0: torch.Tensor, n_steps: int, mean: Sequence[float], std: Sequence[float],
-                        low: float, high: float, domain: Optional[Sequence[float]] = None) -> torch.Tensor:
-        """``domain`` = (length_x, length_y) of the periodic box: only used by 5-feature (velocity) plans."""
+                        low: float, high: float, domain: Optional[Sequence[float]] = None,
+                        force: Optional[torch.Tensor] = None, mu: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``domain`` = (length_x, length_y) of the periodic box: set for velocity-feature rollouts only.
+        ``force``: contiguous [B, X, Y, 1 | n_steps] forcing channel, ``mu``: [B] viscosity channel (ffno_rollout_fwd_ex)."""
         B = frame0.shape[0]
         X, Y = self.size
         with torch.cuda.device(self.device):
             if domain is not None:
                 _lib.check(self.lib.ffno_plan_set_domain(self._plan, float(domain[0]), float(domain[1])),
                            "ffno_plan_set_domain")
-            ws = self._workspace(self.lib.ffno_rollout_workspace_bytes(self._plan, B, n_steps))
             preds = torch.empty(B, X, Y, n_steps, device=self.device, dtype=torch.float32)
             n_feat = len(mean)
             m = (C.c_float * n_feat)(*[float(v) for v in mean])
             s = (C.c_float * n_feat)(*[float(v) for v in std])
-            _lib.check(self.lib.ffno_rollout_fwd(self._plan, frame0.data_ptr(), B, n_steps, m, s, float(low),
-                                                 float(high), preds.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                 _stream(self.device)), "ffno_rollout_fwd")
+            if force is None and mu is None:
+                ws = self._workspace(self.lib.ffno_rollout_workspace_bytes(self._plan, B, n_steps))
+                _lib.check(self.lib.ffno_rollout_fwd(self._plan, frame0.data_ptr(), B, n_steps, m, s, float(low),
+                                                     float(high), preds.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                     _stream(self.device)), "ffno_rollout_fwd")
+            else:
+                f_steps = 0 if force is None else int(force.shape[-1])
+                ex = _lib.RolloutExtras(1 if domain is not None else 0, f_steps, _ptr(force), _ptr(mu))
+                ws = self._workspace(self.lib.ffno_rollout_workspace_bytes_ex(
+                    self._plan, B, n_steps, ex.use_velocity, f_steps, 0 if mu is None else 1))
+                _lib.check(self.lib.ffno_rollout_fwd_ex(self._plan, frame0.data_ptr(), B, n_steps, m, s, float(low),
+                                                        float(high), C.byref(ex), preds.data_ptr(), ws.data_ptr(),
+                                                        ws.numel(), _stream(self.device)), "ffno_rollout_fwd_ex")
         return preds

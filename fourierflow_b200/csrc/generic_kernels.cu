@@ -842,6 +842,45 @@ int launch_rollout_features(const float* frame, long long frame_stride_b, int fr
   return FFNO_OK;
 }
 
+// features of one rollout step with the optional force / mu channels: [w, (q, v,) gx, gy, (f,) (mu)]
+__global__ void __launch_bounds__(256)
+rollout_features_ex_kernel(const float* __restrict__ frame, long long stride_b, int stride_xy,
+                           const float* __restrict__ q, const float* __restrict__ v, const float* __restrict__ force,
+                           int force_steps, int t, const float* __restrict__ mu, float* __restrict__ feat, int nf,
+                           long long total, int X, int Y, float low, float high, MeanStd ms) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int y = (int)(idx % Y);
+  long long r = idx / Y;
+  int x = (int)(r % X);
+  long long b = r / X;
+  float* f = feat + idx * nf;
+  int c = 0;
+  f[c] = (frame[b * stride_b + ((long long)x * Y + y) * stride_xy] - ms.m[c]) / ms.s[c]; ++c;
+  if (q) {
+    f[c] = (q[idx] - ms.m[c]) / ms.s[c]; ++c;
+    f[c] = (v[idx] - ms.m[c]) / ms.s[c]; ++c;
+  }
+  f[c] = (torch_linspace(x, X, low, high) - ms.m[c]) / ms.s[c]; ++c;
+  f[c] = (torch_linspace(y, Y, low, high) - ms.m[c]) / ms.s[c]; ++c;
+  if (force) { f[c] = (force[idx * force_steps + t] - ms.m[c]) / ms.s[c]; ++c; }
+  if (mu) { f[c] = (mu[b] - ms.m[c]) / ms.s[c]; }
+}
+
+int launch_rollout_features_ex(const float* frame, long long frame_stride_b, int frame_stride_xy, const float* q,
+                               const float* v, const float* force, int force_steps, int t, const float* mu, float* feat,
+                               int batch, int X, int Y, float low, float high, const MeanStd& mean_std, cudaStream_t st) {
+  long long total = (long long)batch * X * Y;
+  if (total == 0) return FFNO_OK;
+  const int nf = 3 + (q ? 2 : 0) + (force ? 1 : 0) + (mu ? 1 : 0);
+  rollout_features_ex_kernel<<<ceil_div(total, 256), 256, 0, st>>>(frame, frame_stride_b, frame_stride_xy, q, v, force,
+                                                                   force_steps, force_steps > 1 ? t : 0, mu, feat, nf, total,
+                                                                   X, Y, low, high, mean_std);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("rollout_features_ex_kernel");
+  return FFNO_OK;
+}
+
 __global__ void __launch_bounds__(256)
 rollout_denorm_kernel(const float* __restrict__ fc, float* __restrict__ preds, long long total, int n_steps,
                       int t, MeanStd ms) {

@@ -60,11 +60,16 @@ int launch_fold_head(const float* W0t /*[C][H]*/, const float* b0, const float* 
 
 // Rollout glue (routines/grid_2d_markov.py:286-306, modules/normalizer.py:51,62)
 //   feat[b][x][y][0] = (frame - mean0)/std0 ; feat[..][1] = (lin(x) - mean1)/std1 ; [2] likewise
-struct MeanStd { float m[5]; float s[5]; };   // passed by value: no device copy, graph-capturable
+struct MeanStd { float m[8]; float s[8]; };   // passed by value: no device copy, graph-capturable
 // q, v: velocity features of the frame (NULL: 3 features [w, gx, gy]; else 5: [w, q, v, gx, gy])
 int launch_rollout_features(const float* frame, long long frame_stride_b, int frame_stride_xy, const float* q,
                             const float* v, float* feat, int batch, int X, int Y, float low, float high,
                             const MeanStd& ms, cudaStream_t st);
+// The same with the torus_vis extras appended after the position grid (routines/grid_2d_markov.py:246-260, :288-291):
+// force [B, X, Y, force_steps] (frame `t`, or the only one of a static forcing; NULL: no channel), mu [B] (NULL: none).
+int launch_rollout_features_ex(const float* frame, long long frame_stride_b, int frame_stride_xy, const float* q,
+                               const float* v, const float* force, int force_steps, int t, const float* mu, float* feat,
+                               int batch, int X, int Y, float low, float high, const MeanStd& ms, cudaStream_t st);
 // (q, v) = (psi_y, -psi_x) from the vorticity w[b] at w + b * stride_b + (x * Y + y) * stride_xy on an Lx x Ly periodic
 // domain (routines/grid_2d_markov.py:206-220); scratch: velocity_scratch_floats(batch, X, Y) floats
 size_t velocity_scratch_floats(int batch, int X, int Y);

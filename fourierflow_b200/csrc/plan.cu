@@ -89,7 +89,7 @@ struct ffno_plan {
   // baked into the captured kernel arguments; the first call with a new key runs eagerly, the second captures.
   struct GraphSlot {
     cudaGraphExec_t exec = nullptr;
-    int batch = -1, n_steps = 0, seen = 0;
+    int batch = -1, n_steps = 0, seen = 0, variant = 0;
     void* ws = nullptr;
     MeanStd ms{};
     float low = 0.f, high = 0.f;
@@ -897,28 +897,52 @@ int ffno_rel_l2(const float* x, int64_t x_stride_b, int64_t x_stride_i, const fl
                        static_cast<cudaStream_t>(stream));
 }
 
-size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch, int32_t n_steps) {
-  if (!plan || batch < 0 || n_steps < 0) return 0;
+static bool rollout_layout(const ffno_plan* p, const ffno_rollout_extras* ex, bool* use_velocity, bool* has_force,
+                           bool* has_mu) {
+  // feature count <-> options: [w, (q, v,) gx, gy, (f,) (mu)]; without extras 5 features mean the velocity set
+  *use_velocity = ex ? ex->use_velocity != 0 : p->d.in_features == 5;
+  *has_force = ex && ex->force_steps > 0;
+  *has_mu = ex && ex->mu != nullptr;
+  return p->d.in_features == 3 + (*use_velocity ? 2 : 0) + (*has_force ? 1 : 0) + (*has_mu ? 1 : 0);
+}
+
+size_t ffno_rollout_workspace_bytes_ex(const ffno_plan* plan, int32_t batch, int32_t n_steps, int32_t use_velocity,
+                                       int32_t force_steps, int32_t has_mu) {
+  if (!plan || batch < 0 || n_steps < 0 || force_steps < 0) return 0;
   size_t frame = ((size_t)batch * plan->pts_in * 4 + 255) / 256 * 256;
   size_t preds = ((size_t)batch * plan->pts_in * n_steps * 4 + 255) / 256 * 256;
   size_t vel = 0;
-  if (plan->d.in_features == 5 && plan->d.ndim == 2)      // q, v and the scratch of the four DFT passes
+  if (use_velocity && plan->d.ndim == 2)      // q, v and the scratch of the four DFT passes
     vel = 2 * frame + (velocity_scratch_floats(batch, plan->d.size[0], plan->d.size[1]) * 4 + 255) / 256 * 256;
-  return ffno_workspace_bytes(plan, batch) + frame + preds + vel;
+  size_t force = ((size_t)batch * plan->pts_in * force_steps * 4 + 255) / 256 * 256;
+  size_t mu = has_mu ? ((size_t)batch * 4 + 255) / 256 * 256 : 0;
+  return ffno_workspace_bytes(plan, batch) + frame + preds + vel + force + mu;
 }
 
-int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n_steps, const float* mean_host,
-                     const float* std_host, float low, float high, float* preds, void* workspace,
-                     size_t workspace_bytes, void* stream) {
-  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_rollout_workspace_bytes(p, batch, n_steps)));
+size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch, int32_t n_steps) {
+  return ffno_rollout_workspace_bytes_ex(plan, batch, n_steps, plan && plan->d.in_features == 5, 0, 0);
+}
+
+int ffno_rollout_fwd_ex(ffno_plan* p, const float* frame0, int32_t batch, int32_t n_steps, const float* mean_host,
+                        const float* std_host, float low, float high, const ffno_rollout_extras* ex, float* preds,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  FFNO_REQUIRE(p != nullptr, FFNO_ERR_BAD_ARG, "plan is NULL");
+  bool use_velocity, has_force, has_mu;
+  const bool layout_ok = rollout_layout(p, ex, &use_velocity, &has_force, &has_mu);
+  const int force_steps = has_force ? ex->force_steps : 0;
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes,
+                       ffno_rollout_workspace_bytes_ex(p, batch, n_steps, use_velocity, force_steps, has_mu)));
   if (batch == 0) { p->last_launches = 0; return FFNO_OK; }
   FFNO_REQUIRE(frame0 && preds && mean_host && std_host, FFNO_ERR_BAD_ARG, "NULL argument");
-  FFNO_REQUIRE(p->d.ndim == 2 && (p->d.in_features == 3 || p->d.in_features == 5) && p->d.out_features == 1 &&
-                   !p->d.append_grid && p->d.pad[0] == 0 && p->d.pad[1] == 0 && !p->d.use_fork,
-               FFNO_ERR_UNSUPPORTED,
-               "rollout needs the torus_li/markov (in=3) or torus_kochkov (in=5, velocity features) layout: 2-D grid, out=1");
-  const bool use_velocity = p->d.in_features == 5;
+  FFNO_REQUIRE(p->d.ndim == 2 && p->d.out_features == 1 && !p->d.append_grid && p->d.pad[0] == 0 && p->d.pad[1] == 0 &&
+                   !p->d.use_fork,
+               FFNO_ERR_UNSUPPORTED, "rollout needs the Grid2DMarkovExperiment layout: 2-D periodic grid, out=1, no fork");
+  FFNO_REQUIRE(layout_ok, FFNO_ERR_BAD_ARG,
+               "rollout features [w%s, gx, gy%s%s] do not match the plan's in_features=%d", use_velocity ? ", q, v" : "",
+               has_force ? ", f" : "", has_mu ? ", mu" : "", p->d.in_features);
   FFNO_REQUIRE(n_steps >= 1, FFNO_ERR_BAD_ARG, "n_steps=%d", n_steps);
+  FFNO_REQUIRE(!has_force || (ex->force && (force_steps == 1 || force_steps == n_steps)), FFNO_ERR_BAD_ARG,
+               "force_steps=%d must be 1 (static forcing) or n_steps=%d, with a non-NULL force", force_steps, n_steps);
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
   cudaStream_t caller = static_cast<cudaStream_t>(stream), st;
   FFNO_TRY(fence_in(p, caller, &st));
@@ -927,15 +951,20 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
   char* base = static_cast<char*>(workspace);
   const size_t frame_b = (size_t)batch * X * Y * 4;
   const size_t stack_b = stack_ws_bytes(p, batch);
-  float* frame_st = reinterpret_cast<float*>(base + stack_b);
   const size_t frame_al = (frame_b + 255) / 256 * 256;
   const size_t preds_al = (frame_b * n_steps + 255) / 256 * 256;
-  float* preds_st = reinterpret_cast<float*>(base + stack_b + frame_al);
-  float* vel_q = use_velocity ? reinterpret_cast<float*>(base + stack_b + frame_al + preds_al) : nullptr;
-  float* vel_v = use_velocity ? reinterpret_cast<float*>(base + stack_b + 2 * frame_al + preds_al) : nullptr;
-  float* vel_scratch = use_velocity ? reinterpret_cast<float*>(base + stack_b + 3 * frame_al + preds_al) : nullptr;
+  char* cur = base + stack_b;
+  auto take = [&](size_t bytes) { float* r = reinterpret_cast<float*>(cur); cur += bytes; return r; };
+  float* frame_st = take(frame_al);
+  float* preds_st = take(preds_al);
+  float* vel_q = use_velocity ? take(frame_al) : nullptr;
+  float* vel_v = use_velocity ? take(frame_al) : nullptr;
+  float* vel_scratch = use_velocity ? take((velocity_scratch_floats(batch, X, Y) * 4 + 255) / 256 * 256) : nullptr;
+  float* force_st = has_force ? take((frame_b * force_steps + 255) / 256 * 256) : nullptr;
+  float* mu_st = has_mu ? take(((size_t)batch * 4 + 255) / 256 * 256) : nullptr;
   MeanStd ms{};
   for (int i = 0; i < p->d.in_features; ++i) { ms.m[i] = mean_host[i]; ms.s[i] = std_host[i]; }
+  const bool extras = has_force || has_mu;
 
   // the whole step loop: features -> layer stack -> de-normalise, each forecast feeding the next step
   // (routines/grid_2d_markov.py:263-321); every pointer it touches lives in the caller's workspace
@@ -947,20 +976,28 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
       const int fs_xy = t == 0 ? 1 : n_steps;
       if (use_velocity)       // recomputed from every fed-back forecast (grid_2d_markov.py:268-285)
         FFNO_TRY(launch_velocity(frame, fs_b, fs_xy, batch, X, Y, p->domain[0], p->domain[1], vel_q, vel_v, vel_scratch, st));
-      FFNO_TRY(launch_rollout_features(frame, fs_b, fs_xy, vel_q, vel_v, w.io_in, batch, X, Y, low, high, ms, st));
+      if (extras)
+        FFNO_TRY(launch_rollout_features_ex(frame, fs_b, fs_xy, vel_q, vel_v, force_st, force_steps, t, mu_st, w.io_in, batch,
+                                            X, Y, low, high, ms, st));
+      else
+        FFNO_TRY(launch_rollout_features(frame, fs_b, fs_xy, vel_q, vel_v, w.io_in, batch, X, Y, low, high, ms, st));
       FFNO_TRY(block_fwd_impl(p, w.io_in, batch, w.io_out, nullptr, workspace, st));
       FFNO_TRY(launch_rollout_denorm(w.io_out, preds_st, batch, X * Y, n_steps, t, ms, st));
     }
     return FFNO_OK;
   };
 
+  // inputs into fixed workspace addresses, so that a captured graph stays valid whatever the caller passes next
   FFNO_CUDA_CHECK(cudaMemcpyAsync(frame_st, frame0, frame_b, cudaMemcpyDeviceToDevice, st));
+  if (has_force) FFNO_CUDA_CHECK(cudaMemcpyAsync(force_st, ex->force, frame_b * force_steps, cudaMemcpyDeviceToDevice, st));
+  if (has_mu) FFNO_CUDA_CHECK(cudaMemcpyAsync(mu_st, ex->mu, (size_t)batch * 4, cudaMemcpyDeviceToDevice, st));
   FFNO_TRY(guard_begin(p, st));
   ffno_plan::GraphSlot& g = p->g_rollout;
+  const int variant = (use_velocity ? 1 : 0) | (force_steps << 2) | (has_mu ? 2 : 0);
   bool done = false;
   if (p->graphs && !stream_is_capturing(st)) {
     const bool same = g.batch == batch && g.ws == workspace && g.n_steps == n_steps && g.low == low && g.high == high &&
-                      memcmp(&g.ms, &ms, sizeof(ms)) == 0;
+                      g.variant == variant && memcmp(&g.ms, &ms, sizeof(ms)) == 0;
     if (same && g.exec) {
       FFNO_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
       p->last_launches = g.launches;
@@ -975,7 +1012,7 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
       }
     } else if (!same) {
       g.reset();
-      g.batch = batch; g.ws = workspace; g.n_steps = n_steps; g.low = low; g.high = high; g.ms = ms;
+      g.batch = batch; g.ws = workspace; g.n_steps = n_steps; g.low = low; g.high = high; g.ms = ms; g.variant = variant;
     }
     if (!done) g.seen++;
   }
@@ -987,6 +1024,17 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
   FFNO_TRY(guard_end(p, st));
   FFNO_CUDA_CHECK(cudaMemcpyAsync(preds, preds_st, frame_b * n_steps, cudaMemcpyDeviceToDevice, st));
   return fence_out(p, caller, st);
+}
+
+int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n_steps, const float* mean_host,
+                     const float* std_host, float low, float high, float* preds, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  FFNO_REQUIRE(p != nullptr, FFNO_ERR_BAD_ARG, "plan is NULL");
+  FFNO_REQUIRE(p->d.in_features == 3 || p->d.in_features == 5, FFNO_ERR_UNSUPPORTED,
+               "rollout needs the torus_li/markov (in=3) or torus_kochkov (in=5, velocity features) layout; "
+               "force / mu channels go through ffno_rollout_fwd_ex");
+  return ffno_rollout_fwd_ex(p, frame0, batch, n_steps, mean_host, std_host, low, high, nullptr, preds, workspace,
+                             workspace_bytes, stream);
 }
 
 int ffno_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int32_t N, int32_t K, int32_t a_mn,

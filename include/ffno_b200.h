@@ -208,6 +208,22 @@ FFNO_API int ffno_rollout_fwd(ffno_plan* plan, const float* frame0, int32_t batc
                      float* preds, void* workspace, size_t workspace_bytes, void* stream);
 FFNO_API size_t ffno_rollout_workspace_bytes(const ffno_plan* plan, int32_t batch, int32_t n_steps);
 
+/* The same rollout with the optional feature channels of the torus_vis / torus_vis_force configurations
+ * (append_force, append_mu: routines/grid_2d_markov.py:146-152 training-time, :246-260 and :288-291 in _valid_step).
+ * Features per step: [w, (q, v,) gx, gy, (f,) (mu)]; plan in_features must equal their count. */
+typedef struct ffno_rollout_extras {
+  int32_t use_velocity;   /* 1: stream-function velocities q, v after w (as ffno_rollout_fwd does for in_features = 5) */
+  int32_t force_steps;    /* 0: no forcing channel; 1: static forcing; n_steps: frame t of the forcing at step t */
+  const float* force;     /* device [B, X, Y, force_steps] (the reference's batch['f'], 4-D: its last n_steps frames) */
+  const float* mu;        /* device [B] viscosity per sample, broadcast over the grid; NULL: no channel */
+} ffno_rollout_extras;
+FFNO_API int ffno_rollout_fwd_ex(ffno_plan* plan, const float* frame0, int32_t batch, int32_t n_steps,
+                        const float* mean_host, const float* std_host, float low, float high,
+                        const ffno_rollout_extras* extras, float* preds, void* workspace, size_t workspace_bytes,
+                        void* stream);
+FFNO_API size_t ffno_rollout_workspace_bytes_ex(const ffno_plan* plan, int32_t batch, int32_t n_steps,
+                                       int32_t use_velocity, int32_t force_steps, int32_t has_mu);
+
 /* Velocity features of the torus_kochkov rollout (use_velocity=True, routines/grid_2d_markov.py:82-93, :206-220):
  * (q, v) = (psi_y, -psi_x) of the stream function of the vorticity w (w = -laplace psi) on a periodic
  * length_x x length_y domain, i.e. irfftn(+-2 pi i k psi_hat) with the reference's kx/ky/lap buffers.

@@ -304,13 +304,17 @@ def velocity_features(w: torch.Tensor, domain=((0.0, 2 * math.pi), (0.0, 2 * mat
 
 def markov_rollout(p: Params, data: torch.Tensor, stats: dict, *, modes: int, n_layers: int,
                    n_steps: int = 10, low: float = 0.0, high: float = 1.0, use_velocity: bool = False,
-                   domain=((0.0, 2 * math.pi), (0.0, 2 * math.pi))) -> dict:
+                   domain=((0.0, 2 * math.pi), (0.0, 2 * math.pi)), force: torch.Tensor = None,
+                   mu: torch.Tensor = None) -> dict:
     """``Grid2DMarkovExperiment._valid_step`` with the torus_li/markov config
     (use_position, should_normalize; no force/mu/shuffle/difference) and, with ``use_velocity``, the torus_kochkov
     feature set [w, q, v, gx, gy] (velocity recomputed from every fed-back forecast, :268-285).
 
     data:[B,X,Y,T].  Step 0 consumes the ground-truth frame T−n−1; later steps feed back the
     model's own de-normalised forecast, re-concatenated with the position grid.
+    ``force`` (append_force, :246-255 / :288-289): [B,X,Y] static forcing or [B,X,Y,T'] whose last n_steps
+    frames are used, appended after the position grid; ``mu`` (append_mu, :257-260 / :290-291): [B] viscosity
+    broadcast over the grid, appended last.
     Reference: fourierflow/routines/grid_2d_markov.py:195-326 (loop :263-321).
     """
     B, X, Y, T = data.shape
@@ -326,6 +330,11 @@ def markov_rollout(p: Params, data: torch.Tensor, stats: dict, *, modes: int, n_
             q, v = velocity_features(im, domain)          # :206-220 / :268-285
             im = torch.cat([im, q, v], dim=-1)
         x = torch.cat([im, pos], dim=-1)                  # :222-233 / :286-287
+        if force is not None:                             # :246-255 / :288-289
+            f_t = force if force.dim() == 3 else force[..., -n_steps:][..., t]
+            x = torch.cat([x, f_t.unsqueeze(-1)], dim=-1)
+        if mu is not None:                                # :257-260 / :290-291
+            x = torch.cat([x, mu.reshape(B, 1, 1, 1).expand(B, X, Y, 1)], dim=-1)
         x = (x - mean) / std                              # :296, normalizer.py:51
         im = block_grid2d_forward(p, x, modes=modes, n_layers=n_layers)["forecast"]   # :300-301
         im = im * std[0] + mean[0]                        # :306, normalizer.py:62

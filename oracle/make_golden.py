@@ -122,8 +122,10 @@ def spectral_case(M, name, C, K, shape, seed):
     save(name, {"C": C, "K": K}, arrays)
 
 
-def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed):
-    """routines/grid_2d_markov.py:195-326 driven with the reference's own module objects."""
+def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed, force_dims=0, with_mu=False):
+    """routines/grid_2d_markov.py:195-326 driven with the reference's own module objects.
+    force_dims = 3 / 4: append_force with a static [B,X,Y] / time-varying [B,X,Y,T] forcing (:246-255, :288-289);
+    with_mu: append_mu (:257-260, :290-291)."""
     torch.manual_seed(seed)
     conv = M.FNOFactorized2DBlock(**kwargs).eval()
     perturb_(conv, seed + 100)
@@ -138,11 +140,29 @@ def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed):
     pos = torch.stack(torch.meshgrid(*grids, indexing="ij"), dim=-1)
     pos = pos.unsqueeze(0).repeat(B, 1, 1, 1)
 
+    force = mu = None
+    if force_dims == 3:
+        force = torch.randn(B, X, X, generator=g)
+    elif force_dims == 4:
+        force = torch.randn(B, X, X, T, generator=g)
+    if with_mu:
+        mu = torch.rand(B, generator=g) * 1e-3 + 1e-4
+
+    def extras(t_index, n_frames):
+        """force / mu channels of `n_frames` consecutive frames starting at frame t_index: [B,X,Y,n_frames,E]"""
+        cols = []
+        if force is not None:
+            f = force.unsqueeze(-1).repeat(1, 1, 1, n_frames) if force.dim() == 3 else force[..., t_index:t_index + n_frames]
+            cols.append(f.unsqueeze(-1))
+        if mu is not None:
+            cols.append(mu.reshape(B, 1, 1, 1, 1).repeat(1, X, X, n_frames, 1))
+        return cols
+
     # one training-mode pass accumulates the running statistics (:376-378 → _build_features)
     normalizer.train()
     feats = torch.cat([data[..., :-1].unsqueeze(-1),
-                       pos.unsqueeze(-2).repeat(1, 1, 1, T - 1, 1)], dim=-1)    # [B,X,Y,T-1,3]
-    feats = feats.permute(0, 3, 1, 2, 4).reshape(B * (T - 1), X, X, 3)
+                       pos.unsqueeze(-2).repeat(1, 1, 1, T - 1, 1)] + extras(0, T - 1), dim=-1)    # [B,X,Y,T-1,F]
+    feats = feats.permute(0, 3, 1, 2, 4).reshape(B * (T - 1), X, X, feats.shape[-1])
     normalizer(feats)
     normalizer.eval()
 
@@ -154,6 +174,11 @@ def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed):
                 x = torch.cat([data[..., T - n_steps - 1].unsqueeze(-1), pos], dim=-1)
             else:
                 x = torch.cat([im, pos], dim=-1)
+            if force is not None:      # :246-255: a 4-D force contributes its LAST n_steps frames, frame t at step t
+                f_t = force if force.dim() == 3 else force[..., -n_steps:][..., t]
+                x = torch.cat([x, f_t.unsqueeze(-1)], dim=-1)
+            if mu is not None:
+                x = torch.cat([x, mu.reshape(B, 1, 1, 1).repeat(1, X, X, 1)], dim=-1)
             x = normalizer(x)
             im = conv(x)["forecast"]
             im = normalizer.inverse(im, channel=0)
@@ -167,6 +192,10 @@ def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed):
                   norm_sum=normalizer.sum.numpy(), norm_sum_squared=normalizer.sum_squared.numpy(),
                   norm_count=normalizer.count.numpy(),
                   norm_mean=normalizer.mean.numpy(), norm_std=normalizer.std.numpy())
+    if force is not None:
+        arrays["force"] = force.numpy()
+    if mu is not None:
+        arrays["mu"] = mu.numpy()
     save(name, dict(kwargs, n_steps=n_steps), arrays)
 
 
@@ -238,14 +267,24 @@ def grad_cases(M, LpLoss):
               factor=2, ff_weight_norm=False, gain=1), (2, 12, 10, 4), seed=21)
 
 
+def rollout_extras_cases(M, LpLoss, c2):
+    rollout_case(M, LpLoss, "rollout_force_mu_16", dict(c2, n_layers=4, modes=8, input_dim=5), B=2, X=16, T=12,
+                 n_steps=10, seed=12, force_dims=4, with_mu=True)
+    rollout_case(M, LpLoss, "rollout_force_static_16", dict(c2, n_layers=4, modes=8, input_dim=4), B=2, X=16, T=12,
+                 n_steps=10, seed=13, force_dims=3)
+
+
 def main():
     M, LpLoss = import_reference()
     if "--only-grad" in sys.argv:
         grad_cases(M, LpLoss)
         return
-    init_case(M)
     c2 = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4,
               ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0)
+    if "--only-rollout-extras" in sys.argv:
+        rollout_extras_cases(M, LpLoss, c2)
+        return
+    init_case(M)
     # (1) the C2 architecture on a reduced grid (32x32 keeps modes=16 legal: 17 rfft bins)
     grid2d_case(M, "grid2d_c2arch_32", dict(c2, n_layers=4), (1, 32, 32, 3), seed=0)
     # (2) full-depth C2 model (24 layers), final forecast + last-layer taps only
@@ -285,6 +324,8 @@ def main():
     # (10) 10-step Markov rollout with Normalizer / LpLoss
     rollout_case(M, LpLoss, "rollout_c2arch_16", dict(c2, n_layers=4, modes=8), B=2, X=16, T=12,
                  n_steps=10, seed=11)
+    # (10b) the torus_vis feature sets: append_force (static and time-varying forcing) and append_mu
+    rollout_extras_cases(M, LpLoss, c2)
     # (11) gradients of the one-step training loss (backward row)
     grad_cases(M, LpLoss)
 

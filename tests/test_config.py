@@ -211,3 +211,24 @@ def test_predict_command_parses_a_config_and_refuses_to_run_without_a_gpu(tmp_pa
         pytest.skip("covered by the gpu-marked test in test_gpu_parity.py")
     with pytest.raises(SystemExit, match="no CUDA device"):
         predict.main([str(cfg), "routine.conv.n_layers=2", "--samples", "4"])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXPERIMENTS), reason="reference tree not mounted (GPU box)")
+def test_reference_torus_vis_configs_load_with_force_and_mu_channels():
+    """experiments/torus_vis*/: Grid2DMarkovExperiment with append_force / append_mu (routines/grid_2d_markov.py:146-152)
+    — the feature count the routine builds must equal the conv's input_dim in every shipped F-FNO config."""
+    paths = sorted(glob.glob(os.path.join(REF_EXPERIMENTS, "torus_vis*", "*", "config.yaml")))
+    seen = 0
+    for p in paths:
+        raw = C.load_config(p, resolve=False)
+        r = raw["routine"]
+        if not r.get("conv", {}).get("_target_", "").startswith("fourierflow.modules.FNOFactorized2DBlock"):
+            continue
+        if r["conv"].get("use_fork") or r["conv"].get("dropout", 0) or r["conv"].get("in_dropout", 0):
+            continue
+        routine, cfg = C.load_routine(p)
+        want = 3 + int(bool(r.get("append_force"))) + int(bool(r.get("append_mu")))
+        assert routine.conv.input_dim == want and routine.normalizer.sum.shape == (want,)
+        assert routine.append_force == bool(r.get("append_force")) and routine.append_mu == bool(r.get("append_mu"))
+        seen += 1
+    assert seen >= 4

@@ -231,3 +231,28 @@ def test_rollout_contract_checks():
     exp = Grid2DMarkovExperiment(conv, n_steps=6)
     with pytest.raises(RuntimeError):           # CPU tensor: refused before anything else
         exp.predict(torch.randn(1, 8, 8, 4))
+
+
+def test_rollout_feature_set_options():
+    """append_force / append_mu are part of the feature count; the ablation switches still raise."""
+    from fourierflow_b200.modules import FNOFactorized2DBlock
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    conv5 = FNOFactorized2DBlock(modes=4, width=32, n_layers=1, input_dim=5)
+    exp = Grid2DMarkovExperiment(conv5, n_steps=2, append_force=True, append_mu=True)
+    assert exp.append_force and exp.append_mu and not exp.use_velocity
+    with pytest.raises(RuntimeError, match="input features"):      # 3 + force = 4 features, conv takes 5
+        Grid2DMarkovExperiment(conv5, n_steps=2, append_force=True)
+    for bad in ("shuffle_grid", "learn_difference", "use_fourier_position"):
+        with pytest.raises(RuntimeError, match=bad):
+            Grid2DMarkovExperiment(FNOFactorized2DBlock(modes=4, width=32, n_layers=1, input_dim=3), **{bad: True})
+    # statistics: frame t of a time-varying forcing accompanies input frame t, mu is broadcast
+    B, X, T = 2, 8, 5
+    data, f, mu = torch.randn(B, X, X, T), torch.randn(B, X, X, T), torch.rand(B)
+    exp.accumulate_statistics(data, force=f, mu=mu)
+    mean = exp.normalizer.mean
+    assert torch.allclose(mean[0], data[..., :-1].mean(), atol=1e-5)
+    assert torch.allclose(mean[3], f[..., :-1].mean(), atol=1e-5) and torch.allclose(mean[4], mu.mean(), atol=1e-6)
+    with pytest.raises(RuntimeError, match="batch\\['f'\\]"):
+        exp.accumulate_statistics(data, mu=mu)
+    with pytest.raises(RuntimeError, match="must be \\[B\\]"):
+        exp.accumulate_statistics(data, force=f, mu=torch.rand(B, 1))

@@ -65,6 +65,18 @@ def test_rollout():
     assert rel_err(r["step_losses"], a["step_losses"]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["rollout_force_mu_16", "rollout_force_static_16"])
+def test_rollout_force_mu(name):
+    """append_force (static / time-varying forcing) and append_mu feature sets of the torus_vis configs
+    (routines/grid_2d_markov.py:246-260, :288-291) against the executed reference."""
+    kw, sd, a = load(name)
+    stats = {"sum": a["norm_sum"], "sum_squared": a["norm_sum_squared"], "count": a["norm_count"]}
+    r = O.markov_rollout(sd, a["data"], stats, modes=kw["modes"], n_layers=kw["n_layers"], n_steps=kw["n_steps"],
+                         force=a["force"], mu=a.get("mu"))
+    assert rel_err(r["preds"], a["preds"]) < 1e-5
+    assert rel_err(r["step_losses"], a["step_losses"]) < 1e-5
+
+
 def test_normalizer_stats_restatement():
     x = torch.randn(7, 5, 4, 3)
     st = O.normalizer_stats(x)
