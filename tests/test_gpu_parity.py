@@ -171,8 +171,8 @@ def test_rollout_force_mu_golden(name):
             print(name, it, f"preds {e:.2e} loss {loss.item():.6f} vs {a['loss'].item():.6f}")
             assert e < TOL_UMMA
             assert rel_err(torch.stack(step_losses), a["step_losses"]) < 1e-4
-    with pytest.raises(RuntimeError, match="batch\\['f'\\]"):
-        exp({"data": a["data"].cuda()})
+        with pytest.raises(RuntimeError, match="batch\\['f'\\]"):
+            exp({"data": a["data"].cuda()})
 
 
 def test_config_built_routine_reproduces_the_golden_rollout():
