@@ -52,6 +52,19 @@ class BlockParams(C.Structure):
                 ("layers", C.POINTER(LayerParams)), ("n_layers", C.c_int32)]
 
 
+class LinearGrads(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("weight_g", C.c_void_p), ("weight_v", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [("fourier_weight", C.c_void_p * MAX_DIMS), ("backcast_ff", LinearGrads * MAX_FF_LAYERS)]
+
+
+class BlockGrads(C.Structure):
+    _fields_ = [("in_proj", LinearGrads), ("out0", LinearGrads), ("out1", LinearGrads),
+                ("layers", C.POINTER(LayerGrads)), ("n_layers", C.c_int32)]
+
+
 class RolloutExtras(C.Structure):
     _fields_ = [("use_velocity", C.c_int32), ("force_steps", C.c_int32), ("force", C.c_void_p), ("mu", C.c_void_p)]
 
@@ -95,6 +108,10 @@ EXPORTS = {
     "ffno_rollout_fwd_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p,
                                       C.c_float, C.c_float, C.POINTER(RolloutExtras), C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
+    "ffno_block_bwd_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
+    "ffno_block_bwd": (C.c_int, [C.c_void_p, C.POINTER(BlockParams), C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.POINTER(BlockGrads), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ffno_rel_l2_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "ffno_velocity_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "ffno_velocity_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

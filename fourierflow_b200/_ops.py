@@ -26,13 +26,18 @@ def require_cuda(x: torch.Tensor, what: str) -> None:
         raise RuntimeError(f"{what}: expected float32, got {x.dtype}")
 
 
+def needs_grad(module: nn.Module, x: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters()))
+
+
 def require_inference(module: nn.Module, x: torch.Tensor) -> None:
-    """The CUDA path is forward-only (the reference's timed path runs under no_grad,
-    fourierflow/routines/base.py:54-56).  Refuse to silently drop a graph."""
-    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
+    """Entry points without a CUDA backward (sub-modules called on their own, mesh variants, rollouts: the reference's
+    timed path runs under no_grad, fourierflow/routines/base.py:54-56) refuse to silently drop a graph.  The block
+    forward of FNOFactorized2DBlock is differentiable (ffno_block_bwd)."""
+    if needs_grad(module, x):
         raise RuntimeError(
-            f"{type(module).__name__}: the B200 backend implements the forward pass only; call it under "
-            "torch.no_grad() / torch.inference_mode() (backward is not implemented yet)")
+            f"{type(module).__name__}: this entry point of the B200 backend has the forward pass only; call it under "
+            "torch.no_grad() / torch.inference_mode() (the backward exists for FNOFactorized2DBlock.forward)")
 
 
 def _stream(device: torch.device) -> C.c_void_p:
@@ -117,6 +122,33 @@ def rel_l2(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
                                    y2.stride(1), B, x2.shape[1], out.data_ptr(), _stream(x.device)),
                    "ffno_rel_l2")
     return out
+
+
+class _RelL2(torch.autograd.Function):
+    """Per-sample relative L2 with the CUDA backward (ffno_rel_l2 / ffno_rel_l2_bwd); y is a constant target."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        x2, y2 = x.reshape(x.shape[0], -1).contiguous(), y.reshape(y.shape[0], -1).contiguous()
+        ctx.save_for_backward(x2, y2)
+        ctx.shape = x.shape
+        return rel_l2(x2, y2)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x2, y2 = ctx.saved_tensors
+        dx = torch.empty_like(x2)
+        g = g_out.contiguous().float()
+        with torch.cuda.device(x2.device):
+            _lib.check(_lib.load().ffno_rel_l2_bwd(x2.data_ptr(), y2.data_ptr(), g.data_ptr(), x2.shape[0], x2.shape[1],
+                                                   dx.data_ptr(), _stream(x2.device)), "ffno_rel_l2_bwd")
+        return dx.reshape(ctx.shape), None
+
+
+def rel_l2_differentiable(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    require_cuda(x, "LpLoss.rel")
+    require_cuda(y, "LpLoss.rel")
+    return _RelL2.apply(x, y)
 
 
 def velocity_features(w: torch.Tensor, length_x: float, length_y: float):
@@ -282,6 +314,56 @@ class StackPlan:
             _lib.check(self.lib.ffno_block_fwd(self._plan, x.data_ptr(), B, out.data_ptr(), taps_struct,
                                                ws.data_ptr(), ws.numel(), _stream(self.device)), "ffno_block_fwd")
         return out, taps
+
+    def block_backward(self, x: torch.Tensor, d_forecast: torch.Tensor, in_proj, out, layers: List[LayerSpec],
+                       want_dx: bool):
+        """Gradients of the stack (ffno_block_bwd) -> (dx or None, {id(parameter): gradient tensor}).  Call right after
+        ``sync_params`` with the same modules: the raw parameter pointers of that load are what the weight-norm backward
+        reads; a parameter shared by several layers gets one buffer that receives the sum."""
+        B = x.shape[0]
+        gmap: dict = {}
+
+        def gbuf(prm: Optional[torch.Tensor]):
+            if prm is None or not prm.requires_grad:
+                return None
+            g = gmap.get(id(prm))
+            if g is None:
+                g = torch.zeros(prm.shape, device=self.device, dtype=torch.float32)
+                gmap[id(prm)] = g
+            return g.data_ptr()
+
+        def lin_grads(dst: _lib.LinearGrads, lin: nn.Linear) -> None:
+            if "weight" in lin._parameters and lin._parameters["weight"] is not None:
+                dst.weight = gbuf(lin._parameters["weight"])
+            else:
+                dst.weight_g, dst.weight_v = gbuf(lin.weight_g), gbuf(lin.weight_v)
+                if (dst.weight_g is None) != (dst.weight_v is None):
+                    raise RuntimeError("weight-normed linear: weight_g and weight_v must both (not) require grad")
+            dst.bias = gbuf(lin.bias)
+
+        bg = _lib.BlockGrads()
+        lin_grads(bg.in_proj, in_proj)
+        lin_grads(bg.out0, out[0])
+        lin_grads(bg.out1, out[1])
+        arr = (_lib.LayerGrads * len(layers))()
+        for l, spec in enumerate(layers):
+            for a, w in enumerate(spec.fourier_weight):
+                if w is not None:
+                    arr[l].fourier_weight[a] = gbuf(w)
+            for i, layer in enumerate(spec.backcast_ff.layers):
+                lin_grads(arr[l].backcast_ff[i], layer[0])
+        bg.layers = arr
+        bg.n_layers = len(layers)
+        with torch.cuda.device(self.device):
+            need = self.lib.ffno_block_bwd_workspace_bytes(self._plan, B)
+            ws = getattr(self, "_ws_bwd", None)
+            if ws is None or ws.numel() < need:
+                ws = self._ws_bwd = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            dx = torch.empty_like(x) if want_dx else None
+            _lib.check(self.lib.ffno_block_bwd(self._plan, C.byref(self._structs[0]), x.data_ptr(), d_forecast.data_ptr(),
+                                               B, C.byref(bg), _ptr(dx), ws.data_ptr(), ws.numel(), _stream(self.device)),
+                       "ffno_block_bwd")
+        return dx, gmap
 
     def block_forward_host(self, x_host: torch.Tensor, out_host: torch.Tensor) -> None:
         """Host-buffer entry point (ffno_block_fwd_host): H2D + forward + D2H + stream sync inside."""

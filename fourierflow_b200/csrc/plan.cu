@@ -11,6 +11,7 @@
 #include <new>
 #include <vector>
 
+#include "backward.cuh"
 #include "generic_kernels.cuh"
 #include "umma_kernels.cuh"
 #include "umma_path.cuh"
@@ -73,6 +74,8 @@ struct ffno_plan {
   bool use_umma = false;
   float* d_fwd[3] = {nullptr, nullptr, nullptr};   // [L][ld(2K)]
   float* d_inv[3] = {nullptr, nullptr, nullptr};   // [2K][ld(L)]
+  float* d_fwdT[3] = {nullptr, nullptr, nullptr};  // [2K][ld(L)]: transpose of d_fwd — adjoint of the forward transform
+  float* d_invT[3] = {nullptr, nullptr, nullptr};  // [L][ld(2K)]: transpose of d_inv — adjoint of the inverse transform
   bool loaded = false;
   bool has_io = false;             // lift + head parameters were given (false for a bare spectral layer)
   std::vector<LayerW> layers;
@@ -162,6 +165,7 @@ int build_tables(ffno_plan* p) {
     const int L = p->ext[a], K = p->d.modes[a];
     const int ldf = pad16(2 * K), ldi = pad16(L);
     std::vector<float> f((size_t)L * ldf, 0.f), inv((size_t)2 * K * ldi, 0.f);
+    std::vector<float> fT((size_t)2 * K * ldi, 0.f), invT((size_t)L * ldf, 0.f);      // backward pass (ffno_block_bwd)
     const double s = 1.0 / std::sqrt((double)L);
     for (int l = 0; l < L; ++l)
       for (int k = 0; k < K; ++k) {
@@ -174,11 +178,19 @@ int build_tables(ffno_plan* p) {
         f[(size_t)l * ldf + 2 * k + 1] = (float)(-sn);
         inv[(size_t)(2 * k) * ldi + l] = (float)(ck * c);
         inv[(size_t)(2 * k + 1) * ldi + l] = (float)(-ck * sn);
+        fT[(size_t)(2 * k) * ldi + l] = (float)c;
+        fT[(size_t)(2 * k + 1) * ldi + l] = (float)(-sn);
+        invT[(size_t)l * ldf + 2 * k] = (float)(ck * c);
+        invT[(size_t)l * ldf + 2 * k + 1] = (float)(-ck * sn);
       }
     FFNO_TRY(dev_alloc(p, f.size() * 4, &p->d_fwd[a]));
     FFNO_TRY(dev_alloc(p, inv.size() * 4, &p->d_inv[a]));
     FFNO_CUDA_CHECK(cudaMemcpy(p->d_fwd[a], f.data(), f.size() * 4, cudaMemcpyHostToDevice));
     FFNO_CUDA_CHECK(cudaMemcpy(p->d_inv[a], inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+    FFNO_TRY(dev_alloc(p, fT.size() * 4, &p->d_fwdT[a]));
+    FFNO_TRY(dev_alloc(p, invT.size() * 4, &p->d_invT[a]));
+    FFNO_CUDA_CHECK(cudaMemcpy(p->d_fwdT[a], fT.data(), fT.size() * 4, cudaMemcpyHostToDevice));
+    FFNO_CUDA_CHECK(cudaMemcpy(p->d_invT[a], invT.data(), invT.size() * 4, cudaMemcpyHostToDevice));
   }
   return FFNO_OK;
 }
@@ -1035,6 +1047,182 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
                "force / mu channels go through ffno_rollout_fwd_ex");
   return ffno_rollout_fwd_ex(p, frame0, batch, n_steps, mean_host, std_host, low, high, nullptr, preds, workspace,
                              workspace_bytes, stream);
+}
+
+// ---- backward pass (include/ffno_b200.h: ffno_block_bwd) ---------------------------------------------------------
+namespace {
+
+struct BwdWs {
+  float *xs, *ss, *b, *gx, *gb, *ds, *h, *dh, *F, *dR, *dF, *R, *h0, *dh0, *wT, *dwf;
+  size_t bytes;
+};
+
+size_t bwd_scratch_floats(const ffno_plan* p) {
+  const size_t C = p->d.width, H = p->hidden(), Hh = p->d.head_hidden;
+  size_t m = C * H;
+  if (C * Hh > m) m = C * Hh;
+  if (Hh * (size_t)p->d.out_features > m) m = Hh * (size_t)p->d.out_features;
+  if ((size_t)p->in_total * C > m) m = (size_t)p->in_total * C;
+  for (int a = 0; a < p->d.ndim; ++a)
+    if ((size_t)p->d.modes[a] * 4 * C * C > m) m = (size_t)p->d.modes[a] * 4 * C * C;
+  return m;
+}
+
+BwdWs carve_bwd(const ffno_plan* p, int batch, void* base) {
+  BwdWs w{};
+  Carver c(base);
+  const long long P = (long long)batch * p->pts;
+  const size_t U = (size_t)P * p->d.width, PH = (size_t)P * p->hidden();
+  w.xs = c.take(U * p->d.n_layers);      // x_0 .. x_{L-1}: the input of every layer
+  w.ss = c.take(U * p->d.n_layers);      // the spectral output of every layer
+  w.b = c.take(U);
+  w.gx = c.take(U);
+  w.gb = c.take(U);
+  w.ds = c.take(U);
+  w.h = c.take(PH);
+  w.dh = c.take(PH);
+  size_t spec = 0;
+  for (int a = 0; a < p->d.ndim; ++a) {
+    const size_t sa = U / p->ext[a] * 2 * p->d.modes[a];
+    spec = sa > spec ? sa : spec;
+  }
+  w.F = c.take(spec);
+  w.R = c.take(spec);
+  w.dR = c.take(spec);
+  w.dF = c.take(spec);
+  w.h0 = c.take((size_t)P * p->d.head_hidden);
+  w.dh0 = c.take((size_t)P * p->d.head_hidden);
+  w.wT = c.take(bwd_scratch_floats(p));
+  w.dwf = c.take(bwd_scratch_floats(p));
+  w.bytes = c.off;
+  return w;
+}
+
+// gradient of one (weight-normed or plain) linear from the gradient dwf[out][in] of its folded weight
+int linear_param_grads(const ffno_linear_params& prm, const ffno_linear_grads& g, const float* dwf, int out, int in,
+                       cudaStream_t st) {
+  if (prm.weight) {
+    if (g.weight) FFNO_TRY(launch_axpy(g.weight, dwf, (long long)out * in, st));
+  } else if (g.weight_g && g.weight_v) {
+    FFNO_TRY(launch_wnorm_bwd(dwf, prm.weight_v, prm.weight_g, g.weight_g, g.weight_v, out, in, st));
+  } else {
+    FFNO_REQUIRE(!g.weight_g && !g.weight_v, FFNO_ERR_BAD_ARG, "weight_g and weight_v gradients come together");
+  }
+  return FFNO_OK;
+}
+
+// One linear y[P][out] = x[P][in] W^T + b, W given folded + transposed as wt[in][out]: accumulates the parameter
+// gradients and (dx != NULL) writes dx[P][in] = dy W.  `wide` selects the 64-wide GEMM (dims multiples of 4).
+int linear_bwd(const ffno_plan* p, const Lin& lin, const ffno_linear_params& prm, const ffno_linear_grads& g,
+               const float* x, const float* dy, float* dx, long long P, const BwdWs& w, cudaStream_t st) {
+  const int in = lin.in, out = lin.out;
+  const bool want_w = g.weight || g.weight_v;
+  if (want_w) {
+    FFNO_CUDA_CHECK(cudaMemsetAsync(w.dwf, 0, (size_t)in * out * 4, st));
+    FFNO_TRY(launch_linear_wgrad(dy, x, w.dwf, P, out, in, p->sm_count, st));
+    FFNO_TRY(linear_param_grads(prm, g, w.dwf, out, in, st));
+  }
+  if (g.bias && prm.bias) FFNO_TRY(launch_colsum(dy, g.bias, P, out, st));
+  if (dx) {
+    FFNO_TRY(launch_transpose(lin.wt, w.wT, in, out, 1, st));      // wT[out][in]: the K x N operand of dx = dy W
+    if (in % 4 == 0 && out % 4 == 0)
+      FFNO_TRY(launch_linear(dy, w.wT, nullptr, nullptr, dx, nullptr, P, out, in, false, st));
+    else
+      FFNO_TRY(launch_linear_any(dy, w.wT, nullptr, dx, P, out, in, false, st));
+  }
+  return FFNO_OK;
+}
+
+}  // namespace
+
+size_t ffno_block_bwd_workspace_bytes(const ffno_plan* plan, int32_t batch) {
+  if (!plan || batch < 0) return 0;
+  return carve_bwd(plan, batch, nullptr).bytes;
+}
+
+int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, const float* d_forecast, int32_t batch,
+                   const ffno_block_grads* grads, float* dx, void* workspace, size_t workspace_bytes, void* stream) {
+  FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_block_bwd_workspace_bytes(p, batch)));
+  FFNO_REQUIRE(prm && grads && x && d_forecast, FFNO_ERR_BAD_ARG, "NULL argument");
+  FFNO_REQUIRE(prm->n_layers == p->d.n_layers && grads->n_layers == p->d.n_layers && prm->layers && grads->layers,
+               FFNO_ERR_BAD_ARG, "params / grads must describe the plan's %d layers", p->d.n_layers);
+  FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
+  bool padded = false;
+  for (int a = 0; a < p->d.ndim; ++a) padded |= p->d.pad[a] != 0;
+  FFNO_REQUIRE(!padded && !p->d.append_grid && p->d.n_ff_layers == 2 && !p->d.layer_norm && !p->d.use_fork &&
+                   p->d.spectral_mode == FFNO_MODE_FULL,
+               FFNO_ERR_UNSUPPORTED,
+               "backward is implemented for unpadded stacks with n_ff_layers = 2, no LayerNorm, no fork, mode 'full'");
+  if (batch == 0) return FFNO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long before = g_launch_counter;
+  const BwdWs w = carve_bwd(p, batch, workspace);
+  const LiftGeom g = p->geom();
+  const int C = p->d.width, H = p->hidden(), Hh = p->d.head_hidden, O = p->d.out_features, nl = p->d.n_layers;
+  const long long P = (long long)batch * p->pts;
+  const size_t U = (size_t)P * C;
+  Workspace wf{};            // ff_generic only needs the hidden buffer
+  wf.h0 = w.h;
+
+  // ---- 1. forward in FP32, keeping the input x_l and the spectral output s_l of every layer
+  FFNO_TRY(launch_lift(x, p->lift.wt, p->lift.bias, w.xs, batch, g, st));
+  for (int l = 0; l < nl; ++l) {
+    const LayerW& lw = p->layers[l];
+    float* xl = w.xs + (size_t)l * U;
+    float* sl = w.ss + (size_t)l * U;
+    FFNO_TRY(spectral_generic(p, lw, xl, batch, sl, w.F, w.R, st));
+    // x_{l+1} = x_l + b_l; the last layer's residual sum is dead (the head reads b, grid_2d.py:170-172)
+    FFNO_TRY(ff_generic(p, lw.back, sl, xl, P, l + 1 < nl ? xl + U : nullptr, l + 1 < nl ? nullptr : w.b, wf, st));
+  }
+  FFNO_TRY(launch_linear(w.b, p->out0.wt, p->out0.bias, nullptr, w.h0, nullptr, P, C, Hh, false, st));
+
+  // ---- 2. head: forecast = out1(out0(b))
+  FFNO_TRY(linear_bwd(p, p->out1, prm->out1, grads->out1, w.h0, d_forecast, w.dh0, P, w, st));
+  FFNO_TRY(linear_bwd(p, p->out0, prm->out0, grads->out0, w.b, w.dh0, w.gb, P, w, st));
+
+  // ---- 3. layers, last to first.  gx = dL/dx_{l+1}; the layer's backcast gradient is gx (x_{l+1} = x_l + b_l), or
+  //         the head's for the last layer
+  FFNO_CUDA_CHECK(cudaMemsetAsync(w.gx, 0, U * 4, st));
+  for (int l = nl - 1; l >= 0; --l) {
+    const LayerW& lw = p->layers[l];
+    const ffno_layer_params& lp = prm->layers[l];
+    const ffno_layer_grads& lg = grads->layers[l];
+    const float* xl = w.xs + (size_t)l * U;
+    const float* sl = w.ss + (size_t)l * U;
+    const float* gb = l == nl - 1 ? w.gb : w.gx;
+    // FeedForward (feedforward.py:6-24): h = relu(W1 s + b1), b = W2 h + b2
+    FFNO_TRY(launch_linear(sl, lw.back.lin[0].wt, lw.back.lin[0].bias, nullptr, w.h, nullptr, P, C, H, true, st));
+    FFNO_TRY(linear_bwd(p, lw.back.lin[1], lp.backcast_ff.linear[1], lg.backcast_ff[1], w.h, gb, w.dh, P, w, st));
+    FFNO_TRY(launch_relu_bwd(w.dh, w.h, (long long)P * H, st));
+    FFNO_TRY(linear_bwd(p, lw.back.lin[0], lp.backcast_ff.linear[0], lg.backcast_ff[0], sl, w.dh, w.ds, P, w, st));
+    // spectral operator (grid_2d.py:51-99): s = sum_a Inv_a Mix_a Fwd_a x  =>  gx += sum_a Fwd_a^T Mix_a^T Inv_a^T ds
+    for (int a = p->d.ndim - 1; a >= 0; --a) {
+      long long outer = batch, p_inner = 1;
+      for (int i = 0; i < a; ++i) outer *= p->ext[i];
+      for (int i = a + 1; i < p->d.ndim; ++i) p_inner *= p->ext[i];
+      const int L = p->ext[a], K = p->d.modes[a];
+      const long long inner = p_inner * C;
+      FFNO_TRY(launch_axis_transform(w.ds, p->d_invT[a], w.dR, outer, L, 2 * K, inner, false, st));
+      if (lg.fourier_weight[a]) {
+        FFNO_TRY(launch_axis_transform(xl, p->d_fwd[a], w.F, outer, L, 2 * K, inner, false, st));
+        FFNO_TRY(launch_mix_wgrad(w.F, w.dR, lg.fourier_weight[a], outer, K, p_inner, C, p->sm_count, st));
+      }
+      FFNO_TRY(launch_transpose(lw.wmix[a], w.wT, 2 * C, 2 * C, K, st));
+      FFNO_TRY(launch_mode_mix(w.dR, w.wT, w.dF, outer, K, p_inner, C, st));
+      FFNO_TRY(launch_axis_transform(w.dF, p->d_fwdT[a], w.gx, outer, 2 * K, L, inner, true, st));
+    }
+  }
+
+  // ---- 4. lift (grid_2d.py:157): x_0 = in_proj(x)
+  FFNO_TRY(linear_bwd(p, p->lift, prm->in_proj, grads->in_proj, x, w.gx, dx, P, w, st));
+  p->last_launches = g_launch_counter - before;
+  (void)O;
+  return FFNO_OK;
+}
+
+int ffno_rel_l2_bwd(const float* x, const float* y, const float* g_out, int32_t batch, int64_t n, float* dx, void* stream) {
+  FFNO_REQUIRE(x && y && g_out && dx && batch >= 0 && n >= 1, FFNO_ERR_BAD_ARG, "bad argument");
+  return launch_rel_l2_bwd(x, y, g_out, dx, batch, n, static_cast<cudaStream_t>(stream));
 }
 
 int ffno_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int32_t N, int32_t K, int32_t a_mn,

@@ -20,6 +20,8 @@ class LpLoss:
     def rel_per_sample(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         if self.p != 2:
             raise RuntimeError("fourierflow_b200.LpLoss: only p=2 has a CUDA kernel")
+        if torch.is_grad_enabled() and x.requires_grad:      # training: CUDA backward (ffno_rel_l2_bwd)
+            return _ops.rel_l2_differentiable(x, y)
         return _ops.rel_l2(x, y)
 
     def rel(self, x, y):

@@ -224,6 +224,44 @@ FFNO_API int ffno_rollout_fwd_ex(ffno_plan* plan, const float* frame0, int32_t b
 FFNO_API size_t ffno_rollout_workspace_bytes_ex(const ffno_plan* plan, int32_t batch, int32_t n_steps,
                                        int32_t use_velocity, int32_t force_steps, int32_t has_mu);
 
+/* ---- Backward pass ------------------------------------------------------------------------------
+ * What torch.autograd computes for the reference's training step (routines/grid_2d_markov.py:172-193 `_training_step`:
+ * forecast -> Normalizer.inverse -> LpLoss; routines/base.py:27-52 applies the optimizer), written out as explicit
+ * adjoints.  Supported stacks: FNOFactorized2DBlock / mesh variants WITHOUT padding / grid append, n_ff_layers = 2, no
+ * LayerNorm, no fork, mode 'full' (every torus_li / torus_kochkov / torus_vis config).  Generic FP32 kernels; the forward
+ * is recomputed inside the call (FP32 path) so no state is carried between the forward and the backward.
+ *
+ * Gradient buffers have the shapes of the parameters they belong to and are ACCUMULATED into (+=), like `.grad`: zero
+ * them first; a parameter shared by several layers (share_weight) is given the same buffer in each layer and receives
+ * the sum.  NULL pointers skip that gradient. */
+typedef struct {
+  float* weight;                  /* [out, in]  (plain linear)            */
+  float* weight_g;                /* [out]      (weight-normed linear)    */
+  float* weight_v;                /* [out, in]                            */
+  float* bias;                    /* [out] */
+} ffno_linear_grads;
+typedef struct {
+  float* fourier_weight[FFNO_MAX_DIMS];        /* [C, C, K_a, 2], tensor-axis order as in ffno_layer_params */
+  ffno_linear_grads backcast_ff[FFNO_MAX_FF_LAYERS];
+} ffno_layer_grads;
+typedef struct {
+  ffno_linear_grads in_proj, out0, out1;
+  const ffno_layer_grads* layers;
+  int32_t n_layers;
+} ffno_block_grads;
+/*   x           [B, S.., in_features]   the forward's input
+ *   d_forecast  [B, S.., out_features]  gradient of the loss w.r.t. the forecast
+ *   params      the parameters the plan was loaded with (the weight-norm backward needs the raw g, v)
+ *   dx          [B, S.., in_features] or NULL: gradient w.r.t. the input (overwritten) */
+FFNO_API size_t ffno_block_bwd_workspace_bytes(const ffno_plan* plan, int32_t batch);
+FFNO_API int ffno_block_bwd(ffno_plan* plan, const ffno_block_params* params, const float* x, const float* d_forecast,
+                   int32_t batch, const ffno_block_grads* grads, float* dx, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* Backward of ffno_rel_l2 for contiguous x, y [batch, n]: dx[b, i] = g_out[b] * d out[b] / d x[b, i]
+ * (modules/loss.py:33-46; the mean over the batch is the caller's g_out = 1 / batch). */
+FFNO_API int ffno_rel_l2_bwd(const float* x, const float* y, const float* g_out, int32_t batch, int64_t n, float* dx,
+                    void* stream);
+
 /* Velocity features of the torus_kochkov rollout (use_velocity=True, routines/grid_2d_markov.py:82-93, :206-220):
  * (q, v) = (psi_y, -psi_x) of the stream function of the vorticity w (w = -laplace psi) on a periodic
  * length_x x length_y domain, i.e. irfftn(+-2 pi i k psi_hat) with the reference's kx/ky/lap buffers.

@@ -1,0 +1,121 @@
+"""Backward row: ffno_block_bwd / ffno_rel_l2_bwd through the C ABI and torch.autograd.Function,
+against (i) the gradients the EXECUTED reference computed for its one-step training loss
+(routines/grid_2d_markov.py:172-193; fixtures tests/golden/grad_*.npz made by oracle/make_golden.py) and (ii)
+torch.autograd through the CPU oracle at the C2 layer shape.  Tolerance: max|g - ref| / max|ref| <= 1e-4 per tensor
+(FP32 kernels, atomics over the point reduction; measured ~1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load, rel_err
+from oracle import ffno_oracle as O
+
+
+def build(cls, kw, sd):
+    import fourierflow_b200.modules as M
+    m = getattr(M, cls)(**kw)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _loss(m, x, y):
+    from fourierflow_b200.modules import LpLoss
+    B = x.shape[0]
+    forecast = m(x)["forecast"]
+    return forecast, LpLoss(size_average=True)(forecast.reshape(B, -1), y.reshape(B, -1))
+
+
+@pytest.mark.parametrize("name", ["grad_c2arch_16", "grad_unshared_w32"])
+@pytest.mark.parametrize("path", ["auto", "generic"])
+def test_gradients_match_the_executed_reference(name, path, monkeypatch):
+    """Input gradient + every parameter gradient (weight-norm g / v, shared spectral weights summed over layers, plain
+    linears, biases) of the reference's training loss."""
+    monkeypatch.setenv("FFNO_B200_PATH", path)
+    kw, sd, a = load(name)
+    m = build("FNOFactorized2DBlock", kw, sd).train()
+    x = a["x"].cuda().requires_grad_(True)
+    forecast, loss = _loss(m, x, a["y"].cuda())
+    loss.backward()
+    assert rel_err(forecast, a["forecast"]) < TOL
+    assert abs(loss.item() - a["loss"].item()) < 1e-5 * abs(a["loss"].item())
+    e = rel_err(x.grad, a["grad::x"])
+    print(name, path, f"dx {e:.2e}")
+    assert e < TOL
+    params = dict(m.named_parameters())
+    checked, worst = 0, 0.0
+    for k, ref in a.items():
+        if not k.startswith("grad::") or k == "grad::x":
+            continue
+        g = params[k[6:]].grad
+        assert g is not None, k
+        e = rel_err(g, ref)
+        worst = max(worst, e)
+        assert e < TOL, (k, e)
+        checked += 1
+    print(name, path, f"{checked} parameter gradients, worst {worst:.2e}")
+    assert checked >= 10
+
+
+def test_gradients_accumulate_and_match_oracle_autograd_at_the_c2_layer_shape():
+    """64 x 64, width 64, modes 16, 2 layers, batch 2 (the C2 layer shape): CUDA backward vs torch.autograd through the
+    oracle; a second backward accumulates into .grad like torch does."""
+    torch.manual_seed(3)
+    from fourierflow_b200.modules import FNOFactorized2DBlock
+    m = FNOFactorized2DBlock(modes=16, width=64, n_layers=2, input_dim=3, share_weight=True, factor=4,
+                             ff_weight_norm=True, gain=0.1).cuda().train()
+    x = torch.randn(2, 64, 64, 3, device="cuda")
+    y = torch.randn(2, 64, 64, 1, device="cuda")
+    _, loss = _loss(m, x, y)
+    loss.backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    _, loss = _loss(m, x, y)
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert rel_err(p.grad, 2 * g1[k]) < 1e-5, k
+    # oracle autograd on the CPU
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    leaves = {}
+    for k, v in m.state_dict(keep_vars=True).items():
+        leaves.setdefault(id(v), sd[k].clone().requires_grad_(True))
+    p = {k: leaves[id(v)] for k, v in m.state_dict(keep_vars=True).items()}
+    out = O.block_grid2d_forward(p, x.cpu(), modes=16, n_layers=2)
+    lo = O.lp_loss_rel(out["forecast"].reshape(2, -1), y.cpu().reshape(2, -1))
+    lo.backward()
+    assert abs(lo.item() - loss.item()) < 1e-5 * abs(lo.item())
+    for k, v in m.state_dict(keep_vars=True).items():
+        if v.requires_grad:
+            assert rel_err(g1[k], p[k].grad) < TOL, k
+
+
+def test_rel_l2_backward_matches_autograd():
+    from fourierflow_b200 import _ops
+    x = torch.randn(5, 777, device="cuda", requires_grad=True)
+    y = torch.randn(5, 777, device="cuda")
+    w = torch.rand(5, device="cuda")
+    (_ops.rel_l2_differentiable(x, y) * w).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    ((torch.linalg.vector_norm(xr - y, dim=1) / torch.linalg.vector_norm(y, dim=1)) * w).sum().backward()
+    assert rel_err(x.grad, xr.grad) < 1e-5
+
+
+def test_one_optimizer_step_reduces_the_training_loss():
+    """routines/base.py:27-52 applies the optimizer to these gradients: an SGD step along them must lower the loss."""
+    torch.manual_seed(0)
+    from fourierflow_b200.modules import FNOFactorized2DBlock
+    m = FNOFactorized2DBlock(modes=8, width=64, n_layers=3, input_dim=3, share_weight=True, factor=4,
+                             ff_weight_norm=True, gain=0.1).cuda().train()
+    x = torch.randn(4, 32, 32, 3, device="cuda")
+    y = torch.randn(4, 32, 32, 1, device="cuda")
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        _, loss = _loss(m, x, y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    print("losses", losses)
+    assert losses[-1] < losses[0]

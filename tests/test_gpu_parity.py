@@ -337,8 +337,8 @@ def test_edge_cases():
             m(torch.randn(1, 64, 64, 4, device="cuda"))                                              # wrong feature count
         with pytest.raises(RuntimeError, match="rfft bins"):
             m(torch.randn(1, 8, 8, 3, device="cuda"))                                                # modes 16 > 8//2+1
-    with pytest.raises(RuntimeError, match="forward pass only"):
-        m(torch.randn(1, 64, 64, 3, device="cuda"))                                                  # grad mode on
+    with pytest.raises(RuntimeError, match="forward pass only"):                                     # grad mode on: entry
+        m.spectral_layers[0](torch.randn(1, 64, 64, 64, device="cuda"))                              # points without a backward
 
 
 def test_params_resync_after_inplace_update():
