@@ -116,3 +116,25 @@ def rollout_loss(local: torch.Tensor, n_global: int) -> Tuple[torch.Tensor, torc
     allv = gather_sample_losses(local, n_global)
     step = allv.mean(dim=1)
     return step.sum(), step
+
+
+def allreduce_gradients(params, world_size: int = None, group=None) -> int:
+    """Data-parallel gradient averaging for batch shards — what the reference's dormant DDP plugin would do
+    (commands/train.py:83-84): ONE all-reduce per step over a flat bucket of every ``.grad`` (2 M floats for the C2
+    model: latency-sized, so one bucket), then mean = sum / world.  Every rank must hold gradients for the same
+    parameters in the same order.  Returns the number of elements reduced (0 when there is nothing to exchange)."""
+    if not dist.is_initialized():
+        return 0
+    world = world_size or dist.get_world_size(group)
+    grads = [p.grad for p in params if p.grad is not None]
+    if world == 1 or not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return off

@@ -104,6 +104,67 @@ class Grid2DMarkovExperiment(RoutineMixin, nn.Module):
             self._ms_cache = (key, self.normalizer.mean.tolist(), self.normalizer.std.tolist())
         return self._ms_cache[1], self._ms_cache[2]
 
+    # -- training (routines/grid_2d_markov.py:122-193, :374-390; routines/base.py:27-52) -------------------------
+    def _build_features(self, batch):
+        """One-step input features [x, (q, v,) gx, gy, (f,) (mu)] of ``batch['x']`` [B,X,Y,1], normalised (the
+        normaliser accumulates when in training mode), + noise_std * N(0, 1) (grid_2d_markov.py:122-170).  Feature
+        assembly is host-side tensor plumbing; the velocities come from ffno_velocity_fwd."""
+        x = batch['x']
+        _ops.require_cuda(x, "Grid2DMarkovExperiment")
+        B, X, Y, _ = x.shape
+        self._check_extras(batch.get('f') if self.append_force else None,
+                           batch.get('mu') if self.append_mu else None, B, X, Y)
+        parts = [x]
+        if self.use_velocity:
+            q, v = _ops.velocity_features(x[..., 0], *self.domain_lengths)
+            parts += [q.unsqueeze(-1), v.unsqueeze(-1)]
+        parts.append(self._positions(X, Y, x.device, x.dtype).unsqueeze(0).expand(B, X, Y, 2))
+        if self.append_force:
+            if batch['f'].dim() != 3:
+                raise RuntimeError("Grid2DMarkovExperiment: the training batch carries a static forcing batch['f'] [B,X,Y] "
+                                   "(grid_2d_markov.py:146-148)")
+            parts.append(batch['f'].unsqueeze(-1))
+        if self.append_mu:
+            parts.append(batch['mu'].reshape(B, 1, 1, 1).expand(B, X, Y, 1))
+        feats = self.normalizer(torch.cat(parts, dim=-1))
+        self._ms_cache = None
+        if self.noise_std:
+            feats = feats + torch.randn_like(feats) * self.noise_std
+        return feats
+
+    def _training_step(self, batch):
+        """loss = LpLoss(de-normalised forecast, batch['y']) of one step (grid_2d_markov.py:172-193); differentiable
+        through ffno_block_bwd / ffno_rel_l2_bwd."""
+        x = self._build_features(batch)
+        im = self.conv(x)['forecast']
+        im = self.normalizer.inverse(im, channel=0)
+        BN = im.shape[0]
+        return self.l2_loss(im.reshape(BN, -1), batch['y'].reshape(BN, -1))
+
+    def training_step(self, batch, batch_idx: int = 0, optimizer=None, scheduler=None, current_epoch: int = 1,
+                      clip_val: Optional[float] = None, world_size: int = 1):
+        """grid_2d_markov.py:374-390 + routines/base.py:27-52 without pytorch_lightning: epoch 0 only accumulates the
+        normaliser statistics; afterwards loss -> zero_grad -> backward -> (data-parallel: one all-reduce of the
+        gradients, fourierflow_b200.distributed.allreduce_gradients) -> clip -> optimizer.step -> scheduler.step."""
+        if current_epoch == 0:
+            with torch.no_grad():
+                self._build_features(batch)
+            return None
+        loss = self._training_step(batch)
+        if optimizer is not None:
+            optimizer.zero_grad()
+            loss.backward()
+            if world_size > 1:
+                from ..distributed import allreduce_gradients
+                allreduce_gradients([p for g in optimizer.param_groups for p in g["params"]], world_size)
+            if clip_val:
+                for group in optimizer.param_groups:
+                    torch.nn.utils.clip_grad_value_(group["params"], clip_val)
+            optimizer.step()
+            if scheduler is not None:
+                scheduler.step()
+        return loss
+
     # -- inference -------------------------------------------------------------------------------------
     def forward(self, data):
         return self._valid_step(data)

@@ -69,3 +69,35 @@ def test_shard_bounds_cover_batch():
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in cuts) - min(h - l for l, h in cuts) <= 1
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    D.init_from_env(backend="gloo")
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
+    params[0].grad = torch.full((3, 4), float(rank + 1))
+    params[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+    # params[2] has no gradient on any rank: skipped
+    n = D.allreduce_gradients(params)
+    q.put((rank, n, params[0].grad.clone(), params[1].grad.clone(), params[2].grad))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_averages_over_ranks():
+    """Data-parallel training (the reference's dormant DDP, commands/train.py:83-84): one flat all-reduce, mean over ranks."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, n, g0, g1, g2 in res:
+        assert n == 17 and g2 is None
+        assert torch.allclose(g0, torch.full((3, 4), 1.5))
+        assert torch.allclose(g1, torch.arange(5, dtype=torch.float32) * 1.5)
