@@ -87,6 +87,12 @@ struct ffno_plan {
   std::map<const void*, float*> dedup;   // source pointer -> prepared buffer (shared weights)
   int64_t last_launches = 0;
   UmmaState* umma = nullptr;
+  // Backward on the tcgen05 kernels: the adjoint of the spectral operator is the SAME three kernels with the transposed
+  // tables (d_invT in the forward-transform role, d_fwdT in the inverse role) and the transposed mode blocks — a second
+  // kernel state built on first use and refreshed when the parameters change.
+  UmmaState* umma_adj = nullptr;
+  bool adj_stale = true;
+  std::map<const float*, float*> wmixT;      // forward block matrices -> their per-mode transposes
 
   // CUDA-graph replay of the launch sequence (kills ~120 launch gaps per forward).  A slot is keyed by everything
   // baked into the captured kernel arguments; the first call with a new key runs eagerly, the second captures.
@@ -697,6 +703,7 @@ int ffno_plan_destroy(ffno_plan* plan) {
   }
   if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
   if (plan->umma) umma_destroy(plan->umma);
+  if (plan->umma_adj) umma_destroy(plan->umma_adj);
   for (void* ptr : plan->owned) cudaFree(ptr);
   delete plan;
   return FFNO_OK;
@@ -712,6 +719,7 @@ int ffno_plan_load_params(ffno_plan* p, const ffno_block_params* prm, void* stre
   const int C = p->d.width;
   p->g_block.reset();          // captured graphs point at the previous parameter buffers' contents: rebuild
   p->g_rollout.reset();
+  p->adj_stale = true;
   p->has_io = prm->in_proj.weight || prm->in_proj.weight_v;
   if (p->has_io) {
     FFNO_TRY(prep_linear(p, prm->in_proj, p->in_total, C, &p->lift, st));
@@ -1053,7 +1061,7 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
 namespace {
 
 struct BwdWs {
-  float *xs, *ss, *b, *gx, *gb, *ds, *h, *dh, *F, *dR, *dF, *R, *h0, *dh0, *wT, *dwf;
+  float *xs, *ss, *b, *gx, *gb, *ds, *h, *dh, *F, *dR, *dF, *R, *h0, *dh0, *wT, *dwf, *fc, *fwd_ws;
   size_t bytes;
 };
 
@@ -1082,10 +1090,7 @@ BwdWs carve_bwd(const ffno_plan* p, int batch, void* base) {
   w.h = c.take(PH);
   w.dh = c.take(PH);
   size_t spec = 0;
-  for (int a = 0; a < p->d.ndim; ++a) {
-    const size_t sa = U / p->ext[a] * 2 * p->d.modes[a];
-    spec = sa > spec ? sa : spec;
-  }
+  for (int a = 0; a < p->d.ndim; ++a) spec += U / p->ext[a] * 2 * p->d.modes[a];     // every axis back to back
   w.F = c.take(spec);
   w.R = c.take(spec);
   w.dR = c.take(spec);
@@ -1094,6 +1099,8 @@ BwdWs carve_bwd(const ffno_plan* p, int batch, void* base) {
   w.dh0 = c.take((size_t)P * p->d.head_hidden);
   w.wT = c.take(bwd_scratch_floats(p));
   w.dwf = c.take(bwd_scratch_floats(p));
+  w.fc = c.take((size_t)batch * p->pts_in * p->d.out_features);
+  w.fwd_ws = c.take(p->use_umma ? (stack_ws_bytes(p, batch) + 3) / 4 : 0);      // the tcgen05 forward's own workspace
   w.bytes = c.off;
   return w;
 }
@@ -1135,6 +1142,38 @@ int linear_bwd(const ffno_plan* p, const Lin& lin, const ffno_linear_params& prm
 
 }  // namespace
 
+namespace {
+// (Re)build the adjoint kernel state: transposed mode blocks + the transposed tables in swapped roles.
+int ensure_adjoint(ffno_plan* p, cudaStream_t st) {
+  if (!p->use_umma || !p->adj_stale) return FFNO_OK;
+  const int C = p->d.width;
+  if (!p->umma_adj) FFNO_TRY(umma_create(&p->umma_adj, &p->d, p->ext));
+  std::map<const float*, bool> done;
+  std::vector<UmmaLayerSrc> srcs(p->d.n_layers);
+  for (int l = 0; l < p->d.n_layers; ++l) {
+    for (int a = 0; a < 3; ++a) srcs[l].wmix[a] = nullptr;
+    for (int a = 0; a < p->d.ndim; ++a) {
+      const float* w = p->layers[l].wmix[a];
+      float*& wt = p->wmixT[w];
+      if (!wt) FFNO_TRY(dev_alloc(p, (size_t)p->d.modes[a] * 4 * C * C * 4, &wt));
+      if (!done[w]) {
+        FFNO_TRY(launch_transpose(w, wt, 2 * C, 2 * C, p->d.modes[a], st));
+        done[w] = true;
+      }
+      srcs[l].wmix[a] = wt;
+    }
+    // the FF images of the adjoint state are never used (the FF backward needs the ReLU mask): any valid weights do
+    srcs[l].w1t = p->layers[l].back.lin[0].wt;
+    srcs[l].b1 = p->layers[l].back.lin[0].bias;
+    srcs[l].w2t = p->layers[l].back.lin[1].wt;
+    srcs[l].b2 = p->layers[l].back.lin[1].bias;
+  }
+  FFNO_TRY(umma_load_params(p->umma_adj, srcs.data(), p->d_invT, p->d_fwdT, st));
+  p->adj_stale = false;
+  return FFNO_OK;
+}
+}  // namespace
+
 size_t ffno_block_bwd_workspace_bytes(const ffno_plan* plan, int32_t batch) {
   if (!plan || batch < 0) return 0;
   return carve_bwd(plan, batch, nullptr).bytes;
@@ -1164,15 +1203,31 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   Workspace wf{};            // ff_generic only needs the hidden buffer
   wf.h0 = w.h;
 
-  // ---- 1. forward in FP32, keeping the input x_l and the spectral output s_l of every layer
-  FFNO_TRY(launch_lift(x, p->lift.wt, p->lift.bias, w.xs, batch, g, st));
-  for (int l = 0; l < nl; ++l) {
-    const LayerW& lw = p->layers[l];
-    float* xl = w.xs + (size_t)l * U;
-    float* sl = w.ss + (size_t)l * U;
-    FFNO_TRY(spectral_generic(p, lw, xl, batch, sl, w.F, w.R, st));
-    // x_{l+1} = x_l + b_l; the last layer's residual sum is dead (the head reads b, grid_2d.py:170-172)
-    FFNO_TRY(ff_generic(p, lw.back, sl, xl, P, l + 1 < nl ? xl + U : nullptr, l + 1 < nl ? nullptr : w.b, wf, st));
+  // ---- 1. forward again, keeping the input x_l and the spectral output s_l of every layer (and the last backcast)
+  if (p->use_umma) {
+    // the tcgen05 forward with taps: the same kernels as inference
+    FFNO_TRY(ensure_adjoint(p, st));
+    std::vector<float*> xa(nl), sa(nl);
+    for (int l = 0; l < nl; ++l) {
+      xa[l] = l + 1 < nl ? w.xs + (size_t)(l + 1) * U : nullptr;      // x after layer l = input of layer l + 1
+      sa[l] = w.ss + (size_t)l * U;
+    }
+    ffno_taps taps{};
+    taps.lift = w.xs;
+    taps.x_after = xa.data();
+    taps.spectral = sa.data();
+    taps.b_last = w.b;
+    FFNO_TRY(block_fwd_core(p, x, batch, w.fc, &taps, w.fwd_ws, st));
+  } else {
+    FFNO_TRY(launch_lift(x, p->lift.wt, p->lift.bias, w.xs, batch, g, st));
+    for (int l = 0; l < nl; ++l) {
+      const LayerW& lw = p->layers[l];
+      float* xl = w.xs + (size_t)l * U;
+      float* sl = w.ss + (size_t)l * U;
+      FFNO_TRY(spectral_generic(p, lw, xl, batch, sl, w.F, w.R, st));
+      // x_{l+1} = x_l + b_l; the last layer's residual sum is dead (the head reads b, grid_2d.py:170-172)
+      FFNO_TRY(ff_generic(p, lw.back, sl, xl, P, l + 1 < nl ? xl + U : nullptr, l + 1 < nl ? nullptr : w.b, wf, st));
+    }
   }
   FFNO_TRY(launch_linear(w.b, p->out0.wt, p->out0.bias, nullptr, w.h0, nullptr, P, C, Hh, false, st));
 
@@ -1196,6 +1251,27 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
     FFNO_TRY(launch_relu_bwd(w.dh, w.h, (long long)P * H, st));
     FFNO_TRY(linear_bwd(p, lw.back.lin[0], lp.backcast_ff.linear[0], lg.backcast_ff[0], sl, w.dh, w.ds, P, w, st));
     // spectral operator (grid_2d.py:51-99): s = sum_a Inv_a Mix_a Fwd_a x  =>  gx += sum_a Fwd_a^T Mix_a^T Inv_a^T ds
+    if (p->use_umma) {
+      // tcgen05: the forward's three kernels on the adjoint state; its "F" buffer ends up holding dR_a = Inv_a^T ds
+      // of every axis, which — with the forward spectra F_a of x_l — gives the weight gradients
+      FFNO_TRY(umma_spectral_fwd(p->umma_adj, l, w.ds, batch, w.b, w.dR, w.dF, nullptr, st));
+      FFNO_TRY(launch_axpy(w.gx, w.b, (long long)U, st));
+      bool want_w = false;
+      for (int a = 0; a < p->d.ndim; ++a) want_w |= lg.fourier_weight[a] != nullptr;
+      if (want_w) {
+        FFNO_TRY(umma_forward_spectra(p->umma, xl, batch, w.F, st));
+        for (int a = 0; a < p->d.ndim; ++a) {
+          if (!lg.fourier_weight[a]) continue;
+          long long outer = batch, p_inner = 1;
+          for (int i = 0; i < a; ++i) outer *= p->ext[i];
+          for (int i = a + 1; i < p->d.ndim; ++i) p_inner *= p->ext[i];
+          const size_t off = umma_spec_offset(p->umma, batch, a);
+          FFNO_TRY(launch_mix_wgrad(w.F + off, w.dR + off, lg.fourier_weight[a], outer, p->d.modes[a], p_inner, C,
+                                    p->sm_count, st));
+        }
+      }
+      continue;
+    }
     for (int a = p->d.ndim - 1; a >= 0; --a) {
       long long outer = batch, p_inner = 1;
       for (int i = 0; i < a; ++i) outer *= p->ext[i];

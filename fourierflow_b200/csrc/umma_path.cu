@@ -292,6 +292,25 @@ int umma_spectral_split_fwd(UmmaState* s, int layer, const float* x, int batch, 
   return umma_spectral_fwd(s, layer, x, batch, s_axis[0], F, R, ws, st);
 }
 
+size_t umma_spec_offset(const UmmaState* s, int batch, int axis) { return spec_offset(s, batch, axis); }
+
+int umma_forward_spectra(UmmaState* s, const float* x, int batch, float* F, cudaStream_t st) {
+  AxisXform fwd[3];
+  for (int a = 0; a < s->d.ndim; ++a) {
+    long long outer, p_inner;
+    axis_geom(s, batch, a, &outer, &p_inner);
+    const int Ln = s->ext[a], K = s->d.modes[a];
+    float* Fa = F + spec_offset(s, batch, a);
+    fwd[a] = AxisXform{x, Fa, s->fwd_image[a], outer, p_inner * kUmmaC, Ln, 2 * K, pad16i(2 * K), (Ln + 63) / 64, 0};
+    if (!all_axes_pipe(s)) {
+      if (s->fwd_image[a]) FFNO_TRY(launch_axis_pipe(&fwd[a], 1, s->sm_count, st));
+      else FFNO_TRY(launch_axis_transform(x, s->d_fwd[a], Fa, outer, Ln, 2 * K, p_inner * kUmmaC, false, st));
+    }
+  }
+  if (all_axes_pipe(s)) return launch_axis_pipe(fwd, s->d.ndim, s->sm_count, st, false);
+  return FFNO_OK;
+}
+
 int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* y, float*,
                 cudaStream_t st) {
   const UmmaLayer& L = s->layers[layer];

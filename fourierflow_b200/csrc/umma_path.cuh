@@ -53,6 +53,10 @@ int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float*
 // returns the number of buffers written through *n_written).
 int umma_spectral_split_fwd(UmmaState* s, int layer, const float* x, int batch, float* const s_axis[3], float* F, float* R,
                             float* ws, int* n_written, cudaStream_t st);
+// F_a = Fwd_a x for every axis, axis a at the same offset of F as in the calls above (the backward's weight gradient
+// needs the forward spectra again; nothing else of the spectral operator runs).
+int umma_forward_spectra(UmmaState* s, const float* x, int batch, float* F, cudaStream_t st);
+size_t umma_spec_offset(const UmmaState* s, int batch, int axis);
 int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* y, float* ws,
                 cudaStream_t st);
 
