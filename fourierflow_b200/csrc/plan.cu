@@ -6,6 +6,7 @@
 // The forward enqueues kernels on the caller's stream and never synchronises.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <new>
@@ -92,6 +93,7 @@ struct ffno_plan {
   // kernel state built on first use and refreshed when the parameters change.
   UmmaState* umma_adj = nullptr;
   bool adj_stale = true;
+  bool bwd_fp32 = false;                     // FFNO_B200_BWD=fp32: backward entirely on the FP32 kernels (see ffno_block_bwd)
   std::map<const float*, float*> wmixT;      // forward block matrices -> their per-mode transposes
 
   // CUDA-graph replay of the launch sequence (kills ~120 launch gaps per forward).  A slot is keyed by everything
@@ -664,6 +666,10 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
     p->graphs = !(g && g[0] == '0');
   }
   {
+    const char* b = getenv("FFNO_B200_BWD");
+    p->bwd_fp32 = b && strcmp(b, "fp32") == 0;
+  }
+  {
     const char* c = getenv("FFNO_B200_CHUNK");
     const char* ns = getenv("FFNO_B200_STREAMS");
     p->chunk = c ? atoi(c) : 0;
@@ -1145,7 +1151,7 @@ int linear_bwd(const ffno_plan* p, const Lin& lin, const ffno_linear_params& prm
 namespace {
 // (Re)build the adjoint kernel state: transposed mode blocks + the transposed tables in swapped roles.
 int ensure_adjoint(ffno_plan* p, cudaStream_t st) {
-  if (!p->use_umma || !p->adj_stale) return FFNO_OK;
+  if (!p->use_umma || p->bwd_fp32 || !p->adj_stale) return FFNO_OK;
   const int C = p->d.width;
   if (!p->umma_adj) FFNO_TRY(umma_create(&p->umma_adj, &p->d, p->ext));
   std::map<const float*, bool> done;
@@ -1204,7 +1210,10 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   wf.h0 = w.h;
 
   // ---- 1. forward again, keeping the input x_l and the spectral output s_l of every layer (and the last backcast)
-  if (p->use_umma) {
+  // tc: forward recompute and spectral adjoint on the tcgen05 kernels (3 x BF16, ~1e-5 per element — the precision of the
+  // forward itself); FFNO_B200_BWD=fp32 keeps the whole backward on the FP32 kernels (gradients at FP32 round-off, 1.4x slower)
+  const bool tc = p->use_umma && !p->bwd_fp32;
+  if (tc) {
     // the tcgen05 forward with taps: the same kernels as inference
     FFNO_TRY(ensure_adjoint(p, st));
     std::vector<float*> xa(nl), sa(nl);
@@ -1251,7 +1260,7 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
     FFNO_TRY(launch_relu_bwd(w.dh, w.h, (long long)P * H, st));
     FFNO_TRY(linear_bwd(p, lw.back.lin[0], lp.backcast_ff.linear[0], lg.backcast_ff[0], sl, w.dh, w.ds, P, w, st));
     // spectral operator (grid_2d.py:51-99): s = sum_a Inv_a Mix_a Fwd_a x  =>  gx += sum_a Fwd_a^T Mix_a^T Inv_a^T ds
-    if (p->use_umma) {
+    if (tc) {
       // tcgen05: the forward's three kernels on the adjoint state; its "F" buffer ends up holding dR_a = Inv_a^T ds
       // of every axis, which — with the forward spectra F_a of x_l — gives the weight gradients
       FFNO_TRY(umma_spectral_fwd(p->umma_adj, l, w.ds, batch, w.b, w.dR, w.dF, nullptr, st));

@@ -148,3 +148,54 @@ def test_routine_training_step_matches_the_reference_loop():
     print("routine losses", losses, "oracle first", ref_loss)
     assert abs(losses[0] - ref_loss) < 1e-4 * abs(ref_loss)
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("mode", ["tc", "fp32"])
+def test_full_depth_c2_gradients_vs_fp64_oracle(mode, monkeypatch):
+    """The benchmark's own model (24 layers, 64 x 64, modes 16, shared weights, weight-norm): every parameter gradient and
+    the input gradient against torch.autograd through the oracle in FLOAT64.
+    fp32 (FFNO_B200_BWD=fp32, the whole backward on the FP32 kernels): every tensor within 1e-4 of ITS OWN max|ref|
+    (measured <= 3e-6, the level of the reference's own FP32 autograd).
+    tc (default: forward recompute + spectral adjoint on the tcgen05 kernels, 3 x BF16 = ~1e-5 per element, the precision of
+    the forward itself): the whole gradient within 1e-4 in relative L2, every tensor within 1e-4 of the largest gradient
+    of its kind — sums over points that cancel to 1e-3 of their terms (inner-layer biases / weight_g, max|g| ~ 1e-7..5e-6)
+    carry that element noise amplified, up to ~2e-3 of their own magnitude."""
+    if mode == "fp32":
+        monkeypatch.setenv("FFNO_B200_BWD", "fp32")
+    torch.manual_seed(0)
+    from fourierflow_b200.modules import FNOFactorized2DBlock
+    kw = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4, ff_weight_norm=True, gain=0.1)
+    m = FNOFactorized2DBlock(**kw).cuda().train()
+    B = 2
+    x = torch.randn(B, 64, 64, 3, device="cuda", requires_grad=True)
+    y = torch.randn(B, 64, 64, 1, device="cuda")
+    _, loss = _loss(m, x, y)
+    loss.backward()
+    sdk = m.state_dict(keep_vars=True)
+    leaves = {}
+    for k, v in sdk.items():
+        leaves.setdefault(id(v), v.detach().cpu().double().clone().requires_grad_(True))
+    p = {k: leaves[id(v)] for k, v in sdk.items()}
+    xd = x.detach().cpu().double().requires_grad_(True)
+    out = O.block_grid2d_forward(p, xd, modes=16, n_layers=24)
+    lo = O.lp_loss_rel(out["forecast"].reshape(B, -1), y.cpu().double().reshape(B, -1))
+    lo.backward()
+    assert abs(lo.item() - loss.item()) < 1e-5 * abs(lo.item())
+    assert rel_err(x.grad, xd.grad) < TOL
+    kind_scale = {}
+    for k, v in m.named_parameters():
+        kind = k.split(".")[-1]
+        kind_scale[kind] = max(kind_scale.get(kind, 0.0), p[k].grad.abs().max().item())
+    worst_own, worst_kind, num, den = 0.0, 0.0, 0.0, 0.0
+    for k, v in m.named_parameters():
+        ref = p[k].grad
+        d = (v.grad.double().cpu() - ref)
+        worst_own = max(worst_own, (d.abs().max() / ref.abs().max()).item())
+        worst_kind = max(worst_kind, (d.abs().max() / kind_scale[k.split(".")[-1]]).item())
+        num += (d ** 2).sum().item()
+        den += (ref ** 2).sum().item()
+    l2 = (num / den) ** 0.5
+    print(f"full depth [{mode}]: worst vs own max {worst_own:.2e}, vs kind max {worst_kind:.2e}, whole-gradient L2 {l2:.2e}")
+    assert l2 < TOL and worst_kind < TOL
+    if mode == "fp32":
+        assert worst_own < TOL
