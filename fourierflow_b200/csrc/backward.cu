@@ -105,6 +105,81 @@ atb_kernel(LoadA a, LoadB b, long long rows, int M, int N, int splits, Epi epi) 
     }
 }
 
+// The same reduction with a TM x TN block tile (128 x 64, 64 x 128 or 128 x 128) and (TM / 16) x (TN / 16) outputs per
+// thread; M % TM == 0 and N % TN == 0 required.
+template <int TM, int TN, class LoadA, class LoadB, class Epi>
+__global__ void __launch_bounds__(256)
+atb_big_kernel(LoadA a, LoadB b, long long rows, int M, int N, int splits, Epi epi) {
+  constexpr int CM = TM / 16, CN = TN / 16;
+  __shared__ float As[16][TM + 4];
+  __shared__ float Bs[16][TN + 4];
+  const int z = blockIdx.z / splits, split = blockIdx.z - z * splits;
+  const long long per = (rows + splits - 1) / splits;
+  const long long r_begin = (long long)split * per, r_end = r_begin + per < rows ? r_begin + per : rows;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  float acc[CM][CN];
+#pragma unroll
+  for (int i = 0; i < CM; ++i)
+#pragma unroll
+    for (int j = 0; j < CN; ++j) acc[i][j] = 0.f;
+  // the rows of step r0 + 16 are fetched into registers while step r0 is multiplied
+  float4 va[TM / 64], vb[TN / 64];
+  auto fetch = [&](long long r0) {
+#pragma unroll
+    for (int j = 0; j < TM / 64; ++j) {
+      const int idx = tid + 256 * j, lr = idx / (TM / 4), lc = (idx % (TM / 4)) * 4;
+      va[j] = (r0 + lr < r_end) ? a.load4(z, r0 + lr, m0 + lc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < TN / 64; ++j) {
+      const int idx = tid + 256 * j, lr = idx / (TN / 4), lc = (idx % (TN / 4)) * 4;
+      vb[j] = (r0 + lr < r_end) ? b.load4(z, r0 + lr, n0 + lc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  if (r_begin < r_end) fetch(r_begin);
+  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+#pragma unroll
+    for (int j = 0; j < TM / 64; ++j) {
+      const int idx = tid + 256 * j, lr = idx / (TM / 4), lc = (idx % (TM / 4)) * 4;
+      *reinterpret_cast<float4*>(&As[lr][lc]) = va[j];
+    }
+#pragma unroll
+    for (int j = 0; j < TN / 64; ++j) {
+      const int idx = tid + 256 * j, lr = idx / (TN / 4), lc = (idx % (TN / 4)) * 4;
+      *reinterpret_cast<float4*>(&Bs[lr][lc]) = vb[j];
+    }
+    __syncthreads();
+    if (r0 + 16 < r_end) fetch(r0 + 16);
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float ar[CM], br[CN];
+#pragma unroll
+      for (int h = 0; h < CM / 4; ++h) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[kk][h * 64 + ty * 4]);
+        ar[4 * h] = v.x; ar[4 * h + 1] = v.y; ar[4 * h + 2] = v.z; ar[4 * h + 3] = v.w;
+      }
+#pragma unroll
+      for (int h = 0; h < CN / 4; ++h) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[kk][h * 64 + tx * 4]);
+        br[4 * h] = v.x; br[4 * h + 1] = v.y; br[4 * h + 2] = v.z; br[4 * h + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < CM; ++i)
+#pragma unroll
+        for (int j = 0; j < CN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < CM; ++i)
+#pragma unroll
+    for (int j = 0; j < CN; ++j) {
+      const int m = m0 + (i / 4) * 64 + ty * 4 + (i % 4), n = n0 + (j / 4) * 64 + tx * 4 + (j % 4);
+      epi.add(z, m, n, acc[i][j]);
+    }
+}
+
 int pick_splits(long long rows, int tiles, int sm_count) {
   // enough blocks to fill the GPU twice, at least 256 rows per block
   long long want = (2ll * sm_count + tiles - 1) / tiles;
@@ -218,10 +293,20 @@ rel_l2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
 int launch_linear_wgrad(const float* dy, const float* x, float* dw, long long P, int out, int in, int sm_count,
                         cudaStream_t st) {
   if (P == 0 || out == 0 || in == 0) return FFNO_OK;
-  const int tiles = ceil_div(out, 64) * ceil_div(in, 64);
-  const int splits = pick_splits(P, tiles, sm_count);
-  dim3 grid(ceil_div(out, 64), ceil_div(in, 64), splits);
-  atb_kernel<<<grid, 256, 0, st>>>(RowLoad{dy, out, out}, RowLoad{x, in, in}, P, out, in, splits, PlainAdd{dw, in});
+  const RowLoad la{dy, out, out}, lb{x, in, in};
+  const PlainAdd epi{dw, in};
+  if (P >= 4096 && out % 128 == 0 && in % 64 == 0) {
+    const int splits = pick_splits(P, (out / 128) * (in / 64), sm_count);
+    atb_big_kernel<128, 64><<<dim3(out / 128, in / 64, splits), 256, 0, st>>>(la, lb, P, out, in, splits, epi);
+  } else if (P >= 4096 && out % 64 == 0 && in % 128 == 0) {
+    const int splits = pick_splits(P, (out / 64) * (in / 128), sm_count);
+    atb_big_kernel<64, 128><<<dim3(out / 64, in / 128, splits), 256, 0, st>>>(la, lb, P, out, in, splits, epi);
+  } else {
+    const int tiles = ceil_div(out, 64) * ceil_div(in, 64);
+    const int splits = pick_splits(P, tiles, sm_count);
+    dim3 grid(ceil_div(out, 64), ceil_div(in, 64), splits);
+    atb_kernel<<<grid, 256, 0, st>>>(la, lb, P, out, in, splits, epi);
+  }
   ++g_launch_counter;
   FFNO_LAUNCH_CHECK("atb_kernel<linear>");
   return FFNO_OK;
@@ -233,13 +318,20 @@ int launch_mix_wgrad(const float* F, const float* dR, float* dw, long long outer
   if (rows == 0 || K == 0) return FFNO_OK;
   FFNO_REQUIRE(C % 4 == 0, FFNO_ERR_UNSUPPORTED, "mix wgrad: width %d not a multiple of 4", C);
   const int n2 = 2 * C;
-  const int tiles = ceil_div(n2, 64) * ceil_div(n2, 64) * K;
-  const int splits = pick_splits(rows, tiles, sm_count);
-  FFNO_REQUIRE((long long)K * splits < 65536, FFNO_ERR_UNSUPPORTED, "mix wgrad: %d modes x %d splits", K, splits);
-  dim3 grid(ceil_div(n2, 64), ceil_div(n2, 64), K * splits);
   const long long inner = p_inner * C;
-  atb_kernel<<<grid, 256, 0, st>>>(ModeRowLoad{F, K, C, p_inner, inner}, ModeRowLoad{dR, K, C, p_inner, inner}, rows, n2,
-                                   n2, splits, MixWeightAdd{dw, C, K});
+  const ModeRowLoad la{F, K, C, p_inner, inner}, lb{dR, K, C, p_inner, inner};
+  const MixWeightAdd epi{dw, C, K};
+  if (n2 % 128 == 0 && rows >= 1024) {
+    const int splits = pick_splits(rows, (n2 / 128) * (n2 / 128) * K, sm_count);
+    FFNO_REQUIRE((long long)K * splits < 65536, FFNO_ERR_UNSUPPORTED, "mix wgrad: %d modes x %d splits", K, splits);
+    atb_big_kernel<128, 128><<<dim3(n2 / 128, n2 / 128, K * splits), 256, 0, st>>>(la, lb, rows, n2, n2, splits, epi);
+  } else {
+    const int tiles = ceil_div(n2, 64) * ceil_div(n2, 64) * K;
+    const int splits = pick_splits(rows, tiles, sm_count);
+    FFNO_REQUIRE((long long)K * splits < 65536, FFNO_ERR_UNSUPPORTED, "mix wgrad: %d modes x %d splits", K, splits);
+    dim3 grid(ceil_div(n2, 64), ceil_div(n2, 64), K * splits);
+    atb_kernel<<<grid, 256, 0, st>>>(la, lb, rows, n2, n2, splits, epi);
+  }
   ++g_launch_counter;
   FFNO_LAUNCH_CHECK("atb_kernel<mix>");
   return FFNO_OK;
@@ -248,7 +340,7 @@ int launch_mix_wgrad(const float* F, const float* dR, float* dw, long long outer
 int launch_colsum(const float* x, float* out, long long rows, int N, cudaStream_t st) {
   if (rows == 0 || N == 0) return FFNO_OK;
   FFNO_REQUIRE(N <= 256, FFNO_ERR_UNSUPPORTED, "colsum: %d columns", N);
-  const int rpb = 1024;
+  const int rpb = rows >= (1 << 16) ? 128 : 1024;      // enough blocks to fill the GPU; one atomic per thread and block
   colsum_kernel<<<ceil_div(rows, rpb), 256, 0, st>>>(x, out, rows, N, rpb);
   ++g_launch_counter;
   FFNO_LAUNCH_CHECK("colsum_kernel");

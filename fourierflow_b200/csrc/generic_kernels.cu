@@ -126,6 +126,92 @@ sgemm64_kernel(ALoad a, const float* __restrict__ Bt, long long b_batch_stride, 
   }
 }
 
+// The same product with a 128 x TN block tile (TN = 128 or 64) and 8 x (TN / 16) outputs per thread: half the
+// shared-memory loads per FMA of the 64 x 64 kernel.  Used when the shape fills the tile (the FF linears of the training
+// path and of the generic forward); N % TN == 0 and K % 16 == 0 are required, rows are bounds-checked.
+template <int TN, class ALoad, class Epi>
+__global__ void __launch_bounds__(256)
+sgemm128_kernel(ALoad a, const float* __restrict__ Bt, long long b_batch_stride, long long M, int N, int K, Epi epi) {
+  constexpr int CN = TN / 16;            // output columns per thread: 8 or 4
+  __shared__ float As[16][128 + 4];
+  __shared__ float Bs[16][TN + 4];
+  const int z = blockIdx.z;
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int n0 = blockIdx.y * TN;
+  const float* B = Bt + (long long)z * b_batch_stride;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  float acc[8][CN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < CN; ++j) acc[i][j] = 0.f;
+
+  // the tiles of step k0 + 16 are fetched into registers while step k0 is multiplied (one memory latency per step
+  // would otherwise sit between the two barriers)
+  float4 va[2], vb[TN / 64];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {         // A tile: 128 rows x 16 k
+      const int r = tid / 4 + 64 * j, kk = (tid % 4) * 4;
+      va[j] = (m0 + r < M) ? a.load4(z, m0 + r, k0 + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < TN / 64; ++j) {   // B tile: 16 k x TN columns
+      const int idx = tid + 256 * j, k = idx / (TN / 4), nn = (idx % (TN / 4)) * 4;
+      vb[j] = __ldg(reinterpret_cast<const float4*>(B + (long long)(k0 + k) * N + n0 + nn));
+    }
+  };
+  // (TN = 128: the 64 accumulators leave no registers for the look-ahead — 153 registers, one block per SM, measured
+  // 117 -> 167 us; that tile fetches at the top of its own step instead)
+  constexpr bool kAhead = TN == 64;
+  if (kAhead) fetch(0);
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    if (!kAhead) fetch(k0);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {         // transposed into As[k][row]
+      const int r = tid / 4 + 64 * j, kk = (tid % 4) * 4;
+      As[kk + 0][r] = va[j].x; As[kk + 1][r] = va[j].y; As[kk + 2][r] = va[j].z; As[kk + 3][r] = va[j].w;
+    }
+#pragma unroll
+    for (int j = 0; j < TN / 64; ++j) {
+      const int idx = tid + 256 * j, k = idx / (TN / 4), nn = (idx % (TN / 4)) * 4;
+      *reinterpret_cast<float4*>(&Bs[k][nn]) = vb[j];
+    }
+    __syncthreads();
+    if (kAhead && k0 + 16 < K) fetch(k0 + 16);
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float br[CN];
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        br[0] = b0.x; br[1] = b0.y; br[2] = b0.z; br[3] = b0.w;
+        if (CN == 8) {
+          const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][(TN / 2) + tx * 4]);
+          br[CN - 4] = b1.x; br[CN - 3] = b1.y; br[CN - 2] = b1.z; br[CN - 1] = b1.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < CN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (row < M) {
+      epi.store4(z, row, n0 + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+      if (CN == 8)
+        epi.store4(z, row, n0 + (TN / 2) + tx * 4,
+                   make_float4(acc[i][CN - 4], acc[i][CN - 3], acc[i][CN - 2], acc[i][CN - 1]));
+    }
+  }
+}
+
 // ---- mode mix ----------------------------------------------------------------------------------
 struct MixGeom {
   const float* F;
@@ -177,7 +263,12 @@ struct LinEpi {
   float* y;
   float* y_pre;
   int N, relu;
+  const float* mask;      // backward of a ReLU: zero the outputs whose mask[row][col] <= 0 (NULL: none)
   __device__ void store4(int, long long row, int col, float4 v) const {
+    if (mask) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mask + row * N + col));
+      v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+    }
     if (bias) {
       float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -193,15 +284,21 @@ struct LinEpi {
 };
 
 int launch_linear(const float* x, const float* Wt, const float* bias, const float* residual, float* y,
-                  float* y_pre, long long P, int K, int N, bool relu, cudaStream_t st) {
+                  float* y_pre, long long P, int K, int N, bool relu, cudaStream_t st, const float* relu_mask) {
   FFNO_REQUIRE(K % 4 == 0 && N % 4 == 0, FFNO_ERR_UNSUPPORTED,
                "linear: in=%d / out=%d must be multiples of 4", K, N);
   if (P == 0) return FFNO_OK;
-  dim3 grid(ceil_div(P, 64), ceil_div(N, 64), 1);
-  sgemm64_kernel<<<grid, 256, 0, st>>>(LinALoad{x, K}, Wt, 0, P, N, K,
-                                       LinEpi{bias, residual, y, y_pre, N, relu ? 1 : 0});
+  const LinEpi epi{bias, residual, y, y_pre, N, relu ? 1 : 0, relu_mask};
+  if (P >= 4096 && K % 16 == 0 && N % 128 == 0) {
+    sgemm128_kernel<128><<<dim3(ceil_div(P, 128), N / 128, 1), 256, 0, st>>>(LinALoad{x, K}, Wt, 0, P, N, K, epi);
+  } else if (P >= 4096 && K % 16 == 0 && N % 64 == 0) {
+    sgemm128_kernel<64><<<dim3(ceil_div(P, 128), N / 64, 1), 256, 0, st>>>(LinALoad{x, K}, Wt, 0, P, N, K, epi);
+  } else {
+    dim3 grid(ceil_div(P, 64), ceil_div(N, 64), 1);
+    sgemm64_kernel<<<grid, 256, 0, st>>>(LinALoad{x, K}, Wt, 0, P, N, K, epi);
+  }
   ++g_launch_counter;
-  FFNO_LAUNCH_CHECK("sgemm64_kernel<linear>");
+  FFNO_LAUNCH_CHECK("sgemm_kernel<linear>");
   return FFNO_OK;
 }
 

@@ -20,8 +20,9 @@ int launch_mode_mix(const float* F, const float* Wblk, float* R, long long outer
                     long long p_inner, int C, cudaStream_t st);
 
 // y[P][N] = act(x[P][K] @ Wt[K][N] + bias) (+ residual[P][N]);  optional second store y2 (pre-residual)
+// relu_mask (backward of a ReLU): outputs whose relu_mask[p][n] <= 0 are zeroed
 int launch_linear(const float* x, const float* Wt, const float* bias, const float* residual, float* y,
-                  float* y_pre, long long P, int K, int N, bool relu, cudaStream_t st);
+                  float* y_pre, long long P, int K, int N, bool relu, cudaStream_t st, const float* relu_mask = nullptr);
 
 // b = LayerNorm(y) * g + beta over the last dim (C); out = residual + b (residual may be NULL);
 // b_out optional.  Reference: modules/feedforward.py:17.

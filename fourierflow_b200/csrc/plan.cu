@@ -1127,7 +1127,8 @@ int linear_param_grads(const ffno_linear_params& prm, const ffno_linear_grads& g
 // One linear y[P][out] = x[P][in] W^T + b, W given folded + transposed as wt[in][out]: accumulates the parameter
 // gradients and (dx != NULL) writes dx[P][in] = dy W.  `wide` selects the 64-wide GEMM (dims multiples of 4).
 int linear_bwd(const ffno_plan* p, const Lin& lin, const ffno_linear_params& prm, const ffno_linear_grads& g,
-               const float* x, const float* dy, float* dx, long long P, const BwdWs& w, cudaStream_t st) {
+               const float* x, const float* dy, float* dx, long long P, const BwdWs& w, cudaStream_t st,
+               const float* relu_mask = nullptr) {
   const int in = lin.in, out = lin.out;
   const bool want_w = g.weight || g.weight_v;
   if (want_w) {
@@ -1138,10 +1139,12 @@ int linear_bwd(const ffno_plan* p, const Lin& lin, const ffno_linear_params& prm
   if (g.bias && prm.bias) FFNO_TRY(launch_colsum(dy, g.bias, P, out, st));
   if (dx) {
     FFNO_TRY(launch_transpose(lin.wt, w.wT, in, out, 1, st));      // wT[out][in]: the K x N operand of dx = dy W
-    if (in % 4 == 0 && out % 4 == 0)
-      FFNO_TRY(launch_linear(dy, w.wT, nullptr, nullptr, dx, nullptr, P, out, in, false, st));
-    else
+    if (in % 4 == 0 && out % 4 == 0) {
+      FFNO_TRY(launch_linear(dy, w.wT, nullptr, nullptr, dx, nullptr, P, out, in, false, st, relu_mask));
+    } else {
+      FFNO_REQUIRE(!relu_mask, FFNO_ERR_UNSUPPORTED, "masked linear backward needs dimensions that are multiples of 4");
       FFNO_TRY(launch_linear_any(dy, w.wT, nullptr, dx, P, out, in, false, st));
+    }
   }
   return FFNO_OK;
 }
@@ -1256,15 +1259,14 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
     const float* gb = l == nl - 1 ? w.gb : w.gx;
     // FeedForward (feedforward.py:6-24): h = relu(W1 s + b1), b = W2 h + b2
     FFNO_TRY(launch_linear(sl, lw.back.lin[0].wt, lw.back.lin[0].bias, nullptr, w.h, nullptr, P, C, H, true, st));
-    FFNO_TRY(linear_bwd(p, lw.back.lin[1], lp.backcast_ff.linear[1], lg.backcast_ff[1], w.h, gb, w.dh, P, w, st));
-    FFNO_TRY(launch_relu_bwd(w.dh, w.h, (long long)P * H, st));
+    // (the ReLU's backward is the mask h > 0 applied in the epilogue of the g_h GEMM)
+    FFNO_TRY(linear_bwd(p, lw.back.lin[1], lp.backcast_ff.linear[1], lg.backcast_ff[1], w.h, gb, w.dh, P, w, st, w.h));
     FFNO_TRY(linear_bwd(p, lw.back.lin[0], lp.backcast_ff.linear[0], lg.backcast_ff[0], sl, w.dh, w.ds, P, w, st));
     // spectral operator (grid_2d.py:51-99): s = sum_a Inv_a Mix_a Fwd_a x  =>  gx += sum_a Fwd_a^T Mix_a^T Inv_a^T ds
     if (tc) {
       // tcgen05: the forward's three kernels on the adjoint state; its "F" buffer ends up holding dR_a = Inv_a^T ds
       // of every axis, which — with the forward spectra F_a of x_l — gives the weight gradients
-      FFNO_TRY(umma_spectral_fwd(p->umma_adj, l, w.ds, batch, w.b, w.dR, w.dF, nullptr, st));
-      FFNO_TRY(launch_axpy(w.gx, w.b, (long long)U, st));
+      FFNO_TRY(umma_spectral_fwd(p->umma_adj, l, w.ds, batch, w.gx, w.dR, w.dF, nullptr, st, true));
       bool want_w = false;
       for (int a = 0; a < p->d.ndim; ++a) want_w |= lg.fourier_weight[a] != nullptr;
       if (want_w) {

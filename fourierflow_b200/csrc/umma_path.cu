@@ -217,10 +217,10 @@ static void axis_geom(const UmmaState* s, int batch, int a, long long* outer, lo
 // a caller wants the sum materialised (taps, the standalone ffno_spectral_fwd) or an axis does not fit the pipelined
 // transform kernel.
 int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R, float*,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool accumulate) {
   const UmmaLayer& L = s->layers[layer];
   const bool full = s->d.spectral_mode == FFNO_MODE_FULL;
-  bool first = true;
+  bool first = !accumulate;
   for (int a = s->d.ndim - 1; a >= 0; --a) {
     long long outer, p_inner;
     axis_geom(s, batch, a, &outer, &p_inner);

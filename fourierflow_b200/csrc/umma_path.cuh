@@ -47,8 +47,9 @@ int umma_stack_fwd_pipelined(UmmaState* s, float* xa, float* xb, int batch, floa
 int umma_layer_fwd(UmmaState* s, int layer, const float* x, int batch, float* x_next, float* s_out, float* b_out,
                    float* F, float* R, float* ws, bool want_s, bool want_b, cudaStream_t st,
                    const UmmaFusedHead* head = nullptr);
+// accumulate: s_out += the operator's output instead of s_out = (the backward adds the adjoint onto the gradient stream)
 int umma_spectral_fwd(UmmaState* s, int layer, const float* x, int batch, float* s_out, float* F, float* R,
-                      float* ws, cudaStream_t st);
+                      float* ws, cudaStream_t st, bool accumulate = false);
 // Per-axis outputs, no accumulation (falls back to the summed path into s_axis[0] when a kernel does not qualify;
 // returns the number of buffers written through *n_written).
 int umma_spectral_split_fwd(UmmaState* s, int layer, const float* x, int batch, float* const s_axis[3], float* F, float* R,

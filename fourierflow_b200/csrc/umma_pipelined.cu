@@ -307,7 +307,9 @@ struct AxisSet {
 
 // kPipe: the CTA walks tile, tile + grid, ... of every layer back to back (grid <= n_tiles, n_groups even), its loaders
 // wait for the unit's producer and its epilogue warps post the unit's completion (see PipeDesc).
-template <bool kPipe>
+// kRmw: instantiation for launches with an accumulating axis (summed spectral output of the taps / standalone / backward
+// paths): its epilogue batches the read-modify-write; kept out of the plain instantiation, whose register budget it breaks.
+template <bool kPipe, bool kRmw = false>
 __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_pipe_kernel(const __grid_constant__ AxisSet set) {
   const AxisXform& p = set.ax[blockIdx.y];
   const int n_tiles = set.n_tiles[blockIdx.y];
@@ -429,6 +431,17 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
           if (!p.accumulate && ncols >= 32) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) yp[(size_t)j * stride] = __uint_as_float(v[j]);
+          } else if (kRmw && p.accumulate && ncols >= 32) {
+            // read-modify-write (summed spectral output of the taps / standalone / backward paths): several loads in
+            // flight before the first add — a load -> add -> store chain per column costs one memory latency each
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 8) {      // 8 at a time: the register budget of the kernel (72) allows no more
+              float old[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) old[j] = yp[(size_t)(j0 + j) * stride];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) yp[(size_t)(j0 + j) * stride] = old[j] + __uint_as_float(v[j0 + j]);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -683,12 +696,19 @@ int launch_axis_pipe(const AxisXform* axes, int n_axes, int sm_count, cudaStream
     if (n_groups > 0) FFNO_TRY(encode_axis_tmap(&set.tm[a], p.X, p.outer, p.n_in, p.inner));
   }
   if (max_tiles == 0) return FFNO_OK;
-  FFNO_TRY(ensure_dynamic_smem(axis_pipe_kernel<false>, smem));
+  bool rmw = false;
+  for (int a = 0; a < n_axes; ++a) rmw |= axes[a].accumulate != 0;
+  if (rmw) {
+    FFNO_TRY(ensure_dynamic_smem(axis_pipe_kernel<false, true>, smem));
+  } else {
+    FFNO_TRY(ensure_dynamic_smem(axis_pipe_kernel<false>, smem));
+  }
   int per_axis = sm_count / n_axes;
   if (per_axis < 1) per_axis = 1;
   const int gx = max_tiles < per_axis ? max_tiles : per_axis;
   set.pipe = PipeDesc{};
-  FFNO_CUDA_CHECK(launch_pdl(axis_pipe_kernel<false>, dim3(gx, n_axes), dim3(kAxThreads), smem, st, set));
+  if (rmw) FFNO_CUDA_CHECK(launch_pdl(axis_pipe_kernel<false, true>, dim3(gx, n_axes), dim3(kAxThreads), smem, st, set));
+  else FFNO_CUDA_CHECK(launch_pdl(axis_pipe_kernel<false>, dim3(gx, n_axes), dim3(kAxThreads), smem, st, set));
   ++g_launch_counter;
   return FFNO_OK;
 }
