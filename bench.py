@@ -18,6 +18,10 @@ samples per GPU (weak scaling: 32 samples per rank; N=8 is configs[2], batch 256
   eager_gpu / vs_eager : the reference's own FNOFactorized2DBlock (oracle/_ref, unmodified) moved to the same GPU,
           TF32 off, eager PyTorch, timed in this run — the north star's ">= 10x reference eager" denominator.
 
+  train_step : (informational, rank 0, after the timed region) forward + backward of the reference's one-step training
+          loss through ffno_block_bwd, next to the reference modules' autograd on the same GPU, and the relative L2
+          distance between the two whole gradients.
+
 `--impl reference` times the reference's own CPU implementation (oracle/_ref: the unmodified fourierflow.modules
 files, copied there by oracle/make_ref.sh; the torch-CPU oracle port only if that copy is missing) on the host cores,
 same metric and config, all 32 samples per step.
@@ -356,7 +360,49 @@ def run_ours(args, rank, world, local):
                      "what": "oracle/_ref FNOFactorized2DBlock(**C2).cuda(), eager PyTorch, same input and weights, L2 "
                              "flushed between timed forwards, CUDA events",
                      "max_rel_diff_vs_ours": float((y_gpu_first8 - y_eager).abs().max() / scale)}
-            del ref
+
+    # ---- training step (backward row): forward + backward of the reference's one-step loss
+    #      (routines/grid_2d_markov.py:172-193) through ffno_block_bwd, next to the reference's autograd on this GPU ----
+    train = None
+    if rank == 0 and not args.no_train_step:
+        from fourierflow_b200.modules import LpLoss
+        l2 = LpLoss(size_average=True)
+        yt = torch.randn(B, GRID, GRID, 1, device=dev, generator=torch.Generator(dev).manual_seed(7))
+
+        def ours_train():
+            model.zero_grad(set_to_none=True)
+            loss = l2(model(x)["forecast"].reshape(B, -1), yt.reshape(B, -1))
+            loss.backward()
+            return loss
+
+        ms_train = timed(ours_train, 10, 3, flush)
+        train = {"ms_per_step": ms_train, "samples_per_s": B / (ms_train * 1e-3), "steps": 10, "warmup": 3,
+                 "what": "forward (tcgen05 kernels) + backward (ffno_block_bwd) of LpLoss(forecast, target), batch "
+                         f"{B}, no optimizer step; gradients checked against the reference's in tests/test_gpu_backward.py"}
+        if ref is not None:
+            def ref_train():
+                ref.zero_grad(set_to_none=True)
+                f = ref(x)["forecast"]
+                loss = (torch.linalg.vector_norm((f - yt).reshape(B, -1), dim=1)
+                        / torch.linalg.vector_norm(yt.reshape(B, -1), dim=1)).mean()
+                loss.backward()
+                return loss
+
+            ms_ref_train = timed(ref_train, 10, 3, flush)
+            train["reference_eager_ms_per_step"] = ms_ref_train
+            train["vs_eager"] = ms_ref_train / ms_train
+            # whole-gradient agreement with the reference's autograd on identical weights and data
+            ours_train()
+            ref_train()
+            rp = dict(ref.named_parameters())
+            num = den = 0.0
+            for k, prm in model.named_parameters():
+                d = prm.grad.double() - rp[k].grad.double()
+                num += float((d * d).sum())
+                den += float((rp[k].grad.double() ** 2).sum())
+            train["gradient_rel_l2_vs_reference"] = (num / max(den, 1e-300)) ** 0.5
+        model.zero_grad(set_to_none=True)
+    ref = None
 
     if world > 1:
         dist.barrier()                    # the other ranks leave here; rank 0's CPU leg below holds no GPU busy
@@ -403,6 +449,7 @@ def run_ours(args, rank, world, local):
         "gpu_launches": (int(launches) + (1 if N > 1 else 0)) * args.steps * N,
         "parity": parity,
         "eager_gpu": eager, "vs_eager": (value / N / eager["value"]) if eager else None,
+        "train_step": train,
         "roofline": dominant, "roofline_spectral": roof_spec, "roofline_ff": roof_ff,
         "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": cpu_kind,
                          "sample": f"{cpu_reps} forwards of {cpu_sample} samples through the 24-layer stack "
@@ -419,6 +466,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg and the parity gate (profiling runs under ncu)")
     ap.add_argument("--no-eager-gpu", action="store_true", help="skip the reference-eager-on-GPU leg (profiling runs under ncu)")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the forward + backward leg (rank 0, after the timed region)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.steps is None:
