@@ -6,6 +6,7 @@
 // transposed tables / weights (generic_kernels.cu) plus the reductions over points below that produce the parameter
 // gradients.  Parameter gradients ACCUMULATE (+=) into the caller's buffers, like `.grad` does.
 #include "backward.cuh"
+#include "generic_kernels.cuh"
 
 namespace ffno {
 
@@ -288,7 +289,92 @@ rel_l2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
   for (long long i = threadIdx.x; i < n; i += blockDim.x) dx[b * n + i] = scale * (xb[i] - yb[i]);
 }
 
+// Mesh variants (mesh_3d.py:161-166, :173): the lift zero-pads every spatial axis on the high side, the head reads the
+// unpadded region.  dir 0: dense[b][coord][C] = padded[b][coord][C];  dir 1: padded = dense inside, 0 in the padding.
+__global__ void __launch_bounds__(256)
+crop_pad_kernel(float4* __restrict__ dense, float4* __restrict__ padded, long long total4, LiftGeom g, int dir) {
+  // one thread per float4 of the PADDED tensor
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int C4 = g.C / 4;
+  const int c4 = (int)(idx % C4);
+  long long rem = idx / C4;
+  int coord[3] = {0, 0, 0};
+  bool in_pad = false;
+  for (int a = g.ndim - 1; a >= 0; --a) {
+    const int ext = g.size[a] + g.pad[a];
+    coord[a] = (int)(rem % ext);
+    rem /= ext;
+    in_pad |= coord[a] >= g.size[a];
+  }
+  if (in_pad) {
+    if (dir == 1) padded[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  long long src = rem;
+  for (int a = 0; a < g.ndim; ++a) src = src * g.size[a] + coord[a];
+  if (dir == 0) dense[src * C4 + c4] = padded[idx];
+  else padded[idx] = dense[src * C4 + c4];
+}
+
+__device__ __forceinline__ float linspace01_bwd(int i, int n) {      // float32(np.linspace(0, 1, n)[i]), as lift_kernel does
+  if (n <= 1) return 0.f;
+  if (i == n - 1) return 1.f;
+  return (float)((double)i * (1.0 / (double)(n - 1)));
+}
+
+// rows of the lift's input as the linear sees them: [x (in_features) | linspace grid coordinate per axis] (mesh_3d.py:178-189)
+__global__ void __launch_bounds__(256)
+lift_rows_kernel(const float* __restrict__ x, float* __restrict__ rows, long long n_pts, LiftGeom g) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  const int in_total = g.in_features + (g.append_grid ? g.ndim : 0);
+  float* r = rows + p * in_total;
+  for (int j = 0; j < g.in_features; ++j) r[j] = x[p * g.in_features + j];
+  if (g.append_grid) {
+    long long rem = p;
+    int coord[3] = {0, 0, 0};
+    for (int a = g.ndim - 1; a >= 0; --a) { coord[a] = (int)(rem % g.size[a]); rem /= g.size[a]; }
+    for (int a = 0; a < g.ndim; ++a) r[g.in_features + a] = linspace01_bwd(coord[a], g.size[a]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+take_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int ld, int ncols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ncols) return;
+  const long long r = i / ncols;
+  dst[i] = src[r * ld + (i - r * ncols)];
+}
+
 }  // namespace
+
+int launch_crop_pad(float* dense, float* padded, int batch, const LiftGeom& g, bool to_padded, cudaStream_t st) {
+  long long total4 = (long long)batch * (g.C / 4);
+  for (int a = 0; a < g.ndim; ++a) total4 *= g.size[a] + g.pad[a];
+  if (total4 == 0) return FFNO_OK;
+  crop_pad_kernel<<<ceil_div(total4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(dense), reinterpret_cast<float4*>(padded),
+                                                         total4, g, to_padded ? 1 : 0);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("crop_pad_kernel");
+  return FFNO_OK;
+}
+
+int launch_lift_rows(const float* x, float* rows, long long n_pts, const LiftGeom& g, cudaStream_t st) {
+  if (n_pts == 0) return FFNO_OK;
+  lift_rows_kernel<<<ceil_div(n_pts, 256), 256, 0, st>>>(x, rows, n_pts, g);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("lift_rows_kernel");
+  return FFNO_OK;
+}
+
+int launch_take_cols(const float* src, float* dst, long long rows, int ld, int ncols, cudaStream_t st) {
+  if (rows == 0 || ncols == 0) return FFNO_OK;
+  take_cols_kernel<<<ceil_div(rows * ncols, 256), 256, 0, st>>>(src, dst, rows, ld, ncols);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("take_cols_kernel");
+  return FFNO_OK;
+}
 
 int launch_linear_wgrad(const float* dy, const float* x, float* dw, long long P, int out, int in, int sm_count,
                         cudaStream_t st) {

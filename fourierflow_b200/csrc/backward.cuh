@@ -23,6 +23,13 @@ int launch_wnorm_bwd(const float* dw, const float* v, const float* g, float* dg,
                      cudaStream_t st);
 // dst[z][c][r] = src[z][r][c]
 int launch_transpose(const float* src, float* dst, int rows, int cols, int batch, cudaStream_t st);
+struct LiftGeom;
+// mesh variants: copy between the padded activation layout and the dense (unpadded) one; to_padded zero-fills the padding
+int launch_crop_pad(float* dense, float* padded, int batch, const LiftGeom& g, bool to_padded, cudaStream_t st);
+// rows[p] = [x[p][0..in) | linspace grid coordinates of point p] — the lift's input as its linear sees it
+int launch_lift_rows(const float* x, float* rows, long long n_pts, const LiftGeom& g, cudaStream_t st);
+// dst[r][0..ncols) = src[r][0..ncols) of a [rows][ld] matrix
+int launch_take_cols(const float* src, float* dst, long long rows, int ld, int ncols, cudaStream_t st);
 // LpLoss.rel backward (modules/loss.py:33-46), contiguous x, y [batch][n]
 int launch_rel_l2_bwd(const float* x, const float* y, const float* gout, float* dx, int batch, long long n,
                       cudaStream_t st);

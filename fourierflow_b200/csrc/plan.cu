@@ -1067,7 +1067,7 @@ int ffno_rollout_fwd(ffno_plan* p, const float* frame0, int32_t batch, int32_t n
 namespace {
 
 struct BwdWs {
-  float *xs, *ss, *b, *gx, *gb, *ds, *h, *dh, *F, *dR, *dF, *R, *h0, *dh0, *wT, *dwf, *fc, *fwd_ws;
+  float *xs, *ss, *b, *gx, *gb, *ds, *h, *dh, *F, *dR, *dF, *R, *h0, *dh0, *wT, *dwf, *fc, *fwd_ws, *b_dense, *g_dense, *rows_in, *d_rows;
   size_t bytes;
 };
 
@@ -1106,6 +1106,12 @@ BwdWs carve_bwd(const ffno_plan* p, int batch, void* base) {
   w.wT = c.take(bwd_scratch_floats(p));
   w.dwf = c.take(bwd_scratch_floats(p));
   w.fc = c.take((size_t)batch * p->pts_in * p->d.out_features);
+  const bool mesh = p->pts != p->pts_in || p->d.append_grid;       // padded / grid-appended stacks: dense copies
+  const size_t Pin = (size_t)batch * p->pts_in;
+  w.b_dense = c.take(mesh ? Pin * p->d.width : 0);
+  w.g_dense = c.take(mesh ? Pin * p->d.width : 0);
+  w.rows_in = c.take(mesh ? Pin * p->in_total : 0);
+  w.d_rows = c.take(mesh ? Pin * p->in_total : 0);
   w.fwd_ws = c.take(p->use_umma ? (stack_ws_bytes(p, batch) + 3) / 4 : 0);      // the tcgen05 forward's own workspace
   w.bytes = c.off;
   return w;
@@ -1195,12 +1201,9 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   FFNO_REQUIRE(prm->n_layers == p->d.n_layers && grads->n_layers == p->d.n_layers && prm->layers && grads->layers,
                FFNO_ERR_BAD_ARG, "params / grads must describe the plan's %d layers", p->d.n_layers);
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
-  bool padded = false;
-  for (int a = 0; a < p->d.ndim; ++a) padded |= p->d.pad[a] != 0;
-  FFNO_REQUIRE(!padded && !p->d.append_grid && p->d.n_ff_layers == 2 && !p->d.layer_norm && !p->d.use_fork &&
-                   p->d.spectral_mode == FFNO_MODE_FULL,
-               FFNO_ERR_UNSUPPORTED,
-               "backward is implemented for unpadded stacks with n_ff_layers = 2, no LayerNorm, no fork, mode 'full'");
+  FFNO_REQUIRE(p->d.n_ff_layers == 2 && !p->d.layer_norm && !p->d.use_fork && p->d.spectral_mode == FFNO_MODE_FULL,
+               FFNO_ERR_UNSUPPORTED, "backward is implemented for n_ff_layers = 2, no LayerNorm, no fork, mode 'full'");
+  const bool mesh = p->pts != p->pts_in || p->d.append_grid;       // zero-padded / grid-appended (mesh_3d.py:161-166)
   if (batch == 0) return FFNO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long before = g_launch_counter;
@@ -1241,11 +1244,17 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
       FFNO_TRY(ff_generic(p, lw.back, sl, xl, P, l + 1 < nl ? xl + U : nullptr, l + 1 < nl ? nullptr : w.b, wf, st));
     }
   }
-  FFNO_TRY(launch_linear(w.b, p->out0.wt, p->out0.bias, nullptr, w.h0, nullptr, P, C, Hh, false, st));
-
-  // ---- 2. head: forecast = out1(out0(b))
-  FFNO_TRY(linear_bwd(p, p->out1, prm->out1, grads->out1, w.h0, d_forecast, w.dh0, P, w, st));
-  FFNO_TRY(linear_bwd(p, p->out0, prm->out0, grads->out0, w.b, w.dh0, w.gb, P, w, st));
+  // ---- 2. head: forecast = out1(out0(b)) on the unpadded region (mesh_3d.py:173-174)
+  const long long Pin = (long long)batch * p->pts_in;
+  const float* b_rows = w.b;
+  if (mesh) {
+    FFNO_TRY(launch_crop_pad(w.b_dense, w.b, batch, g, false, st));
+    b_rows = w.b_dense;
+  }
+  FFNO_TRY(launch_linear(b_rows, p->out0.wt, p->out0.bias, nullptr, w.h0, nullptr, Pin, C, Hh, false, st));
+  FFNO_TRY(linear_bwd(p, p->out1, prm->out1, grads->out1, w.h0, d_forecast, w.dh0, Pin, w, st));
+  FFNO_TRY(linear_bwd(p, p->out0, prm->out0, grads->out0, b_rows, w.dh0, mesh ? w.g_dense : w.gb, Pin, w, st));
+  if (mesh) FFNO_TRY(launch_crop_pad(w.g_dense, w.gb, batch, g, true, st));      // zero gradient in the padding
 
   // ---- 3. layers, last to first.  gx = dL/dx_{l+1}; the layer's backcast gradient is gx (x_{l+1} = x_l + b_l), or
   //         the head's for the last layer
@@ -1300,8 +1309,15 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
     }
   }
 
-  // ---- 4. lift (grid_2d.py:157): x_0 = in_proj(x)
-  FFNO_TRY(linear_bwd(p, p->lift, prm->in_proj, grads->in_proj, x, w.gx, dx, P, w, st));
+  // ---- 4. lift (grid_2d.py:157; mesh_3d.py:161-166: grid coordinates appended, linear, zero padding)
+  if (mesh) {
+    FFNO_TRY(launch_crop_pad(w.g_dense, w.gx, batch, g, false, st));
+    FFNO_TRY(launch_lift_rows(x, w.rows_in, Pin, g, st));
+    FFNO_TRY(linear_bwd(p, p->lift, prm->in_proj, grads->in_proj, w.rows_in, w.g_dense, dx ? w.d_rows : nullptr, Pin, w, st));
+    if (dx) FFNO_TRY(launch_take_cols(w.d_rows, dx, Pin, p->in_total, p->d.in_features, st));
+  } else {
+    FFNO_TRY(linear_bwd(p, p->lift, prm->in_proj, grads->in_proj, x, w.gx, dx, P, w, st));
+  }
   p->last_launches = g_launch_counter - before;
   (void)O;
   return FFNO_OK;

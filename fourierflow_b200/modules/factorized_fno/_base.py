@@ -107,6 +107,38 @@ class PlanCacheMixin:
         return plan
 
 
+class StackFunction(torch.autograd.Function):
+    """The forward of a block mirror (FNOFactorized2DBlock / FNOFactorizedMesh2D / FNOFactorizedMesh3D) as one autograd
+    node: forward = ffno_block_fwd (the same kernels as inference), backward = ffno_block_bwd (explicit adjoints; the
+    forward is recomputed there, so nothing but the input is saved).  The parameters are passed as inputs only so that
+    autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        plan = module.plan_for(x.device, x.shape[1:-1])
+        forecast, _ = plan.block_forward(x)
+        ctx.module = module
+        ctx.save_for_backward(x)
+        return forecast
+
+    @staticmethod
+    def backward(ctx, d_forecast):
+        (x,) = ctx.saved_tensors
+        module = ctx.module
+        plan = module.plan_for(x.device, x.shape[1:-1])        # re-syncs if a parameter changed since the forward
+        dx, gmap = plan.block_backward(x, d_forecast.contiguous().float(), module.in_proj, module.out,
+                                       module.__dict__["_spec_cache"], ctx.needs_input_grad[1])
+        return (None, dx) + tuple(gmap.get(id(p)) for p in module._flat_params())
+
+
+def check_trainable(module) -> None:
+    """Options the CUDA backward covers (every shipped F-FNO config): n_ff_layers = 2, no LayerNorm, no fork, mode 'full'."""
+    if getattr(module, "use_fork", False) or module.layer_norm or module.n_ff_layers != 2 or \
+            getattr(module, "mode", "full") != "full":
+        raise RuntimeError(f"{type(module).__name__}: the CUDA backward covers n_ff_layers=2, no LayerNorm, no fork, "
+                           "mode='full' (every shipped F-FNO config); use torch.no_grad() for the others")
+
+
 def check_input(x: torch.Tensor, ndim: int, features: int, what: str) -> torch.Tensor:
     _ops.require_cuda(x, what)
     if x.dim() != ndim + 2 or x.shape[-1] != features:

@@ -16,7 +16,7 @@ import torch.nn as nn
 from ... import _ops
 from ..feedforward import FeedForward
 from ..linear import WNLinear
-from ._base import PlanCacheMixin, check_input, default_path
+from ._base import PlanCacheMixin, StackFunction, check_input, check_trainable, default_path
 
 
 class SpectralConv2d(PlanCacheMixin, nn.Module):
@@ -79,29 +79,6 @@ class SpectralConv2d(PlanCacheMixin, nn.Module):
         return self._plan(x).spectral_forward(0, x)
 
 
-class _BlockFunction(torch.autograd.Function):
-    """FNOFactorized2DBlock.forward as one autograd node: forward = ffno_block_fwd (the same kernels as inference),
-    backward = ffno_block_bwd (explicit adjoints, FP32 kernels; the forward is recomputed there, so nothing but the
-    input is saved).  The parameters are passed as inputs only so that autograd routes their gradients."""
-
-    @staticmethod
-    def forward(ctx, module, x, *params):
-        plan = module.plan_for(x.device, x.shape[1:3])
-        forecast, _ = plan.block_forward(x)
-        ctx.module, ctx.plan = module, plan
-        ctx.save_for_backward(x)
-        return forecast
-
-    @staticmethod
-    def backward(ctx, d_forecast):
-        (x,) = ctx.saved_tensors
-        module = ctx.module
-        plan = module.plan_for(x.device, x.shape[1:3])         # re-syncs if a parameter changed since the forward
-        dx, gmap = plan.block_backward(x, d_forecast.contiguous().float(), module.in_proj, module.out,
-                                       module.__dict__["_spec_cache"], ctx.needs_input_grad[1])
-        return (None, dx) + tuple(gmap.get(id(p)) for p in module._flat_params())
-
-
 class FNOFactorized2DBlock(PlanCacheMixin, nn.Module):
     def __init__(self, modes, width, input_dim=12, dropout=0.0, in_dropout=0.0, n_layers=4,
                  share_weight: bool = False, share_fork=False, factor=2, ff_weight_norm=False, n_ff_layers=2,
@@ -162,10 +139,8 @@ class FNOFactorized2DBlock(PlanCacheMixin, nn.Module):
         x = check_input(x, 2, self.input_dim, "FNOFactorized2DBlock.forward")
         if _ops.needs_grad(self, x):
             # training (routines/grid_2d_markov.py:172-193): differentiable through ffno_block_bwd
-            if self.use_fork or self.layer_norm or self.n_ff_layers != 2 or self.mode != "full":
-                raise RuntimeError("FNOFactorized2DBlock: the CUDA backward covers n_ff_layers=2, no LayerNorm, no fork, "
-                                   "mode='full' (every shipped torus config); use torch.no_grad() for the others")
-            return {'forecast': _BlockFunction.apply(self, x, *self._flat_params()), 'forecast_list': []}
+            check_trainable(self)
+            return {'forecast': StackFunction.apply(self, x, *self._flat_params()), 'forecast_list': []}
         plan = self.plan_for(x.device, x.shape[1:3])
         forecast, taps = plan.block_forward(x, want_forecast_list=self.use_fork)
         return {'forecast': forecast, 'forecast_list': taps.get("forecast_list", [])}

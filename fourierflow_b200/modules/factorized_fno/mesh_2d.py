@@ -12,7 +12,7 @@ import torch.nn as nn
 from ... import _ops
 from ..feedforward import FeedForward
 from ..linear import WNLinear
-from ._base import PlanCacheMixin, check_input, default_path
+from ._base import PlanCacheMixin, StackFunction, check_input, check_trainable, default_path
 
 
 class SpectralConv2d(PlanCacheMixin, nn.Module):
@@ -119,6 +119,8 @@ class FNOFactorizedMesh2D(PlanCacheMixin, nn.Module):
     def forward(self, x):
         """x:[B, X, Y, input_dim-2] → [B, X, Y, 1] (mesh_2d.py:149-165)."""
         x = check_input(x, 2, self.input_dim - 2, "FNOFactorizedMesh2D.forward")
-        _ops.require_inference(self, x)
+        if _ops.needs_grad(self, x):      # training (routines/structured_mesh.py): differentiable through ffno_block_bwd
+            check_trainable(self)
+            return StackFunction.apply(self, x, *self._flat_params())
         out, _ = self.plan_for(x.device, x.shape[1:3]).block_forward(x)
         return out

@@ -11,7 +11,7 @@ import torch.nn as nn
 from ... import _ops
 from ..feedforward import FeedForward
 from ..linear import WNLinear
-from ._base import PlanCacheMixin, check_input, default_path
+from ._base import PlanCacheMixin, StackFunction, check_input, check_trainable, default_path
 
 
 class SpectralConv2d(PlanCacheMixin, nn.Module):
@@ -118,6 +118,8 @@ class FNOFactorizedMesh3D(PlanCacheMixin, nn.Module):
     def forward(self, x):
         """x:[B, S1, S2, S3, input_dim-3] → [B, S1, S2, S3, output_dim] (mesh_3d.py:160-176)."""
         x = check_input(x, 3, self.input_dim - 3, "FNOFactorizedMesh3D.forward")
-        _ops.require_inference(self, x)
+        if _ops.needs_grad(self, x):      # training (routines/structured_mesh.py): differentiable through ffno_block_bwd
+            check_trainable(self)
+            return StackFunction.apply(self, x, *self._flat_params())
         out, _ = self.plan_for(x.device, x.shape[1:4]).block_forward(x)
         return out

@@ -199,6 +199,34 @@ def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed, force_dims=0, 
     save(name, dict(kwargs, n_steps=n_steps), arrays)
 
 
+def mesh_grad_case(M, LpLoss, cls, name, kwargs, shape, out_dim, seed):
+    """The same pin for the mesh variants (routines/structured_mesh.py: LpLoss of the model output against the target):
+    grid-coordinate append, zero padding before the layers and crop before the head are inside the autograd graph."""
+    torch.manual_seed(seed)
+    m = getattr(M, cls)(**kwargs).train()
+    perturb_(m, seed + 100)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(*shape, generator=g).requires_grad_(True)
+    y = torch.randn(*shape[:-1], out_dim, generator=g)
+    B = shape[0]
+    arrays = sd_np(m)
+    arrays["x"] = x.detach().numpy()
+    arrays["y"] = y.numpy()
+    out = m(x)
+    loss = LpLoss(size_average=True)(out.reshape(B, -1), y.reshape(B, -1))
+    loss.backward()
+    arrays["out"] = out.detach().numpy()
+    arrays["loss"] = loss.detach().numpy()
+    arrays["grad::x"] = x.grad.numpy()
+    seen = set()
+    for k, p_ in m.named_parameters():
+        if id(p_) in seen:
+            continue
+        seen.add(id(p_))
+        arrays["grad::" + k] = p_.grad.detach().numpy()
+    save(name, kwargs, arrays)
+
+
 def grad_case(M, LpLoss, name, kwargs, shape, seed):
     """Gradients of the reference's one-step training loss (routines/grid_2d_markov.py:172-193: forecast ->
     LpLoss against the next frame) w.r.t. the input and every parameter, by the reference's own autograd graph —
@@ -265,6 +293,17 @@ def grad_cases(M, LpLoss):
               factor=4, ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0), (2, 16, 16, 3), seed=20)
     grad_case(M, LpLoss, "grad_unshared_w32", dict(modes=5, width=32, n_layers=2, input_dim=4, share_weight=False,
               factor=2, ff_weight_norm=False, gain=1), (2, 12, 10, 4), seed=21)
+    mesh_grad_cases(M, LpLoss)
+
+
+def mesh_grad_cases(M, LpLoss):
+    # mesh variants: grid append + padding + crop; width 64 (tcgen05 path) in 3-D, width 32 (FP32 path) in 2-D
+    mesh_grad_case(M, LpLoss, "FNOFactorizedMesh3D", "grad_mesh3d_w64", dict(modes_x=6, modes_y=6, modes_z=4, width=64,
+                   input_dim=4, output_dim=4, n_layers=2, share_weight=True, factor=4, ff_weight_norm=True,
+                   n_ff_layers=2, layer_norm=False), (2, 8, 8, 8, 1), 4, seed=22)
+    mesh_grad_case(M, LpLoss, "FNOFactorizedMesh2D", "grad_mesh2d_w32", dict(modes_x=6, modes_y=4, width=32, input_dim=4,
+                   n_layers=2, share_weight=False, factor=4, ff_weight_norm=True, n_ff_layers=2, layer_norm=False),
+                   (2, 12, 10, 2), 1, seed=23)
 
 
 def rollout_extras_cases(M, LpLoss, c2):
@@ -281,6 +320,9 @@ def main():
         return
     c2 = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4,
               ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0)
+    if "--only-mesh-grad" in sys.argv:
+        mesh_grad_cases(M, LpLoss)
+        return
     if "--only-rollout-extras" in sys.argv:
         rollout_extras_cases(M, LpLoss, c2)
         return

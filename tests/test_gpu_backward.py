@@ -199,3 +199,33 @@ def test_full_depth_c2_gradients_vs_fp64_oracle(mode, monkeypatch):
     assert l2 < TOL and worst_kind < TOL
     if mode == "fp32":
         assert worst_own < TOL
+
+
+@pytest.mark.parametrize("name,cls", [("grad_mesh3d_w64", "FNOFactorizedMesh3D"), ("grad_mesh2d_w32", "FNOFactorizedMesh2D")])
+def test_mesh_gradients_match_the_executed_reference(name, cls):
+    """Mesh variants (plasticity / airfoil training, routines/structured_mesh.py): the linspace grid append, the zero
+    padding after the lift and the crop before the head are part of the backward (mesh_3d.py:160-176, mesh_2d.py:149-165).
+    3-D width 64 runs the tcgen05 kernels (3 axes), 2-D width 32 the FP32 ones."""
+    kw, sd, a = load(name)
+    m = build(cls, kw, sd).train()
+    x = a["x"].cuda().requires_grad_(True)
+    from fourierflow_b200.modules import LpLoss
+    B = x.shape[0]
+    out = m(x)
+    loss = LpLoss(size_average=True)(out.reshape(B, -1), a["y"].cuda().reshape(B, -1))
+    loss.backward()
+    assert rel_err(out, a["out"]) < TOL
+    assert abs(loss.item() - a["loss"].item()) < 1e-5 * abs(a["loss"].item())
+    e = rel_err(x.grad, a["grad::x"])
+    params = dict(m.named_parameters())
+    checked, worst = 0, 0.0
+    for k, ref in a.items():
+        if not k.startswith("grad::") or k == "grad::x":
+            continue
+        g = params[k[6:]].grad
+        assert g is not None, k
+        worst = max(worst, rel_err(g, ref))
+        assert rel_err(g, ref) < TOL, (k, rel_err(g, ref))
+        checked += 1
+    print(name, f"dx {e:.2e}, {checked} parameter gradients, worst {worst:.2e}")
+    assert e < TOL and checked >= 10

@@ -195,3 +195,28 @@ def test_oracle_is_differentiable_and_matches_reference_gradients(name):
         assert rel_err(g, ref) < 2e-5, k
         checked += 1
     assert checked >= 10
+
+
+@pytest.mark.parametrize("name,modes", [("grad_mesh3d_w64", ("modes_x", "modes_y", "modes_z")),
+                                        ("grad_mesh2d_w32", ("modes_x", "modes_y"))])
+def test_oracle_mesh_gradients_match_reference(name, modes):
+    """Mesh variants of the backward row: grid append, zero padding and crop are inside the graph."""
+    kw, sd, a = load(name)
+    leaves = {}
+    for k, v in sd.items():
+        if id(v) not in leaves:
+            leaves[id(v)] = v.clone().requires_grad_(True)
+    p = {k: leaves[id(v)] for k, v in sd.items()}
+    x = a["x"].clone().requires_grad_(True)
+    out = O.block_mesh_forward(p, x, modes=[kw[m] for m in modes], n_layers=kw["n_layers"])
+    B = x.shape[0]
+    loss = O.lp_loss_rel(out.reshape(B, -1), a["y"].reshape(B, -1))
+    loss.backward()
+    assert rel_err(out, a["out"]) < TOL
+    assert rel_err(x.grad, a["grad::x"]) < 2e-5
+    checked = 0
+    for k, ref in a.items():
+        if k.startswith("grad::") and k != "grad::x":
+            assert rel_err(p[k[6:]].grad, ref) < 2e-5, k
+            checked += 1
+    assert checked >= 10
