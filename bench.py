@@ -376,9 +376,15 @@ def run_ours(args, rank, world, local):
             return loss
 
         ms_train = timed(ours_train, 10, 3, flush)
+        plan.set_backward_mode("fast")
+        ms_train_fast = timed(ours_train, 10, 3, flush)
+        plan.set_backward_mode("default")
         train = {"ms_per_step": ms_train, "samples_per_s": B / (ms_train * 1e-3), "steps": 10, "warmup": 3,
+                 "fast_mode_ms_per_step": ms_train_fast,
                  "what": "forward (tcgen05 kernels) + backward (ffno_block_bwd) of LpLoss(forecast, target), batch "
-                         f"{B}, no optimizer step; gradients checked against the reference's in tests/test_gpu_backward.py"}
+                         f"{B}, no optimizer step; default mode = FP32 forward recompute + tcgen05 spectral adjoint, fast "
+                         "mode = recompute on the tcgen05 kernels too (include/ffno_b200.h: ffno_plan_set_backward_mode); "
+                         "gradients checked against the reference's in tests/test_gpu_backward.py"}
         if ref is not None:
             def ref_train():
                 ref.zero_grad(set_to_none=True)

@@ -315,6 +315,11 @@ class StackPlan:
                                                ws.data_ptr(), ws.numel(), _stream(self.device)), "ffno_block_fwd")
         return out, taps
 
+    def set_backward_mode(self, mode: str) -> None:
+        """'default' (FP32 forward recompute + tcgen05 spectral adjoint), 'fast' (tcgen05 recompute too) or 'fp32'."""
+        _lib.check(self.lib.ffno_plan_set_backward_mode(self._plan, {"default": 0, "fast": 1, "fp32": 2}[mode]),
+                   "ffno_plan_set_backward_mode")
+
     def block_backward(self, x: torch.Tensor, d_forecast: torch.Tensor, in_proj, out, layers: List[LayerSpec],
                        want_dx: bool):
         """Gradients of the stack (ffno_block_bwd) -> (dx or None, {id(parameter): gradient tensor}).  Call right after

@@ -93,6 +93,7 @@ struct ffno_plan {
   // kernel state built on first use and refreshed when the parameters change.
   UmmaState* umma_adj = nullptr;
   bool adj_stale = true;
+  bool bwd_fp32_recompute = false, bwd_fp32_adjoint = false;
   bool bwd_fp32 = false;                     // FFNO_B200_BWD=fp32: backward entirely on the FP32 kernels (see ffno_block_bwd)
   std::map<const float*, float*> wmixT;      // forward block matrices -> their per-mode transposes
 
@@ -666,8 +667,15 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
     p->graphs = !(g && g[0] == '0');
   }
   {
+    // Backward modes (ffno_block_bwd).  default: forward recompute on the FP32 kernels (the ReLU masks are the reference's
+    // to FP32 round-off), spectral adjoint on the tcgen05 kernels.  "fast": recompute on the tcgen05 kernels too — 1.4x
+    // faster, but activations carry the forward's ~1e-5 noise and hidden units that close to the ReLU kink flip their
+    // mask, a discrete change of single gradient terms (up to ~1 % of a bias gradient entry on a 8 k-point batch).
+    // "fp32": everything on the FP32 kernels.  "fp32-adjoint": diagnostics (tcgen05 recompute, FP32 adjoint).
     const char* b = getenv("FFNO_B200_BWD");
     p->bwd_fp32 = b && strcmp(b, "fp32") == 0;
+    p->bwd_fp32_recompute = !(b && (strcmp(b, "fast") == 0 || strcmp(b, "fp32-adjoint") == 0));
+    p->bwd_fp32_adjoint = b && strcmp(b, "fp32-adjoint") == 0;
   }
   {
     const char* c = getenv("FFNO_B200_CHUNK");
@@ -1216,10 +1224,11 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   wf.h0 = w.h;
 
   // ---- 1. forward again, keeping the input x_l and the spectral output s_l of every layer (and the last backcast)
-  // tc: forward recompute and spectral adjoint on the tcgen05 kernels (3 x BF16, ~1e-5 per element — the precision of the
-  // forward itself); FFNO_B200_BWD=fp32 keeps the whole backward on the FP32 kernels (gradients at FP32 round-off, 1.4x slower)
+  // tc: the tcgen05 kernels take part (see the FFNO_B200_BWD modes at plan creation)
   const bool tc = p->use_umma && !p->bwd_fp32;
-  if (tc) {
+  const bool tc_fwd = tc && !p->bwd_fp32_recompute, tc_adj = tc && !p->bwd_fp32_adjoint;
+  if (tc) FFNO_TRY(ensure_adjoint(p, st));
+  if (tc_fwd) {
     // the tcgen05 forward with taps: the same kernels as inference
     FFNO_TRY(ensure_adjoint(p, st));
     std::vector<float*> xa(nl), sa(nl);
@@ -1272,7 +1281,7 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
     FFNO_TRY(linear_bwd(p, lw.back.lin[1], lp.backcast_ff.linear[1], lg.backcast_ff[1], w.h, gb, w.dh, P, w, st, w.h));
     FFNO_TRY(linear_bwd(p, lw.back.lin[0], lp.backcast_ff.linear[0], lg.backcast_ff[0], sl, w.dh, w.ds, P, w, st));
     // spectral operator (grid_2d.py:51-99): s = sum_a Inv_a Mix_a Fwd_a x  =>  gx += sum_a Fwd_a^T Mix_a^T Inv_a^T ds
-    if (tc) {
+    if (tc_adj) {
       // tcgen05: the forward's three kernels on the adjoint state; its "F" buffer ends up holding dR_a = Inv_a^T ds
       // of every axis, which — with the forward spectra F_a of x_l — gives the weight gradients
       FFNO_TRY(umma_spectral_fwd(p->umma_adj, l, w.ds, batch, w.gx, w.dR, w.dF, nullptr, st, true));
@@ -1320,6 +1329,15 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   }
   p->last_launches = g_launch_counter - before;
   (void)O;
+  return FFNO_OK;
+}
+
+int ffno_plan_set_backward_mode(ffno_plan* plan, int32_t mode) {
+  FFNO_REQUIRE(plan != nullptr, FFNO_ERR_BAD_ARG, "plan is NULL");
+  FFNO_REQUIRE(mode >= 0 && mode <= 2, FFNO_ERR_BAD_ARG, "backward mode %d (0 = default, 1 = fast, 2 = fp32)", mode);
+  plan->bwd_fp32 = mode == 2;
+  plan->bwd_fp32_recompute = mode != 1;
+  plan->bwd_fp32_adjoint = false;
   return FFNO_OK;
 }
 

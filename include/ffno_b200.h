@@ -257,6 +257,13 @@ FFNO_API size_t ffno_block_bwd_workspace_bytes(const ffno_plan* plan, int32_t ba
 FFNO_API int ffno_block_bwd(ffno_plan* plan, const ffno_block_params* params, const float* x, const float* d_forecast,
                    int32_t batch, const ffno_block_grads* grads, float* dx, void* workspace, size_t workspace_bytes,
                    void* stream);
+/* Precision / speed of ffno_block_bwd on plans that use the tcgen05 kernels (initial value from FFNO_B200_BWD):
+ *   0 default : forward recompute on the FP32 kernels (ReLU masks equal the reference's to FP32 round-off), spectral
+ *               adjoint on the tcgen05 kernels — every gradient tensor within ~1e-5 of its own max
+ *   1 fast    : recompute on the tcgen05 kernels too (1.4x faster); hidden units within ~1e-5 of the ReLU kink may
+ *               take the other branch: the gradient of the tcgen05-computed forward, not of the reference's
+ *   2 fp32    : everything on the FP32 kernels */
+FFNO_API int ffno_plan_set_backward_mode(ffno_plan* plan, int32_t mode);
 /* Backward of ffno_rel_l2 for contiguous x, y [batch, n]: dx[b, i] = g_out[b] * d out[b] / d x[b, i]
  * (modules/loss.py:33-46; the mean over the batch is the caller's g_out = 1 / batch). */
 FFNO_API int ffno_rel_l2_bwd(const float* x, const float* y, const float* g_out, int32_t batch, int64_t n, float* dx,

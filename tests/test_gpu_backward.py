@@ -150,18 +150,18 @@ def test_routine_training_step_matches_the_reference_loop():
     assert losses[-1] < losses[0]
 
 
-@pytest.mark.parametrize("mode", ["tc", "fp32"])
+@pytest.mark.parametrize("mode", ["default", "fast", "fp32"])
 def test_full_depth_c2_gradients_vs_fp64_oracle(mode, monkeypatch):
     """The benchmark's own model (24 layers, 64 x 64, modes 16, shared weights, weight-norm): every parameter gradient and
     the input gradient against torch.autograd through the oracle in FLOAT64.
-    fp32 (FFNO_B200_BWD=fp32, the whole backward on the FP32 kernels): every tensor within 1e-4 of ITS OWN max|ref|
-    (measured <= 3e-6, the level of the reference's own FP32 autograd).
-    tc (default: forward recompute + spectral adjoint on the tcgen05 kernels, 3 x BF16 = ~1e-5 per element, the precision of
-    the forward itself): the whole gradient within 1e-4 in relative L2, every tensor within 1e-4 of the largest gradient
-    of its kind — sums over points that cancel to 1e-3 of their terms (inner-layer biases / weight_g, max|g| ~ 1e-7..5e-6)
-    carry that element noise amplified, up to ~2e-3 of their own magnitude."""
-    if mode == "fp32":
-        monkeypatch.setenv("FFNO_B200_BWD", "fp32")
+    default (FP32 forward recompute, spectral adjoint on the tcgen05 kernels) and fp32 (everything FP32): every tensor
+    within 1e-4 of the largest gradient of its kind and the whole gradient within 1e-4 in relative L2; fp32 additionally
+    within 1e-4 of each tensor's OWN max|ref| (measured 1e-6: the level of the reference's own FP32 autograd).
+    fast (FFNO_B200_BWD=fast, recompute on the tcgen05 kernels): activations carry the forward's ~1e-5 noise, hidden units
+    that close to the ReLU kink flip their mask — same bounds here (few flips at this initialisation), see
+    test_fast_mode_mask_flips for a case where they show."""
+    if mode != "default":
+        monkeypatch.setenv("FFNO_B200_BWD", mode)
     torch.manual_seed(0)
     from fourierflow_b200.modules import FNOFactorized2DBlock
     kw = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4, ff_weight_norm=True, gain=0.1)
@@ -229,3 +229,27 @@ def test_mesh_gradients_match_the_executed_reference(name, cls):
         checked += 1
     print(name, f"dx {e:.2e}, {checked} parameter gradients, worst {worst:.2e}")
     assert e < TOL and checked >= 10
+
+
+def test_fast_mode_mask_flips(monkeypatch):
+    """FFNO_B200_BWD=fast on the perturbed-weight 3-D fixture (8 k points): the gradient is that of the tcgen05-computed
+    forward — hidden units within ~1e-5 of the ReLU kink take the other branch, each a discrete change of single terms.
+    The whole gradient stays within 2e-2 of the reference's in relative L2 (measured ~5e-3); the default mode holds 1e-4
+    per tensor on the same fixture (test_mesh_gradients_match_the_executed_reference)."""
+    monkeypatch.setenv("FFNO_B200_BWD", "fast")
+    kw, sd, a = load("grad_mesh3d_w64")
+    m = build("FNOFactorizedMesh3D", kw, sd).train()
+    x = a["x"].cuda().requires_grad_(True)
+    from fourierflow_b200.modules import LpLoss
+    B = x.shape[0]
+    LpLoss(size_average=True)(m(x).reshape(B, -1), a["y"].cuda().reshape(B, -1)).backward()
+    params = dict(m.named_parameters())
+    num = den = 0.0
+    for k, ref in a.items():
+        if k.startswith("grad::") and k != "grad::x":
+            d = params[k[6:]].grad.double().cpu() - ref.double()
+            num += float((d * d).sum())
+            den += float((ref.double() ** 2).sum())
+    l2 = (num / den) ** 0.5
+    print(f"fast mode, mesh3d fixture: whole-gradient relative L2 {l2:.2e}, dx {rel_err(x.grad, a['grad::x']):.2e}")
+    assert l2 < 2e-2
