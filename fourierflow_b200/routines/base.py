@@ -1,7 +1,8 @@
 """The inference-side surface of the reference's ``Routine`` base class (fourierflow/routines/base.py:9-102) without
 pytorch_lightning: what ``commands/predict.py:91-105`` and ``commands/train.py:125-148`` call on a routine after
-training — ``load_lightning_model_state``, ``convert_data``, ``warmup``, ``infer``.  The training half (manual
-optimisation, ``configure_optimizers``) is outside the hot path."""
+training — ``load_lightning_model_state``, ``convert_data``, ``warmup``, ``infer`` — plus ``optimize_manually`` for
+the training steps of the routines (the optimizer / scheduler objects are the caller's: ``configure_optimizers`` and the
+Lightning trainer stay outside the hot path)."""
 from __future__ import annotations
 
 from typing import Any, Dict
@@ -16,6 +17,24 @@ REMOVE_KEYS = ['kx', 'ky', 'lap'] + [f'{n}_{s}' for s in (32, 64, 128, 256) for 
 class RoutineMixin:
     def warmup(self) -> None:                       # routines/base.py:24
         pass
+
+    def optimize_manually(self, loss, batch_idx: int = 0, optimizer=None, scheduler=None, clip_val=None,
+                          world_size: int = 1):
+        """routines/base.py:27-52 (accumulate_grad_batches = 1) without pytorch_lightning: zero_grad -> backward ->
+        (data-parallel: one all-reduce of the gradients) -> clip -> step -> scheduler step."""
+        if optimizer is None:
+            return
+        optimizer.zero_grad()
+        loss.backward()
+        if world_size > 1:
+            from ..distributed import allreduce_gradients
+            allreduce_gradients([p for g in optimizer.param_groups for p in g["params"]], world_size)
+        if clip_val:
+            for group in optimizer.param_groups:
+                torch.nn.utils.clip_grad_value_(group["params"], clip_val)
+        optimizer.step()
+        if scheduler is not None:
+            scheduler.step()
 
     def infer(self, data):                          # routines/base.py:54-56
         with torch.no_grad():

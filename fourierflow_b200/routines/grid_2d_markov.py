@@ -151,18 +151,7 @@ class Grid2DMarkovExperiment(RoutineMixin, nn.Module):
                 self._build_features(batch)
             return None
         loss = self._training_step(batch)
-        if optimizer is not None:
-            optimizer.zero_grad()
-            loss.backward()
-            if world_size > 1:
-                from ..distributed import allreduce_gradients
-                allreduce_gradients([p for g in optimizer.param_groups for p in g["params"]], world_size)
-            if clip_val:
-                for group in optimizer.param_groups:
-                    torch.nn.utils.clip_grad_value_(group["params"], clip_val)
-            optimizer.step()
-            if scheduler is not None:
-                scheduler.step()
+        self.optimize_manually(loss, batch_idx, optimizer, scheduler, clip_val, world_size)
         return loss
 
     # -- inference -------------------------------------------------------------------------------------

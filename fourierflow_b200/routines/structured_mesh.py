@@ -1,5 +1,5 @@
 """``StructuredMeshExperiment`` — host-side mirror of fourierflow/routines/structured_mesh.py:8-51
-(validation/test path): ``out = self.model(x)``; relative-L2 against ``y``."""
+(training / validation / test steps): ``out = self.model(x)``; relative-L2 against ``y``."""
 from __future__ import annotations
 
 import torch
@@ -15,6 +15,17 @@ class StructuredMeshExperiment(RoutineMixin, nn.Module):
         self.model = model
         self.l2_loss = LpLoss(size_average=True)
         self.loss_scale = loss_scale
+
+    def training_step(self, batch, batch_idx: int = 0, optimizer=None, scheduler=None, clip_val=None,
+                      world_size: int = 1):
+        """structured_mesh.py:22-32: loss = LpLoss(model(x), y); the scaled loss goes through the manual optimisation
+        (differentiable through ffno_block_bwd); returns the scaled loss like the reference."""
+        x, y = batch['x'], batch['y']
+        B = x.shape[0]
+        out = self.model(x)
+        loss = self.l2_loss(out.reshape(B, -1), y.reshape(B, -1)) * self.loss_scale
+        self.optimize_manually(loss, batch_idx, optimizer, scheduler, clip_val, world_size)
+        return loss
 
     @torch.no_grad()
     def validation_step(self, batch, batch_idx=0):
