@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # FFNO_B200_LIB: load another build of the same library (the FFNO_TIMELINE=1 diagnostics build of tools/*_timeline.py)
 LIB_PATH = os.environ.get("FFNO_B200_LIB") or os.path.join(_HERE, "lib", "libffno_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_DIMS = 3
 MAX_FF_LAYERS = 4
 
@@ -30,7 +30,7 @@ class Desc(C.Structure):
         ("width", C.c_int32), ("in_features", C.c_int32), ("append_grid", C.c_int32),
         ("out_features", C.c_int32), ("head_hidden", C.c_int32), ("n_layers", C.c_int32),
         ("ff_factor", C.c_int32), ("n_ff_layers", C.c_int32), ("layer_norm", C.c_int32),
-        ("use_fork", C.c_int32), ("spectral_mode", C.c_int32), ("path", C.c_int32),
+        ("use_fork", C.c_int32), ("spectral_mode", C.c_int32), ("path", C.c_int32), ("transform", C.c_int32),
     ]
 
 

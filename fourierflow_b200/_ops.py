@@ -192,7 +192,7 @@ class StackPlan:
     def __init__(self, device: torch.device, *, size: Sequence[int], pad: Sequence[int], modes: Sequence[int],
                  width: int, in_features: int, append_grid: bool, out_features: int, head_hidden: int,
                  n_layers: int, ff_factor: int, n_ff_layers: int, layer_norm: bool, use_fork: bool,
-                 mode: str, path: str = "auto"):
+                 mode: str, path: str = "auto", transform: str = "rfft"):
         self.lib = _lib.load()
         self.device = device
         d = _lib.Desc()
@@ -204,6 +204,7 @@ class StackPlan:
         d.out_features, d.head_hidden, d.n_layers = out_features, head_hidden, n_layers
         d.ff_factor, d.n_ff_layers, d.layer_norm = ff_factor, n_ff_layers, int(layer_norm)
         d.use_fork, d.spectral_mode, d.path = int(use_fork), _lib.MODE[mode], _lib.PATH[path]
+        d.transform = {"rfft": 0, "dct": 1}[transform]      # ffno_transform
         self.desc = d
         self.ext = [int(size[a]) + int(pad[a]) for a in range(len(size))]
         self.size = [int(s) for s in size]

@@ -550,6 +550,31 @@ pack_mix_weights_kernel(const float* __restrict__ w, float* __restrict__ Wblk, i
   Wblk[idx] = val;
 }
 
+__global__ void __launch_bounds__(256)
+pack_mix_weights_dct_kernel(const float* __restrict__ w, float* __restrict__ Wblk, int C, int Kpairs, int Kc) {
+  // real weights w[i][o][j] (factorized_cno/mesh_3d.py:33) -> Wblk[k][ri*C+i][ro*C+o] = (ri == ro) ? w[i][o][2k+ri] : 0
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Kpairs * 4 * C * C;
+  if (idx >= total) return;
+  int n2 = 2 * C;
+  int col = (int)(idx % n2);
+  long long t = idx / n2;
+  int row = (int)(t % n2);
+  int k = (int)(t / n2);
+  int ri = row / C, i = row % C, ro = col / C, o = col % C;
+  const int j = 2 * k + ri;
+  Wblk[idx] = (ri == ro && j < Kc) ? w[((long long)i * C + o) * Kc + j] : 0.f;
+}
+
+int launch_pack_mix_weights_dct(const float* w, float* Wblk, int C, int Kpairs, int Kc, cudaStream_t st) {
+  long long total = (long long)Kpairs * 4 * C * C;
+  if (total == 0) return FFNO_OK;
+  pack_mix_weights_dct_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, Wblk, C, Kpairs, Kc);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("pack_mix_weights_dct_kernel");
+  return FFNO_OK;
+}
+
 int launch_pack_mix_weights(const float* w, float* Wblk, int C, int K, cudaStream_t st) {
   long long total = (long long)K * 4 * C * C;
   if (total == 0) return FFNO_OK;

@@ -54,6 +54,8 @@ int launch_weight_fold_transpose(const float* v, const float* g, float* w_t, int
 
 // fourier_weight [Cin][Cout][K][2] -> real block matrices Wblk[k][2C][2C]
 int launch_pack_mix_weights(const float* w, float* Wblk, int C, int K, cudaStream_t st);
+// DCT variant: real weights [Cin][Cout][Kc] -> block-diagonal pair matrices Wblk[k][2C][2C] = diag(W_2k, W_2k+1)
+int launch_pack_mix_weights_dct(const float* w, float* Wblk, int C, int Kpairs, int Kc, cudaStream_t st);
 
 // Weff[j][c] = sum_h W1t[h][j] * W0t[c][h];  beff[j] = sum_h W1t[h][j]*b0[h] + b1[j]   (fp64 accumulate)
 int launch_fold_head(const float* W0t /*[C][H]*/, const float* b0, const float* W1t /*[H][out]*/,

@@ -93,6 +93,7 @@ struct ffno_plan {
   // kernel state built on first use and refreshed when the parameters change.
   UmmaState* umma_adj = nullptr;
   bool adj_stale = true;
+  int dct_modes[3] = {0, 0, 0};      // FFNO_TRANSFORM_DCT: coefficients kept per axis (d.modes then holds PAIRS of them)
   bool bwd_fp32_recompute = false, bwd_fp32_adjoint = false;
   bool bwd_fp32 = false;                     // FFNO_B200_BWD=fp32: backward entirely on the FP32 kernels (see ffno_block_bwd)
   std::map<const float*, float*> wmixT;      // forward block matrices -> their per-mode transposes
@@ -176,6 +177,21 @@ int build_tables(ffno_plan* p) {
     std::vector<float> f((size_t)L * ldf, 0.f), inv((size_t)2 * K * ldi, 0.f);
     std::vector<float> fT((size_t)2 * K * ldi, 0.f), invT((size_t)L * ldf, 0.f);      // backward pass (ffno_block_bwd)
     const double s = 1.0 / std::sqrt((double)L);
+    if (p->d.transform == FFNO_TRANSFORM_DCT) {
+      // Ortho DCT-II basis (modules/dct.py:16-45 with norm='ortho'): X_j = c_j sum_l x_l cos(pi (2 l + 1) j / (2 L)),
+      // c_0 = sqrt(1/L), c_j = sqrt(2/L); the inverse (DCT-III, dct.py:48-88) is the transpose.  Coefficients 2k and
+      // 2k + 1 ride in the (Re, Im) rows of "mode" k, so every kernel downstream is the F-FNO one: the mix of pair k is
+      // the block-diagonal [[W_2k, 0], [0, W_2k+1]] (pack_mix_weights_dct).  Rows past the kept count stay zero.
+      for (int l = 0; l < L; ++l)
+        for (int j = 0; j < p->dct_modes[a]; ++j) {
+          const long long num = ((long long)(2 * l + 1) * j) % (4ll * L);      // angle = pi * num / (2 L), period 4 L
+          const double v = std::cos(M_PI * (double)num / (2.0 * L)) * (j == 0 ? s : s * std::sqrt(2.0));
+          f[(size_t)l * ldf + j] = (float)v;
+          invT[(size_t)l * ldf + j] = (float)v;
+          inv[(size_t)j * ldi + l] = (float)v;
+          fT[(size_t)j * ldi + l] = (float)v;
+        }
+    } else
     for (int l = 0; l < L; ++l)
       for (int k = 0; k < K; ++k) {
         // reduce k*l mod L before the multiply: keeps the angle small and exact for large L
@@ -219,11 +235,19 @@ int validate_desc(const ffno_desc* d) {
                "in_features=%d out_features=%d", d->in_features, d->out_features);
   FFNO_REQUIRE(d->head_hidden >= 1, FFNO_ERR_BAD_ARG, "head_hidden=%d", d->head_hidden);
   FFNO_REQUIRE(d->spectral_mode >= 0 && d->spectral_mode <= 2, FFNO_ERR_BAD_ARG, "spectral_mode=%d", d->spectral_mode);
+  FFNO_REQUIRE(d->transform == FFNO_TRANSFORM_RFFT || d->transform == FFNO_TRANSFORM_DCT, FFNO_ERR_BAD_ARG,
+               "transform=%d", d->transform);
+  FFNO_REQUIRE(d->transform == FFNO_TRANSFORM_RFFT || d->spectral_mode == FFNO_MODE_FULL, FFNO_ERR_UNSUPPORTED,
+               "the DCT variant has no low-pass / no-fourier mode");
   for (int a = 0; a < d->ndim; ++a) {
     FFNO_REQUIRE(d->size[a] >= 1 && d->pad[a] >= 0, FFNO_ERR_BAD_ARG, "size[%d]=%d pad=%d", a, d->size[a], d->pad[a]);
     int L = d->size[a] + d->pad[a];
     // the reference's slice-assign `out_ft[..., :modes] = einsum(x_ft[..., :modes], W)` raises when
     // modes > L//2+1 — same contract here.
+    if (d->transform == FFNO_TRANSFORM_DCT)
+      FFNO_REQUIRE(d->modes[a] >= 1 && d->modes[a] <= L, FFNO_ERR_BAD_ARG,
+                   "modes[%d]=%d exceeds the %d DCT coefficients of a length-%d axis", a, d->modes[a], L, L);
+    else
     FFNO_REQUIRE(d->modes[a] >= 1 && d->modes[a] <= L / 2 + 1, FFNO_ERR_BAD_ARG,
                  "modes[%d]=%d exceeds the %d rfft bins of a length-%d axis", a, d->modes[a], L / 2 + 1, L);
   }
@@ -654,6 +678,11 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
   ffno_plan* p = new (std::nothrow) ffno_plan();
   FFNO_REQUIRE(p != nullptr, FFNO_ERR_BAD_ARG, "out of host memory");
   p->d = *desc;
+  if (desc->transform == FFNO_TRANSFORM_DCT)
+    for (int a = 0; a < desc->ndim; ++a) {
+      p->dct_modes[a] = desc->modes[a];
+      p->d.modes[a] = (desc->modes[a] + 1) / 2;      // coefficient pairs: the "complex modes" of every kernel downstream
+    }
   p->pts = 1;
   p->pts_in = 1;
   for (int a = 0; a < desc->ndim; ++a) {
@@ -689,11 +718,11 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
   p->layers.resize(desc->n_layers);
   int st = build_tables(p);
   if (st == FFNO_OK) {
-    const bool ok = umma_supported(desc, p->ext);
+    const bool ok = umma_supported(&p->d, p->ext);
     if (desc->path == FFNO_PATH_UMMA && !ok)
-      st = set_error(FFNO_ERR_UNSUPPORTED, "shape does not qualify for the tcgen05 path: %s", umma_why_not(desc, p->ext));
+      st = set_error(FFNO_ERR_UNSUPPORTED, "shape does not qualify for the tcgen05 path: %s", umma_why_not(&p->d, p->ext));
     p->use_umma = ok && desc->path != FFNO_PATH_GENERIC;
-    if (st == FFNO_OK && p->use_umma) st = umma_create(&p->umma, desc, p->ext);
+    if (st == FFNO_OK && p->use_umma) st = umma_create(&p->umma, &p->d, p->ext);
   }
   if (st == FFNO_OK) st = create_chunk_streams(p);
   if (st != FFNO_OK) {
@@ -761,7 +790,10 @@ int ffno_plan_load_params(ffno_plan* p, const ffno_block_params* prm, void* stre
         if (it != seen_mix.end()) { dst.wmix[a] = it->second; continue; }
         float*& slot = p->dedup[(const void*)((uintptr_t)(l * 4 + a + 1))];   // stable per (layer, axis) slot
         if (!slot) FFNO_TRY(dev_alloc(p, (size_t)p->d.modes[a] * 4 * C * C * 4, &slot));
-        FFNO_TRY(launch_pack_mix_weights(wsrc, slot, C, p->d.modes[a], st));
+        if (p->d.transform == FFNO_TRANSFORM_DCT)
+          FFNO_TRY(launch_pack_mix_weights_dct(wsrc, slot, C, p->d.modes[a], p->dct_modes[a], st));
+        else
+          FFNO_TRY(launch_pack_mix_weights(wsrc, slot, C, p->d.modes[a], st));
         dst.wmix[a] = slot;
         seen_mix[key] = slot;
       }
@@ -1211,6 +1243,7 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
   FFNO_REQUIRE(p->d.n_ff_layers == 2 && !p->d.layer_norm && !p->d.use_fork && p->d.spectral_mode == FFNO_MODE_FULL,
                FFNO_ERR_UNSUPPORTED, "backward is implemented for n_ff_layers = 2, no LayerNorm, no fork, mode 'full'");
+  FFNO_REQUIRE(p->d.transform == FFNO_TRANSFORM_RFFT, FFNO_ERR_UNSUPPORTED, "backward is implemented for the rfft (F-FNO) stacks");
   const bool mesh = p->pts != p->pts_in || p->d.append_grid;       // zero-padded / grid-appended (mesh_3d.py:161-166)
   if (batch == 0) return FFNO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

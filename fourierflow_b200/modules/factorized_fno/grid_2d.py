@@ -20,6 +20,8 @@ from ._base import PlanCacheMixin, StackFunction, check_input, check_trainable, 
 
 
 class SpectralConv2d(PlanCacheMixin, nn.Module):
+    _transform, _weight_tail = "rfft", (2,)      # the factorized_cno mirrors override these (DCT, real weights)
+
     def __init__(self, in_dim, out_dim, n_modes, forecast_ff, backcast_ff, fourier_weight, factor,
                  ff_weight_norm, n_ff_layers, layer_norm, use_fork, dropout, mode):
         super().__init__()
@@ -33,7 +35,7 @@ class SpectralConv2d(PlanCacheMixin, nn.Module):
         if not self.fourier_weight:
             self.fourier_weight = nn.ParameterList([])
             for _ in range(2):
-                param = nn.Parameter(torch.empty(in_dim, out_dim, n_modes, 2))
+                param = nn.Parameter(torch.empty(in_dim, out_dim, n_modes, *self._weight_tail))
                 nn.init.xavier_normal_(param)
                 self.fourier_weight.append(param)
 
@@ -56,7 +58,8 @@ class SpectralConv2d(PlanCacheMixin, nn.Module):
             x.device, x.shape[1:3], pad=(0, 0), modes=(self.n_modes, self.n_modes), width=self.in_dim,
             in_features=1, append_grid=False, out_features=1, head_hidden=1, n_layers=1,
             ff_factor=self.factor, n_ff_layers=self.n_ff_layers, layer_norm=self.layer_norm,
-            use_fork=self.use_fork, mode=self.mode, path=default_path())
+            use_fork=self.use_fork, mode=self.mode, path=default_path(),
+            transform=self._transform)
         plan.sync_params(self._flat_params(), None, None, [self.layer_spec()])
         return plan
 
@@ -80,6 +83,8 @@ class SpectralConv2d(PlanCacheMixin, nn.Module):
 
 
 class FNOFactorized2DBlock(PlanCacheMixin, nn.Module):
+    _transform, _weight_tail, _layer_cls = "rfft", (2,), SpectralConv2d
+
     def __init__(self, modes, width, input_dim=12, dropout=0.0, in_dropout=0.0, n_layers=4,
                  share_weight: bool = False, share_fork=False, factor=2, ff_weight_norm=False, n_ff_layers=2,
                  gain=1, layer_norm=False, use_fork=False, mode='full'):
@@ -105,13 +110,13 @@ class FNOFactorized2DBlock(PlanCacheMixin, nn.Module):
         if share_weight:
             self.fourier_weight = nn.ParameterList([])
             for _ in range(2):
-                param = nn.Parameter(torch.empty(width, width, modes, 2))
+                param = nn.Parameter(torch.empty(width, width, modes, *self._weight_tail))
                 nn.init.xavier_normal_(param, gain=gain)
                 self.fourier_weight.append(param)
 
         self.spectral_layers = nn.ModuleList([])
         for _ in range(n_layers):
-            self.spectral_layers.append(SpectralConv2d(
+            self.spectral_layers.append(self._layer_cls(
                 in_dim=width, out_dim=width, n_modes=modes, forecast_ff=self.forecast_ff,
                 backcast_ff=self.backcast_ff, fourier_weight=self.fourier_weight, factor=factor,
                 ff_weight_norm=ff_weight_norm, n_ff_layers=n_ff_layers, layer_norm=layer_norm,
@@ -125,7 +130,8 @@ class FNOFactorized2DBlock(PlanCacheMixin, nn.Module):
             device, size, pad=(0, 0), modes=(self.modes, self.modes), width=self.width,
             in_features=self.input_dim, append_grid=False, out_features=1, head_hidden=128,
             n_layers=self.n_layers, ff_factor=self.factor, n_ff_layers=self.n_ff_layers,
-            layer_norm=self.layer_norm, use_fork=self.use_fork, mode=self.mode, path=path or default_path())
+            layer_norm=self.layer_norm, use_fork=self.use_fork, mode=self.mode,
+            path=path or default_path(), transform=self._transform)
         params = self._flat_params()                   # validates the caches first (may drop a stale _spec_cache)
         specs = self.__dict__.get("_spec_cache")
         if specs is None:

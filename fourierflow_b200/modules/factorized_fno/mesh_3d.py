@@ -15,6 +15,8 @@ from ._base import PlanCacheMixin, StackFunction, check_input, check_trainable, 
 
 
 class SpectralConv2d(PlanCacheMixin, nn.Module):
+    _transform, _weight_tail = "rfft", (2,)      # the factorized_cno mirrors override these (DCT, real weights)
+
     def __init__(self, in_dim, out_dim, modes_x, modes_y, modes_z, forecast_ff, backcast_ff, fourier_weight,
                  factor, ff_weight_norm, n_ff_layers, layer_norm, use_fork, dropout):
         super().__init__()
@@ -29,7 +31,7 @@ class SpectralConv2d(PlanCacheMixin, nn.Module):
         if not self.fourier_weight:
             self.fourier_weight = nn.ParameterList([])
             for n_modes in [modes_x, modes_y, modes_z]:
-                param = nn.Parameter(torch.empty(in_dim, out_dim, n_modes, 2))
+                param = nn.Parameter(torch.empty(in_dim, out_dim, n_modes, *self._weight_tail))
                 nn.init.xavier_normal_(param)
                 self.fourier_weight.append(param)
 
@@ -51,7 +53,7 @@ class SpectralConv2d(PlanCacheMixin, nn.Module):
             x.device, x.shape[1:4], pad=(0, 0, 0), modes=(self.modes_x, self.modes_y, self.modes_z),
             width=self.in_dim, in_features=1, append_grid=False, out_features=1, head_hidden=1, n_layers=1,
             ff_factor=self.factor, n_ff_layers=self.n_ff_layers, layer_norm=self.layer_norm,
-            use_fork=self.use_fork, mode='full', path=default_path())
+            use_fork=self.use_fork, mode='full', path=default_path(), transform=self._transform)
         plan.sync_params(self._flat_params(), None, None, [self.layer_spec()])
         return plan
 
@@ -72,6 +74,8 @@ class SpectralConv2d(PlanCacheMixin, nn.Module):
 
 
 class FNOFactorizedMesh3D(PlanCacheMixin, nn.Module):
+    _transform, _weight_tail, _layer_cls = "rfft", (2,), SpectralConv2d
+
     def __init__(self, modes_x, modes_y, modes_z, width, input_dim, output_dim, n_layers, share_weight, factor,
                  ff_weight_norm, n_ff_layers, layer_norm):
         super().__init__()
@@ -86,13 +90,13 @@ class FNOFactorizedMesh3D(PlanCacheMixin, nn.Module):
         if share_weight:
             self.fourier_weight = nn.ParameterList([])
             for n_modes in [modes_x, modes_y, modes_z]:
-                param = nn.Parameter(torch.empty(width, width, n_modes, 2))
+                param = nn.Parameter(torch.empty(width, width, n_modes, *self._weight_tail))
                 nn.init.xavier_normal_(param)
                 self.fourier_weight.append(param)
 
         self.spectral_layers = nn.ModuleList([])
         for _ in range(n_layers):
-            self.spectral_layers.append(SpectralConv2d(
+            self.spectral_layers.append(self._layer_cls(
                 in_dim=width, out_dim=width, modes_x=modes_x, modes_y=modes_y, modes_z=modes_z,
                 forecast_ff=None, backcast_ff=None, fourier_weight=self.fourier_weight, factor=factor,
                 ff_weight_norm=ff_weight_norm, n_ff_layers=n_ff_layers, layer_norm=layer_norm,
@@ -106,7 +110,8 @@ class FNOFactorizedMesh3D(PlanCacheMixin, nn.Module):
             device, size, pad=(self.padding,) * 3, modes=(self.modes_x, self.modes_y, self.modes_z),
             width=self.width, in_features=self.input_dim - 3, append_grid=True, out_features=self.output_dim,
             head_hidden=128, n_layers=self.n_layers, ff_factor=self.factor, n_ff_layers=self.n_ff_layers,
-            layer_norm=self.layer_norm, use_fork=False, mode='full', path=path or default_path())
+            layer_norm=self.layer_norm, use_fork=False, mode='full',
+            path=path or default_path(), transform=self._transform)
         params = self._flat_params()                   # validates the caches first (may drop a stale _spec_cache)
         specs = self.__dict__.get("_spec_cache")
         if specs is None:

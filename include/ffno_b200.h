@@ -36,7 +36,7 @@ extern "C" {
 #define FFNO_API
 #endif
 
-#define FFNO_ABI_VERSION 1
+#define FFNO_ABI_VERSION 2
 #define FFNO_MAX_DIMS 3
 #define FFNO_MAX_FF_LAYERS 4
 
@@ -54,6 +54,13 @@ typedef enum {                /* SpectralConv2d `mode`, grid_2d.py:44,64,69 */
   FFNO_MODE_LOW_PASS = 1,
   FFNO_MODE_NO_FOURIER = 2
 } ffno_spectral_mode;
+
+typedef enum {                /* per-axis transform of the spectral layer */
+  FFNO_TRANSFORM_RFFT = 0,    /* F-FNO: ortho rfft, K complex bins kept, complex channel mix (factorized_fno/*.py) */
+  FFNO_TRANSFORM_DCT = 1      /* factorized CNO sibling: ortho DCT-II, first K coefficients kept, REAL channel mix,
+                                 inverse DCT-III (factorized_cno/mesh_3d.py:55-112, modules/dct.py:16-88);
+                                 fourier_weight is [C, C, K_a] */
+} ffno_transform;
 
 typedef enum {                /* which implementation a plan may use */
   FFNO_PATH_AUTO = 0,         /* tcgen05 kernels when the shape qualifies, else the generic FP32 kernels */
@@ -83,6 +90,7 @@ typedef struct {
   int32_t use_fork;               /* forecast fork (grid_2d.py:48,164-167) */
   int32_t spectral_mode;          /* ffno_spectral_mode */
   int32_t path;                   /* ffno_path */
+  int32_t transform;              /* ffno_transform (ABI 2) */
 } ffno_desc;
 
 /* One WNLinear (modules/linear.py:41-51).  Either `weight` (plain nn.Linear) or weight_g+weight_v

@@ -76,6 +76,29 @@ def feed_forward(p: Params, prefix: str, x: torch.Tensor, n_layers: int = 2,
 # Spectral convolution along one axis
 # ----------------------------------------------------------------------------------------------
 
+def dct_matrix(L: int, dtype=torch.float64) -> torch.Tensor:
+    """Ortho DCT-II matrix ``D[j, l] = c_j cos(pi (2 l + 1) j / (2 L))``, c_0 = sqrt(1/L), c_j = sqrt(2/L): what
+    ``dct(x, norm='ortho')`` of fourierflow/modules/dct.py:16-45 computes through an FFT (Makhoul); its transpose is
+    the ``idct(X, norm='ortho')`` of dct.py:48-88 (DCT-III)."""
+    l = torch.arange(L, dtype=torch.float64)
+    j = torch.arange(L, dtype=torch.float64)[:, None]
+    D = torch.cos(math.pi * (2 * l + 1) * j / (2 * L)) * math.sqrt(2.0 / L)
+    D[0] = D[0] / math.sqrt(2.0)
+    return D.to(dtype)
+
+
+def spectral_axis_dct(x: torch.Tensor, w: torch.Tensor, dim: int, n_modes: int) -> torch.Tensor:
+    """One axis of the factorized cosine operator on channels-last ``x[..., C]``: ortho DCT-II along ``dim`` → keep the
+    first ``n_modes`` coefficients → REAL per-coefficient channel mix ``R[.., j, o] = sum_i X[.., j, i] W[i, o, j]`` →
+    zero-pad to L → DCT-III.  Reference: fourierflow/modules/factorized_cno/grid_2d.py:57-69 (last axis) / :72-86;
+    mesh_3d.py:63-74, :77-91, :94-108."""
+    L = x.shape[dim]
+    D = dct_matrix(L, x.dtype)[:n_modes]                # [K, L]
+    X = torch.einsum("kl,...lc->...kc", D, x.movedim(dim, -2))
+    R = torch.einsum("...ki,iok->...ko", X, w)
+    return torch.einsum("kl,...kc->...lc", D, R).movedim(-2, dim)
+
+
 def spectral_axis(x: torch.Tensor, w: torch.Tensor, dim: int, n_modes: int,
                   mode: str = "full") -> torch.Tensor:
     """One axis of ``forward_fourier`` on a channels-LAST tensor ``x[..., C]``.
@@ -87,6 +110,8 @@ def spectral_axis(x: torch.Tensor, w: torch.Tensor, dim: int, n_modes: int,
     mesh_3d.py:61-73, 76-88, 91-103.  The reference permutes to channels-first and transforms
     dim -1/-2/-3; here the same transform is applied along the matching channels-last axis.
     """
+    if w is not None and w.dim() == 3:                 # real [in, out, K] weights: the factorized_cno sibling
+        return spectral_axis_dct(x, w, dim, n_modes)
     L = x.shape[dim]
     x_ft = torch.fft.rfft(x, dim=dim, norm="ortho")
     x_ft = x_ft.movedim(dim, -2)                       # [..., L/2+1, C]

@@ -70,9 +70,9 @@ def perturb_(module, seed, scale=0.5):
                 p.add_(scale * torch.randn(p.shape, generator=g) * p.abs().mean().clamp(min=0.1))
 
 
-def grid2d_case(M, name, kwargs, shape, seed, taps=True, x_scale=1.0):
+def grid2d_case(M, name, kwargs, shape, seed, taps=True, x_scale=1.0, cls="FNOFactorized2DBlock"):
     torch.manual_seed(seed)
-    m = M.FNOFactorized2DBlock(**kwargs).eval()
+    m = getattr(M, cls)(**kwargs).eval()
     perturb_(m, seed + 100)
     x = x_scale * torch.randn(*shape, generator=torch.Generator().manual_seed(seed + 1))
     arrays = sd_np(m)
@@ -257,6 +257,22 @@ def grad_case(M, LpLoss, name, kwargs, shape, seed):
     save(name, kwargs, arrays)
 
 
+def cno_cases():
+    """The DCT siblings (fourierflow/modules/factorized_cno/*, not exported by modules/__init__.py): same fixtures as
+    the F-FNO ones — generic-path shapes with odd coefficient counts, and width-64 shapes for the tcgen05 path."""
+    import fourierflow.modules.factorized_cno as CNO
+    grid2d_case(CNO, "cno_grid2d_w32", dict(modes=5, width=32, n_layers=2, input_dim=3, share_weight=False, factor=4,
+                ff_weight_norm=True, gain=1), (2, 12, 10, 3), seed=30, cls="CNOFactorized2DBlock")
+    grid2d_case(CNO, "cno_grid2d_w64", dict(modes=16, width=64, n_layers=3, input_dim=3, share_weight=True, factor=4,
+                ff_weight_norm=True, gain=0.5), (1, 32, 32, 3), seed=31, cls="CNOFactorized2DBlock")
+    mesh_case(CNO, "CNOFactorizedMesh2D", "cno_mesh2d_small", dict(modes_x=7, modes_y=4, width=32, input_dim=4,
+              n_layers=2, share_weight=False, factor=4, ff_weight_norm=True, n_ff_layers=2, layer_norm=False),
+              (2, 11, 9, 2), seed=32)
+    mesh_case(CNO, "CNOFactorizedMesh3D", "cno_mesh3d_w64", dict(modes_x=6, modes_y=5, modes_z=4, width=64,
+              input_dim=4, output_dim=4, n_layers=2, share_weight=False, factor=4, ff_weight_norm=True,
+              n_ff_layers=2, layer_norm=False), (1, 8, 8, 8, 1), seed=33)
+
+
 def init_case(M):
     """Seeded-construction checksums: the mirrors must draw the same random numbers in the same order."""
     cases = {
@@ -323,6 +339,9 @@ def main():
     if "--only-mesh-grad" in sys.argv:
         mesh_grad_cases(M, LpLoss)
         return
+    if "--only-cno" in sys.argv:
+        cno_cases()
+        return
     if "--only-rollout-extras" in sys.argv:
         rollout_extras_cases(M, LpLoss, c2)
         return
@@ -368,6 +387,8 @@ def main():
                  n_steps=10, seed=11)
     # (10b) the torus_vis feature sets: append_force (static and time-varying forcing) and append_mu
     rollout_extras_cases(M, LpLoss, c2)
+    # (10c) the factorized cosine (DCT) siblings
+    cno_cases()
     # (11) gradients of the one-step training loss (backward row)
     grad_cases(M, LpLoss)
 

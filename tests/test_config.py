@@ -148,13 +148,15 @@ REF_EXPERIMENTS = "/root/reference/experiments"
 def test_reference_ffno_configs_load_from_the_mounted_tree():
     """Every shipped torus_li F-FNO (markov) config and the plasticity F-FNO configs: routine block -> our modules."""
     paths = sorted(glob.glob(os.path.join(REF_EXPERIMENTS, "torus_li", "markov", "*", "config.yaml")) +
-                   glob.glob(os.path.join(REF_EXPERIMENTS, "plasticity", "ffno*", "*", "config.yaml")))
+                   glob.glob(os.path.join(REF_EXPERIMENTS, "plasticity", "ffno*", "*", "config.yaml")) +
+                   glob.glob(os.path.join(REF_EXPERIMENTS, "plasticity", "fcno", "*", "config.yaml")) +      # DCT siblings
+                   glob.glob(os.path.join(REF_EXPERIMENTS, "torus_kochkov", "fcno", "*", "*", "config.yaml")))
     assert len(paths) >= 4
     seen = 0
     for p in paths:
         raw = C.load_config(p, resolve=False)
         tgt = raw["routine"].get("conv", raw["routine"].get("model", {})).get("_target_", "")
-        if not tgt.startswith("fourierflow.modules.FNOFactorized"):
+        if not tgt.startswith(("fourierflow.modules.FNOFactorized", "fourierflow.modules.CNOFactorized")):
             continue
         routine, _ = C.load_routine(p)
         op = getattr(routine, "conv", None) or routine.model

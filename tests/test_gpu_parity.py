@@ -47,11 +47,12 @@ PATHS = ["generic", "auto"]
 
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name", ["grid2d_c2arch_32", "grid2d_gain1_unshared", "grid2d_ln_w32", "grid2d_fork",
-                                  "grid2d_lowpass", "grid2d_nofourier", "grid2d_nyquist"])
+                                  "grid2d_lowpass", "grid2d_nofourier", "grid2d_nyquist",
+                                  "cno_grid2d_w32", "cno_grid2d_w64"])      # cno_*: the DCT siblings (factorized_cno)
 def test_grid2d_block_golden_per_layer(name, path, monkeypatch):
     monkeypatch.setenv("FFNO_B200_PATH", path)
     kw, sd, a = load(name)
-    m = build("FNOFactorized2DBlock", kw, sd)
+    m = build("CNOFactorized2DBlock" if name.startswith("cno_") else "FNOFactorized2DBlock", kw, sd)
     x = a["x"].cuda()
     with torch.no_grad():
         out = m(x)
@@ -89,7 +90,8 @@ def test_c2_24_layer_stack_golden(path, monkeypatch):
 
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name,cls", [("mesh2d_small", "FNOFactorizedMesh2D"), ("mesh3d_small", "FNOFactorizedMesh3D"),
-                                      ("mesh3d_w64", "FNOFactorizedMesh3D")])
+                                      ("mesh3d_w64", "FNOFactorizedMesh3D"), ("cno_mesh2d_small", "CNOFactorizedMesh2D"),
+                                      ("cno_mesh3d_w64", "CNOFactorizedMesh3D")])
 def test_mesh_blocks_golden(name, cls, path, monkeypatch):
     monkeypatch.setenv("FFNO_B200_PATH", path)
     kw, sd, a = load(name)

@@ -52,6 +52,8 @@ int main(void) {
          sizeof(ffno_layer_params), sizeof(ffno_block_params), sizeof(ffno_taps));
   printf("%zu %zu %zu %zu\n", offsetof(ffno_desc, width), offsetof(ffno_desc, path),
          offsetof(ffno_layer_params, forecast_ff), offsetof(ffno_block_params, layers));
+  printf("%zu %zu %zu %zu %zu %zu\n", offsetof(ffno_desc, transform), sizeof(ffno_rollout_extras), sizeof(ffno_linear_grads),
+         sizeof(ffno_layer_grads), sizeof(ffno_block_grads), offsetof(ffno_block_grads, layers));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -63,7 +65,9 @@ int main(void) {
                                    _lib.BlockParams, _lib.Taps)]
     offs = [_lib.Desc.width.offset, _lib.Desc.path.offset, _lib.LayerParams.forecast_ff.offset,
             _lib.BlockParams.layers.offset]
-    assert [int(v) for v in out] == sizes + offs
+    more = [_lib.Desc.transform.offset, C.sizeof(_lib.RolloutExtras), C.sizeof(_lib.LinearGrads), C.sizeof(_lib.LayerGrads),
+            C.sizeof(_lib.BlockGrads), _lib.BlockGrads.layers.offset]
+    assert [int(v) for v in out] == sizes + offs + more
 
 
 def test_plan_create_fails_loudly_without_a_device(lib):
@@ -120,7 +124,10 @@ def test_seeded_init_matches_reference():
                                       ("grid2d_fork", "FNOFactorized2DBlock"),
                                       ("grid2d_ln_w32", "FNOFactorized2DBlock"),
                                       ("mesh2d_small", "FNOFactorizedMesh2D"),
-                                      ("mesh3d_w64", "FNOFactorizedMesh3D")])
+                                      ("mesh3d_w64", "FNOFactorizedMesh3D"),
+                                      ("cno_grid2d_w64", "CNOFactorized2DBlock"),
+                                      ("cno_mesh2d_small", "CNOFactorizedMesh2D"),
+                                      ("cno_mesh3d_w64", "CNOFactorizedMesh3D")])
 def test_reference_checkpoints_load_strict(name, cls):
     kw, sd, _ = load(name)
     m = _cls(cls)(**kw)
@@ -256,3 +263,19 @@ def test_rollout_feature_set_options():
         exp.accumulate_statistics(data, mu=mu)
     with pytest.raises(RuntimeError, match="must be \\[B\\]"):
         exp.accumulate_statistics(data, force=f, mu=torch.rand(B, 1))
+
+
+def test_cno_mirrors_keep_the_reference_contract():
+    """factorized_cno: real [in, out, modes] weights; shared weights of the mesh variants are 4-D in the reference and
+    cannot run there (mesh_2d.py:118-124 vs :69-72) — the mirrors refuse them at construction; no autograd path."""
+    import fourierflow_b200.modules as M
+    b = M.CNOFactorized2DBlock(modes=5, width=32, input_dim=3, n_layers=2, share_weight=True, factor=4, ff_weight_norm=True)
+    assert [tuple(p.shape) for p in b.fourier_weight] == [(32, 32, 5)] * 2
+    assert b.spectral_layers[1].fourier_weight[0] is b.fourier_weight[0]
+    with pytest.raises(RuntimeError, match="share_weight"):
+        M.CNOFactorizedMesh2D(4, 4, 32, 4, 2, True, 4, True, 2, False)
+    with pytest.raises(RuntimeError, match="share_weight"):
+        M.CNOFactorizedMesh3D(4, 4, 4, 32, 4, 4, 2, True, 4, True, 2, False)
+    from fourierflow_b200.modules.factorized_fno._base import check_trainable
+    with pytest.raises(RuntimeError, match="rfft"):
+        check_trainable(b)

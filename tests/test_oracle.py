@@ -22,7 +22,7 @@ def _grid2d(name):
 
 @pytest.mark.parametrize("name", ["grid2d_c2arch_32", "grid2d_c2_24layers_32", "grid2d_gain1_unshared",
                                   "grid2d_ln_w32", "grid2d_fork", "grid2d_lowpass",
-                                  "grid2d_nofourier", "grid2d_nyquist"])
+                                  "grid2d_nofourier", "grid2d_nyquist", "cno_grid2d_w32", "cno_grid2d_w64"])
 def test_grid2d_block(name):
     kw, a, out, taps = _grid2d(name)
     assert rel_err(out["forecast"], a["forecast"]) < TOL
@@ -37,7 +37,7 @@ def test_grid2d_block(name):
         assert rel_err(taps["s0"], a["tap_s0"]) < TOL
 
 
-@pytest.mark.parametrize("name", ["mesh2d_small", "mesh3d_small", "mesh3d_w64"])
+@pytest.mark.parametrize("name", ["mesh2d_small", "mesh3d_small", "mesh3d_w64", "cno_mesh2d_small", "cno_mesh3d_w64"])
 def test_mesh_block(name):
     kw, sd, a = load(name)
     modes = [kw["modes_x"], kw["modes_y"]] + ([kw["modes_z"]] if "modes_z" in kw else [])
