@@ -204,7 +204,7 @@ class StackPlan:
         d.out_features, d.head_hidden, d.n_layers = out_features, head_hidden, n_layers
         d.ff_factor, d.n_ff_layers, d.layer_norm = ff_factor, n_ff_layers, int(layer_norm)
         d.use_fork, d.spectral_mode, d.path = int(use_fork), _lib.MODE[mode], _lib.PATH[path]
-        d.transform = {"rfft": 0, "dct": 1}[transform]      # ffno_transform
+        d.transform = {"rfft": 0, "dct": 1, "rfft2": 2}[transform]      # ffno_transform
         self.desc = d
         self.ext = [int(size[a]) + int(pad[a]) for a in range(len(size))]
         self.size = [int(s) for s in size]

@@ -575,6 +575,33 @@ int launch_pack_mix_weights_dct(const float* w, float* Wblk, int C, int Kpairs, 
   return FFNO_OK;
 }
 
+__global__ void __launch_bounds__(256)
+c2c_combine_kernel(const float4* __restrict__ Y, float4* __restrict__ out, long long n4, long long row4, int R, int c4, float sgn) {
+  // n4 = outer * R * q * 2 * c4 float4 outputs; row4 = q * 2 * c4 float4 per (o, r) row
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n4) return;
+  const long long within = idx % row4, orow = idx / row4;          // orow = o * R + r
+  const long long o = orow / R, r = orow % R;
+  const int ri = (int)((within / c4) & 1);
+  const long long base = (o * 2 * R + r) * row4;
+  const float4 c = Y[base + within];
+  const float4 sn = Y[base + (long long)R * row4 + (ri ? within - c4 : within + c4)];     // sine sums of the OTHER part
+  const float f = ri ? -sgn : sgn;
+  out[idx] = make_float4(fmaf(f, sn.x, c.x), fmaf(f, sn.y, c.y), fmaf(f, sn.z, c.z), fmaf(f, sn.w, c.w));
+}
+
+int launch_c2c_combine(const float* Y, float* out, long long outer, int R, long long q, int C, float sgn, cudaStream_t st) {
+  FFNO_REQUIRE(C % 4 == 0, FFNO_ERR_UNSUPPORTED, "c2c combine: width %d not a multiple of 4", C);
+  const int c4 = C / 4;
+  const long long row4 = q * 2 * c4, n4 = outer * R * row4;
+  if (n4 == 0) return FFNO_OK;
+  c2c_combine_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(Y), reinterpret_cast<float4*>(out), n4,
+                                                        row4, R, c4, sgn);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("c2c_combine_kernel");
+  return FFNO_OK;
+}
+
 int launch_pack_mix_weights(const float* w, float* Wblk, int C, int K, cudaStream_t st) {
   long long total = (long long)K * 4 * C * C;
   if (total == 0) return FFNO_OK;

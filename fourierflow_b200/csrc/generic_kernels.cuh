@@ -57,6 +57,13 @@ int launch_pack_mix_weights(const float* w, float* Wblk, int C, int K, cudaStrea
 // DCT variant: real weights [Cin][Cout][Kc] -> block-diagonal pair matrices Wblk[k][2C][2C] = diag(W_2k, W_2k+1)
 int launch_pack_mix_weights_dct(const float* w, float* Wblk, int C, int Kpairs, int Kc, cudaStream_t st);
 
+// Complex-to-complex DFT along an axis as TWO real table products + this combine: Y[o][2R][q][2][C] holds, for each of the
+// R output rows, the cosine sums (rows 0..R-1) and the sine sums (rows R..2R-1) of the (Re, Im) input pairs;
+//   out[o][r][q][0][c] = Yc[..0..] + sgn * Ys[..1..],   out[o][r][q][1][c] = Yc[..1..] - sgn * Ys[..0..]
+// sgn = +1: multiply by e^{-i theta} (forward), -1: by e^{+i theta} (inverse).  (torch.fft.rfft2 / irfft2 along dim -2,
+// zongyi_fno/grid_plus_2d.py:57,78.)
+int launch_c2c_combine(const float* Y, float* out, long long outer, int R, long long q, int C, float sgn, cudaStream_t st);
+
 // Weff[j][c] = sum_h W1t[h][j] * W0t[c][h];  beff[j] = sum_h W1t[h][j]*b0[h] + b1[j]   (fp64 accumulate)
 int launch_fold_head(const float* W0t /*[C][H]*/, const float* b0, const float* W1t /*[H][out]*/,
                      const float* b1, float* Weff, float* beff, int C, int H, int out, cudaStream_t st);

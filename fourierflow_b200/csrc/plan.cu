@@ -170,8 +170,37 @@ int pad16(int n) { return (n + 15) / 16 * 16; }
 //   inverse  T[2k][l]   =  c_k cos(..) / sqrt(L),        T[2k+1][l] = -c_k sin(..) / sqrt(L)
 // c_0 = 1, c_k = 2 (Hermitian half), c_{L/2} = 1 for even L; sin(0) = sin(pi l) = 0 drops Im(DC), Im(Nyquist)
 // exactly as the C2R transform at grid_2d.py:72 does.
+// FFNO_TRANSFORM_RFFT2, row axis (complex-to-complex over the 2K retained rows kx = 0..K-1, L-K..L-1): cosine and sine
+// tables side by side, combined by launch_c2c_combine.   forward [L][4K]: T[l][j] = cos(th_jl)/sqrt(L), T[l][2K + j] = sin;
+// inverse [2K][2L]: T[j][l] = cos(th_jl)/sqrt(L), T[j][L + l] = sin, th_jl = 2 pi kx_j l / L.
+int build_c2c_tables(ffno_plan* p) {
+  const int L = p->ext[0], K = p->d.modes[0], R = 2 * K;
+  const int ldf = pad16(2 * R), ldi = pad16(2 * L);
+  std::vector<float> f((size_t)L * ldf, 0.f), inv((size_t)R * ldi, 0.f);
+  const double s = 1.0 / std::sqrt((double)L);
+  for (int l = 0; l < L; ++l)
+    for (int j = 0; j < R; ++j) {
+      const int kx = j < K ? j : L - R + j;
+      const double ang = 2.0 * M_PI * (double)(((long long)kx * l) % L) / (double)L;
+      const double c = std::cos(ang) * s, sn = std::sin(ang) * s;
+      f[(size_t)l * ldf + j] = (float)c;
+      f[(size_t)l * ldf + R + j] = (float)sn;
+      inv[(size_t)j * ldi + l] = (float)c;
+      inv[(size_t)j * ldi + L + l] = (float)sn;
+    }
+  FFNO_TRY(dev_alloc(p, f.size() * 4, &p->d_fwd[0]));
+  FFNO_TRY(dev_alloc(p, inv.size() * 4, &p->d_inv[0]));
+  FFNO_CUDA_CHECK(cudaMemcpy(p->d_fwd[0], f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+  FFNO_CUDA_CHECK(cudaMemcpy(p->d_inv[0], inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+  return FFNO_OK;
+}
+
 int build_tables(ffno_plan* p) {
   for (int a = 0; a < p->d.ndim; ++a) {
+    if (p->d.transform == FFNO_TRANSFORM_RFFT2 && a == 0) {
+      FFNO_TRY(build_c2c_tables(p));
+      continue;
+    }
     const int L = p->ext[a], K = p->d.modes[a];
     const int ldf = pad16(2 * K), ldi = pad16(L);
     std::vector<float> f((size_t)L * ldf, 0.f), inv((size_t)2 * K * ldi, 0.f);
@@ -235,10 +264,19 @@ int validate_desc(const ffno_desc* d) {
                "in_features=%d out_features=%d", d->in_features, d->out_features);
   FFNO_REQUIRE(d->head_hidden >= 1, FFNO_ERR_BAD_ARG, "head_hidden=%d", d->head_hidden);
   FFNO_REQUIRE(d->spectral_mode >= 0 && d->spectral_mode <= 2, FFNO_ERR_BAD_ARG, "spectral_mode=%d", d->spectral_mode);
-  FFNO_REQUIRE(d->transform == FFNO_TRANSFORM_RFFT || d->transform == FFNO_TRANSFORM_DCT, FFNO_ERR_BAD_ARG,
+  FFNO_REQUIRE(d->transform >= FFNO_TRANSFORM_RFFT && d->transform <= FFNO_TRANSFORM_RFFT2, FFNO_ERR_BAD_ARG,
                "transform=%d", d->transform);
-  FFNO_REQUIRE(d->transform == FFNO_TRANSFORM_RFFT || d->spectral_mode == FFNO_MODE_FULL, FFNO_ERR_UNSUPPORTED,
+  FFNO_REQUIRE(d->transform != FFNO_TRANSFORM_DCT || d->spectral_mode == FFNO_MODE_FULL, FFNO_ERR_UNSUPPORTED,
                "the DCT variant has no low-pass / no-fourier mode");
+  if (d->transform == FFNO_TRANSFORM_RFFT2) {
+    // zongyi_fno/grid_plus_2d.py:52-83: one mode count for both axes; 'low-pass' is a bare `raise` there (:74-75)
+    FFNO_REQUIRE(d->ndim == 2, FFNO_ERR_UNSUPPORTED, "the rfft2 (FNOPlus2DBlock) variant is 2-D, ndim=%d", d->ndim);
+    FFNO_REQUIRE(d->spectral_mode != FFNO_MODE_LOW_PASS, FFNO_ERR_UNSUPPORTED, "the rfft2 variant has no low-pass mode");
+    FFNO_REQUIRE(d->modes[0] == d->modes[1], FFNO_ERR_BAD_ARG, "rfft2: modes %d != %d", d->modes[0], d->modes[1]);
+    FFNO_REQUIRE(2 * d->modes[0] <= d->size[0] + d->pad[0], FFNO_ERR_BAD_ARG,
+                 "rfft2: the two %d-row blocks overlap on a %d-row grid", d->modes[0], d->size[0] + d->pad[0]);
+    FFNO_REQUIRE(d->path != FFNO_PATH_UMMA, FFNO_ERR_UNSUPPORTED, "the rfft2 variant runs on the FP32 kernels only");
+  }
   for (int a = 0; a < d->ndim; ++a) {
     FFNO_REQUIRE(d->size[a] >= 1 && d->pad[a] >= 0, FFNO_ERR_BAD_ARG, "size[%d]=%d pad=%d", a, d->size[a], d->pad[a]);
     int L = d->size[a] + d->pad[a];
@@ -322,6 +360,8 @@ Workspace carve(const ffno_plan* p, int batch, void* base) {
   for (int a = 0; a < p->d.ndim; ++a) {
     spec += U / p->ext[a] * 2 * p->d.modes[a];     // every axis' spectra live side by side
   }
+  if (p->d.transform == FFNO_TRANSFORM_RFFT2)       // largest intermediate: cos | sin sums of the inverse row transform
+    spec = (size_t)batch * 2 * p->ext[0] * 2 * p->d.modes[1] * p->d.width;
   w.F = c.take(spec);
   w.R = c.take(spec);
   if (!p->use_umma || p->d.n_ff_layers != 2) {
@@ -338,8 +378,23 @@ Workspace carve(const ffno_plan* p, int batch, void* base) {
 }
 
 // ---- generic forward pieces ---------------------------------------------------------------------------
+// rfft2 -> two K x K corner blocks -> per-(kx, ky) channel mix -> irfft2 (zongyi_fno/grid_plus_2d.py:52-83) as 1-D passes:
+// real DFT along the columns (the F-FNO table), complex DFT along the rows (cos | sin tables + combine), and back.
+int spectral_rfft2(ffno_plan* p, const LayerW& lw, const float* x, int batch, float* s, float* F, float* R, cudaStream_t st) {
+  const int C = p->d.width, M = p->ext[0], N = p->ext[1], K = p->d.modes[1], Rr = 2 * K;
+  const long long row = (long long)2 * K * C;                                        // one (ky, ri, c) row of spectra
+  FFNO_TRY(launch_axis_transform(x, p->d_fwd[1], F, (long long)batch * M, N, 2 * K, C, false, st));       // F: [B][M][K][2][C]
+  FFNO_TRY(launch_axis_transform(F, p->d_fwd[0], R, batch, M, 2 * Rr, row, false, st));                    // R: [B][4K][K][2][C]
+  FFNO_TRY(launch_c2c_combine(R, F, batch, Rr, K, C, 1.f, st));                                            // F: [B][2K][K][2][C]
+  FFNO_TRY(launch_mode_mix(F, lw.wmix[0], R, batch, Rr * K, 1, C, st));                                    // R: same layout
+  FFNO_TRY(launch_axis_transform(R, p->d_inv[0], F, batch, Rr, 2 * M, row, false, st));                    // F: [B][2M][K][2][C]
+  FFNO_TRY(launch_c2c_combine(F, R, batch, M, K, C, -1.f, st));                                            // R: [B][M][K][2][C]
+  return launch_axis_transform(R, p->d_inv[1], s, (long long)batch * M, 2 * K, N, C, false, st);
+}
+
 int spectral_generic(ffno_plan* p, const LayerW& lw, const float* x, int batch, float* s, float* F, float* R,
                      cudaStream_t st) {
+  if (p->d.transform == FFNO_TRANSFORM_RFFT2) return spectral_rfft2(p, lw, x, batch, s, F, R, st);
   const int C = p->d.width;
   bool first = true;
   for (int a = p->d.ndim - 1; a >= 0; --a) {     // reference order: last axis first (grid_2d.py:57,75)
@@ -718,7 +773,7 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
   p->layers.resize(desc->n_layers);
   int st = build_tables(p);
   if (st == FFNO_OK) {
-    const bool ok = umma_supported(&p->d, p->ext);
+    const bool ok = umma_supported(&p->d, p->ext) && desc->transform != FFNO_TRANSFORM_RFFT2;
     if (desc->path == FFNO_PATH_UMMA && !ok)
       st = set_error(FFNO_ERR_UNSUPPORTED, "shape does not qualify for the tcgen05 path: %s", umma_why_not(&p->d, p->ext));
     p->use_umma = ok && desc->path != FFNO_PATH_GENERIC;
@@ -781,7 +836,26 @@ int ffno_plan_load_params(ffno_plan* p, const ffno_block_params* prm, void* stre
   for (int l = 0; l < p->d.n_layers; ++l) {
     const ffno_layer_params& src = prm->layers[l];
     LayerW& dst = p->layers[l];
-    if (p->d.spectral_mode == FFNO_MODE_FULL) {
+    if (p->d.spectral_mode == FFNO_MODE_FULL && p->d.transform == FFNO_TRANSFORM_RFFT2) {
+      // [C][C][K][K][2] x 2 (low / high row block) -> Wblk[(row j, column ky)][2C][2C], rows j = 0..2K-1
+      const int K = p->d.modes[0];
+      const float* w0 = src.fourier_weight[0];
+      const float* w1 = src.fourier_weight[1];
+      FFNO_REQUIRE(w0 && w1, FFNO_ERR_BAD_ARG, "layer %d: fourier_weight[0/1] is NULL", l);
+      const size_t half = (size_t)K * K * 4 * C * C;
+      const void* key = (const void*)w0;
+      auto it = seen_mix.find(key);
+      if (it != seen_mix.end()) {
+        dst.wmix[0] = it->second;
+      } else {
+        float*& slot = p->dedup[(const void*)((uintptr_t)(l * 4 + 1))];
+        if (!slot) FFNO_TRY(dev_alloc(p, 2 * half * 4, &slot));
+        FFNO_TRY(launch_pack_mix_weights(w0, slot, C, K * K, st));
+        FFNO_TRY(launch_pack_mix_weights(w1, slot + half, C, K * K, st));
+        dst.wmix[0] = slot;
+        seen_mix[key] = slot;
+      }
+    } else if (p->d.spectral_mode == FFNO_MODE_FULL) {
       for (int a = 0; a < p->d.ndim; ++a) {
         const float* wsrc = src.fourier_weight[a];
         FFNO_REQUIRE(wsrc != nullptr, FFNO_ERR_BAD_ARG, "layer %d: fourier_weight[%d] is NULL", l, a);

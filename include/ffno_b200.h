@@ -57,9 +57,13 @@ typedef enum {                /* SpectralConv2d `mode`, grid_2d.py:44,64,69 */
 
 typedef enum {                /* per-axis transform of the spectral layer */
   FFNO_TRANSFORM_RFFT = 0,    /* F-FNO: ortho rfft, K complex bins kept, complex channel mix (factorized_fno/*.py) */
-  FFNO_TRANSFORM_DCT = 1      /* factorized CNO sibling: ortho DCT-II, first K coefficients kept, REAL channel mix,
+  FFNO_TRANSFORM_DCT = 1,     /* factorized CNO sibling: ortho DCT-II, first K coefficients kept, REAL channel mix,
                                  inverse DCT-III (factorized_cno/mesh_3d.py:55-112, modules/dct.py:16-88);
                                  fourier_weight is [C, C, K_a] */
+  FFNO_TRANSFORM_RFFT2 = 2    /* un-factorized sibling FNOPlus2DBlock (zongyi_fno/grid_plus_2d.py:52-83): ortho rfft2, the
+                                 two K x K corner blocks (rows 0..K-1 and M-K..M-1, columns 0..K-1) mixed per 2-D mode,
+                                 irfft2.  2-D only, modes[0] == modes[1] == K, 2K <= size[0]; fourier_weight[0] / [1] are
+                                 the [C, C, K, K, 2] weights of the low / high row block; FP32 kernels only */
 } ffno_transform;
 
 typedef enum {                /* which implementation a plan may use */

@@ -139,6 +139,20 @@ def forward_fourier_grid2d(x: torch.Tensor, w0: torch.Tensor, w1: torch.Tensor, 
     return xx + xy
 
 
+def forward_fourier_plus2d(x: torch.Tensor, w0: torch.Tensor, w1: torch.Tensor, n_modes: int) -> torch.Tensor:
+    """``SpectralConv2d.forward_fourier`` of the un-factorized sibling (FNOPlus2DBlock), x:[B,M,N,C] channels-last:
+    rfft2(ortho) -> rows ``:K`` x columns ``:K`` mixed with ``w0``, rows ``-K:`` x columns ``:K`` with ``w1`` (both
+    [in, out, K, K, 2]) -> everything else zero -> irfft2(s=(M, N), ortho).
+    Reference: fourierflow/modules/zongyi_fno/grid_plus_2d.py:52-83."""
+    B, M, N, C = x.shape
+    K = n_modes
+    x_ft = torch.fft.rfft2(x, s=(M, N), dim=(1, 2), norm="ortho")              # [B, M, N/2+1, C]
+    out_ft = torch.zeros_like(x_ft)
+    out_ft[:, :K, :K] = torch.einsum("bxyi,ioxy->bxyo", x_ft[:, :K, :K], torch.view_as_complex(w0.contiguous()))
+    out_ft[:, -K:, :K] = torch.einsum("bxyi,ioxy->bxyo", x_ft[:, -K:, :K], torch.view_as_complex(w1.contiguous()))
+    return torch.fft.irfft2(out_ft, s=(M, N), dim=(1, 2), norm="ortho")
+
+
 def forward_fourier_mesh(x: torch.Tensor, ws: Sequence[torch.Tensor], modes: Sequence[int],
                          mode: str = "full") -> torch.Tensor:
     """``forward_fourier`` of the mesh variants: ``fourier_weight[a]`` acts on spatial axis ``a``
@@ -192,7 +206,10 @@ def block_grid2d_forward(p: Params, x: torch.Tensor, *, modes: int, n_layers: in
         s = x
         if mode != "no-fourier":                         # :44-45
             w0, w1 = _layer_weights(p, l, 2)
-            s = forward_fourier_grid2d(x, w0, w1, modes, mode)
+            if w0.dim() == 5:                            # [in, out, K, K, 2]: the un-factorized FNOPlus2DBlock
+                s = forward_fourier_plus2d(x, w0, w1, modes)
+            else:
+                s = forward_fourier_grid2d(x, w0, w1, modes, mode)
         bb = feed_forward(p, f"spectral_layers.{l}.backcast_ff.", s, n_ff_layers, layer_norm)
         if use_fork:                                     # :48, :164-167
             f = feed_forward(p, f"spectral_layers.{l}.forecast_ff.", s, n_ff_layers, layer_norm)
@@ -205,6 +222,18 @@ def block_grid2d_forward(p: Params, x: torch.Tensor, *, modes: int, n_layers: in
     if not use_fork:
         forecast = _head(p, bb)                          # :171-172 — head on last b, not on x
     return {"forecast": forecast, "forecast_list": forecast_list}
+
+
+def geo_interior_forward(p: Params, uc: torch.Tensor, grid_bias: torch.Tensor, *, modes: int,
+                         n_layers: int) -> torch.Tensor:
+    """Interior of the geo-F-FNO (``FNOFactorizedPointCloud2D``): for i = 1 .. n_layers-1, on the channels-last latent
+    grid, ``uc = uc + backcast_ff_i(forward_fourier_i(uc)) + bs[0](grid)``; the interior layers are the periodic-grid
+    SpectralConv2d with factor 2.  Reference: factorized_fno/point_cloud_2d.py:198-210 (layers built at :170-183)."""
+    for i in range(1, n_layers):
+        w0, w1 = p[f"convs.{i}.fourier_weight.0"], p[f"convs.{i}.fourier_weight.1"]
+        s = forward_fourier_grid2d(uc, w0, w1, modes)
+        uc = uc + feed_forward(p, f"convs.{i}.backcast_ff.", s) + grid_bias
+    return uc
 
 
 def mesh_grid_features(shape: Sequence[int], dtype=torch.float32) -> torch.Tensor:

@@ -273,6 +273,49 @@ def cno_cases():
               n_ff_layers=2, layer_norm=False), (1, 8, 8, 8, 1), seed=33)
 
 
+def geo_case(M, name, kwargs, B, N, seed):
+    """FNOFactorizedPointCloud2D on a random point cloud, iphi=None: the full forward, and the latent grid before /
+    after the interior layers (point_cloud_2d.py:198-210) replayed with the module's own sub-modules."""
+    from einops import rearrange
+    torch.manual_seed(seed)
+    m = M.FNOFactorizedPointCloud2D(**kwargs).eval()
+    perturb_(m, seed + 100)
+    g = torch.Generator().manual_seed(seed + 1)
+    u = torch.rand(B, N, 2, generator=g)
+    arrays = {"sd::" + k: (torch.view_as_real(v) if v.is_complex() else v).detach().numpy()
+              for k, v in m.state_dict().items()
+              if not (kwargs.get("share_weight") and re.match(r"convs\.\d+\.fourier_weight\.\d+$", k))}
+    with torch.no_grad():
+        arrays["u"] = u.numpy()
+        arrays["out"] = m(u).numpy()
+        grid = m.get_grid([B, m.s1, m.s2], u.device).permute(0, 3, 1, 2)
+        v = m.fc0(u).permute(0, 2, 1)
+        uc = m.convs[0](v, x_in=u, iphi=None, code=None, transform=False) + m.bs[0](grid)
+        arrays["uc_in"] = rearrange(uc, "b c h w -> b h w c").contiguous().numpy()
+        arrays["grid_bias"] = m.bs[0](grid)[0].permute(1, 2, 0).contiguous().numpy()
+        for i in range(1, m.n_layers):
+            uc1 = rearrange(m.convs[i](rearrange(uc, "b c h w -> b h w c"))[0], "b h w c -> b c h w")
+            uc = uc + uc1 + m.bs[0](grid)
+        arrays["uc_out"] = rearrange(uc, "b c h w -> b h w c").contiguous().numpy()
+    save(name, kwargs, arrays)
+
+
+def geo_cases(M):
+    geo_case(M, "geo_pointcloud_w32", dict(modes1=4, modes2=4, width=32, in_channels=2, out_channels=1, n_layers=4,
+             s1=12, s2=10, share_weight=False), B=2, N=40, seed=40)
+    geo_case(M, "geo_pointcloud_shared", dict(modes1=6, modes2=5, width=32, in_channels=2, out_channels=1,
+             n_layers=3, s1=14, s2=12, share_weight=True), B=1, N=60, seed=41)
+
+
+def plus_cases(M):
+    """FNOPlus2DBlock (zongyi_fno/grid_plus_2d.py): un-factorized rfft2 spectral layer inside the F-FNO block structure."""
+    grid2d_case(M, "plus2d_w32", dict(modes=4, width=32, n_layers=2, input_dim=3, share_weight=False, factor=4,
+                ff_weight_norm=True, gain=1), (2, 12, 10, 3), seed=50, cls="FNOPlus2DBlock")
+    grid2d_case(M, "plus2d_shared_fork", dict(modes=3, width=16, n_layers=3, input_dim=2, share_weight=True,
+                share_fork=True, use_fork=True, factor=2, ff_weight_norm=True, gain=0.5), (1, 6, 9, 2), seed=51,
+                cls="FNOPlus2DBlock")
+
+
 def init_case(M):
     """Seeded-construction checksums: the mirrors must draw the same random numbers in the same order."""
     cases = {
@@ -339,6 +382,12 @@ def main():
     if "--only-mesh-grad" in sys.argv:
         mesh_grad_cases(M, LpLoss)
         return
+    if "--only-plus" in sys.argv:
+        plus_cases(M)
+        return
+    if "--only-geo" in sys.argv:
+        geo_cases(M)
+        return
     if "--only-cno" in sys.argv:
         cno_cases()
         return
@@ -389,6 +438,10 @@ def main():
     rollout_extras_cases(M, LpLoss, c2)
     # (10c) the factorized cosine (DCT) siblings
     cno_cases()
+    # (10d) geo-F-FNO on point clouds (interior layers = the hot path)
+    geo_cases(M)
+    # (10e) the un-factorized sibling
+    plus_cases(M)
     # (11) gradients of the one-step training loss (backward row)
     grad_cases(M, LpLoss)
 

@@ -34,3 +34,17 @@ def rel_err(y, ref):
     """max|y-ref| / max|ref| — the parity metric of SURVEY.md §8(c)."""
     y, ref = y.detach().double().cpu(), ref.detach().double().cpu()
     return ((y - ref).abs().max() / ref.abs().max().clamp(min=1e-30)).item()
+
+
+def load_geo(name):
+    """geo_* fixtures (FNOFactorizedPointCloud2D): complex weights stored as view_as_real, shared-weight aliases
+    ``convs.{i}.fourier_weight.{a}`` re-created."""
+    kw, sd, arrays = load(name)
+    for k in list(sd):
+        if re.match(r"convs\.\d+\.weights[12]$", k):
+            sd[k] = torch.view_as_complex(sd[k].contiguous())
+    if "fourier_weight.0" in sd:
+        for i in range(1, kw["n_layers"]):
+            for a in range(2):
+                sd[f"convs.{i}.fourier_weight.{a}"] = sd[f"fourier_weight.{a}"]
+    return kw, sd, arrays

@@ -11,7 +11,7 @@ import os
 import pytest
 import torch
 
-from golden_util import load, rel_err
+from golden_util import load, load_geo, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -48,11 +48,13 @@ PATHS = ["generic", "auto"]
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name", ["grid2d_c2arch_32", "grid2d_gain1_unshared", "grid2d_ln_w32", "grid2d_fork",
                                   "grid2d_lowpass", "grid2d_nofourier", "grid2d_nyquist",
-                                  "cno_grid2d_w32", "cno_grid2d_w64"])      # cno_*: the DCT siblings (factorized_cno)
+                                  "cno_grid2d_w32", "cno_grid2d_w64",       # cno_*: the DCT siblings (factorized_cno)
+                                  "plus2d_w32", "plus2d_shared_fork"])      # plus2d_*: un-factorized FNOPlus2DBlock
 def test_grid2d_block_golden_per_layer(name, path, monkeypatch):
     monkeypatch.setenv("FFNO_B200_PATH", path)
     kw, sd, a = load(name)
-    m = build("CNOFactorized2DBlock" if name.startswith("cno_") else "FNOFactorized2DBlock", kw, sd)
+    cls = {"cno": "CNOFactorized2DBlock", "plus2d": "FNOPlus2DBlock"}.get(name.split("_")[0], "FNOFactorized2DBlock")
+    m = build(cls, kw, sd)
     x = a["x"].cuda()
     with torch.no_grad():
         out = m(x)
@@ -464,3 +466,21 @@ def test_spectral_split_sums_to_forward_fourier():
         whole = plan.spectral_forward(0, x)
     assert len(parts) == 2
     assert rel_err(parts[0] + parts[1], whole) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["geo_pointcloud_w32", "geo_pointcloud_shared"])
+def test_geo_ffno_pointcloud_golden(name):
+    """FNOFactorizedPointCloud2D (geo-F-FNO): the interior layers (point_cloud_2d.py:198-210) on the CUDA kernels against
+    the executed reference's latent grids, and the whole forward (torch end layers + CUDA interior) against its output."""
+    kw, sd, a = load_geo(name)
+    m = M().FNOFactorizedPointCloud2D(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        uc = m.interior_forward(a["uc_in"].cuda(), a["grid_bias"].cuda())
+        out = m(a["u"].cuda())
+    e_int, e_out = rel_err(uc, a["uc_out"]), rel_err(out, a["out"])
+    print(name, f"interior {e_int:.2e} forward {e_out:.2e}")
+    assert e_int < TOL_GENERIC and e_out < 2e-5
+    with pytest.raises(RuntimeError):
+        m(a["u"].cuda().requires_grad_())

@@ -126,6 +126,8 @@ def test_seeded_init_matches_reference():
                                       ("mesh2d_small", "FNOFactorizedMesh2D"),
                                       ("mesh3d_w64", "FNOFactorizedMesh3D"),
                                       ("cno_grid2d_w64", "CNOFactorized2DBlock"),
+                                      ("plus2d_w32", "FNOPlus2DBlock"),
+                                      ("plus2d_shared_fork", "FNOPlus2DBlock"),
                                       ("cno_mesh2d_small", "CNOFactorizedMesh2D"),
                                       ("cno_mesh3d_w64", "CNOFactorizedMesh3D")])
 def test_reference_checkpoints_load_strict(name, cls):
@@ -279,3 +281,18 @@ def test_cno_mirrors_keep_the_reference_contract():
     from fourierflow_b200.modules.factorized_fno._base import check_trainable
     with pytest.raises(RuntimeError, match="rfft"):
         check_trainable(b)
+
+
+@pytest.mark.parametrize("name", ["geo_pointcloud_w32", "geo_pointcloud_shared"])
+def test_geo_mirror_loads_reference_checkpoints_strict(name):
+    from golden_util import load_geo
+    import fourierflow_b200.modules as M
+    kw, sd, _ = load_geo(name)
+    m = M.FNOFactorizedPointCloud2D(**kw)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert m.convs[m.n_layers].weights1.dtype == torch.cfloat and not hasattr(m.convs[0], "weights1")
+    if kw["share_weight"]:
+        assert m.convs[1].fourier_weight[0] is m.fourier_weight[0]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.rand(1, 8, 2))

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import load, rel_err
+from golden_util import load, load_geo, rel_err
 from oracle import ffno_oracle as O
 
 TOL = 2e-6   # same torch CPU kernels in (almost) the same order; reference fp32 self-noise ~5e-7
@@ -22,7 +22,8 @@ def _grid2d(name):
 
 @pytest.mark.parametrize("name", ["grid2d_c2arch_32", "grid2d_c2_24layers_32", "grid2d_gain1_unshared",
                                   "grid2d_ln_w32", "grid2d_fork", "grid2d_lowpass",
-                                  "grid2d_nofourier", "grid2d_nyquist", "cno_grid2d_w32", "cno_grid2d_w64"])
+                                  "grid2d_nofourier", "grid2d_nyquist", "cno_grid2d_w32", "cno_grid2d_w64",
+                                  "plus2d_w32", "plus2d_shared_fork"])
 def test_grid2d_block(name):
     kw, a, out, taps = _grid2d(name)
     assert rel_err(out["forecast"], a["forecast"]) < TOL
@@ -45,6 +46,14 @@ def test_mesh_block(name):
                                n_ff_layers=kw["n_ff_layers"], layer_norm=kw["layer_norm"])
     assert out.shape == a["out"].shape
     assert rel_err(out, a["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["geo_pointcloud_w32", "geo_pointcloud_shared"])
+def test_geo_interior(name):
+    """Interior layers of the geo-F-FNO (point_cloud_2d.py:198-210) against the executed reference's latent grids."""
+    kw, sd, a = load_geo(name)
+    uc = O.geo_interior_forward(sd, a["uc_in"], a["grid_bias"], modes=kw["modes1"], n_layers=kw["n_layers"])
+    assert rel_err(uc, a["uc_out"]) < TOL
 
 
 def test_spectral_layer_c2_shape():
