@@ -73,6 +73,7 @@ struct ffno_plan {
   long long pts_in = 0;            // input points per sample
   int in_total = 0;                // in_features + appended grid channels
   bool use_umma = false;
+  bool ff_umma = false;      // FFNO_TRANSFORM_RFFT2: spectral layer on the FP32 kernels, FeedForward on ff_ts_kernel
   float* d_fwd[3] = {nullptr, nullptr, nullptr};   // [L][ld(2K)]
   float* d_inv[3] = {nullptr, nullptr, nullptr};   // [2K][ld(L)]
   float* d_fwdT[3] = {nullptr, nullptr, nullptr};  // [2K][ld(L)]: transpose of d_fwd — adjoint of the forward transform
@@ -498,7 +499,8 @@ int block_fwd_core(ffno_plan* p, const float* x, int batch, float* forecast, con
         FFNO_TRY(spectral_generic(p, lw, cur, batch, w.s, w.F, w.R, st));
         s = w.s;
       }
-      FFNO_TRY(ff_generic(p, lw.back, s, cur, P, nxt, w.b, w, st));
+      if (p->ff_umma) FFNO_TRY(umma_ff_layer(p->umma, l, s, cur, batch, nxt, (last || taps) ? w.b : nullptr, st));
+      else FFNO_TRY(ff_generic(p, lw.back, s, cur, P, nxt, w.b, w, st));
     }
     if (p->d.use_fork) {
       const float* s = (p->d.spectral_mode != FFNO_MODE_NO_FOURIER) ? w.s : cur;
@@ -778,6 +780,13 @@ int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan) {
       st = set_error(FFNO_ERR_UNSUPPORTED, "shape does not qualify for the tcgen05 path: %s", umma_why_not(&p->d, p->ext));
     p->use_umma = ok && desc->path != FFNO_PATH_GENERIC;
     if (st == FFNO_OK && p->use_umma) st = umma_create(&p->umma, &p->d, p->ext);
+    // rfft2 plans: only the FeedForward (width 64 -> 256 -> 64, the block's other half) qualifies for tcgen05
+    p->ff_umma = desc->transform == FFNO_TRANSFORM_RFFT2 && desc->path != FFNO_PATH_GENERIC && umma_supported(&p->d, p->ext) &&
+                 ffno_device_ok() == 1;
+    if (st == FFNO_OK && p->ff_umma) {
+      st = umma_create(&p->umma, &p->d, p->ext);
+      if (st == FFNO_OK) umma_set_ff_only(p->umma);
+    }
   }
   if (st == FFNO_OK) st = create_chunk_streams(p);
   if (st != FFNO_OK) {
@@ -807,7 +816,7 @@ int ffno_plan_destroy(ffno_plan* plan) {
   return FFNO_OK;
 }
 
-int ffno_plan_uses_umma(const ffno_plan* plan) { return plan && plan->use_umma ? 1 : 0; }
+int ffno_plan_uses_umma(const ffno_plan* plan) { return plan && (plan->use_umma || plan->ff_umma) ? 1 : 0; }
 
 int ffno_plan_load_params(ffno_plan* p, const ffno_block_params* prm, void* stream) {
   FFNO_REQUIRE(p && prm, FFNO_ERR_BAD_ARG, "plan/params is NULL");
@@ -887,7 +896,7 @@ int ffno_plan_load_params(ffno_plan* p, const ffno_block_params* prm, void* stre
       else { FFNO_TRY(prep_ff(p, src.forecast_ff, &dst.fork, st)); seen_ff_fork[key] = l; }
     }
   }
-  if (p->use_umma) {
+  if (p->use_umma || p->ff_umma) {
     std::vector<UmmaLayerSrc> srcs(p->d.n_layers);
     for (int l = 0; l < p->d.n_layers; ++l) {
       for (int a = 0; a < 3; ++a) srcs[l].wmix[a] = p->layers[l].wmix[a];
@@ -1004,7 +1013,7 @@ int ffno_ff_fwd(ffno_plan* p, int32_t layer, int32_t which, const float* s, cons
   const long long P = (long long)batch * p->pts;
   if (batch == 0) return FFNO_OK;
   const FFW& ff = which == 0 ? p->layers[layer].back : p->layers[layer].fork;
-  if (p->use_umma && which == 0 && p->d.n_ff_layers == 2 && !p->d.layer_norm)
+  if ((p->use_umma || p->ff_umma) && which == 0 && p->d.n_ff_layers == 2 && !p->d.layer_norm)
     return umma_ff_fwd(p->umma, layer, s, residual, batch, y, w.umma, st);
   if (residual) return ff_generic(p, ff, s, residual, P, y, nullptr, w, st);
   return ff_generic(p, ff, s, nullptr, P, nullptr, y, w, st);

@@ -34,6 +34,7 @@ struct UmmaState {
   float* d_fwd[3] = {nullptr, nullptr, nullptr};
   float* d_inv[3] = {nullptr, nullptr, nullptr};
   bool zigzag = true;                                    // FFNO_ZIGZAG=0: every kernel walks its tiles first-to-last
+  bool ff_only = false;                                  // only the FeedForward runs here (FFNO_TRANSFORM_RFFT2 plans)
   uint8_t* fwd_image[3] = {nullptr, nullptr, nullptr};   // tcgen05 table images (NULL -> FP32 table kernel)
   uint8_t* inv_image[3] = {nullptr, nullptr, nullptr};
   // stage-pipelined forward (launch_stack_pipe): FFNO_B200_PERSIST=1 turns it on, FFNO_B200_PIPE_SMS=f,m,i,ff sets
@@ -99,6 +100,8 @@ int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]) {
   return FFNO_OK;
 }
 
+void umma_set_ff_only(UmmaState* s) { s->ff_only = true; }
+
 void umma_set_sm_limit(UmmaState* s, int n) {
   s->sm_count = (n >= 1 && n < s->hw_sm_count) ? n : s->hw_sm_count;
 }
@@ -125,7 +128,7 @@ static int alloc_bytes(UmmaState* s, size_t bytes, uint8_t** out) {
 int umma_load_params(UmmaState* s, const UmmaLayerSrc* layers, float* const d_fwd[3], float* const d_inv[3],
                      cudaStream_t st) {
   for (int a = 0; a < 3; ++a) { s->d_fwd[a] = d_fwd[a]; s->d_inv[a] = d_inv[a]; }
-  for (int a = 0; a < s->d.ndim; ++a) {
+  for (int a = 0; a < s->d.ndim && !s->ff_only; ++a) {
     const int Ln = s->ext[a], K2 = 2 * s->d.modes[a];
     if (!s->fwd_image[a] && axis_fits_umma(Ln, K2)) {
       FFNO_TRY(alloc_bytes(s, table_image_bytes(Ln, K2), &s->fwd_image[a]));
@@ -141,7 +144,7 @@ int umma_load_params(UmmaState* s, const UmmaLayerSrc* layers, float* const d_fw
   for (int l = 0; l < s->d.n_layers; ++l) {
     UmmaLayer& L = s->layers[l];
     const UmmaLayerSrc& src = layers[l];
-    if (s->d.spectral_mode == FFNO_MODE_FULL) {
+    if (s->d.spectral_mode == FFNO_MODE_FULL && !s->ff_only) {
       for (int a = 0; a < s->d.ndim; ++a) {
         auto key = std::make_pair((const void*)src.wmix[a], a);
         uint8_t*& img = s->mix_cache[key];
@@ -321,12 +324,23 @@ int umma_ff_fwd(UmmaState* s, int layer, const float* s_in, const float* residua
   return launch_ff_ts(s_in, nullptr, nullptr, residual, xo, bo, L.ff_image, L.b1, L.b2, P, s->sm_count, st);
 }
 
+// FeedForward of a layer whose spectral output `s_in` was produced elsewhere (the FP32 rfft2 passes of an
+// FFNO_TRANSFORM_RFFT2 plan): x_next = residual + FF(s_in) and / or b_out = FF(s_in).
+int umma_ff_layer(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* x_next, float* b_out,
+                  cudaStream_t st) {
+  const UmmaLayer& L = s->layers[layer];
+  long long P = batch;
+  for (int a = 0; a < s->d.ndim; ++a) P *= s->ext[a];
+  return launch_ff_ts(s_in, nullptr, nullptr, x_next ? residual : nullptr, x_next, b_out, L.ff_image, L.b1, L.b2, P,
+                      s->sm_count, st);
+}
+
 // ---- stage-pipelined forward ---------------------------------------------------------------------------------------
 // Samples per unit: the smallest group whose tiles align in every stage (0 = this batch cannot be pipelined).
 int umma_pipeline_unit(const UmmaState* s, int batch) {
   bool nopad = true;
   for (int a = 0; a < s->d.ndim; ++a) nopad &= s->d.pad[a] == 0;
-  if (!s->persist_env || !s->concurrent || !s->mix_shared || s->d.ndim != 2 || !all_axes_pipe(s) || !nopad ||
+  if (s->ff_only || !s->persist_env || !s->concurrent || !s->mix_shared || s->d.ndim != 2 || !all_axes_pipe(s) || !nopad ||
       s->d.out_features != 1 || s->d.use_fork || s->ff_layers_dev == nullptr || s->sm_count != s->hw_sm_count)
     return 0;
   int mix_ctas = 0;

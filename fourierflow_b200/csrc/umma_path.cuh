@@ -20,6 +20,11 @@ bool umma_supported(const ffno_desc* d, const int ext[3]);
 const char* umma_why_not(const ffno_desc* d, const int ext[3]);
 int umma_create(UmmaState** out, const ffno_desc* d, const int ext[3]);
 void umma_destroy(UmmaState* s);
+// The state serves the FeedForward only (plans whose spectral layer runs on the FP32 kernels: FFNO_TRANSFORM_RFFT2):
+// no table / mode-weight images are built, only umma_ff_fwd / umma_ff_layer may be called.
+void umma_set_ff_only(UmmaState* s);
+int umma_ff_layer(UmmaState* s, int layer, const float* s_in, const float* residual, int batch, float* x_next, float* b_out,
+                  cudaStream_t st);
 // Persistent-kernel grid cap for the following launches (0 = all SMs): lets independent batch chunks on different
 // streams share the GPU side by side.
 void umma_set_sm_limit(UmmaState* s, int n);

@@ -63,7 +63,8 @@ typedef enum {                /* per-axis transform of the spectral layer */
   FFNO_TRANSFORM_RFFT2 = 2    /* un-factorized sibling FNOPlus2DBlock (zongyi_fno/grid_plus_2d.py:52-83): ortho rfft2, the
                                  two K x K corner blocks (rows 0..K-1 and M-K..M-1, columns 0..K-1) mixed per 2-D mode,
                                  irfft2.  2-D only, modes[0] == modes[1] == K, 2K <= size[0]; fourier_weight[0] / [1] are
-                                 the [C, C, K, K, 2] weights of the low / high row block; FP32 kernels only */
+                                 the [C, C, K, K, 2] weights of the low / high row block; spectral layer on the FP32 kernels,
+                                 FeedForward on tcgen05 when width = 64, ff_factor = 4 */
 } ffno_transform;
 
 typedef enum {                /* which implementation a plan may use */
@@ -151,7 +152,8 @@ FFNO_API int ffno_device_ok(void);
 /* Plan lifetime.  Builds DFT tables (host double -> device) and reserves folded/packed weights. */
 FFNO_API int ffno_plan_create(const ffno_desc* desc, ffno_plan** out_plan);
 FFNO_API int ffno_plan_destroy(ffno_plan* plan);
-/* 1 if the plan runs the tcgen05 (UMMA) kernels, 0 if it runs the generic FP32 kernels. */
+/* 1 if the plan runs tcgen05 (UMMA) kernels (for FFNO_TRANSFORM_RFFT2 plans: the FeedForward only), 0 if it runs the
+   generic FP32 kernels throughout. */
 FFNO_API int ffno_plan_uses_umma(const ffno_plan* plan);
 
 /* Fold weight-norm (linear.py:49), re-layout spectral weights to per-mode real block matrices and

@@ -311,6 +311,8 @@ def plus_cases(M):
     """FNOPlus2DBlock (zongyi_fno/grid_plus_2d.py): un-factorized rfft2 spectral layer inside the F-FNO block structure."""
     grid2d_case(M, "plus2d_w32", dict(modes=4, width=32, n_layers=2, input_dim=3, share_weight=False, factor=4,
                 ff_weight_norm=True, gain=1), (2, 12, 10, 3), seed=50, cls="FNOPlus2DBlock")
+    grid2d_case(M, "plus2d_w64", dict(modes=6, width=64, n_layers=3, input_dim=3, share_weight=True, factor=4,
+                ff_weight_norm=True, gain=0.5), (1, 16, 20, 3), seed=52, cls="FNOPlus2DBlock")      # tcgen05 FeedForward
     grid2d_case(M, "plus2d_shared_fork", dict(modes=3, width=16, n_layers=3, input_dim=2, share_weight=True,
                 share_fork=True, use_fork=True, factor=2, ff_weight_norm=True, gain=0.5), (1, 6, 9, 2), seed=51,
                 cls="FNOPlus2DBlock")

@@ -15,13 +15,18 @@ OUT="$HERE/_ref"
 SRC="$REF/fourierflow/modules"
 [ -d "$SRC" ] || { echo "make_ref: $SRC not found (run in the build container)"; exit 0; }
 rm -rf "$OUT"
-mkdir -p "$OUT/fourierflow/modules/factorized_fno"
-for f in feedforward.py linear.py normalizer.py loss.py factorized_fno/grid_2d.py factorized_fno/mesh_2d.py factorized_fno/mesh_3d.py; do
+mkdir -p "$OUT/fourierflow/modules/factorized_fno" "$OUT/fourierflow/modules/factorized_cno" "$OUT/fourierflow/modules/zongyi_fno"
+# the path itself, then the sibling operators of SURVEY §8 f-4 (tools/sibling_times.py times them next to the mirrors)
+for f in feedforward.py linear.py normalizer.py loss.py factorized_fno/grid_2d.py factorized_fno/mesh_2d.py factorized_fno/mesh_3d.py \
+         dct.py factorized_cno/grid_2d.py factorized_cno/mesh_2d.py factorized_cno/mesh_3d.py factorized_fno/point_cloud_2d.py \
+         zongyi_fno/grid_plus_2d.py; do
   cp "$SRC/$f" "$OUT/fourierflow/modules/$f"
 done
 # stub parents (generated, not copied): the reference's own __init__ files import the whole research stack
 : > "$OUT/fourierflow/__init__.py"
 : > "$OUT/fourierflow/modules/__init__.py"
 : > "$OUT/fourierflow/modules/factorized_fno/__init__.py"
+: > "$OUT/fourierflow/modules/factorized_cno/__init__.py"
+: > "$OUT/fourierflow/modules/zongyi_fno/__init__.py"
 ( cd "$OUT" && sha256sum $(find fourierflow -name '*.py' | sort) > MANIFEST.sha256 )
 echo "oracle/_ref: $(find "$OUT" -name "*.py" | wc -l) files copied verbatim from $SRC"

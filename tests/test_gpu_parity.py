@@ -49,7 +49,7 @@ PATHS = ["generic", "auto"]
 @pytest.mark.parametrize("name", ["grid2d_c2arch_32", "grid2d_gain1_unshared", "grid2d_ln_w32", "grid2d_fork",
                                   "grid2d_lowpass", "grid2d_nofourier", "grid2d_nyquist",
                                   "cno_grid2d_w32", "cno_grid2d_w64",       # cno_*: the DCT siblings (factorized_cno)
-                                  "plus2d_w32", "plus2d_shared_fork"])      # plus2d_*: un-factorized FNOPlus2DBlock
+                                  "plus2d_w32", "plus2d_w64", "plus2d_shared_fork"])      # plus2d_*: un-factorized FNOPlus2DBlock
 def test_grid2d_block_golden_per_layer(name, path, monkeypatch):
     monkeypatch.setenv("FFNO_B200_PATH", path)
     kw, sd, a = load(name)

@@ -23,7 +23,7 @@ def _grid2d(name):
 @pytest.mark.parametrize("name", ["grid2d_c2arch_32", "grid2d_c2_24layers_32", "grid2d_gain1_unshared",
                                   "grid2d_ln_w32", "grid2d_fork", "grid2d_lowpass",
                                   "grid2d_nofourier", "grid2d_nyquist", "cno_grid2d_w32", "cno_grid2d_w64",
-                                  "plus2d_w32", "plus2d_shared_fork"])
+                                  "plus2d_w32", "plus2d_w64", "plus2d_shared_fork"])
 def test_grid2d_block(name):
     kw, a, out, taps = _grid2d(name)
     assert rel_err(out["forecast"], a["forecast"]) < TOL
