@@ -273,3 +273,89 @@ def test_stage_pipelined_rollout_matches_the_launch_per_layer_rollout(monkeypatc
         outs.append((loss.item(), preds.clone(), exp.conv.plan_for(data.device, (64, 64)).pipeline_unit(8)))
     assert outs[0][2] == 2 and outs[1][2] == 0
     assert torch.equal(outs[0][1], outs[1][1]) and outs[0][0] == outs[1][0]
+
+
+# ---- sibling operators at the shapes of their shipped configs -----------------------------------------
+
+def test_cno_plasticity_shape_vs_oracle():
+    """experiments/plasticity/fcno: CNOFactorizedMesh3D on the real mesh 101x31x20 -> 109x39x28, coefficient counts
+    (32, 12, 8) -> pairs (16, 6, 4) on the tcgen05 path, batch 2, 4 layers (factorized_cno/mesh_3d.py:160-176)."""
+    from oracle import ffno_oracle as O
+    torch.manual_seed(81)
+    m = M().CNOFactorizedMesh3D(modes_x=32, modes_y=12, modes_z=8, width=64, input_dim=4, output_dim=4, n_layers=4,
+                                share_weight=False, factor=4, ff_weight_norm=True, n_ff_layers=2, layer_norm=False).eval()
+    x = torch.randn(2, 101, 31, 20, 1, generator=torch.Generator().manual_seed(82))
+    with torch.no_grad():
+        ref = O.block_mesh_forward(sd_of(m), x, modes=(32, 12, 8), n_layers=4)
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())
+    assert mc.plan_for(y.device, (101, 31, 20)).uses_umma
+    e = rel_err(y, ref)
+    print("cno plasticity shape", f"{e:.2e}")
+    assert y.shape == ref.shape and e < TOL
+
+
+def test_cno_odd_coefficient_counts_on_tcgen05_vs_oracle():
+    """An odd number of kept DCT coefficients leaves the Im row of the last pair empty (zero table column, zero weight
+    block): 64x48 grid, 15 coefficients, 24 layers, batch 4 (experiments/torus_kochkov/fcno shape family)."""
+    from oracle import ffno_oracle as O
+    torch.manual_seed(83)
+    m = M().CNOFactorized2DBlock(modes=15, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4,
+                                 ff_weight_norm=True, gain=0.1).eval()
+    x = torch.randn(4, 64, 48, 3, generator=torch.Generator().manual_seed(84))
+    taps = {}
+    with torch.no_grad():
+        ref = O.block_grid2d_forward(sd_of(m), x, modes=15, n_layers=24, taps=taps)["forecast"]
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())["forecast"]
+        _, t = mc.forward_with_taps(x.cuda())
+    assert mc.plan_for(y.device, (64, 48)).uses_umma
+    errs = {"forecast": rel_err(y, ref)}
+    for l in (0, 11, 23):
+        errs[f"x{l}"] = rel_err(t["x"][l], taps[f"x{l}"])
+    print("cno 15 coefficients", {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
+
+
+def test_fnoplus_c2_shape_vs_oracle():
+    """experiments/torus_li/ablation/no_factorization: FNOPlus2DBlock at 64x64, modes 16, batch 8, 4 layers, unshared
+    weights (zongyi_fno/grid_plus_2d.py:143-161): FP32 rfft2 passes + tcgen05 FeedForward."""
+    from oracle import ffno_oracle as O
+    torch.manual_seed(85)
+    m = M().FNOPlus2DBlock(modes=16, width=64, n_layers=4, input_dim=3, share_weight=False, factor=4,
+                           ff_weight_norm=True, gain=0.1).eval()
+    x = torch.randn(8, 64, 64, 3, generator=torch.Generator().manual_seed(86))
+    taps = {}
+    with torch.no_grad():
+        ref = O.block_grid2d_forward(sd_of(m), x, modes=16, n_layers=4, taps=taps)["forecast"]
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc(x.cuda())["forecast"]
+        _, t = mc.forward_with_taps(x.cuda())
+    errs = {"forecast": rel_err(y, ref), "s0": rel_err(t["s"][0], taps["s0"]), "x3": rel_err(t["x"][3], taps["x3"])}
+    print("fnoplus 64x64", {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
+
+
+def test_geo_interior_elasticity_shape_vs_oracle():
+    """experiments/elasticity/ffno: the interior of FNOFactorizedPointCloud2D on the 64x64 latent grid, width 64, modes 16,
+    8 layers (7 interior), batch 4 (factorized_fno/point_cloud_2d.py:198-210)."""
+    from oracle import ffno_oracle as O
+    torch.manual_seed(87)
+    m = M().FNOFactorizedPointCloud2D(modes1=16, modes2=16, width=64, in_channels=2, out_channels=1, n_layers=8,
+                                      s1=64, s2=64).eval()
+    g = torch.Generator().manual_seed(88)
+    uc = torch.randn(4, 64, 64, 64, generator=g)
+    bias = 0.1 * torch.randn(64, 64, 64, generator=g)
+    with torch.no_grad():
+        ref = O.geo_interior_forward(sd_of(m), uc, bias, modes=16, n_layers=8)
+    mc = m.cuda()
+    with torch.no_grad():
+        y = mc.interior_forward(uc.cuda(), bias.cuda())
+    e = rel_err(y, ref)
+    print("geo interior 64x64", f"{e:.2e}")
+    assert e < 1e-5

@@ -15,5 +15,19 @@ exp.accumulate_statistics(data, force=torch.randn(2, 64, 64, device="cuda"), mu=
 with torch.no_grad():
     for _ in range(3):
         out = exp({"data": data, "f": torch.randn(2, 64, 64, device="cuda"), "mu": torch.rand(2, device="cuda")})
+# sibling operators: DCT tables / pair mix on both kernel families, rfft2 passes + tcgen05 FF, geo interior
+from fourierflow_b200.modules import CNOFactorized2DBlock, CNOFactorizedMesh3D, FNOPlus2DBlock, FNOFactorizedPointCloud2D
+with torch.no_grad():
+    for width in (32, 64):
+        c = CNOFactorized2DBlock(modes=7, width=width, n_layers=2, input_dim=3, share_weight=True, factor=4,
+                                 ff_weight_norm=True).cuda().eval()
+        c(torch.randn(2, 24, 20, 3, device="cuda"))
+        p2 = FNOPlus2DBlock(modes=5, width=width, n_layers=2, input_dim=3, share_weight=False, factor=4,
+                            ff_weight_norm=True).cuda().eval()
+        p2(torch.randn(2, 12, 18, 3, device="cuda"))
+    c3 = CNOFactorizedMesh3D(5, 4, 3, 64, 4, 4, 2, False, 4, True, 2, False).cuda().eval()
+    c3(torch.randn(1, 9, 7, 6, 1, device="cuda"))
+    geo = FNOFactorizedPointCloud2D(modes1=4, modes2=4, width=32, in_channels=2, out_channels=1, n_layers=3, s1=12, s2=10).cuda().eval()
+    geo(torch.rand(2, 30, 2, device="cuda"))
 torch.cuda.synchronize()
 print("sanitizer workload done", float(out[0]))
