@@ -405,6 +405,11 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
       const unsigned uo = live ? (unsigned)G / (unsigned)gpi : 0u;
       const unsigned ug = live ? (unsigned)G - uo * (unsigned)gpi : 0u;
       float* ybase = p.Y + ((long long)uo * p.n_out) * p.inner + (long long)ug * 64 + in_group;
+      const uint32_t taddr = tmem + lane_base + (uint32_t)(ds * stage_cols);
+      // Pin both addresses in registers HERE: without the empty asm ptxas sinks the whole chain (and the constant-bank
+      // reloads of the geometry) behind the wait, right in front of the tcgen05.ld (SASS: ~55 instructions and an LDCU
+      // between the barrier test and LDTM; in-kernel timeline: 700-950 cycles with the accumulator stage held, 210 now).
+      asm volatile("" ::"l"(ybase), "r"(taddr), "r"(stride) : "memory");
       mbar_wait(&d_full[ds], (uint32_t)(n >> 1) & 1u);
       tc_fence_after();
       if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 0);
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
         const int c0 = ch * 32;
         uint32_t v[32];
         if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 3);
-        tmem_ld32(tmem + lane_base + (uint32_t)(ds * stage_cols + c0), v);
+        tmem_ld32(taddr + (uint32_t)c0, v);
         if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 4);
         tmem_ld_wait();
         if (warp == kEpiWarp0 && blockIdx.y == 0) TL(5, n, 5);
@@ -466,6 +471,51 @@ __global__ void __launch_bounds__(kPipe ? kAxPipeThreads : kAxThreads, 1) axis_p
       mbar_wait(bar_w, 0);
       const uint32_t idesc = make_idesc_bf16(128, p.npad, 1, 0);
       int item = 0;
+      if (p.kchunks == 1 && !(FFNO_KO & 8)) {
+        // One operand stage per tile (axis lengths <= 64: C2, C5, every inverse with <= 32 modes): operand stage and
+        // accumulator stage are both n & 1, so with the tile loop unrolled by two every descriptor is a loop invariant.
+        // The generic loop below rebuilds them per tile — ~85 SASS instructions (shifts, masks, R2UR, two constant-bank
+        // reloads) between the barrier test and the first tcgen05.mma; in-kernel timeline: 1000-1100 -> 650-800 cycles of
+        // issue per tile, forward-transform launch 17.7 -> 17.2 us.
+        const int ksteps = (p.n_in + 15) >> 4;
+        const uint64_t dA0h = make_smem_desc_sw128(smem_u32(smem), 8192u, 1024u);
+        const uint64_t dBh = desc_kmajor(smem_u32(sB), 0);
+        const uint64_t dBl = dBh + (uint64_t)(b_half >> 4);
+        auto issue_tile = [&](auto STAGE, int n) {
+          constexpr int st = decltype(STAGE)::value;
+          const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+          mbar_wait(&d_empty[st], ph ^ 1u);
+          mbar_wait(&a_full[st], ph);
+          tc_fence_after();
+          if (lane == 0 && blockIdx.y == 0) TL(6, n, 0);
+          const uint64_t dAh = dA0h + (uint64_t)(st * (AXP_A_STAGE >> 4)), dAl = dAh + (uint64_t)(16384 >> 4);
+          const uint32_t d_addr = tmem + (uint32_t)(st * stage_cols);
+          auto issue = [&](auto KS) {
+            constexpr int kSteps = decltype(KS)::value;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint64_t a = (pass == 2) ? dAl : dAh, b = (pass == 1) ? dBl : dBh;
+#pragma unroll
+              for (int ks = 0; ks < kSteps; ++ks)
+                umma_bf16_ss_elect(d_addr, a + (uint64_t)(ks * (2048 >> 4)), b + (uint64_t)(ks * 2), idesc,
+                                   (pass == 0 && ks == 0) ? 0u : 1u);
+            }
+          };
+          switch (ksteps) {       // warp-uniform
+            case 4: issue(std::integral_constant<int, 4>{}); break;
+            case 3: issue(std::integral_constant<int, 3>{}); break;
+            case 2: issue(std::integral_constant<int, 2>{}); break;
+            default: issue(std::integral_constant<int, 1>{}); break;
+          }
+          umma_commit_elect(&a_empty[st]);
+          umma_commit_elect(&d_full[st]);
+          if (lane == 0 && blockIdx.y == 0) TL(6, n, 1);
+        };
+        for (int n = 0; n < my_tiles; n += 2) {
+          issue_tile(std::integral_constant<int, 0>{}, n);
+          if (n + 1 < my_tiles) issue_tile(std::integral_constant<int, 1>{}, n + 1);
+        }
+      } else
       for (int n = 0; n < my_tiles; ++n) {
         const int ds = n & 1;
         mbar_wait(&d_empty[ds], ((uint32_t)(n >> 1) & 1u) ^ 1u);
