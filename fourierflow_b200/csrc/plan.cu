@@ -1326,7 +1326,8 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
   FFNO_REQUIRE(p->d.n_ff_layers == 2 && !p->d.layer_norm && !p->d.use_fork && p->d.spectral_mode == FFNO_MODE_FULL,
                FFNO_ERR_UNSUPPORTED, "backward is implemented for n_ff_layers = 2, no LayerNorm, no fork, mode 'full'");
-  FFNO_REQUIRE(p->d.transform == FFNO_TRANSFORM_RFFT, FFNO_ERR_UNSUPPORTED, "backward is implemented for the rfft (F-FNO) stacks");
+  FFNO_REQUIRE(p->d.transform != FFNO_TRANSFORM_RFFT2, FFNO_ERR_UNSUPPORTED,
+               "backward is implemented for the factorized stacks (rfft and DCT), not for the rfft2 variant");
   const bool mesh = p->pts != p->pts_in || p->d.append_grid;       // zero-padded / grid-appended (mesh_3d.py:161-166)
   if (batch == 0) return FFNO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1412,7 +1413,7 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
           for (int i = a + 1; i < p->d.ndim; ++i) p_inner *= p->ext[i];
           const size_t off = umma_spec_offset(p->umma, batch, a);
           FFNO_TRY(launch_mix_wgrad(w.F + off, w.dR + off, lg.fourier_weight[a], outer, p->d.modes[a], p_inner, C,
-                                    p->sm_count, st));
+                                    p->sm_count, st, p->dct_modes[a]));
         }
       }
       continue;
@@ -1426,7 +1427,7 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
       FFNO_TRY(launch_axis_transform(w.ds, p->d_invT[a], w.dR, outer, L, 2 * K, inner, false, st));
       if (lg.fourier_weight[a]) {
         FFNO_TRY(launch_axis_transform(xl, p->d_fwd[a], w.F, outer, L, 2 * K, inner, false, st));
-        FFNO_TRY(launch_mix_wgrad(w.F, w.dR, lg.fourier_weight[a], outer, K, p_inner, C, p->sm_count, st));
+        FFNO_TRY(launch_mix_wgrad(w.F, w.dR, lg.fourier_weight[a], outer, K, p_inner, C, p->sm_count, st, p->dct_modes[a]));
       }
       FFNO_TRY(launch_transpose(lw.wmix[a], w.wT, 2 * C, 2 * C, K, st));
       FFNO_TRY(launch_mode_mix(w.dR, w.wT, w.dF, outer, K, p_inner, C, st));

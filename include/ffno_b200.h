@@ -241,7 +241,7 @@ FFNO_API size_t ffno_rollout_workspace_bytes_ex(const ffno_plan* plan, int32_t b
 /* ---- Backward pass ------------------------------------------------------------------------------
  * What torch.autograd computes for the reference's training step (routines/grid_2d_markov.py:172-193 `_training_step`:
  * forecast -> Normalizer.inverse -> LpLoss; routines/base.py:27-52 applies the optimizer), written out as explicit
- * adjoints.  Supported stacks: FNOFactorized2DBlock / mesh variants WITHOUT padding / grid append, n_ff_layers = 2, no
+ * adjoints.  Transforms: FFNO_TRANSFORM_RFFT and FFNO_TRANSFORM_DCT (not RFFT2).  Supported stacks: FNOFactorized2DBlock / mesh variants WITHOUT padding / grid append, n_ff_layers = 2, no
  * LayerNorm, no fork, mode 'full' (every torus_li / torus_kochkov / torus_vis config).  Generic FP32 kernels; the forward
  * is recomputed inside the call (FP32 path) so no state is carried between the forward and the backward.
  *
@@ -255,7 +255,7 @@ typedef struct {
   float* bias;                    /* [out] */
 } ffno_linear_grads;
 typedef struct {
-  float* fourier_weight[FFNO_MAX_DIMS];        /* [C, C, K_a, 2], tensor-axis order as in ffno_layer_params */
+  float* fourier_weight[FFNO_MAX_DIMS];        /* [C, C, K_a, 2] ([C, C, K_a] for FFNO_TRANSFORM_DCT), tensor-axis order */
   ffno_linear_grads backcast_ff[FFNO_MAX_FF_LAYERS];
 } ffno_layer_grads;
 typedef struct {

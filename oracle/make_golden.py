@@ -227,13 +227,13 @@ def mesh_grad_case(M, LpLoss, cls, name, kwargs, shape, out_dim, seed):
     save(name, kwargs, arrays)
 
 
-def grad_case(M, LpLoss, name, kwargs, shape, seed):
+def grad_case(M, LpLoss, name, kwargs, shape, seed, cls="FNOFactorized2DBlock"):
     """Gradients of the reference's one-step training loss (routines/grid_2d_markov.py:172-193: forecast ->
     LpLoss against the next frame) w.r.t. the input and every parameter, by the reference's own autograd graph —
     the pin for the backward row: weight-norm (g, v), shared spectral weights accumulated over
     layers, complex einsum / rfft / irfft adjoints."""
     torch.manual_seed(seed)
-    m = M.FNOFactorized2DBlock(**kwargs).train()
+    m = getattr(M, cls)(**kwargs).train()
     perturb_(m, seed + 100)
     g = torch.Generator().manual_seed(seed + 1)
     x = torch.randn(*shape, generator=g).requires_grad_(True)
@@ -357,6 +357,17 @@ def grad_cases(M, LpLoss):
     mesh_grad_cases(M, LpLoss)
 
 
+def cno_grad_cases(LpLoss):
+    """Gradients of the DCT siblings' training loss (experiments/*/fcno): odd coefficient counts, shared weights on the
+    periodic grid (width 64: tcgen05 adjoint), per-axis counts with padding and crop on the 2-D mesh (width 32: FP32)."""
+    import fourierflow.modules.factorized_cno as CNO
+    grad_case(CNO, LpLoss, "grad_cno_grid2d_w64", dict(modes=7, width=64, n_layers=2, input_dim=3, share_weight=True,
+              factor=4, ff_weight_norm=True, gain=0.5), (2, 16, 16, 3), seed=24, cls="CNOFactorized2DBlock")
+    mesh_grad_case(CNO, LpLoss, "CNOFactorizedMesh2D", "grad_cno_mesh2d_w32", dict(modes_x=5, modes_y=4, width=32,
+                   input_dim=4, n_layers=2, share_weight=False, factor=4, ff_weight_norm=True, n_ff_layers=2,
+                   layer_norm=False), (2, 10, 9, 2), 1, seed=25)
+
+
 def mesh_grad_cases(M, LpLoss):
     # mesh variants: grid append + padding + crop; width 64 (tcgen05 path) in 3-D, width 32 (FP32 path) in 2-D
     mesh_grad_case(M, LpLoss, "FNOFactorizedMesh3D", "grad_mesh3d_w64", dict(modes_x=6, modes_y=6, modes_z=4, width=64,
@@ -381,6 +392,9 @@ def main():
         return
     c2 = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4,
               ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0)
+    if "--only-cno-grad" in sys.argv:
+        cno_grad_cases(LpLoss)
+        return
     if "--only-mesh-grad" in sys.argv:
         mesh_grad_cases(M, LpLoss)
         return

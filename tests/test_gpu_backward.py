@@ -28,14 +28,14 @@ def _loss(m, x, y):
     return forecast, LpLoss(size_average=True)(forecast.reshape(B, -1), y.reshape(B, -1))
 
 
-@pytest.mark.parametrize("name", ["grad_c2arch_16", "grad_unshared_w32"])
+@pytest.mark.parametrize("name", ["grad_c2arch_16", "grad_unshared_w32", "grad_cno_grid2d_w64"])
 @pytest.mark.parametrize("path", ["auto", "generic"])
 def test_gradients_match_the_executed_reference(name, path, monkeypatch):
     """Input gradient + every parameter gradient (weight-norm g / v, shared spectral weights summed over layers, plain
     linears, biases) of the reference's training loss."""
     monkeypatch.setenv("FFNO_B200_PATH", path)
     kw, sd, a = load(name)
-    m = build("FNOFactorized2DBlock", kw, sd).train()
+    m = build("CNOFactorized2DBlock" if "cno" in name else "FNOFactorized2DBlock", kw, sd).train()      # cno: DCT sibling
     x = a["x"].cuda().requires_grad_(True)
     forecast, loss = _loss(m, x, a["y"].cuda())
     loss.backward()
@@ -56,7 +56,7 @@ def test_gradients_match_the_executed_reference(name, path, monkeypatch):
         assert e < TOL, (k, e)
         checked += 1
     print(name, path, f"{checked} parameter gradients, worst {worst:.2e}")
-    assert checked >= 10
+    assert checked >= 10 or "cno" in name and checked >= 8
 
 
 def test_gradients_accumulate_and_match_oracle_autograd_at_the_c2_layer_shape():
@@ -201,7 +201,8 @@ def test_full_depth_c2_gradients_vs_fp64_oracle(mode, monkeypatch):
         assert worst_own < TOL
 
 
-@pytest.mark.parametrize("name,cls", [("grad_mesh3d_w64", "FNOFactorizedMesh3D"), ("grad_mesh2d_w32", "FNOFactorizedMesh2D")])
+@pytest.mark.parametrize("name,cls", [("grad_mesh3d_w64", "FNOFactorizedMesh3D"), ("grad_mesh2d_w32", "FNOFactorizedMesh2D"),
+                                      ("grad_cno_mesh2d_w32", "CNOFactorizedMesh2D")])
 def test_mesh_gradients_match_the_executed_reference(name, cls):
     """Mesh variants (plasticity / airfoil training, routines/structured_mesh.py): the linspace grid append, the zero
     padding after the lift and the crop before the head are part of the backward (mesh_3d.py:160-176, mesh_2d.py:149-165).

@@ -484,3 +484,30 @@ def test_geo_ffno_pointcloud_golden(name):
     assert e_int < TOL_GENERIC and e_out < 2e-5
     with pytest.raises(RuntimeError):
         m(a["u"].cuda().requires_grad_())
+
+
+@pytest.mark.parametrize("cls,kw", [("FNOPlus2DBlock", dict(modes=8)), ("CNOFactorized2DBlock", dict(modes=15))])
+def test_rollout_with_sibling_operators_vs_oracle(cls, kw):
+    """The Markov rollout routine around the sibling operators, as experiments/torus_li/ablation/no_factorization
+    (21 configs, FNOPlus2DBlock) and experiments/torus_kochkov/fcno (CNOFactorized2DBlock) configure it: one
+    ffno_rollout_fwd call, 5 steps, against the oracle's rollout on seeded weights and data."""
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    from oracle import ffno_oracle as O
+    X = Y = 32
+    torch.manual_seed(0)
+    conv = getattr(M(), cls)(width=64, n_layers=3, input_dim=3, share_weight=True, factor=4, ff_weight_norm=True,
+                             gain=0.1, **kw).eval()
+    sd = {k: v.detach().clone() for k, v in conv.state_dict().items()}
+    data = torch.randn(3, X, Y, 7, generator=torch.Generator().manual_seed(6))
+    exp = Grid2DMarkovExperiment(conv, n_steps=5).cuda().eval()
+    exp.accumulate_statistics(data.cuda())
+    frames = data[..., :-1].unsqueeze(-1)
+    pos = O.position_features((X, Y), 0.0, 1.0, data.dtype)[None, :, :, None, :].expand(3, X, Y, 6, 2)
+    stats = O.normalizer_stats(torch.cat([frames, pos], dim=-1))
+    ref = O.markov_rollout(sd, data, stats, modes=kw["modes"], n_layers=3, n_steps=5)
+    with torch.no_grad():
+        loss, step_losses, preds, _ = exp({"data": data.cuda()})
+    e = rel_err(preds, ref["preds"])
+    print(cls, f"rollout {e:.2e}")
+    assert e < TOL_UMMA
+    assert abs(loss.item() - ref["loss"].item()) < 2e-4 * abs(ref["loss"].item())

@@ -269,7 +269,7 @@ def test_rollout_feature_set_options():
 
 def test_cno_mirrors_keep_the_reference_contract():
     """factorized_cno: real [in, out, modes] weights; shared weights of the mesh variants are 4-D in the reference and
-    cannot run there (mesh_2d.py:118-124 vs :69-72) — the mirrors refuse them at construction; no autograd path."""
+    cannot run there (mesh_2d.py:118-124 vs :69-72) — the mirrors refuse them at construction."""
     import fourierflow_b200.modules as M
     b = M.CNOFactorized2DBlock(modes=5, width=32, input_dim=3, n_layers=2, share_weight=True, factor=4, ff_weight_norm=True)
     assert [tuple(p.shape) for p in b.fourier_weight] == [(32, 32, 5)] * 2
@@ -279,8 +279,9 @@ def test_cno_mirrors_keep_the_reference_contract():
     with pytest.raises(RuntimeError, match="share_weight"):
         M.CNOFactorizedMesh3D(4, 4, 4, 32, 4, 4, 2, True, 4, True, 2, False)
     from fourierflow_b200.modules.factorized_fno._base import check_trainable
-    with pytest.raises(RuntimeError, match="rfft"):
-        check_trainable(b)
+    check_trainable(b)                                        # the DCT stacks are trainable (ffno_block_bwd)
+    with pytest.raises(RuntimeError, match="rfft2"):
+        check_trainable(M.FNOPlus2DBlock(modes=4, width=32, input_dim=3, n_layers=1, factor=4, ff_weight_norm=True))
 
 
 @pytest.mark.parametrize("name", ["geo_pointcloud_w32", "geo_pointcloud_shared"])
