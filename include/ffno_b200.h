@@ -241,9 +241,11 @@ FFNO_API size_t ffno_rollout_workspace_bytes_ex(const ffno_plan* plan, int32_t b
 /* ---- Backward pass ------------------------------------------------------------------------------
  * What torch.autograd computes for the reference's training step (routines/grid_2d_markov.py:172-193 `_training_step`:
  * forecast -> Normalizer.inverse -> LpLoss; routines/base.py:27-52 applies the optimizer), written out as explicit
- * adjoints.  Transforms: FFNO_TRANSFORM_RFFT and FFNO_TRANSFORM_DCT (not RFFT2).  Supported stacks: FNOFactorized2DBlock / mesh variants WITHOUT padding / grid append, n_ff_layers = 2, no
- * LayerNorm, no fork, mode 'full' (every torus_li / torus_kochkov / torus_vis config).  Generic FP32 kernels; the forward
- * is recomputed inside the call (FP32 path) so no state is carried between the forward and the backward.
+ * adjoints.  Transforms: FFNO_TRANSFORM_RFFT and FFNO_TRANSFORM_DCT (not RFFT2).  Supported stacks: the 2-D grid block and
+ * the mesh variants (grid append, zero padding and crop are part of the adjoint), n_ff_layers = 2, no LayerNorm, no fork,
+ * mode 'full' (every torus_li / torus_kochkov / torus_vis / plasticity / airfoil F-FNO and F-CNO config).  The forward is
+ * recomputed inside the call, so no state is carried between the forward and the backward; which kernels run the
+ * recompute and the spectral adjoint is selected by ffno_plan_set_backward_mode.
  *
  * Gradient buffers have the shapes of the parameters they belong to and are ACCUMULATED into (+=), like `.grad`: zero
  * them first; a parameter shared by several layers (share_weight) is given the same buffer in each layer and receives
