@@ -3,6 +3,7 @@
 from .factorized_cno import CNOFactorized2DBlock, CNOFactorizedMesh2D, CNOFactorizedMesh3D
 from .factorized_fno import FNOFactorized2DBlock, FNOFactorizedMesh2D, FNOFactorizedMesh3D, FNOFactorizedPointCloud2D
 from .feedforward import FeedForward
+from .iphi import IPhi
 from .linear import WNLinear
 from .loss import LpLoss
 from .normalizer import Normalizer

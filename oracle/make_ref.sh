@@ -18,7 +18,7 @@ rm -rf "$OUT"
 mkdir -p "$OUT/fourierflow/modules/factorized_fno" "$OUT/fourierflow/modules/factorized_cno" "$OUT/fourierflow/modules/zongyi_fno"
 # the path itself, then the sibling operators of SURVEY §8 f-4 (tools/sibling_times.py times them next to the mirrors)
 for f in feedforward.py linear.py normalizer.py loss.py factorized_fno/grid_2d.py factorized_fno/mesh_2d.py factorized_fno/mesh_3d.py \
-         dct.py factorized_cno/grid_2d.py factorized_cno/mesh_2d.py factorized_cno/mesh_3d.py factorized_fno/point_cloud_2d.py \
+         dct.py iphi.py factorized_cno/grid_2d.py factorized_cno/mesh_2d.py factorized_cno/mesh_3d.py factorized_fno/point_cloud_2d.py \
          zongyi_fno/grid_plus_2d.py; do
   cp "$SRC/$f" "$OUT/fourierflow/modules/$f"
 done

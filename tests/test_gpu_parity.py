@@ -511,3 +511,41 @@ def test_rollout_with_sibling_operators_vs_oracle(cls, kw):
     print(cls, f"rollout {e:.2e}")
     assert e < TOL_UMMA
     assert abs(loss.item() - ref["loss"].item()) < 2e-4 * abs(ref["loss"].item())
+
+
+def test_elasticity_routine_with_iphi_vs_the_reference_modules(monkeypatch):
+    """experiments/elasticity/ffno: PointCloudExperiment(model=FNOFactorizedPointCloud2D, iphi=IPhi) against the reference's
+    own modules (oracle/_ref: point_cloud_2d.py, iphi.py copied verbatim) on the same GPU with the same weights: the
+    deformation network alone, and the whole prediction with the geometry code."""
+    import sys
+    ref_root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "fourierflow", "modules", "factorized_fno")):
+        pytest.skip("oracle/_ref not built (python -c 'import __graft_entry__ as g; g.build()' where /root/reference exists)")
+    sys.path.insert(0, ref_root)
+    import warnings
+    warnings.filterwarnings("ignore")
+    from fourierflow.modules.factorized_fno.point_cloud_2d import FNOFactorizedPointCloud2D as RefGeo
+    from fourierflow.modules.iphi import IPhi as RefIPhi
+    from fourierflow_b200.routines import PointCloudExperiment
+    kw = dict(modes1=8, modes2=8, width=32, in_channels=2, out_channels=1, n_layers=4, s1=24, s2=20)
+    # the reference's grid / point biases are nn.Conv2d / nn.Conv1d: cuDNN would run them in TF32 by default (5e-4 off)
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    torch.manual_seed(3)
+    ref_model, ref_iphi = RefGeo(**kw).cuda().eval(), RefIPhi(width=32).cuda().eval()
+    model, iphi = M().FNOFactorizedPointCloud2D(**kw), M().IPhi(width=32)
+    model.load_state_dict(ref_model.state_dict(), strict=True)
+    iphi.load_state_dict(ref_iphi.state_dict(), strict=True)
+    exp = PointCloudExperiment(model, iphi, N=100).cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    xy, rr = torch.rand(3, 200, 2, generator=g).cuda(), torch.rand(3, 42, generator=g).cuda()
+    sigma = torch.rand(3, 200, 1, generator=g).cuda()
+    with torch.no_grad():
+        e_phi = rel_err(exp.iphi(xy, code=rr), ref_iphi(xy, code=rr))
+        out, ref = exp({"xy": xy, "rr": rr}), ref_model(xy, code=rr, iphi=ref_iphi)
+        loss = exp.validation_step({"xy": xy, "rr": rr, "sigma": sigma})
+    e = rel_err(out, ref)
+    print(f"iphi {e_phi:.2e} elasticity forward {e:.2e} loss {loss.item():.4f}")
+    assert e_phi < 1e-5 and e < 2e-5
+    with pytest.raises(RuntimeError, match="inference-only"):
+        exp.training_step({"xy": xy, "rr": rr, "sigma": sigma})

@@ -297,3 +297,17 @@ def test_geo_mirror_loads_reference_checkpoints_strict(name):
         assert m.convs[1].fourier_weight[0] is m.fourier_weight[0]
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.rand(1, 8, 2))
+
+
+def test_iphi_mirror_keeps_the_reference_parameters():
+    """modules/iphi.py:14-20: parameter names, shapes and creation order (the reference module itself cannot be built
+    without a GPU: it creates its constants with device="cuda"); forward on CPU runs (torch glue, no CUDA library)."""
+    import fourierflow_b200.modules as M
+    m = M.IPhi(width=32)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [
+        ("fc0.weight", (32, 4)), ("fc0.bias", (32,)), ("fc_code.weight", (32, 42)), ("fc_code.bias", (32,)),
+        ("fc_no_code.weight", (128, 96)), ("fc_no_code.bias", (128,)), ("fc1.weight", (128, 128)), ("fc1.bias", (128,)),
+        ("fc2.weight", (128, 128)), ("fc2.bias", (128,)), ("fc3.weight", (128, 128)), ("fc3.bias", (128,)),
+        ("fc4.weight", (2, 128)), ("fc4.bias", (2,))]
+    x = torch.rand(2, 7, 2)
+    assert m(x, code=torch.rand(2, 42)).shape == x.shape and m(x).shape == x.shape
