@@ -359,7 +359,8 @@ def velocity_features(w: torch.Tensor, domain=((0.0, 2 * math.pi), (0.0, 2 * mat
 def markov_rollout(p: Params, data: torch.Tensor, stats: dict, *, modes: int, n_layers: int,
                    n_steps: int = 10, low: float = 0.0, high: float = 1.0, use_velocity: bool = False,
                    domain=((0.0, 2 * math.pi), (0.0, 2 * math.pi)), force: torch.Tensor = None,
-                   mu: torch.Tensor = None) -> dict:
+                   mu: torch.Tensor = None, use_position: bool = True, shuffle=None,
+                   learn_difference: bool = False) -> dict:
     """``Grid2DMarkovExperiment._valid_step`` with the torus_li/markov config
     (use_position, should_normalize; no force/mu/shuffle/difference) and, with ``use_velocity``, the torus_kochkov
     feature set [w, q, v, gx, gy] (velocity recomputed from every fed-back forecast, :268-285).
@@ -369,6 +370,10 @@ def markov_rollout(p: Params, data: torch.Tensor, stats: dict, *, modes: int, n_
     ``force`` (append_force, :246-255 / :288-289): [B,X,Y] static forcing or [B,X,Y,T'] whose last n_steps
     frames are used, appended after the position grid; ``mu`` (append_mu, :257-260 / :290-291): [B] viscosity
     broadcast over the grid, appended last.
+    Ablation switches: ``use_position=False`` drops the grid features; ``shuffle=(x_idx, y_idx)`` permutes rows / columns
+    of the normalised input and undoes it on the forecast (:297-304); ``learn_difference`` treats the forecast as an
+    increment — the loss target is yy[t] - yy[t-1] (index -1 at t = 0, as the reference writes it, :309-310) and the
+    prediction accumulates from the first input frame (:316-318).
     Reference: fourierflow/routines/grid_2d_markov.py:195-326 (loop :263-321).
     """
     B, X, Y, T = data.shape
@@ -379,22 +384,31 @@ def markov_rollout(p: Params, data: torch.Tensor, stats: dict, *, modes: int, n_
     loss = 0
     step_losses, preds = [], []
     im = data[..., T - n_steps - 1].unsqueeze(-1)         # :236 / :265
+    prev_im = im                                          # :266
     for t in range(n_steps):
         if use_velocity:
             q, v = velocity_features(im, domain)          # :206-220 / :268-285
             im = torch.cat([im, q, v], dim=-1)
-        x = torch.cat([im, pos], dim=-1)                  # :222-233 / :286-287
+        x = torch.cat([im, pos], dim=-1) if use_position else im      # :222-233 / :286-287
         if force is not None:                             # :246-255 / :288-289
             f_t = force if force.dim() == 3 else force[..., -n_steps:][..., t]
             x = torch.cat([x, f_t.unsqueeze(-1)], dim=-1)
         if mu is not None:                                # :257-260 / :290-291
             x = torch.cat([x, mu.reshape(B, 1, 1, 1).expand(B, X, Y, 1)], dim=-1)
         x = (x - mean) / std                              # :296, normalizer.py:51
+        if shuffle is not None:                           # :297-298
+            x = x[:, shuffle[0]][:, :, shuffle[1]]
         im = block_grid2d_forward(p, x, modes=modes, n_layers=n_layers)["forecast"]   # :300-301
+        if shuffle is not None:                           # :303-304
+            im = im[:, :, torch.argsort(shuffle[1])][:, torch.argsort(shuffle[0])]
         im = im * std[0] + mean[0]                        # :306, normalizer.py:62
-        l = lp_loss_rel(im.reshape(B, -1), yy[..., t].reshape(B, -1))                 # :313
+        y = yy[..., t] - yy[..., t - 1] if learn_difference else yy[..., t]           # :309-312
+        l = lp_loss_rel(im.reshape(B, -1), y.reshape(B, -1))                          # :313
         step_losses.append(l)
         loss = loss + l
+        if learn_difference:                              # :316-318
+            im = prev_im + im
+            prev_im = im
         preds.append(im)
     return {"loss": loss, "step_losses": torch.stack(step_losses),
             "preds": torch.cat(preds, dim=-1)}            # :319

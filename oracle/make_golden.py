@@ -199,6 +199,69 @@ def rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed, force_dims=0, 
     save(name, dict(kwargs, n_steps=n_steps), arrays)
 
 
+def ablation_rollout_case(M, LpLoss, name, kwargs, B, X, T, n_steps, seed, use_position=True, shuffle=False,
+                          learn_difference=False):
+    """The ablation switches of `_valid_step` (grid_2d_markov.py:263-321) that five shipped configs use: no position
+    features (use_position=False), a fixed random permutation of the grid rows / columns around the operator
+    (shuffle_grid, :297-304), increments instead of frames (learn_difference, :309-318 — including the reference's
+    `yy[..., t-1]` at t = 0, which wraps to the last frame).  Driven through the reference's own conv / Normalizer / LpLoss."""
+    torch.manual_seed(seed)
+    conv = M.FNOFactorized2DBlock(**kwargs).eval()
+    perturb_(conv, seed + 100)
+    normalizer = M.Normalizer([conv.input_dim], 1e6)
+    l2 = LpLoss(size_average=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    data = torch.randn(B, X, X, 1, generator=g) + 0.3 * torch.cumsum(torch.randn(B, X, X, T, generator=g), dim=-1)
+    pos = torch.stack(torch.meshgrid(torch.linspace(0, 1, steps=X), torch.linspace(0, 1, steps=X), indexing="ij"), dim=-1)
+    pos = pos.unsqueeze(0).repeat(B, 1, 1, 1)
+    x_idx, y_idx = torch.randperm(X, generator=g), torch.randperm(X, generator=g)
+    x_inv, y_inv = torch.argsort(x_idx), torch.argsort(y_idx)
+    normalizer.train()
+    cols = [data[..., :-1].unsqueeze(-1)] + ([pos.unsqueeze(-2).repeat(1, 1, 1, T - 1, 1)] if use_position else [])
+    feats = torch.cat(cols, dim=-1).permute(0, 3, 1, 2, 4).reshape(B * (T - 1), X, X, -1)
+    normalizer(feats)
+    normalizer.eval()
+    yy = data[..., -n_steps:]
+    preds, step_losses, loss = None, [], 0
+    with torch.no_grad():
+        for t in range(n_steps):
+            if t == 0:
+                im = data[..., T - n_steps - 1].unsqueeze(-1)
+                prev_im = im
+            x = torch.cat([im, pos], dim=-1) if use_position else im
+            x = normalizer(x)
+            if shuffle:
+                x = x[:, x_idx][:, :, y_idx]
+            im = conv(x)["forecast"]
+            if shuffle:
+                im = im[:, :, y_inv][:, x_inv]
+            im = normalizer.inverse(im, channel=0)
+            y = yy[..., t] - yy[..., t - 1] if learn_difference else yy[..., t]
+            l = l2(im.reshape(B, -1), y.reshape(B, -1))
+            step_losses.append(l)
+            loss = loss + l
+            if learn_difference:
+                im = prev_im + im
+                prev_im = im
+            preds = im if t == 0 else torch.cat((preds, im), dim=-1)
+    arrays = sd_np(conv)
+    arrays.update(data=data.numpy(), preds=preds.numpy(), loss=np.asarray(loss.item()),
+                  step_losses=torch.stack(step_losses).numpy(), x_idx=x_idx.numpy(), y_idx=y_idx.numpy(),
+                  norm_sum=normalizer.sum.numpy(), norm_sum_squared=normalizer.sum_squared.numpy(),
+                  norm_count=normalizer.count.numpy())
+    save(name, dict(kwargs, n_steps=n_steps, use_position=use_position, shuffle_grid=shuffle,
+                    learn_difference=learn_difference), arrays)
+
+
+def ablation_rollout_cases(M, LpLoss, c2):
+    small = dict(c2, n_layers=3, modes=8)
+    ablation_rollout_case(M, LpLoss, "rollout_nopos_16", dict(small, input_dim=1), B=2, X=16, T=8, n_steps=5, seed=60,
+                          use_position=False)
+    ablation_rollout_case(M, LpLoss, "rollout_shuffle_16", small, B=2, X=16, T=8, n_steps=5, seed=61, shuffle=True)
+    ablation_rollout_case(M, LpLoss, "rollout_difference_16", small, B=2, X=16, T=8, n_steps=5, seed=62,
+                          learn_difference=True)
+
+
 def mesh_grad_case(M, LpLoss, cls, name, kwargs, shape, out_dim, seed):
     """The same pin for the mesh variants (routines/structured_mesh.py: LpLoss of the model output against the target):
     grid-coordinate append, zero padding before the layers and crop before the head are inside the autograd graph."""
@@ -407,6 +470,9 @@ def main():
     if "--only-cno" in sys.argv:
         cno_cases()
         return
+    if "--only-rollout-ablations" in sys.argv:
+        ablation_rollout_cases(M, LpLoss, c2)
+        return
     if "--only-rollout-extras" in sys.argv:
         rollout_extras_cases(M, LpLoss, c2)
         return
@@ -452,6 +518,7 @@ def main():
                  n_steps=10, seed=11)
     # (10b) the torus_vis feature sets: append_force (static and time-varying forcing) and append_mu
     rollout_extras_cases(M, LpLoss, c2)
+    ablation_rollout_cases(M, LpLoss, c2)
     # (10c) the factorized cosine (DCT) siblings
     cno_cases()
     # (10d) geo-F-FNO on point clouds (interior layers = the hot path)

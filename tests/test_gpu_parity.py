@@ -145,6 +145,32 @@ def test_rollout_golden(path, monkeypatch):
     assert rel_err(torch.stack(step_losses), a["step_losses"]) < 1e-4
 
 
+@pytest.mark.parametrize("name", ["rollout_nopos_16", "rollout_shuffle_16", "rollout_difference_16"])
+def test_rollout_ablation_switches_golden(name):
+    """The ablation switches of five shipped configs (use_position=False, shuffle_grid, learn_difference:
+    routines/grid_2d_markov.py:286-318): host step loop around ffno_block_fwd vs the reference-driven fixtures."""
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    kw, sd, a = load(name)
+    n_steps, use_position = kw.pop("n_steps"), kw.pop("use_position")
+    shuffle, diff = kw.pop("shuffle_grid"), kw.pop("learn_difference")
+    conv = build("FNOFactorized2DBlock", kw, sd)
+    exp = Grid2DMarkovExperiment(conv, n_steps=n_steps, use_position=use_position, shuffle_grid=shuffle,
+                                 learn_difference=diff, grid_size=[16]).cuda().eval()
+    if shuffle:      # the permutation is drawn at construction (grid_2d_markov.py:75-80): install the fixture's
+        exp.x_idx, exp.y_idx = a["x_idx"], a["y_idx"]
+        exp.x_inv, exp.y_inv = torch.argsort(a["x_idx"]), torch.argsort(a["y_idx"])
+    exp.normalizer.sum.copy_(a["norm_sum"])
+    exp.normalizer.sum_squared.copy_(a["norm_sum_squared"])
+    exp.normalizer.count.copy_(a["norm_count"])
+    with torch.no_grad():
+        loss, step_losses, preds, _ = exp({"data": a["data"].cuda()})
+    e = rel_err(preds, a["preds"])
+    print(name, f"preds {e:.2e} loss {loss.item():.6f} vs {a['loss'].item():.6f}")
+    assert e < TOL_UMMA
+    assert rel_err(torch.stack(step_losses), a["step_losses"]) < 1e-4
+    assert abs(loss.item() - a["loss"].item()) < 1e-4 * abs(a["loss"].item())
+
+
 @pytest.mark.parametrize("name", ["rollout_force_mu_16", "rollout_force_static_16"])
 def test_rollout_force_mu_golden(name):
     """torus_vis feature sets (append_force with a time-varying / static forcing, append_mu:

@@ -243,7 +243,8 @@ def test_rollout_contract_checks():
 
 
 def test_rollout_feature_set_options():
-    """append_force / append_mu are part of the feature count; the ablation switches still raise."""
+    """append_force / append_mu / use_position are part of the feature count; use_fourier_position raises (it cannot
+    run in the reference either), the other ablation switches select the host step loop."""
     from fourierflow_b200.modules import FNOFactorized2DBlock
     from fourierflow_b200.routines import Grid2DMarkovExperiment
     conv5 = FNOFactorized2DBlock(modes=4, width=32, n_layers=1, input_dim=5)
@@ -251,9 +252,15 @@ def test_rollout_feature_set_options():
     assert exp.append_force and exp.append_mu and not exp.use_velocity
     with pytest.raises(RuntimeError, match="input features"):      # 3 + force = 4 features, conv takes 5
         Grid2DMarkovExperiment(conv5, n_steps=2, append_force=True)
-    for bad in ("shuffle_grid", "learn_difference", "use_fourier_position"):
-        with pytest.raises(RuntimeError, match=bad):
-            Grid2DMarkovExperiment(FNOFactorized2DBlock(modes=4, width=32, n_layers=1, input_dim=3), **{bad: True})
+    conv3 = FNOFactorized2DBlock(modes=4, width=32, n_layers=1, input_dim=3)
+    with pytest.raises(RuntimeError, match="k_max"):
+        Grid2DMarkovExperiment(conv3, use_fourier_position=True)
+    assert Grid2DMarkovExperiment(conv3)._fused
+    for flag in ("shuffle_grid", "learn_difference"):
+        assert not Grid2DMarkovExperiment(conv3, grid_size=[8], **{flag: True})._fused
+    assert not Grid2DMarkovExperiment(FNOFactorized2DBlock(modes=4, width=32, n_layers=1, input_dim=1), use_position=False)._fused
+    with pytest.raises(RuntimeError, match="input features"):      # no position features: 1 input feature, conv takes 3
+        Grid2DMarkovExperiment(conv3, use_position=False)
     # statistics: frame t of a time-varying forcing accompanies input frame t, mu is broadcast
     B, X, T = 2, 8, 5
     data, f, mu = torch.randn(B, X, X, T), torch.randn(B, X, X, T), torch.rand(B)

@@ -74,6 +74,19 @@ def test_rollout():
     assert rel_err(r["step_losses"], a["step_losses"]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["rollout_nopos_16", "rollout_shuffle_16", "rollout_difference_16"])
+def test_rollout_ablation_switches(name):
+    """use_position=False / shuffle_grid / learn_difference (routines/grid_2d_markov.py:286-318, five shipped ablation
+    configs) against fixtures driven through the reference's own conv, Normalizer and LpLoss."""
+    kw, sd, a = load(name)
+    stats = {"sum": a["norm_sum"], "sum_squared": a["norm_sum_squared"], "count": a["norm_count"]}
+    r = O.markov_rollout(sd, a["data"], stats, modes=kw["modes"], n_layers=kw["n_layers"], n_steps=kw["n_steps"],
+                         use_position=kw["use_position"], learn_difference=kw["learn_difference"],
+                         shuffle=(a["x_idx"], a["y_idx"]) if kw["shuffle_grid"] else None)
+    assert rel_err(r["preds"], a["preds"]) < 1e-5
+    assert rel_err(r["step_losses"], a["step_losses"]) < 1e-5
+
+
 @pytest.mark.parametrize("name", ["rollout_force_mu_16", "rollout_force_static_16"])
 def test_rollout_force_mu(name):
     """append_force (static / time-varying forcing) and append_mu feature sets of the torus_vis configs
