@@ -51,8 +51,16 @@ struct MixWeightAdd {
   float* dw;
   int C, K;
   int dct_kc;      // > 0: DCT variant, real weights [C][C][dct_kc]; pair k carries coefficients 2k (Re rows) and 2k + 1 (Im rows)
+  float* dw_hi;    // rfft2 variant: modes k >= ksplit belong to a second weight tensor of the same [C][C][ksplit][2] layout
+  int ksplit;
   __device__ void add(int k, int m, int n, float v) const {
     int ri = m / C, ci = m - ri * C, ro = n / C, co = n - ro * C;
+    if (ksplit > 0) {
+      float* dst = (k >= ksplit ? dw_hi : dw) + (((long long)ci * C + co) * ksplit + (k >= ksplit ? k - ksplit : k)) * 2;
+      if (ri == ro) atomicAdd(dst, v);
+      else atomicAdd(dst + 1, ri == 0 ? v : -v);
+      return;
+    }
     if (dct_kc > 0) {      // only the diagonal blocks of [[W_2k, 0], [0, W_2k+1]] are parameters (pack_mix_weights_dct_kernel)
       const int j = 2 * k + ri;
       if (ri == ro && j < dct_kc) atomicAdd(dw + ((long long)ci * C + co) * dct_kc + j, v);
@@ -405,14 +413,14 @@ int launch_linear_wgrad(const float* dy, const float* x, float* dw, long long P,
 }
 
 int launch_mix_wgrad(const float* F, const float* dR, float* dw, long long outer, int K, long long p_inner, int C,
-                     int sm_count, cudaStream_t st, int dct_kc) {
+                     int sm_count, cudaStream_t st, int dct_kc, float* dw_hi, int ksplit) {
   const long long rows = outer * p_inner;
   if (rows == 0 || K == 0) return FFNO_OK;
   FFNO_REQUIRE(C % 4 == 0, FFNO_ERR_UNSUPPORTED, "mix wgrad: width %d not a multiple of 4", C);
   const int n2 = 2 * C;
   const long long inner = p_inner * C;
   const ModeRowLoad la{F, K, C, p_inner, inner}, lb{dR, K, C, p_inner, inner};
-  const MixWeightAdd epi{dw, C, K, dct_kc};
+  const MixWeightAdd epi{dw, C, K, dct_kc, dw_hi, ksplit};
   if (n2 % 128 == 0 && rows >= 1024) {
     const int splits = pick_splits(rows, (n2 / 128) * (n2 / 128) * K, sm_count);
     FFNO_REQUIRE((long long)K * splits < 65536, FFNO_ERR_UNSUPPORTED, "mix wgrad: %d modes x %d splits", K, splits);

@@ -11,7 +11,7 @@ int launch_linear_wgrad(const float* dy, const float* x, float* dw, long long P,
 // dw[ci][co][k][re|im] += the complex-weight gradient of the per-mode mix (grid_2d.py:65-68) from the forward spectra
 // F and the gradient of the mixed spectra dR, both [outer][K][2][p_inner][C]
 int launch_mix_wgrad(const float* F, const float* dR, float* dw, long long outer, int K, long long p_inner, int C,
-                     int sm_count, cudaStream_t st, int dct_kc = 0);
+                     int sm_count, cudaStream_t st, int dct_kc = 0, float* dw_hi = nullptr, int ksplit = 0);
 // out[n] += sum_r x[r][n]   (N <= 256)
 int launch_colsum(const float* x, float* out, long long rows, int N, cudaStream_t st);
 // dh[i] = h[i] > 0 ? dh[i] : 0

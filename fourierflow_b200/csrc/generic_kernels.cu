@@ -602,6 +602,33 @@ int launch_c2c_combine(const float* Y, float* out, long long outer, int R, long 
   return FFNO_OK;
 }
 
+__global__ void __launch_bounds__(256)
+c2c_expand_kernel(const float4* __restrict__ d, float4* __restrict__ Y, long long n4, long long row4, int R, int c4, float sgn) {
+  // one thread per float4 of d: writes the cosine-row copy and the sine-row entry of the OTHER part
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n4) return;
+  const long long within = idx % row4, orow = idx / row4;
+  const long long o = orow / R, r = orow % R;
+  const int ri = (int)((within / c4) & 1);
+  const long long base = (o * 2 * R + r) * row4;
+  const float4 v = d[idx];
+  Y[base + within] = v;
+  const float f = ri ? -sgn : sgn;      // d_re -> Ys_im * sgn, d_im -> Ys_re * (-sgn)
+  Y[base + (long long)R * row4 + (ri ? within - c4 : within + c4)] = make_float4(f * v.x, f * v.y, f * v.z, f * v.w);
+}
+
+int launch_c2c_expand(const float* d, float* Y, long long outer, int R, long long q, int C, float sgn, cudaStream_t st) {
+  FFNO_REQUIRE(C % 4 == 0, FFNO_ERR_UNSUPPORTED, "c2c expand: width %d not a multiple of 4", C);
+  const int c4 = C / 4;
+  const long long row4 = q * 2 * c4, n4 = outer * R * row4;
+  if (n4 == 0) return FFNO_OK;
+  c2c_expand_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(d), reinterpret_cast<float4*>(Y), n4, row4,
+                                                       R, c4, sgn);
+  ++g_launch_counter;
+  FFNO_LAUNCH_CHECK("c2c_expand_kernel");
+  return FFNO_OK;
+}
+
 int launch_pack_mix_weights(const float* w, float* Wblk, int C, int K, cudaStream_t st) {
   long long total = (long long)K * 4 * C * C;
   if (total == 0) return FFNO_OK;

@@ -63,6 +63,9 @@ int launch_pack_mix_weights_dct(const float* w, float* Wblk, int C, int Kpairs, 
 // sgn = +1: multiply by e^{-i theta} (forward), -1: by e^{+i theta} (inverse).  (torch.fft.rfft2 / irfft2 along dim -2,
 // zongyi_fno/grid_plus_2d.py:57,78.)
 int launch_c2c_combine(const float* Y, float* out, long long outer, int R, long long q, int C, float sgn, cudaStream_t st);
+// Its transpose (backward pass): d[o][R][q][2][C] -> Y[o][2R][q][2][C] with Yc = d, Ys[..0..] = -sgn * d[..1..],
+// Ys[..1..] = sgn * d[..0..].
+int launch_c2c_expand(const float* d, float* Y, long long outer, int R, long long q, int C, float sgn, cudaStream_t st);
 
 // Weff[j][c] = sum_h W1t[h][j] * W0t[c][h];  beff[j] = sum_h W1t[h][j]*b0[h] + b1[j]   (fp64 accumulate)
 int launch_fold_head(const float* W0t /*[C][H]*/, const float* b0, const float* W1t /*[H][out]*/,

@@ -178,6 +178,8 @@ int build_c2c_tables(ffno_plan* p) {
   const int L = p->ext[0], K = p->d.modes[0], R = 2 * K;
   const int ldf = pad16(2 * R), ldi = pad16(2 * L);
   std::vector<float> f((size_t)L * ldf, 0.f), inv((size_t)R * ldi, 0.f);
+  const int ldft = pad16(L), ldit = pad16(R);                       // their transposes (backward pass)
+  std::vector<float> fT((size_t)2 * R * ldft, 0.f), invT((size_t)2 * L * ldit, 0.f);
   const double s = 1.0 / std::sqrt((double)L);
   for (int l = 0; l < L; ++l)
     for (int j = 0; j < R; ++j) {
@@ -188,11 +190,19 @@ int build_c2c_tables(ffno_plan* p) {
       f[(size_t)l * ldf + R + j] = (float)sn;
       inv[(size_t)j * ldi + l] = (float)c;
       inv[(size_t)j * ldi + L + l] = (float)sn;
+      fT[(size_t)j * ldft + l] = (float)c;
+      fT[(size_t)(R + j) * ldft + l] = (float)sn;
+      invT[(size_t)l * ldit + j] = (float)c;
+      invT[(size_t)(L + l) * ldit + j] = (float)sn;
     }
   FFNO_TRY(dev_alloc(p, f.size() * 4, &p->d_fwd[0]));
   FFNO_TRY(dev_alloc(p, inv.size() * 4, &p->d_inv[0]));
+  FFNO_TRY(dev_alloc(p, fT.size() * 4, &p->d_fwdT[0]));
+  FFNO_TRY(dev_alloc(p, invT.size() * 4, &p->d_invT[0]));
   FFNO_CUDA_CHECK(cudaMemcpy(p->d_fwd[0], f.data(), f.size() * 4, cudaMemcpyHostToDevice));
   FFNO_CUDA_CHECK(cudaMemcpy(p->d_inv[0], inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+  FFNO_CUDA_CHECK(cudaMemcpy(p->d_fwdT[0], fT.data(), fT.size() * 4, cudaMemcpyHostToDevice));
+  FFNO_CUDA_CHECK(cudaMemcpy(p->d_invT[0], invT.data(), invT.size() * 4, cudaMemcpyHostToDevice));
   return FFNO_OK;
 }
 
@@ -1202,6 +1212,10 @@ size_t bwd_scratch_floats(const ffno_plan* p) {
   if ((size_t)p->in_total * C > m) m = (size_t)p->in_total * C;
   for (int a = 0; a < p->d.ndim; ++a)
     if ((size_t)p->d.modes[a] * 4 * C * C > m) m = (size_t)p->d.modes[a] * 4 * C * C;
+  if (p->d.transform == FFNO_TRANSFORM_RFFT2) {      // 2 K^2 mode blocks
+    const size_t n = (size_t)2 * p->d.modes[0] * p->d.modes[1] * 4 * C * C;
+    if (n > m) m = n;
+  }
   return m;
 }
 
@@ -1220,6 +1234,7 @@ BwdWs carve_bwd(const ffno_plan* p, int batch, void* base) {
   w.dh = c.take(PH);
   size_t spec = 0;
   for (int a = 0; a < p->d.ndim; ++a) spec += U / p->ext[a] * 2 * p->d.modes[a];     // every axis back to back
+  if (p->d.transform == FFNO_TRANSFORM_RFFT2) spec = (size_t)batch * 2 * p->ext[0] * 2 * p->d.modes[1] * p->d.width;
   w.F = c.take(spec);
   w.R = c.take(spec);
   w.dR = c.take(spec);
@@ -1326,8 +1341,6 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
   FFNO_REQUIRE(p->d.n_ff_layers == 2 && !p->d.layer_norm && !p->d.use_fork && p->d.spectral_mode == FFNO_MODE_FULL,
                FFNO_ERR_UNSUPPORTED, "backward is implemented for n_ff_layers = 2, no LayerNorm, no fork, mode 'full'");
-  FFNO_REQUIRE(p->d.transform != FFNO_TRANSFORM_RFFT2, FFNO_ERR_UNSUPPORTED,
-               "backward is implemented for the factorized stacks (rfft and DCT), not for the rfft2 variant");
   const bool mesh = p->pts != p->pts_in || p->d.append_grid;       // zero-padded / grid-appended (mesh_3d.py:161-166)
   if (batch == 0) return FFNO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1398,6 +1411,30 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
     FFNO_TRY(linear_bwd(p, lw.back.lin[1], lp.backcast_ff.linear[1], lg.backcast_ff[1], w.h, gb, w.dh, P, w, st, w.h));
     FFNO_TRY(linear_bwd(p, lw.back.lin[0], lp.backcast_ff.linear[0], lg.backcast_ff[0], sl, w.dh, w.ds, P, w, st));
     // spectral operator (grid_2d.py:51-99): s = sum_a Inv_a Mix_a Fwd_a x  =>  gx += sum_a Fwd_a^T Mix_a^T Inv_a^T ds
+    if (p->d.transform == FFNO_TRANSFORM_RFFT2) {
+      // un-factorized variant (zongyi_fno/grid_plus_2d.py:52-83): s = InvN C- InvRow Mix C+ FwdRow FwdN x (spectral_rfft2);
+      // the adjoint walks the same seven linear maps backwards with transposed tables, combine^T = expand
+      const int M = p->ext[0], N = p->ext[1], K = p->d.modes[1], Rr = 2 * K;
+      const long long row = (long long)2 * K * C;
+      FFNO_TRY(launch_axis_transform(w.ds, p->d_invT[1], w.dR, (long long)batch * M, N, 2 * K, C, false, st));
+      FFNO_TRY(launch_c2c_expand(w.dR, w.dF, batch, M, K, C, -1.f, st));
+      FFNO_TRY(launch_axis_transform(w.dF, p->d_invT[0], w.dR, batch, 2 * M, Rr, row, false, st));      // dR: d loss / d R
+      if (lg.fourier_weight[0] || lg.fourier_weight[1]) {
+        FFNO_REQUIRE(lg.fourier_weight[0] && lg.fourier_weight[1], FFNO_ERR_BAD_ARG,
+                     "rfft2: both fourier_weight gradients or none");
+        FFNO_TRY(launch_axis_transform(xl, p->d_fwd[1], w.F, (long long)batch * M, N, 2 * K, C, false, st));
+        FFNO_TRY(launch_axis_transform(w.F, p->d_fwd[0], w.R, batch, M, 2 * Rr, row, false, st));
+        FFNO_TRY(launch_c2c_combine(w.R, w.F, batch, Rr, K, C, 1.f, st));                               // F: the mix input
+        FFNO_TRY(launch_mix_wgrad(w.F, w.dR, lg.fourier_weight[0], batch, Rr * K, 1, C, p->sm_count, st, 0,
+                                  lg.fourier_weight[1], K * K));
+      }
+      FFNO_TRY(launch_transpose(lw.wmix[0], w.wT, 2 * C, 2 * C, Rr * K, st));
+      FFNO_TRY(launch_mode_mix(w.dR, w.wT, w.dF, batch, Rr * K, 1, C, st));
+      FFNO_TRY(launch_c2c_expand(w.dF, w.dR, batch, Rr, K, C, 1.f, st));
+      FFNO_TRY(launch_axis_transform(w.dR, p->d_fwdT[0], w.dF, batch, 2 * Rr, M, row, false, st));
+      FFNO_TRY(launch_axis_transform(w.dF, p->d_fwdT[1], w.gx, (long long)batch * M, 2 * K, N, C, true, st));
+      continue;
+    }
     if (tc_adj) {
       // tcgen05: the forward's three kernels on the adjoint state; its "F" buffer ends up holding dR_a = Inv_a^T ds
       // of every axis, which — with the forward spectra F_a of x_l — gives the weight gradients

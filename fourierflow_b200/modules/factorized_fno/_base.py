@@ -133,9 +133,6 @@ class StackFunction(torch.autograd.Function):
 
 def check_trainable(module) -> None:
     """Options the CUDA backward covers (every shipped F-FNO config): n_ff_layers = 2, no LayerNorm, no fork, mode 'full'."""
-    if getattr(module, "_transform", "rfft") not in ("rfft", "dct"):
-        raise RuntimeError(f"{type(module).__name__}: the CUDA backward covers the factorized stacks (rfft and DCT); "
-                           "use torch.no_grad() for the un-factorized rfft2 variant")
     if getattr(module, "use_fork", False) or module.layer_norm or module.n_ff_layers != 2 or \
             getattr(module, "mode", "full") != "full":
         raise RuntimeError(f"{type(module).__name__}: the CUDA backward covers n_ff_layers=2, no LayerNorm, no fork, "

@@ -241,7 +241,8 @@ FFNO_API size_t ffno_rollout_workspace_bytes_ex(const ffno_plan* plan, int32_t b
 /* ---- Backward pass ------------------------------------------------------------------------------
  * What torch.autograd computes for the reference's training step (routines/grid_2d_markov.py:172-193 `_training_step`:
  * forecast -> Normalizer.inverse -> LpLoss; routines/base.py:27-52 applies the optimizer), written out as explicit
- * adjoints.  Transforms: FFNO_TRANSFORM_RFFT and FFNO_TRANSFORM_DCT (not RFFT2).  Supported stacks: the 2-D grid block and
+ * adjoints.  All three transforms (RFFT2: FP32 kernels; its two
+ * fourier_weight gradients are given together or not at all).  Supported stacks: the 2-D grid block and
  * the mesh variants (grid append, zero padding and crop are part of the adjoint), n_ff_layers = 2, no LayerNorm, no fork,
  * mode 'full' (every torus_li / torus_kochkov / torus_vis / plasticity / airfoil F-FNO and F-CNO config).  The forward is
  * recomputed inside the call, so no state is carried between the forward and the backward; which kernels run the
@@ -257,7 +258,7 @@ typedef struct {
   float* bias;                    /* [out] */
 } ffno_linear_grads;
 typedef struct {
-  float* fourier_weight[FFNO_MAX_DIMS];        /* [C, C, K_a, 2] ([C, C, K_a] for FFNO_TRANSFORM_DCT), tensor-axis order */
+  float* fourier_weight[FFNO_MAX_DIMS];        /* shaped like the parameter: [C, C, K_a, 2] | DCT [C, C, K_a] | RFFT2 [C, C, K, K, 2] x 2 */
   ffno_linear_grads backcast_ff[FFNO_MAX_FF_LAYERS];
 } ffno_layer_grads;
 typedef struct {

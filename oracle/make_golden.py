@@ -431,6 +431,16 @@ def cno_grad_cases(LpLoss):
                    layer_norm=False), (2, 10, 9, 2), 1, seed=25)
 
 
+def plus_grad_cases(M, LpLoss):
+    """Gradients of the un-factorized sibling's training loss (experiments/torus_li/ablation/no_factorization*): 5-D mode
+    weights of the two row blocks, shared over the layers (width 32: FP32 kernels throughout; width 64: the forward's
+    FeedForward runs on tcgen05)."""
+    grad_case(M, LpLoss, "grad_plus2d_w32", dict(modes=4, width=32, n_layers=2, input_dim=3, share_weight=True, factor=4,
+              ff_weight_norm=True, gain=0.5), (2, 12, 10, 3), seed=26, cls="FNOPlus2DBlock")
+    grad_case(M, LpLoss, "grad_plus2d_w64", dict(modes=3, width=64, n_layers=2, input_dim=3, share_weight=False, factor=4,
+              ff_weight_norm=True, gain=0.5), (2, 8, 8, 3), seed=27, cls="FNOPlus2DBlock")
+
+
 def mesh_grad_cases(M, LpLoss):
     # mesh variants: grid append + padding + crop; width 64 (tcgen05 path) in 3-D, width 32 (FP32 path) in 2-D
     mesh_grad_case(M, LpLoss, "FNOFactorizedMesh3D", "grad_mesh3d_w64", dict(modes_x=6, modes_y=6, modes_z=4, width=64,
@@ -455,6 +465,9 @@ def main():
         return
     c2 = dict(modes=16, width=64, n_layers=24, input_dim=3, share_weight=True, factor=4,
               ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0)
+    if "--only-plus-grad" in sys.argv:
+        plus_grad_cases(M, LpLoss)
+        return
     if "--only-cno-grad" in sys.argv:
         cno_grad_cases(LpLoss)
         return

@@ -286,9 +286,8 @@ def test_cno_mirrors_keep_the_reference_contract():
     with pytest.raises(RuntimeError, match="share_weight"):
         M.CNOFactorizedMesh3D(4, 4, 4, 32, 4, 4, 2, True, 4, True, 2, False)
     from fourierflow_b200.modules.factorized_fno._base import check_trainable
-    check_trainable(b)                                        # the DCT stacks are trainable (ffno_block_bwd)
-    with pytest.raises(RuntimeError, match="rfft2"):
-        check_trainable(M.FNOPlus2DBlock(modes=4, width=32, input_dim=3, n_layers=1, factor=4, ff_weight_norm=True))
+    check_trainable(b)                                        # the DCT and the un-factorized stacks are trainable
+    check_trainable(M.FNOPlus2DBlock(modes=4, width=32, input_dim=3, n_layers=1, factor=4, ff_weight_norm=True))
 
 
 @pytest.mark.parametrize("name", ["geo_pointcloud_w32", "geo_pointcloud_shared"])

@@ -187,7 +187,7 @@ def test_three_pass_bf16_split_error_budget():
     assert e1 > 1e-4, e1                 # single-pass BF16 breaks the budget on one FeedForward already
 
 
-@pytest.mark.parametrize("name", ["grad_c2arch_16", "grad_unshared_w32", "grad_cno_grid2d_w64"])
+@pytest.mark.parametrize("name", ["grad_c2arch_16", "grad_unshared_w32", "grad_cno_grid2d_w64", "grad_plus2d_w32", "grad_plus2d_w64"])
 def test_oracle_is_differentiable_and_matches_reference_gradients(name):
     """Backward row groundwork: autograd through the oracle restatement reproduces the gradients the
     executed reference computes for its one-step training loss (routines/grid_2d_markov.py:172-193) w.r.t. the input
