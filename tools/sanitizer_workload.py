@@ -29,5 +29,11 @@ with torch.no_grad():
     c3(torch.randn(1, 9, 7, 6, 1, device="cuda"))
     geo = FNOFactorizedPointCloud2D(modes1=4, modes2=4, width=32, in_channels=2, out_channels=1, n_layers=3, s1=12, s2=10).cuda().eval()
     geo(torch.rand(2, 30, 2, device="cuda"))
+# ... and the sibling backward passes (DCT pair layout, rfft2 adjoint with c2c_expand / two-tensor weight gradient)
+for mod in (CNOFactorized2DBlock(modes=5, width=64, n_layers=2, input_dim=3, share_weight=True, factor=4, ff_weight_norm=True),
+            FNOPlus2DBlock(modes=3, width=32, n_layers=2, input_dim=3, share_weight=False, factor=4, ff_weight_norm=True)):
+    mod = mod.cuda().train()
+    xs = torch.randn(2, 12, 10, 3, device="cuda", requires_grad=True)
+    LpLoss()(mod(xs)["forecast"].reshape(2, -1), torch.randn(2, 120, device="cuda")).backward()
 torch.cuda.synchronize()
 print("sanitizer workload done", float(out[0]))
