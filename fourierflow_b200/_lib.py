@@ -111,6 +111,8 @@ EXPORTS = {
     "ffno_block_bwd_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
     "ffno_block_bwd": (C.c_int, [C.c_void_p, C.POINTER(BlockParams), C.c_void_p, C.c_void_p, C.c_int32,
                                  C.POINTER(BlockGrads), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ffno_layers_bwd": (C.c_int, [C.c_void_p, C.POINTER(BlockParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.POINTER(BlockGrads), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ffno_plan_set_backward_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "ffno_rel_l2_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "ffno_velocity_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),

@@ -322,10 +322,12 @@ class StackPlan:
                    "ffno_plan_set_backward_mode")
 
     def block_backward(self, x: torch.Tensor, d_forecast: torch.Tensor, in_proj, out, layers: List[LayerSpec],
-                       want_dx: bool):
+                       want_dx: bool, layer_bias: Optional[torch.Tensor] = None, want_dbias: bool = False):
         """Gradients of the stack (ffno_block_bwd) -> (dx or None, {id(parameter): gradient tensor}).  Call right after
         ``sync_params`` with the same modules: the raw parameter pointers of that load are what the weight-norm backward
-        reads; a parameter shared by several layers gets one buffer that receives the sum."""
+        reads; a parameter shared by several layers gets one buffer that receives the sum.
+        ``in_proj is None``: the layer loop alone (ffno_layers_bwd, plans without lift / head): ``x`` is x_0,
+        ``d_forecast`` is dL/dx_L, ``layer_bias`` [points, C] is added after every layer -> (dx, gmap, d_bias or None)."""
         B = x.shape[0]
         gmap: dict = {}
 
@@ -348,9 +350,10 @@ class StackPlan:
             dst.bias = gbuf(lin.bias)
 
         bg = _lib.BlockGrads()
-        lin_grads(bg.in_proj, in_proj)
-        lin_grads(bg.out0, out[0])
-        lin_grads(bg.out1, out[1])
+        if in_proj is not None:
+            lin_grads(bg.in_proj, in_proj)
+            lin_grads(bg.out0, out[0])
+            lin_grads(bg.out1, out[1])
         arr = (_lib.LayerGrads * len(layers))()
         for l, spec in enumerate(layers):
             for a, w in enumerate(spec.fourier_weight):
@@ -366,6 +369,12 @@ class StackPlan:
             if ws is None or ws.numel() < need:
                 ws = self._ws_bwd = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
             dx = torch.empty_like(x) if want_dx else None
+            if in_proj is None:
+                d_bias = torch.zeros_like(layer_bias) if (want_dbias and layer_bias is not None) else None
+                _lib.check(self.lib.ffno_layers_bwd(self._plan, C.byref(self._structs[0]), x.data_ptr(), d_forecast.data_ptr(),
+                                                    _ptr(layer_bias), B, C.byref(bg), _ptr(dx), _ptr(d_bias), ws.data_ptr(),
+                                                    ws.numel(), _stream(self.device)), "ffno_layers_bwd")
+                return dx, gmap, d_bias
             _lib.check(self.lib.ffno_block_bwd(self._plan, C.byref(self._structs[0]), x.data_ptr(), d_forecast.data_ptr(),
                                                B, C.byref(bg), _ptr(dx), ws.data_ptr(), ws.numel(), _stream(self.device)),
                        "ffno_block_bwd")

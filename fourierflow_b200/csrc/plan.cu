@@ -1332,13 +1332,21 @@ size_t ffno_block_bwd_workspace_bytes(const ffno_plan* plan, int32_t batch) {
   return carve_bwd(plan, batch, nullptr).bytes;
 }
 
-int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, const float* d_forecast, int32_t batch,
-                   const ffno_block_grads* grads, float* dx, void* workspace, size_t workspace_bytes, void* stream) {
+// Layer loop alone (ffno_layers_bwd): no lift / head; x is x_0, d_forecast is dL/dx_L, every layer adds `bias`.
+struct LayersOnly {
+  const float* bias;      // [pts, C] added after every layer's residual sum, broadcast over the batch (NULL: none)
+  float* d_bias;          // += its gradient (NULL: skipped)
+};
+
+static int block_bwd_core(ffno_plan* p, const ffno_block_params* prm, const float* x, const float* d_forecast, int32_t batch,
+                          const ffno_block_grads* grads, float* dx, void* workspace, size_t workspace_bytes, void* stream,
+                          const LayersOnly* lo) {
   FFNO_TRY(check_ready(p, batch, workspace, workspace_bytes, ffno_block_bwd_workspace_bytes(p, batch)));
   FFNO_REQUIRE(prm && grads && x && d_forecast, FFNO_ERR_BAD_ARG, "NULL argument");
   FFNO_REQUIRE(prm->n_layers == p->d.n_layers && grads->n_layers == p->d.n_layers && prm->layers && grads->layers,
                FFNO_ERR_BAD_ARG, "params / grads must describe the plan's %d layers", p->d.n_layers);
-  FFNO_REQUIRE(p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
+  FFNO_REQUIRE(lo || p->has_io, FFNO_ERR_STATE, "plan was loaded without lift/head parameters");
+  FFNO_REQUIRE(!lo || (p->pts == p->pts_in && !p->d.append_grid), FFNO_ERR_UNSUPPORTED, "layer-loop backward: no padding / grid append");
   FFNO_REQUIRE(p->d.n_ff_layers == 2 && !p->d.layer_norm && !p->d.use_fork && p->d.spectral_mode == FFNO_MODE_FULL,
                FFNO_ERR_UNSUPPORTED, "backward is implemented for n_ff_layers = 2, no LayerNorm, no fork, mode 'full'");
   const bool mesh = p->pts != p->pts_in || p->d.append_grid;       // zero-padded / grid-appended (mesh_3d.py:161-166)
@@ -1355,7 +1363,7 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
 
   // ---- 1. forward again, keeping the input x_l and the spectral output s_l of every layer (and the last backcast)
   // tc: the tcgen05 kernels take part (see the FFNO_B200_BWD modes at plan creation)
-  const bool tc = p->use_umma && !p->bwd_fp32;
+  const bool tc = p->use_umma && !p->bwd_fp32 && !lo;      // (the layer-loop form runs on the FP32 kernels)
   const bool tc_fwd = tc && !p->bwd_fp32_recompute, tc_adj = tc && !p->bwd_fp32_adjoint;
   if (tc) FFNO_TRY(ensure_adjoint(p, st));
   if (tc_fwd) {
@@ -1373,7 +1381,8 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
     taps.b_last = w.b;
     FFNO_TRY(block_fwd_core(p, x, batch, w.fc, &taps, w.fwd_ws, st));
   } else {
-    FFNO_TRY(launch_lift(x, p->lift.wt, p->lift.bias, w.xs, batch, g, st));
+    if (lo) FFNO_CUDA_CHECK(cudaMemcpyAsync(w.xs, x, U * 4, cudaMemcpyDeviceToDevice, st));
+    else FFNO_TRY(launch_lift(x, p->lift.wt, p->lift.bias, w.xs, batch, g, st));
     for (int l = 0; l < nl; ++l) {
       const LayerW& lw = p->layers[l];
       float* xl = w.xs + (size_t)l * U;
@@ -1381,11 +1390,18 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
       FFNO_TRY(spectral_generic(p, lw, xl, batch, sl, w.F, w.R, st));
       // x_{l+1} = x_l + b_l; the last layer's residual sum is dead (the head reads b, grid_2d.py:170-172)
       FFNO_TRY(ff_generic(p, lw.back, sl, xl, P, l + 1 < nl ? xl + U : nullptr, l + 1 < nl ? nullptr : w.b, wf, st));
+      if (lo && lo->bias && l + 1 < nl)      // x_{l+1} += bias, every sample (point_cloud_2d.py:205-206)
+        for (int bi = 0; bi < batch; ++bi) FFNO_TRY(launch_axpy(xl + U + (size_t)bi * (U / batch), lo->bias, (long long)(U / batch), st));
     }
   }
   // ---- 2. head: forecast = out1(out0(b)) on the unpadded region (mesh_3d.py:173-174)
   const long long Pin = (long long)batch * p->pts_in;
   const float* b_rows = w.b;
+  if (lo) {
+    // no head: the incoming gradient is dL/dx_L, which reaches the last layer's backcast AND its residual input
+    FFNO_CUDA_CHECK(cudaMemcpyAsync(w.gb, d_forecast, U * 4, cudaMemcpyDeviceToDevice, st));
+    FFNO_CUDA_CHECK(cudaMemcpyAsync(w.gx, d_forecast, U * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
   if (mesh) {
     FFNO_TRY(launch_crop_pad(w.b_dense, w.b, batch, g, false, st));
     b_rows = w.b_dense;
@@ -1394,11 +1410,14 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   FFNO_TRY(linear_bwd(p, p->out1, prm->out1, grads->out1, w.h0, d_forecast, w.dh0, Pin, w, st));
   FFNO_TRY(linear_bwd(p, p->out0, prm->out0, grads->out0, b_rows, w.dh0, mesh ? w.g_dense : w.gb, Pin, w, st));
   if (mesh) FFNO_TRY(launch_crop_pad(w.g_dense, w.gb, batch, g, true, st));      // zero gradient in the padding
+  }
 
   // ---- 3. layers, last to first.  gx = dL/dx_{l+1}; the layer's backcast gradient is gx (x_{l+1} = x_l + b_l), or
   //         the head's for the last layer
-  FFNO_CUDA_CHECK(cudaMemsetAsync(w.gx, 0, U * 4, st));
+  if (!lo) FFNO_CUDA_CHECK(cudaMemsetAsync(w.gx, 0, U * 4, st));
   for (int l = nl - 1; l >= 0; --l) {
+    if (lo && lo->d_bias)      // bias enters x_{l+1} of every layer: d_bias += sum over the samples of dL/dx_{l+1}
+      for (int bi = 0; bi < batch; ++bi) FFNO_TRY(launch_axpy(lo->d_bias, w.gx + (size_t)bi * (U / batch), (long long)(U / batch), st));
     const LayerW& lw = p->layers[l];
     const ffno_layer_params& lp = prm->layers[l];
     const ffno_layer_grads& lg = grads->layers[l];
@@ -1473,7 +1492,9 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   }
 
   // ---- 4. lift (grid_2d.py:157; mesh_3d.py:161-166: grid coordinates appended, linear, zero padding)
-  if (mesh) {
+  if (lo) {
+    if (dx) FFNO_CUDA_CHECK(cudaMemcpyAsync(dx, w.gx, U * 4, cudaMemcpyDeviceToDevice, st));
+  } else if (mesh) {
     FFNO_TRY(launch_crop_pad(w.g_dense, w.gx, batch, g, false, st));
     FFNO_TRY(launch_lift_rows(x, w.rows_in, Pin, g, st));
     FFNO_TRY(linear_bwd(p, p->lift, prm->in_proj, grads->in_proj, w.rows_in, w.g_dense, dx ? w.d_rows : nullptr, Pin, w, st));
@@ -1484,6 +1505,18 @@ int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, c
   p->last_launches = g_launch_counter - before;
   (void)O;
   return FFNO_OK;
+}
+
+int ffno_block_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x, const float* d_forecast, int32_t batch,
+                   const ffno_block_grads* grads, float* dx, void* workspace, size_t workspace_bytes, void* stream) {
+  return block_bwd_core(p, prm, x, d_forecast, batch, grads, dx, workspace, workspace_bytes, stream, nullptr);
+}
+
+int ffno_layers_bwd(ffno_plan* p, const ffno_block_params* prm, const float* x0, const float* d_out, const float* bias,
+                    int32_t batch, const ffno_block_grads* grads, float* dx, float* d_bias, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  const LayersOnly lo{bias, d_bias};
+  return block_bwd_core(p, prm, x0, d_out, batch, grads, dx, workspace, workspace_bytes, stream, &lo);
 }
 
 int ffno_plan_set_backward_mode(ffno_plan* plan, int32_t mode) {

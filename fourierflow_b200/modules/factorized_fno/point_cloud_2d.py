@@ -82,6 +82,28 @@ class SpectralConv2d(nn.Module):
         return self.ifft2d(torch.cat([lo, hi], dim=-2), x_out, iphi, code)
 
 
+class _InteriorFunction(torch.autograd.Function):
+    """The interior layer loop as one autograd node: forward = the device-resident loop, backward = ffno_layers_bwd
+    (explicit adjoints on the FP32 kernels; the loop is recomputed there, only its input is saved).  The parameters are
+    inputs only so that autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, module, uc, grid_bias, *params):
+        ctx.module = module
+        ctx.save_for_backward(uc, grid_bias)
+        return module._interior_run(uc, grid_bias)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        uc, grid_bias = ctx.saved_tensors
+        module = ctx.module
+        plan = module._interior_plan(uc.device)
+        d_uc, gmap, d_bias = plan.block_backward(
+            uc, d_out.contiguous().float(), None, None, module.__dict__["_spec_cache"], ctx.needs_input_grad[1],
+            layer_bias=grid_bias, want_dbias=ctx.needs_input_grad[2])
+        return (None, d_uc, d_bias) + tuple(gmap.get(id(p)) for p in module._interior_params())
+
+
 class FNOFactorizedPointCloud2D(PlanCacheMixin, nn.Module):
     def __init__(self, modes1, modes2, width, in_channels, out_channels, n_layers=4, is_mesh=True, s1=40, s2=40,
                  share_weight=False):
@@ -141,11 +163,26 @@ class FNOFactorizedPointCloud2D(PlanCacheMixin, nn.Module):
         layer) -> the latent field after layers 1 .. n_layers-1:  uc <- uc + backcast_ff(forward_fourier(uc)) + grid_bias
         (point_cloud_2d.py:198-210), device-resident."""
         _ops.require_cuda(uc, "FNOFactorizedPointCloud2D.interior_forward")
-        _ops.require_inference(self, uc)
         if self.n_layers < 2:
             return uc
+        uc, grid_bias = uc.contiguous(), grid_bias.contiguous()
+        if torch.is_grad_enabled() and (uc.requires_grad or grid_bias.requires_grad or
+                                        any(p.requires_grad for p in self._interior_params())):
+            return _InteriorFunction.apply(self, uc, grid_bias, *self._interior_params())      # training: ffno_layers_bwd
+        return self._interior_run(uc, grid_bias)
+
+    def _interior_params(self):
+        """Distinct parameters of the interior layers, in a fixed order (the autograd node's parameter inputs)."""
+        seen, out = set(), []
+        for i in range(1, self.n_layers):
+            for p in self.convs[i].parameters():
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    out.append(p)
+        return out
+
+    def _interior_run(self, uc: torch.Tensor, grid_bias: torch.Tensor) -> torch.Tensor:
         plan = self._interior_plan(uc.device)
-        uc = uc.contiguous()
         for l in range(self.n_layers - 1):
             s = plan.spectral_forward(l, uc)
             uc = plan.ff_forward(l, 0, s, uc + grid_bias)      # FF(s) + residual, residual = uc + grid bias
@@ -155,7 +192,6 @@ class FNOFactorizedPointCloud2D(PlanCacheMixin, nn.Module):
     def forward(self, u, code=None, x_in=None, x_out=None, iphi=None):
         """u:[B, N, 2] mesh coordinates (and features) -> [B, N, out_channels] (point_cloud_2d.py:173-227)."""
         _ops.require_cuda(u, "FNOFactorizedPointCloud2D.forward")
-        _ops.require_inference(self, u)
         if self.is_mesh and x_in is None:
             x_in = u
         if self.is_mesh and x_out is None:

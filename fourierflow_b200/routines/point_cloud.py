@@ -1,6 +1,7 @@
 """``PointCloudExperiment`` — host-side mirror of fourierflow/routines/point_cloud.py:9-65 (elasticity: the geo-F-FNO on
 the mesh points ``xy`` with the geometry code ``rr`` and the learned deformation ``iphi``), without pytorch_lightning.
-Inference / evaluation only: the geo operator has no CUDA backward."""
+Training goes through torch autograd for the point-cloud end layers / ``iphi`` and through ffno_layers_bwd for the
+interior layer loop."""
 from __future__ import annotations
 
 import torch
@@ -33,6 +34,16 @@ class PointCloudExperiment(RoutineMixin, nn.Module):
 
     test_step = validation_step
 
-    def training_step(self, batch, batch_idx=0, **kwargs):
-        raise RuntimeError("PointCloudExperiment (B200 backend): the geo operator is inference-only (no CUDA backward for the "
-                           "point-cloud end layers); train with the reference, evaluate / predict here")
+    def training_step(self, batch, batch_idx: int = 0, optimizer=None, scheduler=None, clip_val=None, world_size: int = 1):
+        """point_cloud.py:29-43: data loss + 0 x the deformation regulariser on N random points, then the manual
+        optimisation (routines/base.py:27-52)."""
+        xy, rr, sigma = batch['xy'].cuda(), batch['rr'].cuda(), batch['sigma'].cuda()
+        B = rr.shape[0]
+        out = self.model(xy, code=rr, iphi=self.iphi)
+        loss_data = self.l2_loss(out.reshape(B, -1), sigma.reshape(B, -1))
+        samples_x = torch.rand(B, self.N, 2, device=xy.device) * 3 - 1
+        samples_xi = self.iphi(samples_x, code=rr)
+        loss_reg = self.l2_loss(samples_xi.reshape(B, -1), samples_x.reshape(B, -1))
+        loss = loss_data + 0 * loss_reg
+        self.optimize_manually(loss, batch_idx, optimizer, scheduler, clip_val, world_size)
+        return loss

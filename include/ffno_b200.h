@@ -280,6 +280,14 @@ FFNO_API int ffno_block_bwd(ffno_plan* plan, const ffno_block_params* params, co
  *   1 fast    : recompute on the tcgen05 kernels too (1.4x faster); hidden units within ~1e-5 of the ReLU kink may
  *               take the other branch: the gradient of the tcgen05-computed forward, not of the reference's
  *   2 fp32    : everything on the FP32 kernels */
+/* Backward of the LAYER LOOP alone, for plans loaded without lift / head (the interior of the geo-F-FNO,
+ * factorized_fno/point_cloud_2d.py:198-210):  x_{l+1} = x_l + backcast_ff_l(spectral_l(x_l)) + bias,  l = 0 .. n_layers-1,
+ * `bias` [points, C] broadcast over the batch (NULL: none).  d_out = dL/dx_{n_layers} [B, points, C]; writes
+ * dx = dL/dx_0 (NULL: skipped), accumulates the layer gradients (grads->layers; in_proj / out0 / out1 are ignored) and
+ * d_bias += dL/dbias (NULL: skipped).  FP32 kernels; workspace as ffno_block_bwd. */
+FFNO_API int ffno_layers_bwd(ffno_plan* plan, const ffno_block_params* params, const float* x0, const float* d_out,
+                    const float* bias, int32_t batch, const ffno_block_grads* grads, float* dx, float* d_bias,
+                    void* workspace, size_t workspace_bytes, void* stream);
 FFNO_API int ffno_plan_set_backward_mode(ffno_plan* plan, int32_t mode);
 /* Backward of ffno_rel_l2 for contiguous x, y [batch, n]: dx[b, i] = g_out[b] * d out[b] / d x[b, i]
  * (modules/loss.py:33-46; the mean over the batch is the caller's g_out = 1 / batch). */

@@ -363,6 +363,44 @@ def geo_case(M, name, kwargs, B, N, seed):
     save(name, kwargs, arrays)
 
 
+def geo_grad_case(M, LpLoss, name, kwargs, B, N, seed):
+    """Gradients through the geo-F-FNO: (i) of the training loss LpLoss(model(u), y) w.r.t. every parameter the forward
+    uses (routines/point_cloud.py:29-43, iphi = None), and (ii) of <r, interior(uc, bias)> w.r.t. uc, the grid bias and
+    the interior layers' parameters — the pin of ffno_layers_bwd — with the interior replayed from the module's own
+    sub-modules (point_cloud_2d.py:198-210)."""
+    from einops import rearrange
+    torch.manual_seed(seed)
+    m = M.FNOFactorizedPointCloud2D(**kwargs).train()
+    perturb_(m, seed + 100)
+    g = torch.Generator().manual_seed(seed + 1)
+    u = torch.rand(B, N, 2, generator=g)
+    y = torch.randn(B, N, 1, generator=g)
+    arrays = {"sd::" + k: (torch.view_as_real(v) if v.is_complex() else v).detach().numpy() for k, v in m.state_dict().items()}
+    arrays.update(u=u.numpy(), y=y.numpy())
+    out = m(u)
+    loss = LpLoss(size_average=True)(out.reshape(B, -1), y.reshape(B, -1))
+    loss.backward()
+    arrays["out"], arrays["loss"] = out.detach().numpy(), loss.detach().numpy()
+    for k, p_ in m.named_parameters():
+        if p_.grad is not None:
+            gr = p_.grad.detach()
+            arrays["grad::" + k] = (torch.view_as_real(gr) if gr.is_complex() else gr).numpy()
+    m.zero_grad()
+    uc = torch.randn(B, m.s1, m.s2, m.width, generator=g).requires_grad_(True)       # channels-last latent grid
+    bias = (0.1 * torch.randn(m.s1, m.s2, m.width, generator=g)).requires_grad_(True)
+    r = torch.randn(B, m.s1, m.s2, m.width, generator=g)
+    h = uc
+    for i in range(1, m.n_layers):
+        h = h + m.convs[i](h)[0] + bias
+    (h * r).sum().backward()
+    arrays.update(uc_in=uc.detach().numpy(), grid_bias=bias.detach().numpy(), r=r.numpy(), uc_out=h.detach().numpy())
+    arrays["igrad::uc"], arrays["igrad::bias"] = uc.grad.numpy(), bias.grad.numpy()
+    for k, p_ in m.named_parameters():
+        if p_.grad is not None and k.startswith("convs."):
+            arrays["igrad::" + k] = p_.grad.detach().numpy()
+    save(name, kwargs, arrays)
+
+
 def geo_cases(M):
     geo_case(M, "geo_pointcloud_w32", dict(modes1=4, modes2=4, width=32, in_channels=2, out_channels=1, n_layers=4,
              s1=12, s2=10, share_weight=False), B=2, N=40, seed=40)
@@ -479,6 +517,10 @@ def main():
         return
     if "--only-geo" in sys.argv:
         geo_cases(M)
+        return
+    if "--only-geo-grad" in sys.argv:
+        geo_grad_case(M, LpLoss, "grad_geo_pointcloud", dict(modes1=4, modes2=4, width=32, in_channels=2, out_channels=1,
+                      n_layers=4, s1=12, s2=10, share_weight=False), B=2, N=40, seed=42)
         return
     if "--only-cno" in sys.argv:
         cno_cases()

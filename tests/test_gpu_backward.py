@@ -273,3 +273,45 @@ def test_structured_mesh_training_step():
     assert losses[-1] < losses[0]
     with torch.no_grad():
         assert abs(exp.validation_step(batch).item() * 2.0 - losses[-1]) < 0.05 * losses[-1]
+
+
+def test_geo_ffno_gradients_match_the_executed_reference():
+    """geo-F-FNO training (experiments/elasticity/ffno): (i) ffno_layers_bwd alone — gradients of <r, interior(uc, bias)>
+    w.r.t. the latent grid, the grid bias and the interior parameters; (ii) the whole training loss through the torch end
+    layers + the interior autograd node, against the reference's autograd (fixture grad_geo_pointcloud)."""
+    from golden_util import load_geo
+    import fourierflow_b200.modules as M
+    kw, sd, a = load_geo("grad_geo_pointcloud")
+    m = M.FNOFactorizedPointCloud2D(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    uc, bias = a["uc_in"].cuda().requires_grad_(True), a["grid_bias"].cuda().requires_grad_(True)
+    out = m.interior_forward(uc, bias)
+    (out * a["r"].cuda()).sum().backward()
+    errs = {"uc_out": rel_err(out, a["uc_out"]), "d_uc": rel_err(uc.grad, a["igrad::uc"]), "d_bias": rel_err(bias.grad, a["igrad::bias"])}
+    params = dict(m.named_parameters())
+    n_int = 0
+    for k, ref in a.items():
+        if k.startswith("igrad::convs."):
+            errs[k] = rel_err(params[k[7:]].grad, ref)
+            n_int += 1
+    print("geo interior", {k: f"{v:.1e}" for k, v in list(errs.items())[:3]}, f"{n_int} parameter gradients, worst {max(errs.values()):.2e}")
+    assert n_int >= 18 and max(errs.values()) < TOL, errs
+    m.zero_grad()
+    u = a["u"].cuda()
+    B = u.shape[0]
+    outp = m(u)
+    loss = M.LpLoss(size_average=True)(outp.reshape(B, -1), a["y"].cuda().reshape(B, -1))
+    loss.backward()
+    assert rel_err(outp, a["out"]) < TOL and abs(loss.item() - a["loss"].item()) < 1e-5 * abs(a["loss"].item())
+    worst, n = 0.0, 0
+    for k, ref in a.items():
+        if k.startswith("grad::"):
+            g = params[k[6:]].grad
+            assert g is not None, k
+            g = torch.view_as_real(g) if g.is_complex() else g
+            e = rel_err(g, ref)
+            worst, n = max(worst, e), n + 1
+            assert e < TOL, (k, e)
+    print(f"geo training loss: {n} parameter gradients, worst {worst:.2e}")
+    assert n >= 25

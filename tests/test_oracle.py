@@ -243,3 +243,21 @@ def test_oracle_mesh_gradients_match_reference(name, modes):
             assert rel_err(p[k[6:]].grad, ref) < 2e-5, k
             checked += 1
     assert checked >= 10
+
+
+def test_oracle_geo_interior_gradients_match_reference():
+    """Autograd through the oracle's interior loop reproduces the reference's gradients of <r, interior(uc, bias)> w.r.t.
+    the latent grid, the grid bias and the interior layers' parameters (the pin of ffno_layers_bwd)."""
+    kw, sd, a = load_geo("grad_geo_pointcloud")
+    p = {k: (v.clone().requires_grad_(True) if k.startswith("convs.") and not v.is_complex() else v) for k, v in sd.items()}
+    uc, bias = a["uc_in"].clone().requires_grad_(True), a["grid_bias"].clone().requires_grad_(True)
+    out = O.geo_interior_forward(p, uc, bias, modes=kw["modes1"], n_layers=kw["n_layers"])
+    (out * a["r"]).sum().backward()
+    assert rel_err(out, a["uc_out"]) < TOL
+    assert rel_err(uc.grad, a["igrad::uc"]) < 2e-5 and rel_err(bias.grad, a["igrad::bias"]) < 2e-5
+    checked = 0
+    for k, ref in a.items():
+        if k.startswith("igrad::convs."):
+            assert rel_err(p[k[7:]].grad, ref) < 2e-5, k
+            checked += 1
+    assert checked >= 18
