@@ -69,7 +69,9 @@ def main(argv=None) -> int:
         times.append(time.time() - t0)
     elapsed = min(times)
     n = len(batch["data"])
+    loss = float(routine.infer(batch)[0])                 # sum over the steps of the batch-mean relative L2 (:313-315)
     print(json.dumps({
+        "rollout_loss": loss,
         "inference_time": elapsed / n / (routine.step_size * n_steps),
         "unit": "s per sample and simulated time unit (commands/predict.py:103-104)",
         "elapsed_s": elapsed, "samples": n, "n_steps": n_steps, "step_size": routine.step_size,

@@ -580,3 +580,32 @@ def test_elasticity_routine_with_iphi_vs_the_reference_modules(monkeypatch):
         l1 = exp.training_step({"xy": xy, "rr": rr, "sigma": sigma}, optimizer=opt)
     print(f"training step loss {l0.item():.4f} -> {l1.item():.4f}")
     assert l1.item() < l0.item()
+
+
+def test_predict_command_on_a_mat_file_and_a_lightning_checkpoint(tmp_path, capsys):
+    """python -m fourierflow_b200.predict with the reference's data and checkpoint formats (commands/predict.py:87-105):
+    a .mat file holding 'u' [N, X, Y, T] (builders/ns_markov.py:57-59) and a Lightning checkpoint {'state_dict': ...} of the
+    routine (routines/base.py:79-102, normaliser statistics included).  The reported rollout loss must be the one the
+    routine computes directly from the same tensors."""
+    import json
+    import scipy.io
+    from fourierflow_b200 import predict
+    from fourierflow_b200.routines import Grid2DMarkovExperiment
+    from test_config import MARKOV_YAML
+    cfg = tmp_path / "config.yaml"
+    cfg.write_text(MARKOV_YAML)
+    u = torch.randn(6, 32, 32, 8, generator=torch.Generator().manual_seed(9))
+    scipy.io.savemat(str(tmp_path / "ns.mat"), {"u": u.numpy()})
+    torch.manual_seed(11)
+    conv = M().FNOFactorized2DBlock(modes=16, width=64, n_layers=2, input_dim=3, share_weight=True, factor=4,
+                                    ff_weight_norm=True, gain=0.1, dropout=0.0, in_dropout=0.0)
+    src = Grid2DMarkovExperiment(conv, n_steps=3).cuda().eval()
+    src.accumulate_statistics(u.cuda())
+    torch.save({"state_dict": {k: v.cpu() for k, v in src.state_dict().items()}, "epoch": 1}, tmp_path / "last.ckpt")
+    with torch.no_grad():
+        want = float(src({"data": u.cuda()})[0])
+    assert predict.main([str(cfg), "routine.conv.n_layers=2", "routine.n_steps=3", "--mat", str(tmp_path / "ns.mat"),
+                         "--checkpoint", str(tmp_path / "last.ckpt"), "--samples", "6", "--repeats", "1"]) == 0
+    rec = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert rec["samples"] == 6 and rec["grid"] == [32, 32] and rec["data"].endswith("ns.mat")
+    assert abs(rec["rollout_loss"] - want) < 1e-5 * abs(want), (rec["rollout_loss"], want)
